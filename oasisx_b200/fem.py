@@ -1,0 +1,267 @@
+"""Host-side function spaces, dof maps, CSR patterns and (device-mirrored) functions.
+
+Stands in for the slice of ``dolfinx.fem`` / ``dolfinx.la`` that the reference's IPCS loop touches
+(SURVEY.md N3, N12, N15): ``functionspace``, ``Function`` (``.x.array``, ``.interpolate``),
+``Constant``, ``locate_dofs_topological`` / ``locate_dofs_geometrical`` and the sparsity pattern
+behind ``dolfinx.fem.petsc.create_matrix`` (``/root/reference/src/oasisx/fracstep.py:293-352``).
+
+A :class:`Function` owns a host numpy array.  Once the solver binds it to a device vector the host
+array becomes a *mirror*: reading ``.x.array`` pulls from the GPU if the GPU copy is newer and marks
+the host copy as possibly edited, so that it is pushed back before the next device stage.  Inside
+``FractionalStep_AB_CN.solve`` nothing touches the host mirrors.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+from .mesh import _EDGE_VERTS, Mesh
+
+__all__ = [
+    "Constant",
+    "DofMap",
+    "Function",
+    "FunctionSpace",
+    "Vector",
+    "build_csr_pattern",
+    "functionspace",
+    "locate_dofs_geometrical",
+    "locate_dofs_topological",
+]
+
+
+class IndexMap:
+    """Owned-first / ghosts-last index map (``dolfinx.common.IndexMap`` look-alike)."""
+
+    def __init__(self, size_local: int, ghosts=None, owners=None, size_global=None, offset=0):
+        self.size_local = int(size_local)
+        self.ghosts = np.zeros(0, np.int64) if ghosts is None else np.asarray(ghosts, np.int64)
+        self.owners = np.zeros(0, np.int32) if owners is None else np.asarray(owners, np.int32)
+        self.num_ghosts = len(self.ghosts)
+        self.size_global = self.size_local if size_global is None else int(size_global)
+        self.local_range = (int(offset), int(offset) + self.size_local)
+
+
+class DofMap:
+    def __init__(self, cell_dofs: np.ndarray, index_map: IndexMap, bs: int = 1):
+        self.list = np.ascontiguousarray(cell_dofs, dtype=np.int32)
+        self.index_map = index_map
+        self.index_map_bs = bs
+
+    def cell_dofs(self, c: int) -> np.ndarray:
+        return self.list[c]
+
+
+class _Element:
+    def __init__(self, cell: str, degree: int):
+        d = 2 if cell == "triangle" else 3
+        pts = [np.zeros(d)] + [np.eye(d)[i] for i in range(d)]
+        if degree == 2:
+            pts += [0.5 * (pts[a] + pts[b]) for a, b in _EDGE_VERTS[d]]
+        self.interpolation_points = np.array(pts)
+        self.degree = degree
+
+
+def _lex_order(x: np.ndarray) -> np.ndarray:
+    """Permutation sorting points by (z, y, x): spatial locality for SpMV gathers."""
+    span = max(float(np.ptp(x)), 1e-300)
+    q = np.round(x / span * 2**40).astype(np.int64)
+    return np.lexsort((q[:, 0], q[:, 1], q[:, 2]))
+
+
+class FunctionSpace:
+    """Scalar Lagrange P1/P2 space (``bs == 1``) or its blocked vector version (``bs == gdim``)."""
+
+    def __init__(self, mesh: Mesh, degree: int, bs: int = 1, _scalar: "FunctionSpace | None" = None):
+        if degree not in (1, 2):
+            raise NotImplementedError("only Lagrange degree 1 and 2 are on the B200 hot path")
+        self.mesh = mesh
+        self.degree = degree
+        self.bs = bs
+        self.element = _Element(mesh.cell_name(), degree)
+        if _scalar is not None:
+            self._x = _scalar._x
+            self.dofmap = DofMap(_scalar.dofmap.list, _scalar.dofmap.index_map, bs)
+            self._scalar = _scalar
+            return
+        self._scalar = self
+        cells = mesh.geometry.dofmap.astype(np.int64)
+        nv = mesh.geometry.x.shape[0]
+        if degree == 1:
+            x = mesh.geometry.x
+            cell_dofs = cells
+        else:
+            edges = mesh.topology.entities(1)
+            ce = mesh.topology.cell_entities(1)
+            x = np.vstack([mesh.geometry.x, 0.5 * (mesh.geometry.x[edges[:, 0]] + mesh.geometry.x[edges[:, 1]])])
+            cell_dofs = np.hstack([cells, nv + ce])
+        # renumber for locality (DOLFINx applies a graph reordering here [ext]); vertex-first
+        # numbering would scatter every P2 row's columns over the whole vector
+        order = _lex_order(x)
+        new_of_old = np.empty(len(order), dtype=np.int64)
+        new_of_old[order] = np.arange(len(order))
+        self._x = np.ascontiguousarray(x[order])
+        self.dofmap = DofMap(new_of_old[cell_dofs], IndexMap(len(order)), 1)
+
+    # -- dolfinx.fem.FunctionSpace surface -------------------------------------------------
+    @property
+    def num_sub_spaces(self) -> int:
+        return self.bs if self.bs > 1 else 0
+
+    def sub(self, i: int) -> "_SubSpace":
+        assert 0 <= i < self.bs and self.bs > 1
+        return _SubSpace(self, i)
+
+    def tabulate_dof_coordinates(self) -> np.ndarray:
+        return self._x
+
+    @property
+    def num_dofs(self) -> int:
+        return self._x.shape[0]
+
+    def entity_closure_dofs(self, edim: int, entities: np.ndarray) -> np.ndarray:
+        """Sorted unique dofs on the closure of the given mesh entities."""
+        top = self.mesh.topology
+        ents = top.entities(edim)[np.asarray(entities, dtype=np.int64)]
+        verts = np.unique(ents.ravel())
+        cells = self.mesh.geometry.dofmap
+        # vertex dof lookup: geometry vertex v -> dof, via any cell containing it
+        vdof = np.empty(self.mesh.geometry.x.shape[0], dtype=np.int64)
+        nvloc = cells.shape[1]
+        vdof[cells.ravel()] = self.dofmap.list[:, :nvloc].ravel()
+        dofs = [vdof[verts]]
+        if self.degree == 2 and edim >= 1:
+            nv = self.mesh.geometry.x.shape[0]
+            edges = top.entities(1)
+            ekey = edges[:, 0] * nv + edges[:, 1]  # sorted by construction (np.unique)
+            ce = top.cell_entities(1)
+            edof = np.empty(len(edges), dtype=np.int64)
+            edof[ce.ravel()] = self.dofmap.list[:, nvloc:].ravel()
+            k = ents.shape[1]
+            for a in range(k):
+                for b in range(a + 1, k):
+                    key = np.minimum(ents[:, a], ents[:, b]) * nv + np.maximum(ents[:, a], ents[:, b])
+                    dofs.append(edof[np.searchsorted(ekey, key)])
+        return np.unique(np.concatenate(dofs)).astype(np.int32)
+
+
+class _SubSpace:
+    def __init__(self, parent: FunctionSpace, i: int):
+        self.parent, self.i = parent, i
+
+    def collapse(self):
+        """(component space, map into the blocked parent): ``map[j] = bs*j + i`` (Appendix D)."""
+        Vi = self.parent._scalar
+        n = Vi.num_dofs
+        return Vi, np.arange(n, dtype=np.int32) * self.parent.bs + self.i
+
+
+def functionspace(mesh: Mesh, element) -> FunctionSpace:
+    """``functionspace(mesh, ("Lagrange", k))`` or ``("Lagrange", k, (gdim,))``.  Scalar spaces of
+    equal degree on one mesh share a dof map (one ``A`` serves every velocity component)."""
+    family, degree = element[0], int(element[1])
+    if family not in ("Lagrange", "CG", "P"):
+        raise NotImplementedError(family)
+    cache = mesh.__dict__.setdefault("_spaces", {})
+    if degree not in cache:
+        cache[degree] = FunctionSpace(mesh, degree)
+    scalar = cache[degree]
+    if len(element) > 2 and element[2]:
+        return FunctionSpace(mesh, degree, bs=int(element[2][0]), _scalar=scalar)
+    return scalar
+
+
+class Constant:
+    def __init__(self, mesh, value):
+        self.value = np.asarray(value, dtype=np.float64)
+
+    def __float__(self):
+        return float(self.value)
+
+
+class Vector:
+    """Host mirror of a (possibly device-resident) vector; ``dolfinx.la.Vector`` look-alike."""
+
+    def __init__(self, n: int):
+        self._host = np.zeros(n, dtype=np.float64)
+        self._binding = None  # object with pull(host) / push(host)
+        self._dev_newer = False
+        self._host_touched = False
+
+    @property
+    def array(self) -> np.ndarray:
+        if self._binding is not None:
+            if self._dev_newer:
+                self._binding.pull(self._host)
+                self._dev_newer = False
+            self._host_touched = True
+        return self._host
+
+    def array_ro(self) -> np.ndarray:
+        """Up-to-date host copy that the caller promises not to modify (no push-back)."""
+        if self._binding is not None and self._dev_newer:
+            self._binding.pull(self._host)
+            self._dev_newer = False
+        return self._host
+
+    def flush(self):
+        if self._binding is not None and self._host_touched:
+            self._binding.push(self._host)
+            self._host_touched = False
+
+    def mark_device_written(self):
+        self._dev_newer = True
+        self._host_touched = False
+
+    # serial: owner->ghost / ghost->owner exchanges are no-ops (multi-GPU halos live on the device)
+    def scatter_forward(self):
+        pass
+
+    def scatter_reverse(self, mode=None):
+        pass
+
+    @property
+    def petsc_vec(self):
+        return self
+
+
+class Function:
+    def __init__(self, V: FunctionSpace, name: str = "f"):
+        self.function_space = V
+        self.name = name
+        self.x = Vector(V.num_dofs * V.bs)
+
+    def interpolate(self, f: Callable[[np.ndarray], np.ndarray]):
+        """Nodal interpolation of ``f(x)``, ``x`` of shape (3, n) (``Function.interpolate`` for
+        Lagrange, Appendix D)."""
+        V = self.function_space
+        vals = np.asarray(f(V.tabulate_dof_coordinates().T), dtype=np.float64)
+        if V.bs == 1:
+            self.x.array[:] = vals.reshape(-1)
+        else:
+            self.x.array[:] = np.ascontiguousarray(vals.reshape(V.bs, -1).T).reshape(-1)
+
+
+def locate_dofs_topological(V: FunctionSpace, entity_dim: int, entities) -> np.ndarray:
+    return V.entity_closure_dofs(entity_dim, np.asarray(entities))
+
+
+def locate_dofs_geometrical(V: FunctionSpace, marker) -> np.ndarray:
+    return np.flatnonzero(np.asarray(marker(V.tabulate_dof_coordinates().T), dtype=bool)).astype(np.int32)
+
+
+def build_csr_pattern(row_dofs: np.ndarray, col_dofs: np.ndarray, n_rows: int, n_cols: int):
+    """CSR sparsity of a cell-integral bilinear form: row r couples to every column dof of every
+    cell containing r; columns sorted per row (``create_matrix`` semantics, Appendix D).
+    Host/numpy builder used for small meshes and as the bit-exact check of the device builder."""
+    nr, nc = row_dofs.shape[1], col_dofs.shape[1]
+    rows = np.repeat(row_dofs.astype(np.int64), nc, axis=1).ravel()
+    cols = np.tile(col_dofs.astype(np.int64), (1, nr)).ravel()
+    key = np.unique(rows * n_cols + cols)
+    r = key // n_cols
+    indices = (key % n_cols).astype(np.int32)
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(indptr, r + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr.astype(np.int32 if indptr[-1] < 2**31 else np.int64), indices
