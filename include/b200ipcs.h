@@ -1,0 +1,181 @@
+/*
+ * b200ipcs.h -- C ABI of libb200ipcs.so: the B200 (sm_100a) implementation of the oasisx IPCS
+ * fractional-step time loop.
+ *
+ * oasisx itself has no FFI layer: every numerical call of the hot path goes from
+ * src/oasisx/fracstep.py into DOLFINx (C++ assemblers + FFCx tabulate_tensor kernels) and PETSc
+ * (Mat/Vec/KSP).  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference lines it replaces.  All paths are relative
+ * to /root/reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host arrays are BORROWED for the duration of the call and
+ *     copied to the device -- the library never keeps a host pointer;
+ *   - every function returns 0 on success and a negative code on failure; b2_last_error() gives
+ *     the message (CUDA error string included);
+ *   - one host thread per context; calls are ordered on one CUDA stream owned by the context;
+ *   - solver stages report PETSc KSPConvergedReason integers (>0 converged: 2 RTOL, 3 ATOL;
+ *     <0 diverged: -3 ITS, -5 BREAKDOWN, -9 NANORINF), as the reference's callers assert on
+ *     them (fracstep.py:681,684);
+ *   - FP64 values, int32 indices (fracstep.py:63); velocity-space vectors are stored on the
+ *     device interleaved by component ([dof][gdim], == the blocked layout of `solver.u`,
+ *     fracstep.py:698-705) and addressed per component through `comp`.
+ */
+#ifndef B200IPCS_H
+#define B200IPCS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_ctx b2_ctx;
+
+#define B2_ABI_VERSION 1
+#define B2_NCCL_UID_BYTES 128
+
+/* function spaces: V = one velocity component (all components share it, fracstep.py:190),
+ * Q = pressure (fracstep.py:212) */
+enum { B2_SPACE_V = 0, B2_SPACE_Q = 1 };
+
+/* CSR patterns of `create_matrix` (fracstep.py:293-352): rows x columns */
+enum { B2_PAT_VV = 0, B2_PAT_VQ = 1, B2_PAT_QV = 2, B2_PAT_QQ = 3 };
+
+/* matrices; comp selects i for the three per-direction families */
+enum {
+  B2_MAT_M = 0,  /* _M   u*v              fracstep.py:292,373 */
+  B2_MAT_K = 1,  /* _K   grad u.grad v    fracstep.py:297-300,375 */
+  B2_MAT_A = 2,  /* _A   convection / LHS fracstep.py:294,435-472 */
+  B2_MAT_AP = 3, /* _Ap  grad p.grad q    fracstep.py:321-324,379 */
+  B2_MAT_P = 4,  /* _p_vdxi_Mat[i]  p*dv/dx_i   fracstep.py:311-315,395 */
+  B2_MAT_G = 5,  /* _grad_p_Mat[i]  dp/dx_i*v   fracstep.py:348-352,399 */
+  B2_MAT_D = 6,  /* _divu_Mat[i]    du/dx_i*q   fracstep.py:332-336,403 */
+  B2_MAT_MQ = 7  /* Projector mass matrix on Q, function.py:63-71 */
+};
+
+/* state vectors (fracstep.py:191-216) */
+enum {
+  B2_VEC_U = 0,      /* _u[i]      */
+  B2_VEC_U1 = 1,     /* _u1[i]     */
+  B2_VEC_U2 = 2,     /* _u2[i]     */
+  B2_VEC_UAB = 3,    /* _uab[i]    */
+  B2_VEC_RHS1 = 4,   /* _rhs1[i]   */
+  B2_VEC_BFIRST = 5, /* _b_first[i]*/
+  B2_VEC_B0 = 6,     /* _b0[i]     */
+  B2_VEC_PSURF = 7,  /* assembled _p_surf[i] (PressureBC natural term, fracstep.py:461-465) */
+  B2_VEC_B3 = 8,     /* _b3 for all components */
+  B2_VEC_WRK = 9,    /* _wrk_comp for all components */
+  B2_VEC_PS = 16,    /* _ps */
+  B2_VEC_P = 17,     /* _p  */
+  B2_VEC_DP = 18,    /* _dp */
+  B2_VEC_B2 = 19,    /* _b2 */
+  B2_VEC_MQ = 20     /* int psi_q dx (row sums of the Q mass matrix; used for the mean, :581-591) */
+};
+
+/* the three KSPSolver instances of fracstep.py:231-255 (+ the Projector's, function.py:84) */
+enum { B2_SOLVER_TENTATIVE = 0, B2_SOLVER_PRESSURE = 1, B2_SOLVER_SCALAR = 2, B2_SOLVER_PROJECTOR = 3 };
+
+typedef struct b2_stats {
+  int32_t its_tentative[3]; /* Krylov iterations of the last tentative solve, per component */
+  int32_t its_pressure;
+  int32_t its_update[3];
+  int32_t its_projector;
+  int64_t kernel_launches; /* kernels launched by this context since creation */
+  double ms_assemble_first, ms_tentative, ms_pressure, ms_update; /* CUDA-event times, last step */
+  double ms_step;
+  int64_t bytes_h2d, bytes_d2h; /* cumulative host<->device traffic through this ABI */
+} b2_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int b2_abi_version(void);
+int b2_device_count(void);
+/* Fills `uid` (B2_NCCL_UID_BYTES) on rank 0; the host layer distributes it to the other ranks. */
+int b2_nccl_unique_id(void* uid);
+/* One context per rank/GPU.  nranks == 1: `nccl_uid` may be NULL and NCCL is never loaded.
+ * Replaces mesh.comm / PETSc communicator plumbing (fracstep.py:231-255). */
+int b2_create(b2_ctx** ctx, int device, int nranks, int rank, const void* nccl_uid);
+void b2_destroy(b2_ctx* ctx);
+const char* b2_last_error(const b2_ctx* ctx);
+/* pinned host staging buffers for callers that want async copies */
+void* b2_host_alloc(int64_t bytes);
+void b2_host_free(void* p);
+
+/* ---- mesh, spaces, halos (what DOLFINx hands over: SURVEY.md Appendix D adapter list) -- */
+/* mesh.geometry.x (n_nodes x 3, padded) and mesh.geometry.dofmap (n_cells x (gdim+1)); cells =
+ * owned cells followed by the ghost cells that touch an owned dof. */
+int b2_set_mesh(b2_ctx* ctx, int gdim, int64_t n_nodes, const double* x, int64_t n_cells,
+                const int32_t* cell_nodes);
+/* V.dofmap.list / Q.dofmap.list with local indices, owned dofs first then ghosts
+ * (index_map.size_local / num_ghosts).  degree in {1,2}.  fracstep.py:187-190,212 */
+int b2_set_space(b2_ctx* ctx, int space, int degree, int64_t n_owned, int64_t n_ghost,
+                 const int32_t* cell_dofs);
+/* Halo plan of one space (index_map.ghosts/owners turned into pack lists): for neighbour k,
+ * send the owned entries send_idx[send_off[k]:send_off[k+1]] and receive into the ghost block
+ * [n_owned + recv_off[k], n_owned + recv_off[k+1]).  Replaces Vector.scatter_forward and the
+ * implicit MatMult gather. */
+int b2_set_halo(b2_ctx* ctx, int space, int n_neighbors, const int32_t* neighbor_ranks,
+                const int64_t* send_off, const int32_t* send_idx, const int64_t* recv_off);
+/* Global (all-rank) sizes for the two means of fracstep.py:573-591. */
+int b2_set_global_sizes(b2_ctx* ctx, int64_t n_global_v, int64_t n_global_q);
+
+/* ---- sparsity (create_matrix, fracstep.py:293,294,300,315,324,336,352) ---------------- */
+int b2_build_patterns(b2_ctx* ctx);
+int64_t b2_pattern_nnz(b2_ctx* ctx, int pattern);
+/* copies indptr (n_rows+1) and indices (nnz) back: the bit-exact CSR check of north_star */
+int b2_get_pattern(b2_ctx* ctx, int pattern, int32_t* indptr, int32_t* indices);
+
+/* ---- boundary conditions (bcs.py:116-139, 245-253) ------------------------------------ */
+/* merged dof list of all DirichletBCs of velocity component `comp` (local indices) */
+int b2_set_velocity_bc_dofs(b2_ctx* ctx, int comp, int64_t n, const int32_t* dofs);
+/* g_i at those dofs, same order: the result of update_bc() + what set_bc reads (bcs.py:128-139) */
+int b2_set_velocity_bc_values(b2_ctx* ctx, int comp, int64_t n, const double* values);
+/* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253) */
+int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
+
+/* ---- _preassemble (fracstep.py:360-409) ----------------------------------------------- */
+int b2_preassemble(b2_ctx* ctx, const double* body_force, int low_memory, int rotational);
+
+/* ---- state access (Function.x.array, fracstep.py:432-434,673,689-693) ----------------- */
+/* comp >= 0: one component (n = dofs of the space incl. ghosts); comp == -1 on a velocity vector:
+ * the whole interleaved array (n = gdim * dofs) */
+int b2_set_vector(b2_ctx* ctx, int vec, int comp, const double* host, int64_t n);
+int b2_get_vector(b2_ctx* ctx, int vec, int comp, double* host, int64_t n);
+/* Mat.getValuesCSR() values (test/test_tentative_velocity.py:28) in pattern order */
+int b2_get_matrix_values(b2_ctx* ctx, int mat, int comp, double* host);
+/* y = Mat * x on host arrays (Mat.mult; parity-test hook) */
+int b2_mat_mult(b2_ctx* ctx, int mat, int comp, const double* x, double* y);
+
+/* ---- solver options (ksp.py:38-53) ------------------------------ */
+int b2_set_solver_option(b2_ctx* ctx, int solver, const char* key, const char* value);
+
+/* ---- the stages, one-to-one with the reference methods -------------------------------- */
+int b2_assemble_first(b2_ctx* ctx, double dt, double nu);        /* fracstep.py:411-472 */
+int b2_tentative_assemble(b2_ctx* ctx);                          /* fracstep.py:474-506 */
+int b2_tentative_solve(b2_ctx* ctx, double* diff, int32_t* reasons); /* fracstep.py:508-525 */
+int b2_pressure_assemble(b2_ctx* ctx, double dt);                /* fracstep.py:527-551 */
+int b2_pressure_solve(b2_ctx* ctx, double nu, int32_t* reason);  /* fracstep.py:553-605 */
+int b2_velocity_update(b2_ctx* ctx, double dt, int32_t* reasons);/* fracstep.py:607-658 */
+/* whole step (fracstep.py:660-696) with the BC values already uploaded */
+int b2_step(b2_ctx* ctx, double dt, double nu, double max_error, int max_iter, double* diff);
+
+/* ---- Projector (function.py:108-133) on Q: solve MQ x = rhs ---------------------------- */
+int b2_project_q(b2_ctx* ctx, const double* rhs, double* x, int32_t* reason);
+
+/* ---- functionals (assemble_scalar, demo/taylor_green.py:204-207) ----------------------- */
+/* sum_k int (u_h,k - e_k)^2 dx where e is given nodally in a P2 (or P1 for Q) space of the same
+ * mesh: `exact` has the layout of the vector it is compared with. */
+int b2_l2_diff_sq(b2_ctx* ctx, int vec, const double* exact, int64_t n, double* out);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+int b2_get_stats(b2_ctx* ctx, b2_stats* out);
+/* Times `reps` launches of one hot kernel on the context's stream with CUDA events (device
+ * resident operands).  kernel: 0 = SpMM A*u (gdim RHS), 1 = convection assembly + fused combine,
+ * 2 = SpMV Ap*dp, 3 = SpMM M*u.  Returns average ms per launch and the algorithmic bytes moved. */
+int b2_bench_kernel(b2_ctx* ctx, int kernel, int reps, double* ms_per_launch, double* bytes_per_launch);
+int b2_synchronize(b2_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200IPCS_H */

@@ -1,0 +1,288 @@
+"""ctypes binding of ``libb200ipcs.so`` (``include/b200ipcs.h``).
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible, constructing a
+:class:`Context` raises.  The library is built in-tree by ``oasisx_b200/build.py``
+(``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200ipcs.so")
+
+# ids of include/b200ipcs.h
+SPACE_V, SPACE_Q = 0, 1
+PAT_VV, PAT_VQ, PAT_QV, PAT_QQ = 0, 1, 2, 3
+MAT_M, MAT_K, MAT_A, MAT_AP, MAT_P, MAT_G, MAT_D, MAT_MQ = range(8)
+VEC_U, VEC_U1, VEC_U2, VEC_UAB, VEC_RHS1, VEC_BFIRST, VEC_B0, VEC_PSURF, VEC_B3, VEC_WRK = range(10)
+VEC_PS, VEC_P, VEC_DP, VEC_B2, VEC_MQ = 16, 17, 18, 19, 20
+SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
+
+# every symbol include/b200ipcs.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
+    "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_set_velocity_bc_values", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
+    "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
+    "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
+    "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("its_tentative", C.c_int32 * 3),
+        ("its_pressure", C.c_int32),
+        ("its_update", C.c_int32 * 3),
+        ("its_projector", C.c_int32),
+        ("kernel_launches", C.c_int64),
+        ("ms_assemble_first", C.c_double),
+        ("ms_tentative", C.c_double),
+        ("ms_pressure", C.c_double),
+        ("ms_update", C.c_double),
+        ("ms_step", C.c_double),
+        ("bytes_h2d", C.c_int64),
+        ("bytes_d2h", C.c_int64),
+    ]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} not found: build it with `python -m oasisx_b200.build` "
+            "(oasisx_b200 has no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    sig = {
+        "b2_abi_version": (i32, []),
+        "b2_device_count": (i32, []),
+        "b2_nccl_unique_id": (i32, [vp]),
+        "b2_create": (i32, [C.POINTER(vp), i32, i32, i32, vp]),
+        "b2_destroy": (None, [vp]),
+        "b2_last_error": (C.c_char_p, [vp]),
+        "b2_host_alloc": (vp, [i64]),
+        "b2_host_free": (None, [vp]),
+        "b2_set_mesh": (i32, [vp, i32, i64, vp, i64, vp]),
+        "b2_set_space": (i32, [vp, i32, i32, i64, i64, vp]),
+        "b2_set_halo": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "b2_set_global_sizes": (i32, [vp, i64, i64]),
+        "b2_build_patterns": (i32, [vp]),
+        "b2_pattern_nnz": (i64, [vp, i32]),
+        "b2_get_pattern": (i32, [vp, i32, vp, vp]),
+        "b2_set_velocity_bc_dofs": (i32, [vp, i32, i64, vp]),
+        "b2_set_velocity_bc_values": (i32, [vp, i32, i64, vp]),
+        "b2_set_pressure_bc_dofs": (i32, [vp, i64, vp]),
+        "b2_preassemble": (i32, [vp, vp, i32, i32]),
+        "b2_set_vector": (i32, [vp, i32, i32, vp, i64]),
+        "b2_get_vector": (i32, [vp, i32, i32, vp, i64]),
+        "b2_get_matrix_values": (i32, [vp, i32, i32, vp]),
+        "b2_mat_mult": (i32, [vp, i32, i32, vp, vp]),
+        "b2_set_solver_option": (i32, [vp, i32, C.c_char_p, C.c_char_p]),
+        "b2_assemble_first": (i32, [vp, dbl, dbl]),
+        "b2_tentative_assemble": (i32, [vp]),
+        "b2_tentative_solve": (i32, [vp, vp, vp]),
+        "b2_pressure_assemble": (i32, [vp, dbl]),
+        "b2_pressure_solve": (i32, [vp, dbl, vp]),
+        "b2_velocity_update": (i32, [vp, dbl, vp]),
+        "b2_step": (i32, [vp, dbl, dbl, dbl, i32, vp]),
+        "b2_project_q": (i32, [vp, vp, vp, vp]),
+        "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
+        "b2_get_stats": (i32, [vp, vp]),
+        "b2_bench_kernel": (i32, [vp, i32, i32, vp, vp]),
+        "b2_synchronize": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One ``b2_ctx`` (one rank / one GPU)."""
+
+    def __init__(self, device: int = 0, nranks: int = 1, rank: int = 0, nccl_uid: bytes | None = None):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        uid = C.create_string_buffer(nccl_uid, 128) if nccl_uid is not None else None
+        rc = self.lib.b2_create(C.byref(self._h), device, nranks, rank, uid)
+        if rc != 0:
+            msg = self.lib.b2_last_error(None).decode()
+            raise B200Error(f"b2_create failed ({rc}): {msg}")
+        self.gdim = 0
+        self.n = {SPACE_V: 0, SPACE_Q: 0}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise B200Error(f"{what} failed ({rc}): {self.lib.b2_last_error(self._h).decode()}")
+
+    # ---- setup ---------------------------------------------------------------------------
+    def set_mesh(self, gdim: int, x: np.ndarray, cell_nodes: np.ndarray):
+        x, cn = _f64(x), _i32(cell_nodes)
+        assert x.shape[1] == 3 and cn.shape[1] == gdim + 1
+        self.gdim = gdim
+        self._check(self.lib.b2_set_mesh(self._h, gdim, x.shape[0], _ptr(x), cn.shape[0], _ptr(cn)), "b2_set_mesh")
+
+    def set_space(self, space: int, degree: int, n_owned: int, n_ghost: int, cell_dofs: np.ndarray):
+        cd = _i32(cell_dofs)
+        self.n[space] = n_owned + n_ghost
+        self._check(self.lib.b2_set_space(self._h, space, degree, n_owned, n_ghost, _ptr(cd)), "b2_set_space")
+
+    def set_global_sizes(self, nv: int, nq: int):
+        self._check(self.lib.b2_set_global_sizes(self._h, nv, nq), "b2_set_global_sizes")
+
+    def build_patterns(self):
+        self._check(self.lib.b2_build_patterns(self._h), "b2_build_patterns")
+
+    def pattern(self, which: int, n_rows: int):
+        nnz = self.lib.b2_pattern_nnz(self._h, which)
+        if nnz < 0:
+            raise B200Error("pattern not built")
+        indptr = np.empty(n_rows + 1, dtype=np.int32)
+        indices = np.empty(nnz, dtype=np.int32)
+        self._check(self.lib.b2_get_pattern(self._h, which, _ptr(indptr), _ptr(indices)), "b2_get_pattern")
+        return indptr, indices
+
+    def pattern_nnz(self, which: int) -> int:
+        return int(self.lib.b2_pattern_nnz(self._h, which))
+
+    def set_velocity_bc_dofs(self, comp: int, dofs):
+        d = _i32(dofs)
+        self._check(self.lib.b2_set_velocity_bc_dofs(self._h, comp, d.size, _ptr(d)), "b2_set_velocity_bc_dofs")
+
+    def set_velocity_bc_values(self, comp: int, values):
+        v = _f64(values)
+        self._check(self.lib.b2_set_velocity_bc_values(self._h, comp, v.size, _ptr(v)), "b2_set_velocity_bc_values")
+
+    def set_pressure_bc_dofs(self, dofs):
+        d = _i32(dofs)
+        self._check(self.lib.b2_set_pressure_bc_dofs(self._h, d.size, _ptr(d)), "b2_set_pressure_bc_dofs")
+
+    def preassemble(self, body_force, low_memory: bool, rotational: bool):
+        f = _f64(list(body_force) + [0.0] * (3 - len(body_force)))
+        self._check(self.lib.b2_preassemble(self._h, _ptr(f), int(low_memory), int(rotational)), "b2_preassemble")
+
+    # ---- state ---------------------------------------------------------------------------
+    def set_vector(self, vec: int, comp: int, host: np.ndarray):
+        h = _f64(host)
+        self._check(self.lib.b2_set_vector(self._h, vec, comp, _ptr(h), h.size), "b2_set_vector")
+
+    def get_vector(self, vec: int, comp: int, out: np.ndarray) -> np.ndarray:
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        self._check(self.lib.b2_get_vector(self._h, vec, comp, _ptr(out), out.size), "b2_get_vector")
+        return out
+
+    def matrix_values(self, mat: int, comp: int, nnz: int) -> np.ndarray:
+        out = np.empty(nnz, dtype=np.float64)
+        self._check(self.lib.b2_get_matrix_values(self._h, mat, comp, _ptr(out)), "b2_get_matrix_values")
+        return out
+
+    def mat_mult(self, mat: int, comp: int, x: np.ndarray, n_rows: int) -> np.ndarray:
+        x = _f64(x)
+        y = np.empty(n_rows, dtype=np.float64)
+        self._check(self.lib.b2_mat_mult(self._h, mat, comp, _ptr(x), _ptr(y)), "b2_mat_mult")
+        return y
+
+    def set_solver_option(self, solver: int, key: str, value):
+        self._check(
+            self.lib.b2_set_solver_option(self._h, solver, str(key).encode(), str(value).encode()),
+            "b2_set_solver_option",
+        )
+
+    # ---- stages --------------------------------------------------------------------------
+    def assemble_first(self, dt: float, nu: float):
+        self._check(self.lib.b2_assemble_first(self._h, dt, nu), "b2_assemble_first")
+
+    def tentative_assemble(self):
+        self._check(self.lib.b2_tentative_assemble(self._h), "b2_tentative_assemble")
+
+    def tentative_solve(self):
+        diff = C.c_double(0.0)
+        reasons = np.zeros(3, dtype=np.int32)
+        self._check(self.lib.b2_tentative_solve(self._h, C.byref(diff), _ptr(reasons)), "b2_tentative_solve")
+        return diff.value, reasons[: self.gdim].copy()
+
+    def pressure_assemble(self, dt: float):
+        self._check(self.lib.b2_pressure_assemble(self._h, dt), "b2_pressure_assemble")
+
+    def pressure_solve(self, nu: float) -> int:
+        reason = C.c_int32(0)
+        self._check(self.lib.b2_pressure_solve(self._h, float(nu), C.byref(reason)), "b2_pressure_solve")
+        return reason.value
+
+    def velocity_update(self, dt: float):
+        reasons = np.zeros(3, dtype=np.int32)
+        self._check(self.lib.b2_velocity_update(self._h, dt, _ptr(reasons)), "b2_velocity_update")
+        return reasons[: self.gdim].copy()
+
+    def step(self, dt: float, nu: float, max_error: float, max_iter: int) -> float:
+        diff = C.c_double(0.0)
+        self._check(self.lib.b2_step(self._h, dt, nu, max_error, max_iter, C.byref(diff)), "b2_step")
+        return diff.value
+
+    def project_q(self, rhs: np.ndarray):
+        rhs = _f64(rhs)
+        x = np.empty_like(rhs)
+        reason = C.c_int32(0)
+        self._check(self.lib.b2_project_q(self._h, _ptr(rhs), _ptr(x), C.byref(reason)), "b2_project_q")
+        return x, reason.value
+
+    def l2_diff_sq(self, vec: int, exact: np.ndarray) -> float:
+        e = _f64(exact)
+        out = C.c_double(0.0)
+        self._check(self.lib.b2_l2_diff_sq(self._h, vec, _ptr(e), e.size, C.byref(out)), "b2_l2_diff_sq")
+        return out.value
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.b2_get_stats(self._h, C.byref(s)), "b2_get_stats")
+        return s
+
+    def bench_kernel(self, kernel: int, reps: int):
+        ms, nbytes = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.b2_bench_kernel(self._h, kernel, reps, C.byref(ms), C.byref(nbytes)), "b2_bench_kernel")
+        return ms.value, nbytes.value
+
+    def synchronize(self):
+        self._check(self.lib.b2_synchronize(self._h), "b2_synchronize")

@@ -1,0 +1,308 @@
+// elem.cuh -- affine simplex geometry, reference tensors in constant memory, and the cell
+// (element) kernels that replace the FFCx tabulate_tensor + DOLFINx assemble_matrix /
+// assemble_vector pairs of /root/reference/src/oasisx/fracstep.py:289-404,435-437.
+#pragma once
+#include "common.cuh"
+
+#define B2_TABLE_QUAL static __constant__ const
+#include "ref_tables.h"
+
+// ---- element traits: (gdim, velocity degree) -> table accessors ----------------------------
+template <int D, int DEG>
+struct El;
+
+#define B2_DEFINE_EL(D_, DEG_, NV_)                                                            \
+  template <>                                                                                  \
+  struct El<D_, DEG_> {                                                                        \
+    static constexpr int D = D_, DEG = DEG_, NV = NV_, NQ = D_ + 1;                                        \
+    __device__ static __forceinline__ double MV(int i, int j) { return REF_D##D_##P##DEG_##_MV[i][j]; } \
+    __device__ static __forceinline__ double SV(int a, int b, int i, int j) { return REF_D##D_##P##DEG_##_SV[a][b][i][j]; } \
+    __device__ static __forceinline__ double T(int a, int dl, int i, int j) { return REF_D##D_##P##DEG_##_T[a][dl][i][j]; } \
+    __device__ static __forceinline__ double PX(int dl, int j, int q) { return REF_D##D_##P##DEG_##_PX[dl][j][q]; } \
+    __device__ static __forceinline__ double GX(int dl, int j, int q) { return REF_D##D_##P##DEG_##_GX[dl][j][q]; } \
+    __device__ static __forceinline__ double SQ(int a, int b, int q, int r) { return REF_D##D_##P##DEG_##_SQ[a][b][q][r]; } \
+    __device__ static __forceinline__ double MQ(int q, int r) { return REF_D##D_##P##DEG_##_MQ[q][r]; } \
+    __device__ static __forceinline__ double LV(int j) { return REF_D##D_##P##DEG_##_LV[j]; }   \
+    __device__ static __forceinline__ double LQ(int q) { return REF_D##D_##P##DEG_##_LQ[q]; }   \
+  };
+
+B2_DEFINE_EL(2, 1, 3)
+B2_DEFINE_EL(2, 2, 6)
+B2_DEFINE_EL(3, 1, 4)
+B2_DEFINE_EL(3, 2, 10)
+
+// ---- geometry --------------------------------------------------------------------------------
+// J[k][dl] = d x_k / d xi_dl ;  Kinv = J^{-1}  (Kinv[dl][k]) ;  physical gradient
+// d/dx_k = sum_dl Kinv[dl][k] d/dxi_dl   
+template <int D>
+struct Geo {
+  double Kinv[D][D];
+  double detJ;  // |det J|
+};
+
+template <int D>
+__device__ __forceinline__ Geo<D> cell_geometry(const double* __restrict__ x,
+                                                const int* __restrict__ nodes) {
+  Geo<D> g;
+  double X[D + 1][D];
+#pragma unroll
+  for (int v = 0; v <= D; ++v) {
+    const double* p = x + 3 * (size_t)nodes[v];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[v][k] = p[k];
+  }
+  double J[D][D];
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int dl = 0; dl < D; ++dl) J[k][dl] = X[dl + 1][k] - X[0][k];
+  if constexpr (D == 2) {
+    double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    double id = 1.0 / det;
+    g.Kinv[0][0] = J[1][1] * id;
+    g.Kinv[0][1] = -J[0][1] * id;
+    g.Kinv[1][0] = -J[1][0] * id;
+    g.Kinv[1][1] = J[0][0] * id;
+    g.detJ = fabs(det);
+  } else {
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    double id = 1.0 / det;
+    g.Kinv[0][0] = c00 * id;
+    g.Kinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    g.Kinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    g.Kinv[1][0] = c01 * id;
+    g.Kinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    g.Kinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    g.Kinv[2][0] = c02 * id;
+    g.Kinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    g.Kinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    g.detJ = fabs(det);
+  }
+  return g;
+}
+
+// position of column `col` in CSR row [lo, hi) (columns sorted); -1 if absent
+__device__ __forceinline__ int csr_find(const int* __restrict__ cols, int lo, int hi, int col) {
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int c = __ldg(cols + mid);
+    if (c < col)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// ---- one-off (pre)assembly kernels: one thread per (cell, local row) -----------------------
+enum { B2_FORM_MASS_V = 0, B2_FORM_STIFF_V = 1, B2_FORM_MASS_Q = 2, B2_FORM_STIFF_Q = 3 };
+
+template <int D, int DEG, int FORM>
+__global__ void k_assemble_square(int64_t n_cells, const double* __restrict__ x,
+                                  const int* __restrict__ cell_nodes, const int* __restrict__ cdofs,
+                                  int n_rows_owned, const int* __restrict__ rowptr,
+                                  const int* __restrict__ cols, double* __restrict__ vals) {
+  using E = El<D, DEG>;
+  constexpr bool onV = (FORM == B2_FORM_MASS_V || FORM == B2_FORM_STIFF_V);
+  constexpr int ND = onV ? E::NV : E::NQ;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cells * ND) return;
+  int64_t c = t / ND;
+  int i = (int)(t - c * ND);
+  const int* dofs = cdofs + c * ND;
+  int row = dofs[i];
+  if (row >= n_rows_owned) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  double G[D][D];
+  if constexpr (FORM == B2_FORM_STIFF_V || FORM == B2_FORM_STIFF_Q) {
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += g.Kinv[a][k] * g.Kinv[b][k];
+        G[a][b] = s * g.detJ;
+      }
+  }
+  int lo = rowptr[row], hi = rowptr[row + 1];
+  for (int j = 0; j < ND; ++j) {
+    double v = 0;
+    if constexpr (FORM == B2_FORM_MASS_V) v = g.detJ * E::MV(i, j);
+    if constexpr (FORM == B2_FORM_MASS_Q) v = g.detJ * E::MQ(i, j);
+    if constexpr (FORM == B2_FORM_STIFF_V) {
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) v += G[a][b] * E::SV(a, b, i, j);
+    }
+    if constexpr (FORM == B2_FORM_STIFF_Q) {
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) v += G[a][b] * E::SQ(a, b, i, j);
+    }
+    int pos = csr_find(cols, lo, hi, dofs[j]);
+    atomicAdd(vals + pos, v);
+  }
+}
+
+// P_c[j,q] = int psi_q d_c phi_j and G_c[j,q] = int d_c psi_q phi_j on the V x Q pattern; the D
+// direction values of one nonzero are stored contiguously ([nnz][D]).
+template <int D, int DEG>
+__global__ void k_assemble_PG(int64_t n_cells, const double* __restrict__ x,
+                              const int* __restrict__ cell_nodes, const int* __restrict__ vdofs,
+                              const int* __restrict__ qdofs, int n_rows_owned,
+                              const int* __restrict__ rowptr, const int* __restrict__ cols,
+                              double* __restrict__ Pvals, double* __restrict__ Gvals) {
+  using E = El<D, DEG>;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cells * E::NV) return;
+  int64_t c = t / E::NV;
+  int j = (int)(t - c * E::NV);
+  int row = vdofs[c * E::NV + j];
+  if (row >= n_rows_owned) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  int lo = rowptr[row], hi = rowptr[row + 1];
+  for (int q = 0; q < E::NQ; ++q) {
+    int pos = csr_find(cols, lo, hi, qdofs[c * E::NQ + q]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double p = 0, gg = 0;
+#pragma unroll
+      for (int dl = 0; dl < D; ++dl) {
+        p += g.Kinv[dl][k] * E::PX(dl, j, q);
+        gg += g.Kinv[dl][k] * E::GX(dl, j, q);
+      }
+      atomicAdd(Pvals + (size_t)pos * D + k, g.detJ * p);
+      atomicAdd(Gvals + (size_t)pos * D + k, g.detJ * gg);
+    }
+  }
+}
+
+// D_c[q,j] = int d_c phi_j psi_q on the Q x V pattern ([nnz][D])
+template <int D, int DEG>
+__global__ void k_assemble_D(int64_t n_cells, const double* __restrict__ x,
+                             const int* __restrict__ cell_nodes, const int* __restrict__ vdofs,
+                             const int* __restrict__ qdofs, int n_rows_owned,
+                             const int* __restrict__ rowptr, const int* __restrict__ cols,
+                             double* __restrict__ Dvals) {
+  using E = El<D, DEG>;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cells * E::NQ) return;
+  int64_t c = t / E::NQ;
+  int q = (int)(t - c * E::NQ);
+  int row = qdofs[c * E::NQ + q];
+  if (row >= n_rows_owned) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  int lo = rowptr[row], hi = rowptr[row + 1];
+  for (int j = 0; j < E::NV; ++j) {
+    int pos = csr_find(cols, lo, hi, vdofs[c * E::NV + j]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double p = 0;
+#pragma unroll
+      for (int dl = 0; dl < D; ++dl) p += g.Kinv[dl][k] * E::PX(dl, j, q);
+      atomicAdd(Dvals + (size_t)pos * D + k, g.detJ * p);
+    }
+  }
+}
+
+// b0[j][c] = int f_c phi_j (fracstep.py:387-390), mQ[q] = int psi_q (the measure for :581-591)
+template <int D, int DEG>
+__global__ void k_assemble_loads(int64_t n_cells, const double* __restrict__ x,
+                                 const int* __restrict__ cell_nodes, const int* __restrict__ vdofs,
+                                 const int* __restrict__ qdofs, int nV_owned, int nQ_owned,
+                                 double f0, double f1, double f2, double* __restrict__ b0,
+                                 double* __restrict__ mQ) {
+  using E = El<D, DEG>;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  const double f[3] = {f0, f1, f2};
+  for (int j = 0; j < E::NV; ++j) {
+    int row = vdofs[c * E::NV + j];
+    if (row >= nV_owned) continue;
+    double l = g.detJ * E::LV(j);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      if (f[k] != 0.0) atomicAdd(b0 + (size_t)row * D + k, f[k] * l);
+  }
+  for (int q = 0; q < E::NQ; ++q) {
+    int row = qdofs[c * E::NQ + q];
+    if (row < nQ_owned) atomicAdd(mQ + row, g.detJ * E::LQ(q));
+  }
+}
+
+// assemble_matrix(..., bcs=) semantics on a square matrix (fracstep.py:379, Appendix D):
+// BC rows and columns zeroed, unit diagonal.
+__global__ void k_apply_bc_rows_cols(int n_rows, const int* __restrict__ rowptr,
+                                     const int* __restrict__ cols, const uint8_t* __restrict__ is_bc,
+                                     double* __restrict__ vals) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  bool rb = is_bc[row];
+  for (int p = rowptr[row]; p < rowptr[row + 1]; ++p) {
+    int c = cols[p];
+    if (rb || is_bc[c]) vals[p] = (c == row) ? 1.0 : 0.0;
+  }
+}
+
+// ---- per-step convection assembly (fracstep.py:435-437) --------------------------------------
+// C[i,j] += |detJ| sum_{a,dl} w[a][dl] T[a][dl][i][j],  w[a][dl] = sum_k Kinv[dl][k] uab_k[dof_a]
+// One thread per cell; the element matrix is produced row by row (NV accumulators live in
+// registers) and scattered with FP64 reductions (RED.ADD.F64) onto the CSR values.
+template <int D, int DEG>
+__global__ void __launch_bounds__(128)
+k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
+             const int* __restrict__ vdofs, int n_rows_owned, const double* __restrict__ uab,
+             const int* __restrict__ rowptr, const int* __restrict__ cols,
+             double* __restrict__ Avals) {
+  using E = El<D, DEG>;
+  constexpr int NV = E::NV;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  int dofs[NV];
+#pragma unroll
+  for (int a = 0; a < NV; ++a) dofs[a] = vdofs[c * NV + a];
+  double w[NV][D];
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double u[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) u[k] = uab[(size_t)dofs[a] * D + k];
+#pragma unroll
+    for (int dl = 0; dl < D; ++dl) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s += g.Kinv[dl][k] * u[k];
+      w[a][dl] = s * g.detJ;
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < NV; ++i) {
+    int row = dofs[i];
+    if (row >= n_rows_owned) continue;
+    double r[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) r[j] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int dl = 0; dl < D; ++dl) {
+        const double wv = w[a][dl];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) r[j] = fma(wv, E::T(a, dl, i, j), r[j]);
+      }
+    int lo = rowptr[row], hi = rowptr[row + 1];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      int pos = csr_find(cols, lo, hi, dofs[j]);
+      atomicAdd(Avals + pos, r[j]);
+    }
+  }
+}

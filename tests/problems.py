@@ -1,0 +1,93 @@
+"""Shared problem set-ups for the parity tests: the Taylor-Green vortex of
+``/root/reference/demo/taylor_green.py:36-53,126-182`` (2D, and its z-extruded 3D version,
+SURVEY.md F5) built both for the CUDA path (``oasisx_b200``) and for the oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+from oasisx_b200 import fem, mesh as bmesh
+
+
+class TaylorGreen:
+    def __init__(self, nu: float, gdim: int):
+        self.nu, self.gdim = nu, gdim
+        self.t_u = 0.0
+        self.t_p = 0.0
+
+    def eval_x(self, x):
+        return -np.cos(np.pi * x[0]) * np.sin(np.pi * x[1]) * np.exp(-2.0 * self.nu * np.pi**2 * self.t_u)
+
+    def eval_y(self, x):
+        return np.cos(np.pi * x[1]) * np.sin(np.pi * x[0]) * np.exp(-2.0 * self.nu * np.pi**2 * self.t_u)
+
+    def eval_z(self, x):
+        return np.zeros_like(x[0])
+
+    def eval_p(self, x):
+        return -0.25 * (np.cos(2 * np.pi * x[0]) + np.cos(2 * np.pi * x[1])) * np.exp(-4 * self.nu * np.pi**2 * self.t_p)
+
+    @property
+    def components(self):
+        return [self.eval_x, self.eval_y, self.eval_z][: self.gdim]
+
+
+def make_mesh(gdim: int, N: int):
+    if gdim == 2:
+        return bmesh.create_rectangle(None, [[-1.0, -1.0], [1.0, 1.0]], [N, N])
+    return bmesh.create_box(None, [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], [N, N, N])
+
+
+def boundary_facets(msh):
+    d = msh.topology.dim
+    msh.topology.create_connectivity(d - 1, d)
+    return bmesh.exterior_facet_indices(msh.topology)
+
+
+def make_oracle(msh, deg_u, tg: TaylorGreen, dt, **kw):
+    from oracle.ipcs_oracle import OracleIPCS
+
+    d = msh.geometry.dim
+    V = fem.functionspace(msh, ("Lagrange", deg_u))
+    Q = fem.functionspace(msh, ("Lagrange", 1))
+    bd = fem.locate_dofs_topological(V, d - 1, boundary_facets(msh))
+    o = OracleIPCS(msh.geometry.x, msh.geometry.dofmap, d, V.dofmap.list, Q.dofmap.list,
+                   V.tabulate_dof_coordinates(), Q.tabulate_dof_coordinates(), deg_u,
+                   bcs_u=[[(bd, f)] for f in tg.components], **kw)
+    xV, xQ = V.tabulate_dof_coordinates().T, Q.tabulate_dof_coordinates().T
+    tg.t_u = -dt
+    o.u2 = [f(xV) for f in tg.components]
+    tg.t_u = 0.0
+    o.u1 = [f(xV) for f in tg.components]
+    tg.t_p = -dt / 2
+    o.p = tg.eval_p(xQ)
+    return o
+
+
+def make_solver(msh, deg_u, tg: TaylorGreen, dt, solver_options=None, **kw):
+    """The set-up of ``demo/taylor_green.py:135-182`` against oasisx_b200."""
+    import oasisx_b200 as oasisx
+
+    d = msh.geometry.dim
+    facets = boundary_facets(msh)
+    value = np.int32(3)
+    tags = bmesh.meshtags(msh, d - 1, facets, np.full_like(facets, value, dtype=np.int32))
+    bcs_u = [[oasisx.DirichletBC(f, oasisx.LocatorMethod.TOPOLOGICAL, (tags, value))] for f in tg.components]
+    if solver_options is None:
+        lu = {"ksp_type": "preonly", "pc_type": "lu"}
+        solver_options = {"tentative": lu, "pressure": lu, "scalar": lu}
+    s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[],
+                                    solver_options=solver_options, options={"low_memory_version": False}, **kw)
+    tg.t_u = -dt
+    for i, f in enumerate(tg.components):
+        s._u2[i].interpolate(f)
+    tg.t_u = 0.0
+    for i, f in enumerate(tg.components):
+        s._u1[i].interpolate(f)
+    tg.t_p = -dt / 2
+    s._p.interpolate(tg.eval_p)
+    return s
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))

@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.
+
+Tolerances are north_star's: CSR sparsity bit-exact; assembled FP64 entries <= 1e-12 relative
+(measured against the row/matrix max, SURVEY.md Appendix C tolerance note); per-step fields <= 1e-8
+relative with the solvers run to rtol 1e-12 ("preonly+lu" equivalent)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oasisx_b200 import _lib as L
+from oasisx_b200 import fem
+from problems import TaylorGreen, make_mesh, make_oracle, make_solver, relerr
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(2, 8, 2), (3, 4, 2), (2, 8, 1), (3, 3, 1)]
+
+
+def _csr(mat):
+    ip, ix, v = mat.getValuesCSR()
+    return sp.csr_matrix((v, ix, ip), shape=mat.getSize())
+
+
+@pytest.mark.parametrize("gdim,N,deg", CASES)
+def test_patterns_bit_exact(gdim, N, deg):
+    msh = make_mesh(gdim, N)
+    s = make_solver(msh, deg, TaylorGreen(0.01, gdim), 0.01)
+    V, Q = fem.functionspace(msh, ("Lagrange", deg)), fem.functionspace(msh, ("Lagrange", 1))
+    for pat, (R, C) in {L.PAT_VV: (V, V), L.PAT_VQ: (V, Q), L.PAT_QV: (Q, V), L.PAT_QQ: (Q, Q)}.items():
+        ip, ix = fem.build_csr_pattern(R.dofmap.list, C.dofmap.list, R.num_dofs, C.num_dofs)
+        dip, dix = s._ctx.pattern(pat, R.num_dofs)
+        assert dip.dtype == np.int32 and dix.dtype == np.int32
+        np.testing.assert_array_equal(dip, ip)
+        np.testing.assert_array_equal(dix, ix)
+
+
+@pytest.mark.parametrize("gdim,N,deg", CASES)
+def test_preassembled_matrices(gdim, N, deg):
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(0.01, gdim)
+    s = make_solver(msh, deg, tg, 0.01)
+    o = make_oracle(msh, deg, tg, 0.01)
+    pairs = [(s._M, o.M), (s._K, o.K), (s._Ap, o.Ap)]
+    for i in range(gdim):
+        pairs += [(s._p_vdxi_Mat[i], o.P[i]), (s._grad_p_Mat[i], o.G[i]), (s._divu_Mat[i], o.D[i])]
+    for dev, ref in pairs:
+        A = _csr(dev)
+        assert abs(A - ref).max() <= 1e-12 * abs(ref).max()
+    b0 = s._b0[0].x.array_ro()
+    np.testing.assert_allclose(b0, 0.0, atol=0)
+
+
+@pytest.mark.parametrize("gdim,N,deg", CASES)
+@pytest.mark.parametrize("body_force", [False, True])
+def test_assemble_first_and_tentative_rhs(gdim, N, deg, body_force):
+    """A, b_first and rhs1 after assemble_first + velocity_tentative_assemble
+    (test/test_tentative_velocity.py:172-173,235)."""
+    dt, nu = 0.1, 0.5
+    f = [0.3, -0.1, 0.2][:gdim] if body_force else None
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    s = make_solver(msh, deg, tg, dt, body_force=f)
+    o = make_oracle(msh, deg, tg, dt, body_force=f)
+    ps = lambda x: x[1] + 0.5 * x[0] ** 2
+    s._ps.interpolate(ps)
+    o.ps = ps(o.xQ.T)
+    tg.t_u = dt
+    [[bc.update_bc() for bc in b] for b in s._bcs_u]
+    o.update_bcs()
+    s.assemble_first(dt, nu)
+    o.assemble_first(dt, nu)
+    A = _csr(s._A)
+    assert abs(A - o.A).max() <= 1e-12 * abs(o.A).max()
+    for i in range(gdim):
+        assert relerr(s._b_first[i].x.array_ro(), o.b_first[i]) <= 1e-12
+    s.velocity_tentative_assemble()
+    o.velocity_tentative_assemble()
+    for i in range(gdim):
+        assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i]) <= 1e-12
+    diff, reasons = s.velocity_tentative_solve()
+    odiff, _ = o.velocity_tentative_solve()
+    assert (reasons > 0).all()
+    for i in range(gdim):
+        assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i]) <= 1e-12  # now with BC values applied
+        assert relerr(s._u[i].x.array_ro(), o.u[i]) <= 1e-9
+    assert abs(diff - odiff) <= 1e-8 * odiff
+
+
+@pytest.mark.parametrize("gdim,N,deg", [(2, 8, 2), (3, 4, 2), (2, 8, 1)])
+def test_spmv_matches_oracle(gdim, N, deg):
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(0.01, gdim)
+    s = make_solver(msh, deg, tg, 0.01)
+    o = make_oracle(msh, deg, tg, 0.01)
+    rng = np.random.default_rng(0)
+    xv, xq = rng.uniform(-1, 1, o.nV), rng.uniform(-1, 1, o.nQ)
+    for dev, ref, x in [(s._M, o.M, xv), (s._K, o.K, xv), (s._Ap, o.Ap, xq), (s._p_vdxi_Mat[1], o.P[1], xq),
+                        (s._divu_Mat[0], o.D[0], xv)]:
+        y = np.zeros(ref.shape[0])
+        dev.mult(x, y)
+        assert relerr(y, ref @ x) <= 1e-13
+
+
+@pytest.mark.parametrize("gdim,N,deg,steps", [(2, 8, 2, 5), (3, 4, 2, 3), (2, 16, 2, 3), (2, 8, 1, 3)])
+def test_time_steps_match_oracle(gdim, N, deg, steps):
+    """Per-step velocity and pressure fields (demo/taylor_green.py:199-213 loop), <= 1e-8 relative."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    s = make_solver(msh, deg, tg, dt)
+    o = make_oracle(msh, deg, tg, dt)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(steps):
+        tg.t_u += dt
+        tg.t_p += dt
+        d1 = s.solve(dt, nu, max_iter=1)
+        d2 = o.solve(dt, nu, max_iter=1)
+        for i in range(gdim):
+            assert relerr(s._u[i].x.array_ro(), o.u[i]) <= 1e-8, (n, i)
+            assert relerr(s._u1[i].x.array_ro(), o.u1[i]) <= 1e-8
+            assert relerr(s._u2[i].x.array_ro(), o.u2[i]) <= 1e-8
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
+        assert abs(d1 - d2) <= 1e-7 * max(d2, 1e-300)
+    # blocked output vector == interleaved components (fracstep.py:698-705)
+    u = s.u.x.array
+    for i in range(gdim):
+        np.testing.assert_array_equal(u[i::gdim], s._u[i].x.array_ro())
+    st = s.stats()
+    assert st.kernel_launches > 0 and st.its_pressure > 0
+
+
+def test_inner_iterations_and_staged_calls_equal_fused_step():
+    """solve() == the staged sequence of fracstep.py:673-693 with max_iter=2."""
+    dt, nu = 0.01, 0.01
+    msh = make_mesh(2, 8)
+    tg = TaylorGreen(nu, 2)
+    s = make_solver(msh, 2, tg, dt)
+    o = make_oracle(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = dt, dt / 2
+    s.solve(dt, nu, max_error=1e-30, max_iter=2)
+    o.solve(dt, nu, max_error=1e-30, max_iter=2)
+    for i in range(2):
+        assert relerr(s._u[i].x.array_ro(), o.u[i]) <= 1e-8
+    assert relerr(s._p.x.array_ro(), o.p) <= 1e-8
+
+
+def test_rotational_pressure_update():
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(2, 8)
+    tg = TaylorGreen(nu, 2)
+    s = make_solver(msh, 2, tg, dt, rotational=True)
+    o = make_oracle(msh, 2, tg, dt, rotational=True)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(3):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8
+        for i in range(2):
+            assert relerr(s._u[i].x.array_ro(), o.u[i]) <= 1e-8
+
+
+def test_krylov_options_and_reasons():
+    """Explicit Krylov options (Appendix G) reach the device; reasons are PETSc codes."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(3, 4)
+    tg = TaylorGreen(nu, 3)
+    opts = {
+        "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+        "pressure": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+        "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+    }
+    s = make_solver(msh, 2, tg, dt, solver_options=opts)
+    o = make_oracle(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = dt, dt / 2
+    [[bc.update_bc() for bc in b] for b in s._bcs_u]
+    s._ps.x.array[:] = s._p.x.array
+    s.assemble_first(dt, nu)
+    s.velocity_tentative_assemble()
+    _, r = s.velocity_tentative_solve()
+    assert set(r.tolist()) <= {2, 3}
+    s.pressure_assemble(dt)
+    assert s.pressure_solve(nu) in (2, 3)
+    assert set(s.velocity_update(dt).tolist()) <= {2, 3}
+    o.solve(dt, nu, max_iter=1)
+    for i in range(3):
+        assert relerr(s._u[i].x.array_ro(), o.u[i]) <= 1e-7
+    # an impossible iteration budget reports KSP_DIVERGED_ITS
+    s._solver_p.updateOptions({"ksp_max_it": 2, "ksp_rtol": 1e-14})
+    s.pressure_assemble(dt)
+    assert s.pressure_solve(nu) == -3
