@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""bench.py -- IPCS time steps per second, 3D Taylor-Green P2-P1 on an N^3 box (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh 96]
+
+One "step" = one ``FractionalStep_AB_CN.solve(dt, nu, max_iter=1)`` (fracstep.py:660-696) on the
+z-extruded Taylor-Green problem of SURVEY.md 8(d): box [-1,1]^3, N^3 x 6 Kuhn tetrahedra, P2-P1,
+nu = 0.01, dt = 0.005, BiCGStab+Jacobi (velocity), CG+Jacobi (pressure, null space projected; mass),
+rtol 1e-10.
+
+  value   device-timed steps/s with every input (state, BC values of all timed steps) resident in HBM;
+  e2e     the same steps through the public Python API (host evaluation of the callable BCs, H2D of
+          the BC values, D2H of the step result), wall clock between two device synchronisations;
+  roofline  the dominant kernel (CSR SpMM of the P2xP2 operator on gdim right-hand sides) timed live
+          with CUDA events on the context's stream, algorithmic bytes / time vs MEASURED_PEAKS.json;
+  cpu_baseline  the CPU restatement (oracle/) on the box's host cores on a bounded sample.
+
+``--impl reference`` times the CPU restatement only (the DOLFINx/PETSc reference cannot be installed
+here: DESIGN.md).  No torch: ranks are launched by torchrun but only RANK/WORLD_SIZE are read.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
+DT, NU = 0.005, 0.01
+KRYLOV = {
+    "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+    "pressure": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+    "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = [float(r[0]) for r in rows if len(r) >= 7]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["power_w_max"] = max(float(r[2]) for r in rows if len(r) >= 7)
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[3 + k].strip() == "Active" for r in rows if len(r) >= 7):
+                        out["reasons"].append(nm)
+        except Exception:
+            pass
+        return out
+
+
+def bc_series(solver, tg, t_first: float, n_steps: int):
+    """g_i at the merged BC dofs for n_steps consecutive steps, evaluated on the host ahead of time."""
+    out = []
+    for i, bcl in enumerate(solver._bcs_u):
+        bc = bcl[0]
+        vals = np.empty((n_steps, len(bc._dofs)))
+        for s in range(n_steps):
+            tg.t_u = t_first + s * DT
+            vals[s] = bc._value(bc._xT)
+        out.append(vals)
+    return out
+
+
+def cpu_sample(n_cpu: int, n_steps: int):
+    """Time the CPU restatement (oracle/ipcs_oracle.py: numpy assembly + SuperLU, the reference demo's
+    preonly+lu) on an n_cpu^3 box; returns (seconds per step, cells)."""
+    from problems import TaylorGreen, make_mesh, make_oracle
+
+    tg = TaylorGreen(NU, 3)
+    msh = make_mesh(3, n_cpu)
+    o = make_oracle(msh, 2, tg, DT)
+    tg.t_u, tg.t_p = 0.0, -DT / 2
+    tg.t_u += DT
+    o.solve(DT, NU, max_iter=1)  # warm-up: LU factorisations of M and Ap are one-off set-up
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        tg.t_u += DT
+        o.solve(DT, NU, max_iter=1)
+    return (time.perf_counter() - t0) / n_steps, msh.num_cells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.cpu_mesh
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    sec, cells = cpu_sample(n_cpu, min(K, 3))
+    target_cells = 6 * args.mesh**3
+    # the restatement is O(cells^>1) with sparse LU; a linear scale to the target mesh is therefore
+    # generous to the CPU side
+    sps = (1.0 / sec) * cells / target_cells
+    try:
+        import threadpoolctl
+
+        cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D Taylor-Green P2-P1 {args.mesh}^3 box, dt={DT}, nu={NU}", "mesh": args.mesh},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"numpy/SuperLU restatement, {min(K,3)} steps on a {n_cpu}^3 box "
+                                   f"({sec:.2f} s/step), scaled linearly by cell count to {args.mesh}^3",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm; DOLFINx/PETSc are not installable in this image",
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": args.gpus, "unavailable":
+                              "multi-GPU partitioning (slab halo + NCCL allreduce) is not built yet"}))
+        return
+    from problems import TaylorGreen, make_mesh, make_solver
+
+    N, K, W = args.mesh, args.steps, max(args.warmup, 3)
+    t_setup = time.perf_counter()
+    tg = TaylorGreen(NU, 3)
+    msh = make_mesh(3, N)
+    solver = make_solver(msh, 2, tg, DT, solver_options=KRYLOV)
+    ctx = solver._ctx
+    t_setup = time.perf_counter() - t_setup
+    nbc = sum(len(b[0]._dofs) for b in solver._bcs_u)
+
+    # ---- device-timed region: state and the BC values of every step already in HBM -------------
+    series = bc_series(solver, tg, DT, W + K)
+    for i, v in enumerate(series):
+        ctx.set_velocity_bc_series(i, v)
+    solver._flush()
+    for s in range(W):
+        ctx.select_bc_step(s)
+        ctx.step(DT, NU, 1e-12, 1)
+    st0 = ctx.stats()
+    launches0 = st0.kernel_launches
+    sampler = ClockSampler(0)
+    sampler.start()
+    ctx.synchronize()
+    ctx.event_record(0)
+    its = []
+    stage_ms = np.zeros(4)
+    for s in range(K):
+        ctx.select_bc_step(W + s)
+        ctx.step(DT, NU, 1e-12, 1)
+        st = ctx.stats()
+        its.append((max(st.its_tentative), st.its_pressure, max(st.its_update)))
+        stage_ms += [st.ms_assemble_first, st.ms_tentative, st.ms_pressure, st.ms_update]
+    ctx.event_record(1)
+    ctx.synchronize()
+    ms_total = ctx.event_elapsed_ms(0, 1)
+    clocks = sampler.stop()
+    launches = ctx.stats().kernel_launches - launches0
+    ms_per_step = ms_total / K
+    value = 1000.0 / ms_per_step
+
+    # ---- end to end through the public API: callable BCs on the host, H2D, D2H ------------------
+    solver._written(solver._u, solver._u1, solver._u2, solver._p, solver._ps, solver._dp)
+    tg.t_u = (W + K) * DT
+    ctx.select_bc_step(-1)
+    stA = ctx.stats()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    for s in range(K):
+        tg.t_u += DT
+        tg.t_p += DT
+        solver.solve(DT, NU, max_iter=1)
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / K
+    stB = ctx.stats()
+    e2e = {"value": 1.0 / e2e_s, "unit": "steps/s",
+           "h2d_bytes_per_step": (stB.bytes_h2d - stA.bytes_h2d) // K,
+           "d2h_bytes_per_step": (stB.bytes_d2h - stA.bytes_d2h) // K}
+
+    # ---- roofline of the dominant kernel, measured live ----------------------------------------
+    peak, peak_kind = measured_peaks()
+    ms_k, bytes_k = ctx.bench_kernel(0, 20)
+    achieved = bytes_k / (ms_k * 1e-3) / 1e9
+    ms_m, bytes_m = ctx.bench_kernel(3, 20)
+    ms_a, bytes_a = ctx.bench_kernel(1, 5)
+    ms_q, bytes_q = ctx.bench_kernel(2, 50)
+    roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 CSR, 3 RHS)", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
+                "other_kernels": {
+                    "spmm_mass_GBs": bytes_m / (ms_m * 1e-3) / 1e9,
+                    "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
+                    "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
+
+    # ---- CPU restatement on the host cores, bounded sample -------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        sec, cells = cpu_sample(args.cpu_mesh, 2)
+        sps = (1.0 / sec) * cells / msh.num_cells
+        cpu = {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port",
+               "sample": f"numpy/SuperLU restatement, 2 steps on a {args.cpu_mesh}^3 box ({sec:.2f} s/step), "
+                         f"scaled linearly by cell count to {N}^3", "host_cpus": os.cpu_count()}
+
+    V, Q = solver._Vi[0][0], solver._Q
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D Taylor-Green P2-P1 {N}^3 box (z-extruded exact solution), dt={DT}, nu={NU}, "
+                               "max_iter=1, rtol=1e-10", "mesh": N, "cells": msh.num_cells,
+                   "dofs": 3 * V.num_dofs + Q.num_dofs, "nnz_vv": ctx.pattern_nnz(0),
+                   "l2": "working set per step >> 126 MB L2 (matrices alone "
+                         f"{(3 * 8 + 4) * ctx.pattern_nnz(0) / 1e9:.2f} GB); no flush needed",
+                   "krylov": KRYLOV, "setup_s": t_setup},
+        "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
+                       "update": int(np.median([i[2] for i in its]))},
+        "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "bc_dofs": nbc,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", type=int, default=96, help="cubes per direction (BASELINE: 96; 48 = configs[2])")
+    ap.add_argument("--cpu-mesh", type=int, default=12, help="box size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,11 @@ int b2_get_pattern(b2_ctx* ctx, int pattern, int32_t* indptr, int32_t* indices);
 int b2_set_velocity_bc_dofs(b2_ctx* ctx, int comp, int64_t n, const int32_t* dofs);
 /* g_i at those dofs, same order: the result of update_bc() + what set_bc reads (bcs.py:128-139) */
 int b2_set_velocity_bc_values(b2_ctx* ctx, int comp, int64_t n, const double* values);
+/* Prefetch g_i for `n_steps` consecutive time steps ([n_steps][n], device resident) and pick the
+ * one the next tentative solve applies: lets a driver evaluate time-dependent callables ahead of the
+ * device and keeps the per-step H2D copy out of the step (update_bc, bcs.py:128-133). */
+int b2_set_velocity_bc_series(b2_ctx* ctx, int comp, int n_steps, int64_t n, const double* values);
+int b2_select_bc_step(b2_ctx* ctx, int step);
 /* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253) */
 int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
 
@@ -174,6 +179,9 @@ int b2_get_stats(b2_ctx* ctx, b2_stats* out);
  * 2 = SpMV Ap*dp, 3 = SpMM M*u.  Returns average ms per launch and the algorithmic bytes moved. */
 int b2_bench_kernel(b2_ctx* ctx, int kernel, int reps, double* ms_per_launch, double* bytes_per_launch);
 int b2_synchronize(b2_ctx* ctx);
+/* CUDA events on the context's stream (slots 0..7) for callers that time a region of stage calls. */
+int b2_event_record(b2_ctx* ctx, int slot);
+int b2_event_elapsed_ms(b2_ctx* ctx, int slot_start, int slot_stop, double* ms);
 
 #ifdef __cplusplus
 }

@@ -27,10 +27,11 @@ SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
     "b2_build_patterns", "b2_pattern_nnz", "b2_get_pattern", "b2_set_velocity_bc_dofs",
-    "b2_set_velocity_bc_values", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
+    "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
     "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_event_record", "b2_event_elapsed_ms",
 ]
 
 
@@ -88,6 +89,8 @@ def load_library() -> C.CDLL:
         "b2_get_pattern": (i32, [vp, i32, vp, vp]),
         "b2_set_velocity_bc_dofs": (i32, [vp, i32, i64, vp]),
         "b2_set_velocity_bc_values": (i32, [vp, i32, i64, vp]),
+        "b2_set_velocity_bc_series": (i32, [vp, i32, i32, i64, vp]),
+        "b2_select_bc_step": (i32, [vp, i32]),
         "b2_set_pressure_bc_dofs": (i32, [vp, i64, vp]),
         "b2_preassemble": (i32, [vp, vp, i32, i32]),
         "b2_set_vector": (i32, [vp, i32, i32, vp, i64]),
@@ -107,6 +110,8 @@ def load_library() -> C.CDLL:
         "b2_get_stats": (i32, [vp, vp]),
         "b2_bench_kernel": (i32, [vp, i32, i32, vp, vp]),
         "b2_synchronize": (i32, [vp]),
+        "b2_event_record": (i32, [vp, i32]),
+        "b2_event_elapsed_ms": (i32, [vp, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -194,6 +199,15 @@ class Context:
     def set_velocity_bc_values(self, comp: int, values):
         v = _f64(values)
         self._check(self.lib.b2_set_velocity_bc_values(self._h, comp, v.size, _ptr(v)), "b2_set_velocity_bc_values")
+
+    def set_velocity_bc_series(self, comp: int, values: np.ndarray):
+        v = _f64(values)
+        assert v.ndim == 2
+        self._check(self.lib.b2_set_velocity_bc_series(self._h, comp, v.shape[0], v.shape[1], _ptr(v)),
+                    "b2_set_velocity_bc_series")
+
+    def select_bc_step(self, step: int):
+        self._check(self.lib.b2_select_bc_step(self._h, step), "b2_select_bc_step")
 
     def set_pressure_bc_dofs(self, dofs):
         d = _i32(dofs)
@@ -283,6 +297,14 @@ class Context:
         ms, nbytes = C.c_double(0.0), C.c_double(0.0)
         self._check(self.lib.b2_bench_kernel(self._h, kernel, reps, C.byref(ms), C.byref(nbytes)), "b2_bench_kernel")
         return ms.value, nbytes.value
+
+    def event_record(self, slot: int):
+        self._check(self.lib.b2_event_record(self._h, slot), "b2_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0.0)
+        self._check(self.lib.b2_event_elapsed_ms(self._h, a, b, C.byref(ms)), "b2_event_elapsed_ms")
+        return ms.value
 
     def synchronize(self):
         self._check(self.lib.b2_synchronize(self._h), "b2_synchronize")

@@ -69,6 +69,9 @@ struct b2_ctx {
   // boundary conditions
   DBuf<int> bc_dofs[B2_MAXK];
   DBuf<double> bc_vals[B2_MAXK];
+  DBuf<double> bc_series[B2_MAXK];  // [n_steps][n] prefetched values
+  int bc_series_steps[B2_MAXK] = {0, 0, 0};
+  int bc_step = -1;                 // >= 0: apply bc_series[.][bc_step] instead of bc_vals
   DBuf<uint8_t> is_bc_row_v, is_bc_q;
   DBuf<int> pbc_dofs;
   bool has_pbc = false;
@@ -86,6 +89,7 @@ struct b2_ctx {
   KSPOpts ksp[4];
   b2_stats stats{};
   cudaEvent_t ev[6];
+  cudaEvent_t user_ev[8];
   double last_dt = 0.0;
 
   double* vec(int id) {
@@ -398,8 +402,12 @@ void apply_velocity_bcs(b2_ctx* c, double* v) {
   for (int k = 0; k < c->gdim; ++k)
     if (c->bc_dofs[k].n) {
       B2_REQUIRE(c->bc_vals[k].n == c->bc_dofs[k].n, "velocity BC values not set");
-      B2_LAUNCH(c, k_set_bc, blocks_for(c->bc_dofs[k].n, 256), 256, c->bc_dofs[k].n, c->bc_dofs[k].p, c->bc_vals[k].p,
-                c->gdim, k, v);
+      const double* vals = c->bc_vals[k].p;
+      if (c->bc_step >= 0) {
+        B2_REQUIRE(c->bc_step < c->bc_series_steps[k], "b2_select_bc_step beyond the prefetched series");
+        vals = c->bc_series[k].p + (size_t)c->bc_step * c->bc_dofs[k].n;
+      }
+      B2_LAUNCH(c, k_set_bc, blocks_for(c->bc_dofs[k].n, 256), 256, c->bc_dofs[k].n, c->bc_dofs[k].p, vals, c->gdim, k, v);
     }
 }
 
@@ -710,6 +718,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     B2_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned)));
     B2_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned), c->stream));
     for (auto& e : c->ev) B2_CUDA(cudaEventCreate(&e));
+    for (auto& e : c->user_ev) B2_CUDA(cudaEventCreate(&e));
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -728,6 +737,7 @@ void b2_destroy(b2_ctx* c) {
   cudaFreeHost(c->h_sums);
   cudaFree(c->d_counter);
   for (auto& e : c->ev) cudaEventDestroy(e);
+  for (auto& e : c->user_ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -833,8 +843,26 @@ int b2_set_velocity_bc_values(b2_ctx* c, int comp, int64_t n, const double* valu
     B2_REQUIRE(n == c->bc_dofs[comp].n, "BC value count does not match the dof list");
     if (n) B2_CUDA(cudaMemcpyAsync(c->bc_vals[comp].p, values, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->bc_step = -1;  // fresh values override a prefetched series
     c->stats.bytes_h2d += sizeof(double) * n;
   });
+}
+
+int b2_set_velocity_bc_series(b2_ctx* c, int comp, int n_steps, int64_t n, const double* values) {
+  return guarded(c, [&] {
+    B2_REQUIRE(comp >= 0 && comp < c->gdim, "bad component");
+    B2_REQUIRE(n == c->bc_dofs[comp].n && n_steps >= 0, "BC series does not match the dof list");
+    c->bc_series[comp].alloc((int64_t)n_steps * n);
+    c->bc_series_steps[comp] = n_steps;
+    if (n_steps * n)
+      B2_CUDA(cudaMemcpyAsync(c->bc_series[comp].p, values, sizeof(double) * n_steps * n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_h2d += sizeof(double) * n_steps * n;
+  });
+}
+
+int b2_select_bc_step(b2_ctx* c, int step) {
+  return guarded(c, [&] { c->bc_step = step; });
 }
 
 int b2_set_pressure_bc_dofs(b2_ctx* c, int64_t n, const int32_t* dofs) {
@@ -1034,6 +1062,23 @@ int b2_get_stats(b2_ctx* c, b2_stats* out) {
 
 int b2_synchronize(b2_ctx* c) {
   return guarded(c, [&] { B2_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int b2_event_record(b2_ctx* c, int slot) {
+  return guarded(c, [&] {
+    B2_REQUIRE(slot >= 0 && slot < 8, "event slot out of range");
+    B2_CUDA(cudaEventRecord(c->user_ev[slot], c->stream));
+  });
+}
+
+int b2_event_elapsed_ms(b2_ctx* c, int a, int b, double* ms) {
+  return guarded(c, [&] {
+    B2_REQUIRE(a >= 0 && a < 8 && b >= 0 && b < 8, "event slot out of range");
+    B2_CUDA(cudaEventSynchronize(c->user_ev[b]));
+    float f = 0;
+    B2_CUDA(cudaEventElapsedTime(&f, c->user_ev[a], c->user_ev[b]));
+    *ms = f;
+  });
 }
 
 int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, double* bytes_per_launch) {

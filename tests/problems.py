@@ -88,6 +88,14 @@ def make_solver(msh, deg_u, tg: TaylorGreen, dt, solver_options=None, **kw):
     return s
 
 
-def relerr(a, b):
+def relerr(a, b, scale=None):
+    """max|a-b| / scale, scale = max|b| unless given (pass the max over all components when one
+    component is identically zero, e.g. w in the z-extruded Taylor-Green field)."""
     a, b = np.asarray(a), np.asarray(b)
-    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    if scale is None:
+        scale = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / max(scale, 1e-300))
+
+
+def vscale(vs):
+    return max(float(np.max(np.abs(v))) for v in vs)
