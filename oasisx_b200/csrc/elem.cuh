@@ -229,7 +229,7 @@ __global__ void k_assemble_loads(int64_t n_cells, const double* __restrict__ x,
     double l = g.detJ * E::LV(j);
 #pragma unroll
     for (int k = 0; k < D; ++k)
-      if (f[k] != 0.0) atomicAdd(b0 + (size_t)row * D + k, f[k] * l);
+      if (f[k] != 0.0) atomicAdd(b0 + (size_t)row * (D == 3 ? 4 : D) + k, f[k] * l);
   }
   for (int q = 0; q < E::NQ; ++q) {
     int row = qdofs[c * E::NQ + q];
@@ -274,7 +274,7 @@ k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restric
   for (int a = 0; a < NV; ++a) {
     double u[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) u[k] = uab[(size_t)dofs[a] * D + k];
+    for (int k = 0; k < D; ++k) u[k] = __ldg(uab + (size_t)dofs[a] * (D == 3 ? 4 : D) + k);
 #pragma unroll
     for (int dl = 0; dl < D; ++dl) {
       double s = 0;

@@ -151,19 +151,65 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
   }
 }
 
-// ---- CSR SpMM: y[row][k] = sum_p vals[p] * x[cols[p]][k] (* colscale[cols[p]]) ---------------
+// ---- component-interleaved vectors ---------------------------------------------------------
+// Velocity-space vectors hold K components per dof at stride KP = 4 for K = 3 (one aligned 32-byte
+// sector per dof: the SpMM gather is ONE 256-bit load per nonzero instead of three 8-byte loads that
+// each cost an L1 wavefront), KP = K otherwise.  The pad slot is kept at zero by every kernel.
+template <int K>
+struct Pad {
+  static constexpr int KP = (K == 3) ? 4 : K;
+};
+
+template <int K>
+__device__ __forceinline__ void ldk(const double* p, double (&v)[Pad<K>::KP]) {
+  if constexpr (K == 3) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  } else if constexpr (K == 2) {
+    double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x;
+    v[1] = t.y;
+  } else {
+    v[0] = *p;
+  }
+}
+// read-only (non-coherent) path: for operands no thread of the kernel writes
+template <int K>
+__device__ __forceinline__ void ldk_nc(const double* p, double (&v)[Pad<K>::KP]) {
+  if constexpr (K == 3) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  } else if constexpr (K == 2) {
+    double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = t.x;
+    v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+template <int K>
+__device__ __forceinline__ void stk(double* p, const double (&v)[Pad<K>::KP]) {
+  if constexpr (K == 3) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  } else if constexpr (K == 2) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  } else {
+    *p = v[0];
+  }
+}
+
+// ---- CSR SpMM: y[row][k] = sum_p vals[p] * x[cols[p]][k] --------------------------------------
 // LPR lanes cooperate on one row (rows of P2 matrices hold ~28 entries, P1 ~15); a warp therefore
 // streams 32/LPR consecutive rows: the value/column loads of one warp instruction cover a
-// contiguous stretch of the CSR arrays.  Persistent grid (grid-stride over row groups) so the
-// number of partial sums for the fused dot products stays small.
+// contiguous stretch of the CSR arrays.  The nonzero loop is unrolled by two so that two
+// column->gather chains are in flight per lane.  Persistent grid (grid-stride over row groups) so
+// the number of partial sums for the fused dot products stays small.
 //   DOT == 0: no reduction          DOT == 1: sums[k] = y_k . w_k
 //   DOT == 2: sums[k] = y_k . w_k , sums[K+k] = y_k . y_k
-template <int K, int LPR, bool SCALE, int DOT>
+template <int K, int LPR, int DOT>
 __global__ void __launch_bounds__(256)
 k_spmm(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-       const double* __restrict__ vals, const double* __restrict__ x,
-       const double* __restrict__ colscale, double* __restrict__ y, const double* __restrict__ w,
-       KryState* st, int fin, double* partials, unsigned* counter) {
+       const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+       const double* __restrict__ w, KryState* st, int fin, double* partials, unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x % LPR;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -175,30 +221,47 @@ k_spmm(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
   const int n_iter = (n_rows + ngroups - 1) / ngroups;
   for (int it = 0; it < n_iter; ++it) {
     const int row = it * ngroups + group;
-    double acc[K];
+    double acc[KP], acc2[KP];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int k = 0; k < KP; ++k) acc[k] = acc2[k] = 0.0;
     if (row < n_rows) {
       const int end = __ldg(rowptr + row + 1);
-      for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
-        const int c = __ldg(cols + p);
-        double v = __ldg(vals + p);
-        if constexpr (SCALE) v *= __ldg(colscale + c);
-        const double* xc = x + (size_t)c * K;
+      int p = __ldg(rowptr + row) + lane;
+      for (; p + LPR < end; p += 2 * LPR) {
+        const int c0 = __ldg(cols + p), c1 = __ldg(cols + p + LPR);
+        const double v0 = __ldg(vals + p), v1 = __ldg(vals + p + LPR);
+        double x0[KP], x1[KP];
+        ldk_nc<K>(x + (size_t)c0 * KP, x0);
+        ldk_nc<K>(x + (size_t)c1 * KP, x1);
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(xc + k), acc[k]);
+        for (int k = 0; k < KP; ++k) {
+          acc[k] = fma(v0, x0[k], acc[k]);
+          acc2[k] = fma(v1, x1[k], acc2[k]);
+        }
+      }
+      if (p < end) {
+        const int c0 = __ldg(cols + p);
+        const double v0 = __ldg(vals + p);
+        double x0[KP];
+        ldk_nc<K>(x + (size_t)c0 * KP, x0);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = fma(v0, x0[k], acc[k]);
       }
     }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] += acc2[k];
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1)
 #pragma unroll
       for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     if (row < n_rows && lane == 0) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) y[(size_t)row * K + k] = acc[k];
+      if constexpr (KP > K) acc[KP - 1] = 0.0;
+      stk<K>(y + (size_t)row * KP, acc);
       if constexpr (DOT >= 1) {
+        double wv[KP];
+        ldk<K>(w + (size_t)row * KP, wv);
 #pragma unroll
-        for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], w[(size_t)row * K + k], dots[k]);
+        for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], wv[k], dots[k]);
       }
       if constexpr (DOT == 2) {
 #pragma unroll
@@ -215,60 +278,88 @@ k_spmm(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
 // ---- fused "matrix-vector strategy" of assemble_first (fracstep.py:438-472) ------------------
 // In:  A = C(uab) (just assembled), M, Kst.   Out, in ONE pass over the nonzeros:
 //   b_first[row] = (M/dt - nu/2 K - 1/2 C) u1 + b0 (+ p_surf)        (:438-465)
-//   A            =  M/dt + nu/2 K + 1/2 C, unit rows on Dirichlet dofs (:468-472)
-//   dinv[row]    = 1 / A[row,row]                                      (Jacobi for the Krylov solve)
+//   A            =  D^-1 (M/dt + nu/2 K + 1/2 C), unit rows on Dirichlet dofs (:468-472), stored
+//                   ROW-SCALED by its own diagonal D when `scale` (left Jacobi preconditioning, the
+//                   PETSc default side for BiCGStab [ext]): the Krylov kernels then need no
+//                   preconditioner gather at all.  b2_get_matrix_values undoes the scaling.
+//   dinv[row]    = 1 / D[row]  (1 when !scale)
 template <int K, int LPR>
 __global__ void __launch_bounds__(256)
 k_combine_first(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
                 double* __restrict__ A, const double* __restrict__ M, const double* __restrict__ Kst,
                 double inv_dt, double half_nu, const double* __restrict__ u1,
                 const double* __restrict__ b0, const double* __restrict__ psurf,
-                const uint8_t* __restrict__ is_bc_row, double* __restrict__ bfirst,
+                const uint8_t* __restrict__ is_bc_row, int scale, double* __restrict__ bfirst,
                 double* __restrict__ dinv) {
+  constexpr int KP = Pad<K>::KP;
   const int lane = threadIdx.x % LPR;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int ngroups = (gridDim.x * blockDim.x) / LPR;
   const int n_iter = (n_rows + ngroups - 1) / ngroups;
   for (int it = 0; it < n_iter; ++it) {
     const int row = it * ngroups + group;
-    double acc[K];
+    double acc[KP];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
     double diag = 0.0;
+    bool bc = false;
+    int start = 0, end = 0;
     if (row < n_rows) {
-      const bool bc = is_bc_row[row];
-      const int end = __ldg(rowptr + row + 1);
-      for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
+      bc = is_bc_row[row];
+      start = __ldg(rowptr + row);
+      end = __ldg(rowptr + row + 1);
+      // phase 1: the diagonal entry of the new left-hand side
+      for (int p = start + lane; p < end; p += LPR)
+        if (__ldg(cols + p) == row) diag = (inv_dt * __ldg(M + p) + 0.5 * A[p]) + half_nu * __ldg(Kst + p);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);
+    if (bc) diag = 1.0;
+    const double invd = (scale && row < n_rows) ? 1.0 / diag : 1.0;
+    if (row < n_rows) {
+      for (int p = start + lane; p < end; p += LPR) {
         const int c = __ldg(cols + p);
         const double m = inv_dt * __ldg(M + p);
         const double kk = half_nu * __ldg(Kst + p);
         const double cv = 0.5 * A[p];
         const double r = (m - cv) - kk;
-        double a = (m + cv) + kk;
-        const double* xc = u1 + (size_t)c * K;
+        double a = ((m + cv) + kk) * invd;
+        double xc[KP];
+        ldk_nc<K>(u1 + (size_t)c * KP, xc);
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = fma(r, __ldg(xc + k), acc[k]);
+        for (int k = 0; k < KP; ++k) acc[k] = fma(r, xc[k], acc[k]);
         if (bc) a = (c == row) ? 1.0 : 0.0;
         A[p] = a;
-        if (c == row) diag = a;
       }
     }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
+    for (int o = LPR / 2; o > 0; o >>= 1)
 #pragma unroll
       for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-      diag += __shfl_xor_sync(0xffffffffu, diag, o);
-    }
     if (row < n_rows && lane == 0) {
+      double bv[KP];
+      ldk_nc<K>(b0 + (size_t)row * KP, bv);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        double v = acc[k] + b0[(size_t)row * K + k];
-        if (psurf != nullptr) v += psurf[(size_t)row * K + k];
-        bfirst[(size_t)row * K + k] = v;
+      for (int k = 0; k < K; ++k) acc[k] += bv[k];
+      if (psurf != nullptr) {
+        ldk_nc<K>(psurf + (size_t)row * KP, bv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += bv[k];
       }
-      dinv[row] = 1.0 / diag;
+      if constexpr (KP > K) acc[KP - 1] = 0.0;
+      stk<K>(bfirst + (size_t)row * KP, acc);
+      dinv[row] = invd;
     }
   }
+}
+
+// vals[p] *= s[row] (or /= when `divide`): used to hand the caller the unscaled A
+__global__ void k_scale_rows(int n_rows, const int* __restrict__ rowptr, const double* __restrict__ s, int divide,
+                             const double* __restrict__ in, double* __restrict__ out) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const double f = divide ? 1.0 / s[row] : s[row];
+  for (int p = rowptr[row]; p < rowptr[row + 1]; ++p) out[p] = in[p] * f;
 }
 
 // ---- rectangular products on the V x Q and Q x V patterns ([nnz][K] values) --------------------
@@ -276,13 +367,14 @@ k_combine_first(int n_rows, const int* __restrict__ rowptr, const int* __restric
 template <int K, int LPR>
 __global__ void __launch_bounds__(256)
 k_rect_vq(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-          const double* __restrict__ vals, const double* __restrict__ xq,
-          const double* __restrict__ add, double scale, double* __restrict__ out) {
+          const double* __restrict__ vals, const double* __restrict__ xq, const double* add,
+          double scale, double* out) {
+  constexpr int KP = Pad<K>::KP;
   const int lane = threadIdx.x % LPR;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  double acc[K];
+  double acc[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  for (int k = 0; k < KP; ++k) acc[k] = 0.0;
   if (row < n_rows) {
     const int end = __ldg(rowptr + row + 1);
     for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
@@ -296,11 +388,13 @@ k_rect_vq(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
   if (row < n_rows && lane == 0) {
+    double a[KP];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double a = add != nullptr ? add[(size_t)row * K + k] : 0.0;
-      out[(size_t)row * K + k] = a + scale * acc[k];
-    }
+    for (int k = 0; k < KP; ++k) a[k] = 0.0;
+    if (add != nullptr) ldk<K>(add + (size_t)row * KP, a);
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = fma(scale, acc[k], a[k]);
+    stk<K>(out + (size_t)row * KP, a);
   }
 }
 
@@ -310,15 +404,17 @@ __global__ void __launch_bounds__(256)
 k_rect_qv(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
           const double* __restrict__ vals, const double* __restrict__ xv, double scale,
           const uint8_t* __restrict__ zero_row, double* __restrict__ out) {
+  constexpr int KP = Pad<K>::KP;
   const int lane = threadIdx.x % LPR;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   double acc = 0.0;
   if (row < n_rows) {
     const int end = __ldg(rowptr + row + 1);
     for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
-      const double* xc = xv + (size_t)__ldg(cols + p) * K;
+      double xc[KP];
+      ldk_nc<K>(xv + (size_t)__ldg(cols + p) * KP, xc);
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc = fma(__ldg(vals + (size_t)p * K + k), __ldg(xc + k), acc);
+      for (int k = 0; k < K; ++k) acc = fma(__ldg(vals + (size_t)p * K + k), xc[k], acc);
     }
   }
 #pragma unroll
@@ -327,8 +423,7 @@ k_rect_qv(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ co
 }
 
 // ---- small vector kernels ----------------------------------------------------------------
-__global__ void k_lincomb2(int64_t n, double a, const double* __restrict__ x, double b,
-                           const double* __restrict__ y, double* __restrict__ out) {
+__global__ void k_lincomb2(int64_t n, double a, const double* x, double b, const double* y, double* out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = a * x[i] + b * y[i];
 }
@@ -338,11 +433,11 @@ __global__ void k_fill(int64_t n, double v, double* __restrict__ out) {
     out[i] = v;
 }
 
-// vec[dofs[i]][comp] = values[i]   (set_bc, bcs.py:135-139)
+// vec[dofs[i]][comp] = values[i]   (set_bc, bcs.py:135-139); stride = KP
 __global__ void k_set_bc(int64_t n, const int* __restrict__ dofs, const double* __restrict__ values,
-                         int K, int comp, double* __restrict__ vec) {
+                         int stride, int comp, double* __restrict__ vec) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) vec[(size_t)dofs[i] * K + comp] = values[i];
+  if (i < n) vec[(size_t)dofs[i] * stride + comp] = values[i];
 }
 
 __global__ void k_mark(int64_t n, const int* __restrict__ dofs, uint8_t* __restrict__ mask) {
@@ -351,13 +446,21 @@ __global__ void k_mark(int64_t n, const int* __restrict__ dofs, uint8_t* __restr
 }
 
 // strided component copies between the interleaved device layout and per-component host views
-__global__ void k_extract(int64_t n, int K, int comp, const double* __restrict__ src, double* __restrict__ dst) {
+__global__ void k_extract(int64_t n, int stride, int comp, const double* __restrict__ src, double* __restrict__ dst) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = src[i * K + comp];
+    dst[i] = src[i * stride + comp];
 }
-__global__ void k_insert(int64_t n, int K, int comp, const double* __restrict__ src, double* __restrict__ dst) {
+__global__ void k_insert(int64_t n, int stride, int comp, const double* __restrict__ src, double* __restrict__ dst) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i * K + comp] = src[i];
+    dst[i * stride + comp] = src[i];
+}
+// [n][K] (the blocked layout of solver.u) <-> [n][KP]
+__global__ void k_repack(int64_t n, int K, int sstride, int dstride, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * K; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t / K;
+    int k = (int)(t - i * K);
+    dst[i * dstride + k] = src[i * sstride + k];
+  }
 }
 
 // diagonal of a square CSR matrix -> dinv = 1/diag
@@ -371,19 +474,24 @@ __global__ void k_inv_diag(int n_rows, const int* __restrict__ rowptr, const int
   dinv[row] = 1.0 / d;
 }
 
-// sums[k] = sum_i w_i * (a[i][k] - b[i][k])^2  (b may be null; w may be null => 1).  FIN_STORE:
-// totals land in out[0..K).
+// out[k] = sum_i (a[i][k] - b[i][k])^2  (b may be null)
 template <int K>
 __global__ void __launch_bounds__(256)
 k_sqdiff(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* out,
          double* partials, unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   double s[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double av[KP], bv[KP];
+    ldk<K>(a + i * KP, av);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) bv[k] = 0.0;
+    if (b != nullptr) ldk<K>(b + i * KP, bv);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      double d = a[i * K + k] - (b != nullptr ? b[i * K + k] : 0.0);
+      double d = av[k] - bv[k];
       s[k] = fma(d, d, s[k]);
     }
   }
@@ -442,24 +550,37 @@ __global__ void __launch_bounds__(256)
 k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
           const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
           double* __restrict__ p, KryState* st, double* partials, unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   double s[3 * K];
 #pragma unroll
   for (int i = 0; i < 3 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
+    double bv[KP], rv[KP], pv[KP];
+    ldk<K>(b + i * KP, bv);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) rv[k] = bv[k];
+    if (q != nullptr) {
+      double qv[KP];
+      ldk<K>(q + i * KP, qv);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) rv[k] -= qv[k];
+    } else {
+      double z[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) z[k] = 0.0;
+      stk<K>(x + i * KP, z);
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) pv[k] = di * rv[k];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const double bv = b[i * K + k];
-      double rv = bv;
-      if (q != nullptr) rv -= q[i * K + k];
-      else x[i * K + k] = 0.0;
-      const double zv = di * rv;
-      r[i * K + k] = rv;
-      p[i * K + k] = zv;
-      s[k] = fma(rv, zv, s[k]);
-      s[K + k] = fma(bv, bv, s[K + k]);
-      s[2 * K + k] = fma(rv, rv, s[2 * K + k]);
+      s[k] = fma(rv[k], pv[k], s[k]);
+      s[K + k] = fma(bv[k], bv[k], s[K + k]);
+      s[2 * K + k] = fma(rv[k], rv[k], s[2 * K + k]);
     }
+    stk<K>(r + i * KP, rv);
+    stk<K>(p + i * KP, pv);
   }
   double total[3 * K];
   if (grid_reduce<3 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_INIT, st, total);
@@ -471,82 +592,99 @@ __global__ void __launch_bounds__(256)
 k_cg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             KryState* st, double* partials, unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double alpha[K];
-  int act[K];
+  double alpha[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    act[k] = st->active[k];
-    alpha[k] = st->alpha[k];
-  }
+  for (int k = 0; k < KP; ++k) alpha[k] = (k < K && st->active[k]) ? st->alpha[k] : 0.0;
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
+    double pv[KP], qv[KP], xv[KP], rv[KP];
+    ldk_nc<K>(p + i * KP, pv);
+    ldk_nc<K>(q + i * KP, qv);
+    ldk<K>(x + i * KP, xv);
+    ldk<K>(r + i * KP, rv);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      xv[k] = fma(alpha[k], pv[k], xv[k]);
+      rv[k] = fma(-alpha[k], qv[k], rv[k]);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (!act[k]) continue;
-      const int64_t j = i * K + k;
-      x[j] = fma(alpha[k], p[j], x[j]);
-      const double rv = fma(-alpha[k], q[j], r[j]);
-      r[j] = rv;
-      s[k] = fma(rv * di, rv, s[k]);
-      s[K + k] = fma(rv, rv, s[K + k]);
+      s[k] = fma(rv[k] * di, rv[k], s[k]);
+      s[K + k] = fma(rv[k], rv[k], s[K + k]);
     }
+    stk<K>(x + i * KP, xv);
+    stk<K>(r + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_UPDATE, st, total);
 }
 
-// p = dinv r + beta p
+// p = dinv r + beta p   (components that have converged keep their p: alpha is then 0 anyway)
 template <int K>
 __global__ void __launch_bounds__(256)
 k_cg_p(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
        double* __restrict__ p, const KryState* st) {
+  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double beta[K];
-  int act[K];
+  double beta[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    act[k] = st->active[k];
-    beta[k] = st->beta[k];
-  }
+  for (int k = 0; k < KP; ++k) beta[k] = k < K ? st->beta[k] : 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
+    double rv[KP], pv[KP];
+    ldk_nc<K>(r + i * KP, rv);
+    ldk<K>(p + i * KP, pv);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (!act[k]) continue;
-      const int64_t j = i * K + k;
-      p[j] = fma(beta[k], p[j], di * r[j]);
-    }
+    for (int k = 0; k < KP; ++k) pv[k] = fma(beta[k], pv[k], di * rv[k]);
+    stk<K>(p + i * KP, pv);
   }
 }
 
-// ---- BiCGStab, right-preconditioned with Jacobi, on K systems sharing one matrix ---------------
-// init: r = b - q (or r = b, x = 0); rhat = r; p = r; sums bb, rr
+// ---- BiCGStab on K systems sharing one (already left-preconditioned, row-scaled) matrix ----------
+// init: r = dinv b - q (or r = dinv b, x = 0); rhat = r; p = r; sums bb = |dinv b|^2, rr
 template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
-            double* __restrict__ x, double* __restrict__ r, double* __restrict__ rhat,
-            double* __restrict__ p, KryState* st, double* partials, unsigned* counter) {
+            const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+            double* __restrict__ rhat, double* __restrict__ p, KryState* st, double* partials,
+            unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = dinv[i];
+    double bv[KP], rv[KP];
+    ldk<K>(b + i * KP, bv);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      bv[k] *= di;
+      rv[k] = bv[k];
+    }
+    if (q != nullptr) {
+      double qv[KP];
+      ldk<K>(q + i * KP, qv);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) rv[k] -= qv[k];
+    } else {
+      double z[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) z[k] = 0.0;
+      stk<K>(x + i * KP, z);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const int64_t j = i * K + k;
-      const double bv = b[j];
-      double rv = bv;
-      if (q != nullptr) rv -= q[j];
-      else x[j] = 0.0;
-      r[j] = rv;
-      rhat[j] = rv;
-      p[j] = rv;
-      s[k] = fma(bv, bv, s[k]);
-      s[K + k] = fma(rv, rv, s[K + k]);
+      s[k] = fma(bv[k], bv[k], s[k]);
+      s[K + k] = fma(rv[k], rv[k], s[K + k]);
     }
+    stk<K>(r + i * KP, rv);
+    stk<K>(rhat + i * KP, rv);
+    stk<K>(p + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_INIT, st, total);
@@ -556,81 +694,86 @@ k_bcgs_init(int64_t n, const double* __restrict__ b, const double* __restrict__ 
 template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_s(int64_t n, const double* __restrict__ v, double* __restrict__ r, const KryState* st) {
+  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double alpha[K];
-  int act[K];
+  double alpha[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    act[k] = st->active[k];
-    alpha[k] = st->alpha[k];
-  }
+  for (int k = 0; k < KP; ++k) alpha[k] = (k < K && st->active[k]) ? st->alpha[k] : 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double vv[KP], rv[KP];
+    ldk_nc<K>(v + i * KP, vv);
+    ldk<K>(r + i * KP, rv);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (!act[k]) continue;
-      const int64_t j = i * K + k;
-      r[j] = fma(-alpha[k], v[j], r[j]);
-    }
+    for (int k = 0; k < KP; ++k) rv[k] = fma(-alpha[k], vv[k], rv[k]);
+    stk<K>(r + i * KP, rv);
   }
 }
 
-// x += dinv (alpha p + omega s) ; r = s - omega t ; sums rr, rho' = rhat . r
+// x += alpha p + omega s ; r = s - omega t ; sums rr, rho' = rhat . r
 template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_update(int64_t n, const double* __restrict__ p, const double* __restrict__ t,
-              const double* __restrict__ rhat, const double* __restrict__ dinv,
-              double* __restrict__ x, double* __restrict__ r, KryState* st, double* partials,
-              unsigned* counter) {
+              const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
+              KryState* st, double* partials, unsigned* counter) {
+  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double alpha[K], omega[K];
-  int act[K];
+  double alpha[KP], omega[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    act[k] = st->active[k];
-    alpha[k] = st->alpha[k];
-    omega[k] = st->omega[k];
+  for (int k = 0; k < KP; ++k) {
+    const bool a = k < K && st->active[k];
+    alpha[k] = a ? st->alpha[k] : 0.0;
+    omega[k] = a ? st->omega[k] : 0.0;
   }
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double di = dinv[i];
+    double pv[KP], tv[KP], hv[KP], xv[KP], rv[KP];
+    ldk_nc<K>(p + i * KP, pv);
+    ldk_nc<K>(t + i * KP, tv);
+    ldk_nc<K>(rhat + i * KP, hv);
+    ldk<K>(x + i * KP, xv);
+    ldk<K>(r + i * KP, rv);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      xv[k] = fma(alpha[k], pv[k], fma(omega[k], rv[k], xv[k]));
+      rv[k] = fma(-omega[k], tv[k], rv[k]);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (!act[k]) continue;
-      const int64_t j = i * K + k;
-      const double sv = r[j];
-      x[j] = fma(di, fma(alpha[k], p[j], omega[k] * sv), x[j]);
-      const double rv = fma(-omega[k], t[j], sv);
-      r[j] = rv;
-      s[k] = fma(rv, rv, s[k]);
-      s[K + k] = fma(rhat[j], rv, s[K + k]);
+      s[k] = fma(rv[k], rv[k], s[k]);
+      s[K + k] = fma(hv[k], rv[k], s[K + k]);
     }
+    stk<K>(x + i * KP, xv);
+    stk<K>(r + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_UPDATE, st, total);
 }
 
-// p = r + beta (p - omega v)
+// p = r + beta (p - omega v)   (frozen for converged components)
 template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_p(int64_t n, const double* __restrict__ r, const double* __restrict__ v,
          double* __restrict__ p, const KryState* st) {
+  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double beta[K], omega[K];
-  int act[K];
+  double beta[KP], omega[KP];
+  bool act[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    act[k] = st->active[k];
-    beta[k] = st->beta[k];
-    omega[k] = st->omega[k];
+  for (int k = 0; k < KP; ++k) {
+    act[k] = k < K && st->active[k];
+    beta[k] = act[k] ? st->beta[k] : 0.0;
+    omega[k] = act[k] ? st->omega[k] : 0.0;
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double rv[KP], vv[KP], pv[KP];
+    ldk_nc<K>(r + i * KP, rv);
+    ldk_nc<K>(v + i * KP, vv);
+    ldk<K>(p + i * KP, pv);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (!act[k]) continue;
-      const int64_t j = i * K + k;
-      p[j] = fma(beta[k], fma(-omega[k], v[j], p[j]), r[j]);
-    }
+    for (int k = 0; k < KP; ++k)
+      if (act[k]) pv[k] = fma(beta[k], fma(-omega[k], vv[k], pv[k]), rv[k]);
+    stk<K>(p + i * KP, pv);
   }
 }
