@@ -23,7 +23,11 @@ struct CSR {
   DBuf<int> rowptr, cols;
   int n_rows = 0, n_cols = 0;
   int64_t nnz = 0;
-  int lpr = 8;  // lanes per row used by the SpMM kernels on this pattern
+  int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
+  // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
+  DBuf<int> slice_ptr, scols, diag_t;
+  int64_t slots = 0;
+  bool has_sell() const { return slice_ptr.p != nullptr; }
 };
 
 struct Space {
@@ -58,7 +62,6 @@ struct b2_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
-  int KP() const { return gdim == 3 ? 4 : gdim; }  // component stride of velocity-space vectors
   int64_t n_nodes = 0, n_cells = 0;
   DBuf<double> x;
   DBuf<int> cell_nodes;
@@ -124,7 +127,7 @@ void alloc_vec(b2_ctx* c, int id, int space, int K) {
   DVec& v = c->vecs[id];
   v.K = K;
   v.space = space;
-  v.buf.alloc(c->sp[space].n_local() * (K > 1 ? c->KP() : 1));
+  v.buf.alloc(c->sp[space].n_local() * K);
   v.buf.zero(c->stream);
 }
 
@@ -197,6 +200,32 @@ void build_pattern(b2_ctx* c, const Space& rs, const Space& cs, CSR& out) {
   out.lpr = avg >= 48 ? 16 : (avg >= 20 ? 8 : 4);
 }
 
+// SELL-32 companion of a square CSR pattern: slice offsets (in slots), padded column indices,
+// position of the diagonal in each row.
+void build_sell(b2_ctx* c, CSR& pat) {
+  const int n_rows = pat.n_rows;
+  const int n_slices = (n_rows + 31) / 32;
+  DBuf<int> entries;
+  entries.alloc(n_slices + 1);
+  entries.zero(c->stream);
+  B2_LAUNCH(c, k_sell_slice_len, blocks_for(n_slices, 256), 256, n_rows, pat.rowptr.p, entries.p);
+  pat.slice_ptr.alloc(n_slices + 1);
+  size_t tmp_bytes = 0;
+  B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, entries.p, pat.slice_ptr.p, n_slices + 1, c->stream));
+  DBuf<char> tmp;
+  tmp.alloc((int64_t)tmp_bytes);
+  B2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, entries.p, pat.slice_ptr.p, n_slices + 1, c->stream));
+  int slots = 0;
+  B2_CUDA(cudaMemcpyAsync(&slots, pat.slice_ptr.p + n_slices, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  pat.slots = slots;
+  pat.scols.alloc(slots);
+  pat.scols.zero(c->stream);
+  pat.diag_t.alloc(n_rows);
+  B2_LAUNCH(c, k_sell_fill_cols, blocks_for(n_rows, 256), 256, n_rows, pat.rowptr.p, pat.cols.p, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 // ---- dispatch helpers -------------------------------------------------------------------------
 template <typename F>
 void dispatch_elem(const b2_ctx* c, F&& f) {
@@ -208,30 +237,20 @@ void dispatch_elem(const b2_ctx* c, F&& f) {
   else throw B2Error(-3, "unsupported (gdim, degree)");
 }
 
-template <int K, int LPR, int DOT>
-void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, double* y, const double* w,
+template <int K, int DOT>
+void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
-  int grid = pgrid(c, (int64_t)pat.n_rows * LPR, 256, c->spmm_blocks_per_sm);
-  B2_LAUNCH(c, (k_spmm<K, LPR, DOT>), grid, 256, pat.n_rows, pat.rowptr.p, pat.cols.p, vals, x, y, w, st, fin,
+  int grid = pgrid(c, (int64_t)pat.n_rows, 256, c->spmm_blocks_per_sm);
+  B2_LAUNCH(c, (k_spmm<K, DOT>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y, w, st, fin,
             c->partials.p, c->d_counter);
 }
 
-template <int K, int LPR>
-void launch_spmm_kl(b2_ctx* c, const CSR& pat, const double* vals, const double* x, double* y, const double* w,
-                    KryState* st, int fin, int dot) {
-  if (dot == 0) launch_spmm_t<K, LPR, 0>(c, pat, vals, x, y, w, st, fin);
-  else if (dot == 1) launch_spmm_t<K, LPR, 1>(c, pat, vals, x, y, w, st, fin);
-  else launch_spmm_t<K, LPR, 2>(c, pat, vals, x, y, w, st, fin);
-}
-
 template <int K>
-void launch_spmm_k(b2_ctx* c, const CSR& pat, const double* vals, const double* x, double* y, const double* w,
+void launch_spmm_k(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin, int dot) {
-  switch (pat.lpr) {
-    case 4: launch_spmm_kl<K, 4>(c, pat, vals, x, y, w, st, fin, dot); break;
-    case 16: launch_spmm_kl<K, 16>(c, pat, vals, x, y, w, st, fin, dot); break;
-    default: launch_spmm_kl<K, 8>(c, pat, vals, x, y, w, st, fin, dot); break;
-  }
+  if (dot == 0) launch_spmm_t<K, 0>(c, pat, vals, x, ld, y, w, st, fin);
+  else if (dot == 1) launch_spmm_t<K, 1>(c, pat, vals, x, ld, y, w, st, fin);
+  else launch_spmm_t<K, 2>(c, pat, vals, x, ld, y, w, st, fin);
 }
 
 // Owner -> ghost exchange of an interleaved vector before it is gathered by columns
@@ -244,11 +263,13 @@ void halo_forward(b2_ctx* c, int space, double* v, int K) {
 
 void spmm(b2_ctx* c, const CSR& pat, const double* vals, int K, double* x, double* y, const double* w = nullptr,
           KryState* st = nullptr, int fin = FIN_NONE, int dot = 0, int xspace = -1) {
+  B2_REQUIRE(pat.has_sell(), "SpMM needs the SELL layout of the pattern");
   if (xspace >= 0) halo_forward(c, xspace, x, K);
+  const int ld = pat.n_cols;  // square operators: vectors of the space, owned + ghosts
   switch (K) {
-    case 1: launch_spmm_k<1>(c, pat, vals, x, y, w, st, fin, dot); break;
-    case 2: launch_spmm_k<2>(c, pat, vals, x, y, w, st, fin, dot); break;
-    case 3: launch_spmm_k<3>(c, pat, vals, x, y, w, st, fin, dot); break;
+    case 1: launch_spmm_k<1>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
+    case 2: launch_spmm_k<2>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
+    case 3: launch_spmm_k<3>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
     default: throw B2Error(-3, "K must be 1..3");
   }
 }
@@ -258,19 +279,20 @@ template <int K>
 void krylov_iterations(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals, const double* dinv, int space,
                        double* x, double* r, double* p, double* q, double* t, double* rhat, int n_iter) {
   const int64_t n = pat.n_rows;
+  const int ld = pat.n_cols;
   const int g = pgrid(c, n, 256, 8);
   KryState* st = c->d_st;
   for (int it = 0; it < n_iter; ++it) {
     if (o.type == 0) {
       spmm(c, pat, vals, K, p, q, p, st, FIN_CG_PQ, 1, space);
-      B2_LAUNCH(c, k_cg_update<K>, g, 256, n, p, q, dinv, x, r, st, c->partials.p, c->d_counter);
-      B2_LAUNCH(c, k_cg_p<K>, g, 256, n, r, dinv, p, st);
+      B2_LAUNCH(c, k_cg_update<K>, g, 256, n, ld, p, q, dinv, x, r, st, c->partials.p, c->d_counter);
+      B2_LAUNCH(c, k_cg_p<K>, g, 256, n, ld, r, dinv, p, st);
     } else {
       spmm(c, pat, vals, K, p, q, rhat, st, FIN_BCGS_V, 1, space);                // v = A p
-      B2_LAUNCH(c, k_bcgs_s<K>, g, 256, n, q, r, st);                             // s = r - alpha v
+      B2_LAUNCH(c, k_bcgs_s<K>, g, 256, n, ld, q, r, st);                            // s = r - alpha v
       spmm(c, pat, vals, K, r, t, r, st, FIN_BCGS_T, 2, space);                   // t = A s
-      B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, p, t, rhat, x, r, st, c->partials.p, c->d_counter);
-      B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, r, q, p, st);
+      B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, ld, p, t, rhat, x, r, st, c->partials.p, c->d_counter);
+      B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, ld, r, q, p, st);
     }
   }
 }
@@ -279,6 +301,7 @@ template <int K>
 void krylov_init(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals, const double* dinv, int space,
                  const double* b, double* x, double* r, double* p, double* q, double* rhat) {
   const int64_t n = pat.n_rows;
+  const int ld = pat.n_cols;
   const int g = pgrid(c, n, 256, 8);
   const double* q0 = nullptr;
   if (o.nonzero_guess) {
@@ -286,9 +309,9 @@ void krylov_init(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals
     q0 = q;
   }
   if (o.type == 0)
-    B2_LAUNCH(c, k_cg_init<K>, g, 256, n, b, q0, dinv, x, r, p, c->d_st, c->partials.p, c->d_counter);
+    B2_LAUNCH(c, k_cg_init<K>, g, 256, n, ld, b, q0, dinv, x, r, p, c->d_st, c->partials.p, c->d_counter);
   else
-    B2_LAUNCH(c, k_bcgs_init<K>, g, 256, n, b, q0, dinv, x, r, rhat, p, c->d_st, c->partials.p, c->d_counter);
+    B2_LAUNCH(c, k_bcgs_init<K>, g, 256, n, ld, b, q0, dinv, x, r, rhat, p, c->d_st, c->partials.p, c->d_counter);
 }
 
 // Solves K systems  A x_k = b_k  (interleaved storage) with the options of solver `which`.
@@ -349,41 +372,39 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   const int K = c->gdim;
   const Space& V = c->sp[B2_SPACE_V];
   const CSR& vv = c->pat[B2_PAT_VV];
+  const int ld = (int)V.n_local();
   double *u1 = c->vec(B2_VEC_U1), *u2 = c->vec(B2_VEC_U2), *uab = c->vec(B2_VEC_UAB);
   halo_forward(c, B2_SPACE_V, u1, K);
   halo_forward(c, B2_SPACE_V, u2, K);
-  const int64_t nl = V.n_local() * c->KP();
+  const int64_t nl = V.n_local() * K;
   B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.5, u1, -0.5, u2, uab);  // :432-434
   c->A.zero(c->stream);                                                   // :435
   dispatch_elem(c, [&](auto e) {
     using E = decltype(e);
-    B2_LAUNCH(c, (k_convection<E::D, E::DEG>), blocks_for(c->n_cells, 128), 128, c->n_cells, c->x.p,
-              c->cell_nodes.p, V.cell_dofs.p, (int)V.n_owned, uab, vv.rowptr.p, vv.cols.p, c->A.p);
+    B2_LAUNCH(c, (k_convection<E::D, E::DEG>), blocks_for(c->n_cells, 128), 128, c->n_cells, c->x.p, c->cell_nodes.p,
+              V.cell_dofs.p, (int)V.n_owned, uab, ld, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->A.p);
   });
   const double* psurf = c->vecs.count(B2_VEC_PSURF) ? c->vec(B2_VEC_PSURF) : nullptr;
-  auto comb = [&](auto kc, auto lc) {
-    constexpr int KK = decltype(kc)::value, L = decltype(lc)::value;
-    B2_LAUNCH(c, (k_combine_first<KK, L>), pgrid(c, (int64_t)vv.n_rows * L), 256, vv.n_rows, vv.rowptr.p, vv.cols.p, c->A.p,
-              c->M.p, c->Kst.p, 1.0 / dt, 0.5 * nu, u1, c->vec(B2_VEC_B0), psurf, c->is_bc_row_v.p,
-              (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0), c->vec(B2_VEC_BFIRST), c->dinvA.p);
+  const int scale = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
+  auto comb = [&](auto kc) {
+    constexpr int KK = decltype(kc)::value;
+    B2_LAUNCH(c, (k_combine_first<KK>), pgrid(c, vv.n_rows), 256, vv.n_rows, vv.slice_ptr.p, vv.scols.p, vv.diag_t.p,
+              c->A.p, c->M.p, c->Kst.p, 1.0 / dt, 0.5 * nu, u1, ld, c->vec(B2_VEC_B0), psurf, c->is_bc_row_v.p, scale,
+              c->vec(B2_VEC_BFIRST), c->dinvA.p);
   };
-  auto comb_k = [&](auto kc) {
-    if (vv.lpr == 4) comb(kc, std::integral_constant<int, 4>{});
-    else if (vv.lpr == 16) comb(kc, std::integral_constant<int, 16>{});
-    else comb(kc, std::integral_constant<int, 8>{});
-  };
-  if (K == 2) comb_k(std::integral_constant<int, 2>{});
-  else comb_k(std::integral_constant<int, 3>{});
+  if (K == 2) comb(std::integral_constant<int, 2>{});
+  else comb(std::integral_constant<int, 3>{});
   c->last_dt = dt;
 }
 
 template <int K>
 void rect_vq(b2_ctx* c, const double* vals, const double* xq, const double* add, double scale, double* out) {
   const CSR& vq = c->pat[B2_PAT_VQ];
+  const int ld = (int)c->sp[B2_SPACE_V].n_local();
   if (vq.lpr >= 8)
-    B2_LAUNCH(c, (k_rect_vq<K, 8>), blocks_for((int64_t)vq.n_rows * 8, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, scale, out);
+    B2_LAUNCH(c, (k_rect_vq<K, 8>), blocks_for((int64_t)vq.n_rows * 8, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, ld, scale, out);
   else
-    B2_LAUNCH(c, (k_rect_vq<K, 4>), blocks_for((int64_t)vq.n_rows * 4, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, scale, out);
+    B2_LAUNCH(c, (k_rect_vq<K, 4>), blocks_for((int64_t)vq.n_rows * 4, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, ld, scale, out);
 }
 
 void stage_tentative_assemble(b2_ctx* c) {
@@ -404,13 +425,14 @@ void apply_velocity_bcs(b2_ctx* c, double* v) {
         B2_REQUIRE(c->bc_step < c->bc_series_steps[k], "b2_select_bc_step beyond the prefetched series");
         vals = c->bc_series[k].p + (size_t)c->bc_step * c->bc_dofs[k].n;
       }
-      B2_LAUNCH(c, k_set_bc, blocks_for(c->bc_dofs[k].n, 256), 256, c->bc_dofs[k].n, c->bc_dofs[k].p, vals, c->KP(), k, v);
+      B2_LAUNCH(c, k_set_bc, blocks_for(c->bc_dofs[k].n, 256), 256, c->bc_dofs[k].n, c->bc_dofs[k].p, vals,
+                v + (size_t)k * c->sp[B2_SPACE_V].n_local());
     }
 }
 
 template <int K>
-void sqdiff(b2_ctx* c, int64_t n, const double* a, const double* b, double* out_dev) {
-  B2_LAUNCH(c, k_sqdiff<K>, pgrid(c, n), 256, n, a, b, out_dev, c->partials.p, c->d_counter);
+void sqdiff(b2_ctx* c, int64_t n, int ld, const double* a, const double* b, double* out_dev) {
+  B2_LAUNCH(c, k_sqdiff<K>, pgrid(c, n), 256, n, ld, a, b, out_dev, c->partials.p, c->d_counter);
 }
 
 void read_sums(b2_ctx* c, int n) {
@@ -425,12 +447,12 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
   const Space& V = c->sp[B2_SPACE_V];
   double *rhs1 = c->vec(B2_VEC_RHS1), *u = c->vec(B2_VEC_U), *wrk = c->vec(B2_VEC_WRK);
   apply_velocity_bcs(c, rhs1);                                                                  // :517-518
-  B2_CUDA(cudaMemcpyAsync(wrk, u, sizeof(double) * V.n_local() * c->KP(), cudaMemcpyDeviceToDevice, c->stream));  // :520
+  B2_CUDA(cudaMemcpyAsync(wrk, u, sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));  // :520
   int32_t its[B2_MAXK] = {0, 0, 0};
   krylov_solve(c, B2_SOLVER_TENTATIVE, c->pat[B2_PAT_VV], c->A.p, c->dinvA.p, B2_SPACE_V, K, rhs1, u, reasons, its);  // :521
   for (int k = 0; k < K; ++k) c->stats.its_tentative[k] = its[k];
-  if (K == 2) sqdiff<2>(c, V.n_owned, wrk, u, c->d_sums);
-  else sqdiff<3>(c, V.n_owned, wrk, u, c->d_sums);
+  if (K == 2) sqdiff<2>(c, V.n_owned, (int)V.n_local(), wrk, u, c->d_sums);
+  else sqdiff<3>(c, V.n_owned, (int)V.n_local(), wrk, u, c->d_sums);
   read_sums(c, K);
   double d = 0.0;
   for (int k = 0; k < K; ++k) d += std::sqrt(c->h_sums[k]);  // :523-524 (sum of per-component 2-norms)
@@ -445,10 +467,11 @@ void stage_pressure_assemble(b2_ctx* c, double dt) {
   halo_forward(c, B2_SPACE_V, u, c->gdim);
   const uint8_t* zr = c->has_pbc ? c->is_bc_q.p : nullptr;
   const int grid = blocks_for((int64_t)qv.n_rows * 16, 256);
+  const int ld = (int)c->sp[B2_SPACE_V].n_local();
   if (c->gdim == 2)
-    B2_LAUNCH(c, (k_rect_qv<2, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, -1.0 / dt, zr, c->vec(B2_VEC_B2));
+    B2_LAUNCH(c, (k_rect_qv<2, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ld, -1.0 / dt, zr, c->vec(B2_VEC_B2));
   else
-    B2_LAUNCH(c, (k_rect_qv<3, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, -1.0 / dt, zr, c->vec(B2_VEC_B2));
+    B2_LAUNCH(c, (k_rect_qv<3, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ld, -1.0 / dt, zr, c->vec(B2_VEC_B2));
 }
 
 void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
@@ -480,10 +503,11 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
     double* u = c->vec(B2_VEC_U);
     const int grid = blocks_for((int64_t)qv.n_rows * 16, 256);
     // rhs <- -0.5 nu sum_i D_i u_i (reusing b2 as scratch: it is rebuilt by the next pressure_assemble)
+    const int ldv = (int)c->sp[B2_SPACE_V].n_local();
     if (c->gdim == 2)
-      B2_LAUNCH(c, (k_rect_qv<2, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, -0.5 * nu, (const uint8_t*)nullptr, rhs);
+      B2_LAUNCH(c, (k_rect_qv<2, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ldv, -0.5 * nu, (const uint8_t*)nullptr, rhs);
     else
-      B2_LAUNCH(c, (k_rect_qv<3, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, -0.5 * nu, (const uint8_t*)nullptr, rhs);
+      B2_LAUNCH(c, (k_rect_qv<3, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ldv, -0.5 * nu, (const uint8_t*)nullptr, rhs);
     double* mq = c->wq[2].p;  // q work vector is free between solves
     spmm(c, qq, c->MQ.p, 1, t0, mq);
     B2_LAUNCH(c, k_lincomb2, pgrid(c, n), 256, n, 1.0, mq, 1.0, rhs, rhs);
@@ -547,7 +571,7 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
   stage_velocity_update(c, dt, ru);
   // u2 <- u1 ; u1 <- u ; p <- ps   (:689-693): swap the two history buffers, one copy each
   std::swap(c->vecs[B2_VEC_U1].buf, c->vecs[B2_VEC_U2].buf);
-  B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_U1), c->vec(B2_VEC_U), sizeof(double) * V.n_local() * c->KP(), cudaMemcpyDeviceToDevice, c->stream));
+  B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_U1), c->vec(B2_VEC_U), sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_P), c->vec(B2_VEC_PS), sizeof(double) * Q.n_local(), cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaEventRecord(c->ev[5], c->stream));
   B2_CUDA(cudaEventSynchronize(c->ev[5]));
@@ -571,18 +595,18 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
   for (int id : {B2_VEC_U, B2_VEC_U1, B2_VEC_U2, B2_VEC_UAB, B2_VEC_RHS1, B2_VEC_BFIRST, B2_VEC_B0, B2_VEC_B3, B2_VEC_WRK})
     alloc_vec(c, id, B2_SPACE_V, K);
   for (int id : {B2_VEC_PS, B2_VEC_P, B2_VEC_DP, B2_VEC_B2, B2_VEC_MQ}) alloc_vec(c, id, B2_SPACE_Q, 1);
-  for (auto& w : c->wv) { w.alloc(V.n_local() * c->KP()); w.zero(c->stream); }
+  for (auto& w : c->wv) { w.alloc(V.n_local() * K); w.zero(c->stream); }
   for (auto& w : c->wq) { w.alloc(Q.n_local()); w.zero(c->stream); }
-  c->stage.alloc(std::max<int64_t>(std::max<int64_t>(V.n_local() * c->KP(), vv.nnz), 1));
+  c->stage.alloc(std::max<int64_t>(std::max<int64_t>(V.n_local() * K, vv.nnz), 1));
   // matrices
-  c->M.alloc(vv.nnz); c->M.zero(c->stream);
-  c->Kst.alloc(vv.nnz); c->Kst.zero(c->stream);
-  c->A.alloc(vv.nnz); c->A.zero(c->stream);
-  c->Ap.alloc(qq.nnz); c->Ap.zero(c->stream);
+  c->M.alloc(vv.slots); c->M.zero(c->stream);
+  c->Kst.alloc(vv.slots); c->Kst.zero(c->stream);
+  c->A.alloc(vv.slots); c->A.zero(c->stream);
+  c->Ap.alloc(qq.slots); c->Ap.zero(c->stream);
   c->P.alloc(vq.nnz * K); c->P.zero(c->stream);
   c->G.alloc(vq.nnz * K); c->G.zero(c->stream);
   c->D.alloc(qv.nnz * K); c->D.zero(c->stream);
-  if (c->rotational) { c->MQ.alloc(qq.nnz); c->MQ.zero(c->stream); }
+  if (c->rotational) { c->MQ.alloc(qq.slots); c->MQ.zero(c->stream); }
   c->dinvA.alloc(V.n_local()); c->dinvM.alloc(V.n_local()); c->dinvAp.alloc(Q.n_local());
   c->onesV.alloc(V.n_local()); c->onesQ.alloc(Q.n_local());
   B2_LAUNCH(c, k_fill, pgrid(c, V.n_local()), 256, V.n_local(), 1.0, c->onesV.p);
@@ -596,20 +620,20 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
     constexpr int D = E::D, DEG = E::DEG;
     const int64_t nc = c->n_cells;
     B2_LAUNCH(c, (k_assemble_square<D, DEG, B2_FORM_MASS_V>), blocks_for(nc * E::NV, 128), 128, nc, c->x.p, c->cell_nodes.p,
-              V.cell_dofs.p, vv.n_rows, vv.rowptr.p, vv.cols.p, c->M.p);                       // :373
+              V.cell_dofs.p, vv.n_rows, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->M.p);                       // :373
     B2_LAUNCH(c, (k_assemble_square<D, DEG, B2_FORM_STIFF_V>), blocks_for(nc * E::NV, 128), 128, nc, c->x.p, c->cell_nodes.p,
-              V.cell_dofs.p, vv.n_rows, vv.rowptr.p, vv.cols.p, c->Kst.p);                     // :375
+              V.cell_dofs.p, vv.n_rows, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->Kst.p);                     // :375
     B2_LAUNCH(c, (k_assemble_square<D, DEG, B2_FORM_STIFF_Q>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p,
-              Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, c->Ap.p);                      // :379
+              Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, qq.slice_ptr.p, c->Ap.p);                      // :379
     if (c->rotational)
       B2_LAUNCH(c, (k_assemble_square<D, DEG, B2_FORM_MASS_Q>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p,
-                Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, c->MQ.p);                    // function.py:63-71
+                Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, qq.slice_ptr.p, c->MQ.p);                    // function.py:63-71
     B2_LAUNCH(c, (k_assemble_PG<D, DEG>), blocks_for(nc * E::NV, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
               Q.cell_dofs.p, vq.n_rows, vq.rowptr.p, vq.cols.p, c->P.p, c->G.p);              // :395,399
     B2_LAUNCH(c, (k_assemble_D<D, DEG>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
               Q.cell_dofs.p, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p);                      // :403
     B2_LAUNCH(c, (k_assemble_loads<D, DEG>), blocks_for(nc, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
-              (int)V.n_owned, (int)Q.n_owned, f[0], f[1], f[2], c->vec(B2_VEC_B0), c->vec(B2_VEC_MQ));  // :387-390
+              (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), f[0], f[1], f[2], c->vec(B2_VEC_B0), c->vec(B2_VEC_MQ));  // :387-390
   });
   // Dirichlet masks
   c->is_bc_row_v.alloc(V.n_local()); c->is_bc_row_v.zero(c->stream);
@@ -618,13 +642,13 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
     B2_LAUNCH(c, k_mark, blocks_for(c->bc_dofs[0].n, 256), 256, c->bc_dofs[0].n, c->bc_dofs[0].p, c->is_bc_row_v.p);
   if (c->has_pbc) {
     B2_LAUNCH(c, k_mark, blocks_for(c->pbc_dofs.n, 256), 256, c->pbc_dofs.n, c->pbc_dofs.p, c->is_bc_q.p);
-    B2_LAUNCH(c, k_apply_bc_rows_cols, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.rowptr.p, qq.cols.p, c->is_bc_q.p, c->Ap.p);
+    B2_LAUNCH(c, k_apply_bc_rows_cols, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.slice_ptr.p, qq.scols.p, qq.diag_t.p, c->is_bc_q.p, c->Ap.p);
   }
-  B2_LAUNCH(c, k_inv_diag, blocks_for(vv.n_rows, 256), 256, vv.n_rows, vv.rowptr.p, vv.cols.p, c->M.p, c->dinvM.p);
-  B2_LAUNCH(c, k_inv_diag, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.rowptr.p, qq.cols.p, c->Ap.p, c->dinvAp.p);
+  B2_LAUNCH(c, k_inv_diag, blocks_for(vv.n_rows, 256), 256, vv.n_rows, vv.slice_ptr.p, vv.diag_t.p, c->M.p, c->dinvM.p);
+  B2_LAUNCH(c, k_inv_diag, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.slice_ptr.p, qq.diag_t.p, c->Ap.p, c->dinvAp.p);
   if (c->rotational) {
     c->dinvMQ.alloc(Q.n_local());
-    B2_LAUNCH(c, k_inv_diag, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.rowptr.p, qq.cols.p, c->MQ.p, c->dinvMQ.p);
+    B2_LAUNCH(c, k_inv_diag, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.slice_ptr.p, qq.diag_t.p, c->MQ.p, c->dinvMQ.p);
   }
   // measure of the domain = sum mQ  (:581-584)
   B2_LAUNCH(c, k_sums, pgrid(c, Q.n_owned), 256, Q.n_owned, c->vec(B2_VEC_MQ), (const double*)nullptr, c->d_sums, c->partials.p, c->d_counter);
@@ -801,6 +825,8 @@ int b2_build_patterns(b2_ctx* c) {
     build_pattern(c, V, Q, c->pat[B2_PAT_VQ]);
     build_pattern(c, Q, V, c->pat[B2_PAT_QV]);
     build_pattern(c, Q, Q, c->pat[B2_PAT_QQ]);
+    build_sell(c, c->pat[B2_PAT_VV]);
+    build_sell(c, c->pat[B2_PAT_QQ]);
     c->patterns_built = true;
   });
 }
@@ -883,18 +909,13 @@ int b2_set_vector(b2_ctx* c, int vec, int comp, const double* host, int64_t n) {
     B2_REQUIRE(it != c->vecs.end(), "unknown vector id");
     DVec& v = it->second;
     const int64_t nl = c->sp[v.space].n_local();
-    const int stride = v.K > 1 ? c->KP() : 1;
-    if (v.K == 1) {
-      B2_REQUIRE(n == nl, "size mismatch in b2_set_vector");
-      B2_CUDA(cudaMemcpyAsync(v.buf.p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    } else if (comp < 0) {  // whole blocked array [n][K] -> device [n][KP]
+    if (v.K > 1 && comp < 0) {  // whole blocked array [n][K] -> component-major
       B2_REQUIRE(n == nl * v.K, "size mismatch in b2_set_vector");
       B2_CUDA(cudaMemcpyAsync(c->stage.p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-      B2_LAUNCH(c, k_repack, pgrid(c, n), 256, nl, v.K, v.K, stride, c->stage.p, v.buf.p);
+      B2_LAUNCH(c, k_from_blocked, pgrid(c, n), 256, nl, v.K, (int)nl, c->stage.p, v.buf.p);
     } else {
-      B2_REQUIRE(comp < v.K && n == nl, "size/component mismatch in b2_set_vector");
-      B2_CUDA(cudaMemcpyAsync(c->stage.p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-      B2_LAUNCH(c, k_insert, pgrid(c, n), 256, n, stride, comp, c->stage.p, v.buf.p);
+      B2_REQUIRE(comp >= 0 && comp < v.K && n == nl, "size/component mismatch in b2_set_vector");
+      B2_CUDA(cudaMemcpyAsync(v.buf.p + (size_t)comp * nl, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     }
     B2_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.bytes_h2d += sizeof(double) * n;
@@ -908,52 +929,58 @@ int b2_get_vector(b2_ctx* c, int vec, int comp, double* host, int64_t n) {
     B2_REQUIRE(it != c->vecs.end(), "unknown vector id");
     DVec& v = it->second;
     const int64_t nl = c->sp[v.space].n_local();
-    const int stride = v.K > 1 ? c->KP() : 1;
-    if (v.K == 1) {
-      B2_REQUIRE(n == nl, "size mismatch in b2_get_vector");
-      B2_CUDA(cudaMemcpyAsync(host, v.buf.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
-    } else if (comp < 0) {
+    if (v.K > 1 && comp < 0) {
       B2_REQUIRE(n == nl * v.K, "size mismatch in b2_get_vector");
-      B2_LAUNCH(c, k_repack, pgrid(c, n), 256, nl, v.K, stride, v.K, v.buf.p, c->stage.p);
+      B2_LAUNCH(c, k_to_blocked, pgrid(c, n), 256, nl, v.K, (int)nl, v.buf.p, c->stage.p);
       B2_CUDA(cudaMemcpyAsync(host, c->stage.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     } else {
-      B2_REQUIRE(comp < v.K && n == nl, "size/component mismatch in b2_get_vector");
-      B2_LAUNCH(c, k_extract, pgrid(c, n), 256, n, stride, comp, v.buf.p, c->stage.p);
-      B2_CUDA(cudaMemcpyAsync(host, c->stage.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+      B2_REQUIRE(comp >= 0 && comp < v.K && n == nl, "size/component mismatch in b2_get_vector");
+      B2_CUDA(cudaMemcpyAsync(host, v.buf.p + (size_t)comp * nl, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     }
     B2_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.bytes_d2h += sizeof(double) * n;
   });
 }
 
+}  // extern "C"
+
+namespace {
+
+// CSR-ordered copy of a matrix' values (SELL operators are converted; A is un-row-scaled)
+void csr_values(b2_ctx* c, int mat, int comp, DBuf<double>& out, const CSR** pat_out) {
+  const CSR* pat = nullptr;
+  int stride = 1;
+  const DBuf<double>* v = matrix_values(c, mat, &pat, &stride);
+  B2_REQUIRE(v->p != nullptr, "matrix not assembled (rotational/low-memory option?)");
+  out.alloc(pat->nnz);
+  if (stride == 1) {
+    B2_REQUIRE(pat->has_sell(), "square operator without SELL layout");
+    B2_LAUNCH(c, k_sell_convert, blocks_for(pat->n_rows, 256), 256, pat->n_rows, pat->rowptr.p, pat->slice_ptr.p, 0, v->p,
+              out.p, mat == B2_MAT_A ? c->dinvA.p : (const double*)nullptr);
+  } else {
+    B2_REQUIRE(comp >= 0 && comp < stride, "bad component");
+    B2_LAUNCH(c, k_extract, pgrid(c, pat->nnz), 256, pat->nnz, stride, comp, v->p, out.p);
+  }
+  *pat_out = pat;
+}
+
+}  // namespace
+
+extern "C" {
+
 int b2_get_matrix_values(b2_ctx* c, int mat, int comp, double* host) {
   return guarded(c, [&] {
     B2_REQUIRE(c->preassembled, "matrices exist after b2_preassemble");
+    DBuf<double> tmp;
     const CSR* pat = nullptr;
-    int stride = 1;
-    const DBuf<double>* v = matrix_values(c, mat, &pat, &stride);
-    B2_REQUIRE(v->p != nullptr, "matrix not assembled (rotational/low-memory option?)");
-    if (mat == B2_MAT_A) {  // stored row-scaled by dinvA: hand back the reference's matrix
-      DBuf<double> tmp;
-      tmp.alloc(pat->nnz);
-      B2_LAUNCH(c, k_scale_rows, blocks_for(pat->n_rows, 256), 256, pat->n_rows, pat->rowptr.p, c->dinvA.p, 1, v->p, tmp.p);
-      B2_CUDA(cudaMemcpyAsync(host, tmp.p, sizeof(double) * pat->nnz, cudaMemcpyDeviceToHost, c->stream));
-      B2_CUDA(cudaStreamSynchronize(c->stream));
-    } else if (stride == 1) {
-      B2_CUDA(cudaMemcpyAsync(host, v->p, sizeof(double) * pat->nnz, cudaMemcpyDeviceToHost, c->stream));
-    } else {
-      B2_REQUIRE(comp >= 0 && comp < stride, "bad component");
-      DBuf<double> tmp;
-      tmp.alloc(pat->nnz);
-      B2_LAUNCH(c, k_extract, pgrid(c, pat->nnz), 256, pat->nnz, stride, comp, v->p, tmp.p);
-      B2_CUDA(cudaMemcpyAsync(host, tmp.p, sizeof(double) * pat->nnz, cudaMemcpyDeviceToHost, c->stream));
-      B2_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    csr_values(c, mat, comp, tmp, &pat);
+    B2_CUDA(cudaMemcpyAsync(host, tmp.p, sizeof(double) * pat->nnz, cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.bytes_d2h += sizeof(double) * pat->nnz;
   });
 }
 
+// y = Mat * x through a plain CSR row kernel (parity-test hook, not a hot path)
 int b2_mat_mult(b2_ctx* c, int mat, int comp, const double* x, double* y) {
   return guarded(c, [&] {
     B2_REQUIRE(c->preassembled, "matrices exist after b2_preassemble");
@@ -961,22 +988,19 @@ int b2_mat_mult(b2_ctx* c, int mat, int comp, const double* x, double* y) {
     int stride = 1;
     const DBuf<double>* v = matrix_values(c, mat, &pat, &stride);
     B2_REQUIRE(v->p != nullptr, "matrix not assembled");
-    DBuf<double> dx, dy, vals;
+    DBuf<double> dx, dy;
     dx.alloc(pat->n_cols);
     dy.alloc(pat->n_rows);
     B2_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * pat->n_cols, cudaMemcpyHostToDevice, c->stream));
-    const double* vp = v->p;
-    if (mat == B2_MAT_A) {
-      vals.alloc(pat->nnz);
-      B2_LAUNCH(c, k_scale_rows, blocks_for(pat->n_rows, 256), 256, pat->n_rows, pat->rowptr.p, c->dinvA.p, 1, v->p, vals.p);
-      vp = vals.p;
-    } else if (stride > 1) {
-      B2_REQUIRE(comp >= 0 && comp < stride, "bad component");
-      vals.alloc(pat->nnz);
-      B2_LAUNCH(c, k_extract, pgrid(c, pat->nnz), 256, pat->nnz, stride, comp, v->p, vals.p);
-      vp = vals.p;
+    if (stride == 1 && mat != B2_MAT_A) {
+      spmm(c, *pat, v->p, 1, dx.p, dy.p);  // the production SELL kernel
+    } else {
+      DBuf<double> vals;
+      const CSR* p2 = nullptr;
+      csr_values(c, mat, comp, vals, &p2);
+      B2_LAUNCH(c, (k_rect_vq<1, 4>), blocks_for((int64_t)pat->n_rows * 4, 256), 256, pat->n_rows, pat->rowptr.p, pat->cols.p,
+                vals.p, dx.p, (const double*)nullptr, pat->n_rows, 1.0, dy.p);
     }
-    spmm(c, *pat, vp, 1, dx.p, dy.p);
     B2_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(double) * pat->n_rows, cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -1052,25 +1076,17 @@ int b2_l2_diff_sq(b2_ctx* c, int vec, const double* exact, int64_t n, double* ou
     B2_REQUIRE(it != c->vecs.end(), "unknown vector id");
     DVec& v = it->second;
     const Space& S = c->sp[v.space];
-    B2_REQUIRE(n == S.n_local() * v.K, "size mismatch in b2_l2_diff_sq");
-    const int64_t npad = S.n_local() * c->KP();
-    // e = u_h - exact (nodal); ||e||^2 = sum_k e_k^T Mass e_k with the space's mass matrix
+    const int64_t nl = S.n_local();
+    B2_REQUIRE(n == nl * v.K, "size mismatch in b2_l2_diff_sq");
+    // e = u_h - exact (nodal, blocked [n][K] on the host); ||e||^2 = sum_k e_k^T M e_k
     B2_REQUIRE(v.space == B2_SPACE_V, "b2_l2_diff_sq: only velocity-space vectors in this version");
     double* e = c->wv[0].p;
     double* me = c->wv[1].p;
     B2_CUDA(cudaMemcpyAsync(c->stage.p, exact, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemsetAsync(e, 0, sizeof(double) * npad, c->stream));
-    B2_LAUNCH(c, k_repack, pgrid(c, n), 256, S.n_local(), v.K, v.K, c->KP(), c->stage.p, e);
-    B2_LAUNCH(c, k_lincomb2, pgrid(c, npad), 256, npad, 1.0, v.buf.p, -1.0, e, e);
-    // reuse the fused dot of the SpMM: sums[k] = (M e)_k . e_k ; park the totals in a scratch state
-    std::memset(c->h_st, 0, sizeof(KryState));
-    c->h_st->K = v.K;
-    B2_CUDA(cudaMemcpyAsync(c->d_st, c->h_st, sizeof(KryState), cudaMemcpyHostToDevice, c->stream));
+    B2_LAUNCH(c, k_from_blocked, pgrid(c, n), 256, nl, v.K, (int)nl, c->stage.p, e);
+    B2_LAUNCH(c, k_lincomb2, pgrid(c, n), 256, n, 1.0, v.buf.p, -1.0, e, e);
     spmm(c, c->pat[B2_PAT_VV], c->M.p, v.K, e, me, nullptr, nullptr, FIN_NONE, 0, B2_SPACE_V);
-    // dot on the device
-    const int64_t no = S.n_owned;
-    // sum_k me_k . e_k via k_sqdiff-like pass: (a-b)^2 form does not fit, so use lincomb + sums
-    B2_LAUNCH(c, k_dot_all, pgrid(c, no * c->KP()), 256, no * c->KP(), me, e, c->d_sums, c->partials.p, c->d_counter);
+    B2_LAUNCH(c, k_dot_all, pgrid(c, S.n_owned), 256, S.n_owned, v.K, (int)nl, me, e, c->d_sums, c->partials.p, c->d_counter);
     read_sums(c, 1);
     *out = c->h_sums[0];
   });

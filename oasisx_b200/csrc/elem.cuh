@@ -97,6 +97,11 @@ __device__ __forceinline__ int csr_find(const int* __restrict__ cols, int lo, in
   return lo;
 }
 
+// SELL-32 slot of entry t of row `row` (see linalg.cuh)
+__device__ __forceinline__ size_t sell_slot_of(const int* __restrict__ slice_ptr, int row, int t) {
+  return (size_t)__ldg(slice_ptr + (row >> 5)) + ((size_t)t << 5) + (row & 31);
+}
+
 // ---- one-off (pre)assembly kernels: one thread per (cell, local row) -----------------------
 enum { B2_FORM_MASS_V = 0, B2_FORM_STIFF_V = 1, B2_FORM_MASS_Q = 2, B2_FORM_STIFF_Q = 3 };
 
@@ -104,7 +109,8 @@ template <int D, int DEG, int FORM>
 __global__ void k_assemble_square(int64_t n_cells, const double* __restrict__ x,
                                   const int* __restrict__ cell_nodes, const int* __restrict__ cdofs,
                                   int n_rows_owned, const int* __restrict__ rowptr,
-                                  const int* __restrict__ cols, double* __restrict__ vals) {
+                                  const int* __restrict__ cols, const int* __restrict__ slice_ptr,
+                                  double* __restrict__ vals) {
   using E = El<D, DEG>;
   constexpr bool onV = (FORM == B2_FORM_MASS_V || FORM == B2_FORM_STIFF_V);
   constexpr int ND = onV ? E::NV : E::NQ;
@@ -146,7 +152,7 @@ __global__ void k_assemble_square(int64_t n_cells, const double* __restrict__ x,
         for (int b = 0; b < D; ++b) v += G[a][b] * E::SQ(a, b, i, j);
     }
     int pos = csr_find(cols, lo, hi, dofs[j]);
-    atomicAdd(vals + pos, v);
+    atomicAdd(vals + sell_slot_of(slice_ptr, row, pos - lo), v);
   }
 }
 
@@ -215,7 +221,7 @@ __global__ void k_assemble_D(int64_t n_cells, const double* __restrict__ x,
 template <int D, int DEG>
 __global__ void k_assemble_loads(int64_t n_cells, const double* __restrict__ x,
                                  const int* __restrict__ cell_nodes, const int* __restrict__ vdofs,
-                                 const int* __restrict__ qdofs, int nV_owned, int nQ_owned,
+                                 const int* __restrict__ qdofs, int nV_owned, int nQ_owned, int ld,
                                  double f0, double f1, double f2, double* __restrict__ b0,
                                  double* __restrict__ mQ) {
   using E = El<D, DEG>;
@@ -229,25 +235,11 @@ __global__ void k_assemble_loads(int64_t n_cells, const double* __restrict__ x,
     double l = g.detJ * E::LV(j);
 #pragma unroll
     for (int k = 0; k < D; ++k)
-      if (f[k] != 0.0) atomicAdd(b0 + (size_t)row * (D == 3 ? 4 : D) + k, f[k] * l);
+      if (f[k] != 0.0) atomicAdd(b0 + (size_t)k * ld + row, f[k] * l);
   }
   for (int q = 0; q < E::NQ; ++q) {
     int row = qdofs[c * E::NQ + q];
     if (row < nQ_owned) atomicAdd(mQ + row, g.detJ * E::LQ(q));
-  }
-}
-
-// assemble_matrix(..., bcs=) semantics on a square matrix (fracstep.py:379, Appendix D):
-// BC rows and columns zeroed, unit diagonal.
-__global__ void k_apply_bc_rows_cols(int n_rows, const int* __restrict__ rowptr,
-                                     const int* __restrict__ cols, const uint8_t* __restrict__ is_bc,
-                                     double* __restrict__ vals) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
-  bool rb = is_bc[row];
-  for (int p = rowptr[row]; p < rowptr[row + 1]; ++p) {
-    int c = cols[p];
-    if (rb || is_bc[c]) vals[p] = (c == row) ? 1.0 : 0.0;
   }
 }
 
@@ -258,9 +250,9 @@ __global__ void k_apply_bc_rows_cols(int n_rows, const int* __restrict__ rowptr,
 template <int D, int DEG>
 __global__ void __launch_bounds__(128)
 k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
-             const int* __restrict__ vdofs, int n_rows_owned, const double* __restrict__ uab,
+             const int* __restrict__ vdofs, int n_rows_owned, const double* __restrict__ uab, int ld,
              const int* __restrict__ rowptr, const int* __restrict__ cols,
-             double* __restrict__ Avals) {
+             const int* __restrict__ slice_ptr, double* __restrict__ Avals) {
   using E = El<D, DEG>;
   constexpr int NV = E::NV;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,7 +266,7 @@ k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restric
   for (int a = 0; a < NV; ++a) {
     double u[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) u[k] = __ldg(uab + (size_t)dofs[a] * (D == 3 ? 4 : D) + k);
+    for (int k = 0; k < D; ++k) u[k] = __ldg(uab + (size_t)k * ld + dofs[a]);
 #pragma unroll
     for (int dl = 0; dl < D; ++dl) {
       double s = 0;
@@ -302,7 +294,7 @@ k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restric
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       int pos = csr_find(cols, lo, hi, dofs[j]);
-      atomicAdd(Avals + pos, r[j]);
+      atomicAdd(Avals + sell_slot_of(slice_ptr, row, pos - lo), r[j]);
     }
   }
 }

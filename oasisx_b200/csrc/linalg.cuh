@@ -151,117 +151,116 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
   }
 }
 
-// ---- component-interleaved vectors ---------------------------------------------------------
-// Velocity-space vectors hold K components per dof at stride KP = 4 for K = 3 (one aligned 32-byte
-// sector per dof: the SpMM gather is ONE 256-bit load per nonzero instead of three 8-byte loads that
-// each cost an L1 wavefront), KP = K otherwise.  The pad slot is kept at zero by every kernel.
-template <int K>
-struct Pad {
-  static constexpr int KP = (K == 3) ? 4 : K;
-};
-
-template <int K>
-__device__ __forceinline__ void ldk(const double* p, double (&v)[Pad<K>::KP]) {
-  if constexpr (K == 3) {
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-  } else if constexpr (K == 2) {
-    double2 t = *reinterpret_cast<const double2*>(p);
-    v[0] = t.x;
-    v[1] = t.y;
-  } else {
-    v[0] = *p;
-  }
-}
-// read-only (non-coherent) path: for operands no thread of the kernel writes
-template <int K>
-__device__ __forceinline__ void ldk_nc(const double* p, double (&v)[Pad<K>::KP]) {
-  if constexpr (K == 3) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-  } else if constexpr (K == 2) {
-    double2 t = __ldg(reinterpret_cast<const double2*>(p));
-    v[0] = t.x;
-    v[1] = t.y;
-  } else {
-    v[0] = __ldg(p);
-  }
-}
-template <int K>
-__device__ __forceinline__ void stk(double* p, const double (&v)[Pad<K>::KP]) {
-  if constexpr (K == 3) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-  } else if constexpr (K == 2) {
-    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-  } else {
-    *p = v[0];
-  }
+// ---- storage ------------------------------------------------------------------------------------
+// Vectors: component-major (SoA): component k of a velocity-space vector lives at v + k*ld, ld = dofs
+// of the space incl. ghosts.  Square operators (M, K, A on VxV; Ap, MQ on QxQ): sliced ELLPACK with
+// 32-row slices ("SELL-32"): entry t of row r is at slice_ptr[r/32] + 32*t + r%32, rows padded to
+// the longest row of their slice with (col = r, val = 0).  One thread owns one row; at step t the 32
+// lanes of a warp read 32 consecutive values and 32 consecutive column indices (2 + 1 L1 wavefronts)
+// and, because the host numbers dofs by stencil class (fem._class_order), their 32 gathered vector
+// entries are (nearly) consecutive too.  No cross-lane reduction is needed.  The CSR pattern of
+// create_matrix stays the public face (b2_get_pattern); CSR position p of row r maps to the SELL
+// slot slice_ptr[r/32] + 32*(p - rowptr[r]) + r%32.
+__device__ __forceinline__ size_t sell_slot(const int* __restrict__ slice_ptr, int row, int t) {
+  return (size_t)__ldg(slice_ptr + (row >> 5)) + ((size_t)t << 5) + (row & 31);
 }
 
-// ---- CSR SpMM: y[row][k] = sum_p vals[p] * x[cols[p]][k] --------------------------------------
-// LPR lanes cooperate on one row (rows of P2 matrices hold ~28 entries, P1 ~15); a warp therefore
-// streams 32/LPR consecutive rows: the value/column loads of one warp instruction cover a
-// contiguous stretch of the CSR arrays.  The nonzero loop is unrolled by two so that two
-// column->gather chains are in flight per lane.  Persistent grid (grid-stride over row groups) so
-// the number of partial sums for the fused dot products stays small.
+__global__ void k_sell_slice_len(int n_rows, const int* __restrict__ rowptr, int* __restrict__ slice_entries) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int n_slices = (n_rows + 31) >> 5;
+  if (s >= n_slices) return;
+  int mx = 0;
+  for (int r = s << 5; r < min(n_rows, (s + 1) << 5); ++r) mx = max(mx, rowptr[r + 1] - rowptr[r]);
+  slice_entries[s] = mx << 5;
+}
+
+__global__ void k_sell_fill_cols(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
+                                 const int* __restrict__ slice_ptr, int* __restrict__ scols,
+                                 int* __restrict__ diag_t) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int s = row >> 5;
+  const int len = (slice_ptr[s + 1] - slice_ptr[s]) >> 5;
+  const int start = rowptr[row], n = rowptr[row + 1] - start;
+  int dt = -1;
+  for (int t = 0; t < len; ++t) {
+    int c = t < n ? cols[start + t] : row;
+    if (t < n && c == row) dt = t;
+    scols[(size_t)slice_ptr[s] + ((size_t)t << 5) + (row & 31)] = c;
+  }
+  if (diag_t != nullptr) diag_t[row] = dt;
+}
+
+// values between CSR order and SELL slots (to_sell: pads are left untouched = 0)
+__global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr,
+                               int to_sell, const double* __restrict__ in, double* __restrict__ out,
+                               const double* __restrict__ row_scale) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int start = rowptr[row], n = rowptr[row + 1] - start;
+  const size_t base = (size_t)slice_ptr[row >> 5] + (row & 31);
+  const double f = row_scale != nullptr ? 1.0 / row_scale[row] : 1.0;  // undo a row scaling on the way out
+  for (int t = 0; t < n; ++t) {
+    if (to_sell) out[base + ((size_t)t << 5)] = in[start + t];
+    else out[start + t] = in[base + ((size_t)t << 5)] * f;
+  }
+}
+
+// ---- SELL SpMM: y_k[row] = sum_t vals[slot] * x_k[cols[slot]], k < K ------------------------------
 //   DOT == 0: no reduction          DOT == 1: sums[k] = y_k . w_k
 //   DOT == 2: sums[k] = y_k . w_k , sums[K+k] = y_k . y_k
-template <int K, int LPR, int DOT>
+// Persistent grid: warp w of the grid walks slices w, w + nwarps, ...  The t-loop is unrolled by 4:
+// four independent (column -> gather) chains per thread keep enough loads in flight to cover HBM
+// latency at < 100% occupancy.
+template <int K, int DOT>
 __global__ void __launch_bounds__(256)
-k_spmm(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-       const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+       const double* __restrict__ vals, const double* __restrict__ x, int ld, double* __restrict__ y,
        const double* __restrict__ w, KryState* st, int fin, double* partials, unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   if (st != nullptr && st->done) return;
-  const int lane = threadIdx.x % LPR;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int ngroups = (gridDim.x * blockDim.x) / LPR;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
   constexpr int ND = DOT == 0 ? 1 : DOT * K;
   double dots[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) dots[i] = 0.0;
-  const int n_iter = (n_rows + ngroups - 1) / ngroups;
-  for (int it = 0; it < n_iter; ++it) {
-    const int row = it * ngroups + group;
-    double acc[KP], acc2[KP];
+  for (int s = warp; s < n_slices; s += nwarps) {
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    const int* cp = cols + base + lane;
+    const double* vp = vals + base + lane;
+    double acc[K];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = acc2[k] = 0.0;
-    if (row < n_rows) {
-      const int end = __ldg(rowptr + row + 1);
-      int p = __ldg(rowptr + row) + lane;
-      for (; p + LPR < end; p += 2 * LPR) {
-        const int c0 = __ldg(cols + p), c1 = __ldg(cols + p + LPR);
-        const double v0 = __ldg(vals + p), v1 = __ldg(vals + p + LPR);
-        double x0[KP], x1[KP];
-        ldk_nc<K>(x + (size_t)c0 * KP, x0);
-        ldk_nc<K>(x + (size_t)c1 * KP, x1);
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    int t = 0;
+    for (; t + 4 <= len; t += 4) {
+      int c[4];
+      double v[4];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          acc[k] = fma(v0, x0[k], acc[k]);
-          acc2[k] = fma(v1, x1[k], acc2[k]);
-        }
+      for (int u = 0; u < 4; ++u) {
+        c[u] = __ldg(cp + ((t + u) << 5));
+        v[u] = __ldg(vp + ((t + u) << 5));
       }
-      if (p < end) {
-        const int c0 = __ldg(cols + p);
-        const double v0 = __ldg(vals + p);
-        double x0[KP];
-        ldk_nc<K>(x + (size_t)c0 * KP, x0);
 #pragma unroll
-        for (int k = 0; k < KP; ++k) acc[k] = fma(v0, x0[k], acc[k]);
-      }
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fma(v[u], __ldg(x + (size_t)k * ld + c[u]), acc[k]);
     }
+    for (; t < len; ++t) {
+      const int c = __ldg(cp + (t << 5));
+      const double v = __ldg(vp + (t << 5));
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] += acc2[k];
+      for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
+    }
+    if (row < n_rows) {
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (row < n_rows && lane == 0) {
-      if constexpr (KP > K) acc[KP - 1] = 0.0;
-      stk<K>(y + (size_t)row * KP, acc);
+      for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
       if constexpr (DOT >= 1) {
-        double wv[KP];
-        ldk<K>(w + (size_t)row * KP, wv);
 #pragma unroll
-        for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], wv[k], dots[k]);
+        for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], w[(size_t)k * ld + row], dots[k]);
       }
       if constexpr (DOT == 2) {
 #pragma unroll
@@ -276,105 +275,76 @@ k_spmm(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
 }
 
 // ---- fused "matrix-vector strategy" of assemble_first (fracstep.py:438-472) ------------------
-// In:  A = C(uab) (just assembled), M, Kst.   Out, in ONE pass over the nonzeros:
+// In:  A = C(uab) (just assembled), M, Kst, all in SELL slots.   Out, in ONE pass over the slots:
 //   b_first[row] = (M/dt - nu/2 K - 1/2 C) u1 + b0 (+ p_surf)        (:438-465)
 //   A            =  D^-1 (M/dt + nu/2 K + 1/2 C), unit rows on Dirichlet dofs (:468-472), stored
 //                   ROW-SCALED by its own diagonal D when `scale` (left Jacobi preconditioning, the
 //                   PETSc default side for BiCGStab [ext]): the Krylov kernels then need no
-//                   preconditioner gather at all.  b2_get_matrix_values undoes the scaling.
+//                   preconditioner at all.  b2_get_matrix_values undoes the scaling.
 //   dinv[row]    = 1 / D[row]  (1 when !scale)
-template <int K, int LPR>
+template <int K>
 __global__ void __launch_bounds__(256)
-k_combine_first(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-                double* __restrict__ A, const double* __restrict__ M, const double* __restrict__ Kst,
-                double inv_dt, double half_nu, const double* __restrict__ u1,
-                const double* __restrict__ b0, const double* __restrict__ psurf,
-                const uint8_t* __restrict__ is_bc_row, int scale, double* __restrict__ bfirst,
-                double* __restrict__ dinv) {
-  constexpr int KP = Pad<K>::KP;
-  const int lane = threadIdx.x % LPR;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int ngroups = (gridDim.x * blockDim.x) / LPR;
-  const int n_iter = (n_rows + ngroups - 1) / ngroups;
-  for (int it = 0; it < n_iter; ++it) {
-    const int row = it * ngroups + group;
-    double acc[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
-    double diag = 0.0;
-    bool bc = false;
-    int start = 0, end = 0;
-    if (row < n_rows) {
-      bc = is_bc_row[row];
-      start = __ldg(rowptr + row);
-      end = __ldg(rowptr + row + 1);
-      // phase 1: the diagonal entry of the new left-hand side
-      for (int p = start + lane; p < end; p += LPR)
-        if (__ldg(cols + p) == row) diag = (inv_dt * __ldg(M + p) + 0.5 * A[p]) + half_nu * __ldg(Kst + p);
+k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+                const int* __restrict__ diag_t, double* __restrict__ A, const double* __restrict__ M,
+                const double* __restrict__ Kst, double inv_dt, double half_nu,
+                const double* __restrict__ u1, int ld, const double* __restrict__ b0,
+                const double* __restrict__ psurf, const uint8_t* __restrict__ is_bc_row, int scale,
+                double* __restrict__ bfirst, double* __restrict__ dinv) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  for (int s = warp; s < n_slices; s += nwarps) {
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    const bool live = row < n_rows;
+    const bool bc = live && is_bc_row[row];
+    double invd = 1.0;
+    if (live && scale && !bc) {
+      const size_t pd = (size_t)base + ((size_t)__ldg(diag_t + row) << 5) + lane;
+      invd = 1.0 / ((inv_dt * __ldg(M + pd) + 0.5 * A[pd]) + half_nu * __ldg(Kst + pd));
     }
+    double acc[K];
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);
-    if (bc) diag = 1.0;
-    const double invd = (scale && row < n_rows) ? 1.0 / diag : 1.0;
-    if (row < n_rows) {
-      for (int p = start + lane; p < end; p += LPR) {
-        const int c = __ldg(cols + p);
-        const double m = inv_dt * __ldg(M + p);
-        const double kk = half_nu * __ldg(Kst + p);
-        const double cv = 0.5 * A[p];
-        const double r = (m - cv) - kk;
-        double a = ((m + cv) + kk) * invd;
-        double xc[KP];
-        ldk_nc<K>(u1 + (size_t)c * KP, xc);
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int t = 0; t < len; ++t) {
+      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
+      const int c = __ldg(cols + p);
+      const double m = inv_dt * __ldg(M + p);
+      const double kk = half_nu * __ldg(Kst + p);
+      const double cv = 0.5 * A[p];
+      const double r = (m - cv) - kk;
+      double a = ((m + cv) + kk) * invd;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) acc[k] = fma(r, xc[k], acc[k]);
-        if (bc) a = (c == row) ? 1.0 : 0.0;
-        A[p] = a;
-      }
+      for (int k = 0; k < K; ++k) acc[k] = fma(r, __ldg(u1 + (size_t)k * ld + c), acc[k]);
+      if (bc) a = (live && c == row && t == __ldg(diag_t + row)) ? 1.0 : 0.0;
+      A[p] = a;
     }
+    if (live) {
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (row < n_rows && lane == 0) {
-      double bv[KP];
-      ldk_nc<K>(b0 + (size_t)row * KP, bv);
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += bv[k];
-      if (psurf != nullptr) {
-        ldk_nc<K>(psurf + (size_t)row * KP, bv);
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] += bv[k];
+      for (int k = 0; k < K; ++k) {
+        double v = acc[k] + b0[(size_t)k * ld + row];
+        if (psurf != nullptr) v += psurf[(size_t)k * ld + row];
+        bfirst[(size_t)k * ld + row] = v;
       }
-      if constexpr (KP > K) acc[KP - 1] = 0.0;
-      stk<K>(bfirst + (size_t)row * KP, acc);
       dinv[row] = invd;
     }
   }
 }
 
-// vals[p] *= s[row] (or /= when `divide`): used to hand the caller the unscaled A
-__global__ void k_scale_rows(int n_rows, const int* __restrict__ rowptr, const double* __restrict__ s, int divide,
-                             const double* __restrict__ in, double* __restrict__ out) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
-  const double f = divide ? 1.0 / s[row] : s[row];
-  for (int p = rowptr[row]; p < rowptr[row + 1]; ++p) out[p] = in[p] * f;
-}
-
-// ---- rectangular products on the V x Q and Q x V patterns ([nnz][K] values) --------------------
-// out[row][k] = add[row][k] + scale * sum_p vals[p][k] * xq[cols[p]]   (P_i ps, G_i dp)
+// ---- rectangular products on the V x Q and Q x V CSR patterns ([nnz][K] values) -----------------
+// out_k[row] = add_k[row] + scale * sum_p vals[p][k] * xq[cols[p]]   (P_i ps, G_i dp)
 template <int K, int LPR>
 __global__ void __launch_bounds__(256)
 k_rect_vq(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-          const double* __restrict__ vals, const double* __restrict__ xq, const double* add,
+          const double* __restrict__ vals, const double* __restrict__ xq, const double* add, int ld,
           double scale, double* out) {
-  constexpr int KP = Pad<K>::KP;
   const int lane = threadIdx.x % LPR;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  double acc[KP];
+  double acc[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
   if (row < n_rows) {
     const int end = __ldg(rowptr + row + 1);
     for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
@@ -388,33 +358,29 @@ k_rect_vq(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ co
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
   if (row < n_rows && lane == 0) {
-    double a[KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) a[k] = 0.0;
-    if (add != nullptr) ldk<K>(add + (size_t)row * KP, a);
-#pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = fma(scale, acc[k], a[k]);
-    stk<K>(out + (size_t)row * KP, a);
+    for (int k = 0; k < K; ++k) {
+      const double a = add != nullptr ? add[(size_t)k * ld + row] : 0.0;
+      out[(size_t)k * ld + row] = fma(scale, acc[k], a);
+    }
   }
 }
 
-// out[q] = scale * sum_p sum_k vals[p][k] * xv[cols[p]][k]            (sum_i D_i u_i)
+// out[q] = scale * sum_p sum_k vals[p][k] * xv_k[cols[p]]            (sum_i D_i u_i)
 template <int K, int LPR>
 __global__ void __launch_bounds__(256)
 k_rect_qv(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-          const double* __restrict__ vals, const double* __restrict__ xv, double scale,
+          const double* __restrict__ vals, const double* __restrict__ xv, int ld, double scale,
           const uint8_t* __restrict__ zero_row, double* __restrict__ out) {
-  constexpr int KP = Pad<K>::KP;
   const int lane = threadIdx.x % LPR;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   double acc = 0.0;
   if (row < n_rows) {
     const int end = __ldg(rowptr + row + 1);
     for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) {
-      double xc[KP];
-      ldk_nc<K>(xv + (size_t)__ldg(cols + p) * KP, xc);
+      const int c = __ldg(cols + p);
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc = fma(__ldg(vals + (size_t)p * K + k), xc[k], acc);
+      for (int k = 0; k < K; ++k) acc = fma(__ldg(vals + (size_t)p * K + k), __ldg(xv + (size_t)k * ld + c), acc);
     }
   }
 #pragma unroll
@@ -433,11 +399,11 @@ __global__ void k_fill(int64_t n, double v, double* __restrict__ out) {
     out[i] = v;
 }
 
-// vec[dofs[i]][comp] = values[i]   (set_bc, bcs.py:135-139); stride = KP
+// vec[dofs[i]] = values[i]   (set_bc, bcs.py:135-139) on one component
 __global__ void k_set_bc(int64_t n, const int* __restrict__ dofs, const double* __restrict__ values,
-                         int stride, int comp, double* __restrict__ vec) {
+                         double* __restrict__ vec) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) vec[(size_t)dofs[i] * stride + comp] = values[i];
+  if (i < n) vec[dofs[i]] = values[i];
 }
 
 __global__ void k_mark(int64_t n, const int* __restrict__ dofs, uint8_t* __restrict__ mask) {
@@ -445,53 +411,64 @@ __global__ void k_mark(int64_t n, const int* __restrict__ dofs, uint8_t* __restr
   if (i < n) mask[dofs[i]] = 1;
 }
 
-// strided component copies between the interleaved device layout and per-component host views
+// strided copies: one direction value family out of [nnz][K] matrix values
 __global__ void k_extract(int64_t n, int stride, int comp, const double* __restrict__ src, double* __restrict__ dst) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[i * stride + comp];
 }
-__global__ void k_insert(int64_t n, int stride, int comp, const double* __restrict__ src, double* __restrict__ dst) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i * stride + comp] = src[i];
-}
-// [n][K] (the blocked layout of solver.u) <-> [n][KP]
-__global__ void k_repack(int64_t n, int K, int sstride, int dstride, const double* __restrict__ src, double* __restrict__ dst) {
+// component-major [K][ld] <-> blocked [n][K] (the layout of solver.u, fracstep.py:698-705)
+__global__ void k_to_blocked(int64_t n, int K, int ld, const double* __restrict__ src, double* __restrict__ dst) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * K; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t i = t / K;
     int k = (int)(t - i * K);
-    dst[i * dstride + k] = src[i * sstride + k];
+    dst[t] = src[(size_t)k * ld + i];
+  }
+}
+__global__ void k_from_blocked(int64_t n, int K, int ld, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * K; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t / K;
+    int k = (int)(t - i * K);
+    dst[(size_t)k * ld + i] = src[t];
   }
 }
 
-// diagonal of a square CSR matrix -> dinv = 1/diag
-__global__ void k_inv_diag(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
+// dinv[row] = 1 / (diagonal entry of a SELL matrix)
+__global__ void k_inv_diag(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ diag_t,
                            const double* __restrict__ vals, double* __restrict__ dinv) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
-  double d = 1.0;
-  for (int p = rowptr[row]; p < rowptr[row + 1]; ++p)
-    if (cols[p] == row) d = vals[p];
-  dinv[row] = 1.0 / d;
+  dinv[row] = 1.0 / vals[sell_slot(slice_ptr, row, diag_t[row])];
 }
 
-// out[k] = sum_i (a[i][k] - b[i][k])^2  (b may be null)
+// assemble_matrix(..., bcs=) semantics on a square SELL matrix (fracstep.py:379, Appendix D): BC rows
+// and columns zeroed, unit diagonal.
+__global__ void k_apply_bc_rows_cols(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+                                     const int* __restrict__ diag_t, const uint8_t* __restrict__ is_bc,
+                                     double* __restrict__ vals) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int s = row >> 5;
+  const int len = (slice_ptr[s + 1] - slice_ptr[s]) >> 5;
+  const bool rb = is_bc[row];
+  for (int t = 0; t < len; ++t) {
+    const size_t p = (size_t)slice_ptr[s] + ((size_t)t << 5) + (row & 31);
+    const int c = cols[p];
+    if (rb || is_bc[c]) vals[p] = (t == diag_t[row]) ? 1.0 : 0.0;
+  }
+}
+
+// out[k] = sum_i (a_k[i] - b_k[i])^2  (b may be null)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_sqdiff(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* out,
+k_sqdiff(int64_t n, int ld, const double* __restrict__ a, const double* __restrict__ b, double* out,
          double* partials, unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   double s[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) s[k] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double av[KP], bv[KP];
-    ldk<K>(a + i * KP, av);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) bv[k] = 0.0;
-    if (b != nullptr) ldk<K>(b + i * KP, bv);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      double d = av[k] - bv[k];
+      double d = a[(size_t)k * ld + i] - (b != nullptr ? b[(size_t)k * ld + i] : 0.0);
       s[k] = fma(d, d, s[k]);
     }
   }
@@ -519,13 +496,13 @@ k_sums(int64_t n, const double* __restrict__ x, const double* __restrict__ w, do
   }
 }
 
-// out[0] = sum_i a[i] * b[i]
+// out[0] = sum_k sum_i a_k[i] * b_k[i]
 __global__ void __launch_bounds__(256)
-k_dot_all(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* out,
+k_dot_all(int64_t n, int K, int ld, const double* __restrict__ a, const double* __restrict__ b, double* out,
           double* partials, unsigned* counter) {
   double s[1] = {0.0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s[0] = fma(a[i], b[i], s[0]);
+    for (int k = 0; k < K; ++k) s[0] = fma(a[(size_t)k * ld + i], b[(size_t)k * ld + i], s[0]);
   double total[1];
   if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
 }
@@ -547,40 +524,28 @@ __global__ void k_shift(int64_t n, double* __restrict__ x, const double* __restr
 //       sums rz, bb, rr
 template <int K>
 __global__ void __launch_bounds__(256)
-k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
+k_cg_init(int64_t n, int ld, const double* __restrict__ b, const double* __restrict__ q,
           const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
           double* __restrict__ p, KryState* st, double* partials, unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   double s[3 * K];
 #pragma unroll
   for (int i = 0; i < 3 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
-    double bv[KP], rv[KP], pv[KP];
-    ldk<K>(b + i * KP, bv);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) rv[k] = bv[k];
-    if (q != nullptr) {
-      double qv[KP];
-      ldk<K>(q + i * KP, qv);
-#pragma unroll
-      for (int k = 0; k < KP; ++k) rv[k] -= qv[k];
-    } else {
-      double z[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) z[k] = 0.0;
-      stk<K>(x + i * KP, z);
-    }
-#pragma unroll
-    for (int k = 0; k < KP; ++k) pv[k] = di * rv[k];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      s[k] = fma(rv[k], pv[k], s[k]);
-      s[K + k] = fma(bv[k], bv[k], s[K + k]);
-      s[2 * K + k] = fma(rv[k], rv[k], s[2 * K + k]);
+      const size_t j = (size_t)k * ld + i;
+      const double bv = b[j];
+      double rv = bv;
+      if (q != nullptr) rv -= q[j];
+      else x[j] = 0.0;
+      const double zv = di * rv;
+      r[j] = rv;
+      p[j] = zv;
+      s[k] = fma(rv, zv, s[k]);
+      s[K + k] = fma(bv, bv, s[K + k]);
+      s[2 * K + k] = fma(rv, rv, s[2 * K + k]);
     }
-    stk<K>(r + i * KP, rv);
-    stk<K>(p + i * KP, pv);
   }
   double total[3 * K];
   if (grid_reduce<3 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_INIT, st, total);
@@ -589,59 +554,58 @@ k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
 // x += alpha p ; r -= alpha q ; sums rz' = r.dinv r , rr = r.r
 template <int K>
 __global__ void __launch_bounds__(256)
-k_cg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q,
+k_cg_update(int64_t n, int ld, const double* __restrict__ p, const double* __restrict__ q,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             KryState* st, double* partials, unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double alpha[KP];
+  double alpha[K];
+  bool act[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) alpha[k] = (k < K && st->active[k]) ? st->alpha[k] : 0.0;
+  for (int k = 0; k < K; ++k) {
+    act[k] = st->active[k];
+    alpha[k] = st->alpha[k];
+  }
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
-    double pv[KP], qv[KP], xv[KP], rv[KP];
-    ldk_nc<K>(p + i * KP, pv);
-    ldk_nc<K>(q + i * KP, qv);
-    ldk<K>(x + i * KP, xv);
-    ldk<K>(r + i * KP, rv);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      xv[k] = fma(alpha[k], pv[k], xv[k]);
-      rv[k] = fma(-alpha[k], qv[k], rv[k]);
-    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      s[k] = fma(rv[k] * di, rv[k], s[k]);
-      s[K + k] = fma(rv[k], rv[k], s[K + k]);
+      if (!act[k]) continue;
+      const size_t j = (size_t)k * ld + i;
+      x[j] = fma(alpha[k], p[j], x[j]);
+      const double rv = fma(-alpha[k], q[j], r[j]);
+      r[j] = rv;
+      s[k] = fma(rv * di, rv, s[k]);
+      s[K + k] = fma(rv, rv, s[K + k]);
     }
-    stk<K>(x + i * KP, xv);
-    stk<K>(r + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_UPDATE, st, total);
 }
 
-// p = dinv r + beta p   (components that have converged keep their p: alpha is then 0 anyway)
+// p = dinv r + beta p
 template <int K>
 __global__ void __launch_bounds__(256)
-k_cg_p(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
+k_cg_p(int64_t n, int ld, const double* __restrict__ r, const double* __restrict__ dinv,
        double* __restrict__ p, const KryState* st) {
-  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double beta[KP];
+  double beta[K];
+  bool act[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) beta[k] = k < K ? st->beta[k] : 0.0;
+  for (int k = 0; k < K; ++k) {
+    act[k] = st->active[k];
+    beta[k] = st->beta[k];
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
-    double rv[KP], pv[KP];
-    ldk_nc<K>(r + i * KP, rv);
-    ldk<K>(p + i * KP, pv);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) pv[k] = fma(beta[k], pv[k], di * rv[k]);
-    stk<K>(p + i * KP, pv);
+    for (int k = 0; k < K; ++k) {
+      if (!act[k]) continue;
+      const size_t j = (size_t)k * ld + i;
+      p[j] = fma(beta[k], p[j], di * r[j]);
+    }
   }
 }
 
@@ -649,42 +613,28 @@ k_cg_p(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
 // init: r = dinv b - q (or r = dinv b, x = 0); rhat = r; p = r; sums bb = |dinv b|^2, rr
 template <int K>
 __global__ void __launch_bounds__(256)
-k_bcgs_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
+k_bcgs_init(int64_t n, int ld, const double* __restrict__ b, const double* __restrict__ q,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             double* __restrict__ rhat, double* __restrict__ p, KryState* st, double* partials,
             unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i];
-    double bv[KP], rv[KP];
-    ldk<K>(b + i * KP, bv);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      bv[k] *= di;
-      rv[k] = bv[k];
-    }
-    if (q != nullptr) {
-      double qv[KP];
-      ldk<K>(q + i * KP, qv);
-#pragma unroll
-      for (int k = 0; k < KP; ++k) rv[k] -= qv[k];
-    } else {
-      double z[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) z[k] = 0.0;
-      stk<K>(x + i * KP, z);
-    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      s[k] = fma(bv[k], bv[k], s[k]);
-      s[K + k] = fma(rv[k], rv[k], s[K + k]);
+      const size_t j = (size_t)k * ld + i;
+      const double bv = di * b[j];
+      double rv = bv;
+      if (q != nullptr) rv -= q[j];
+      else x[j] = 0.0;
+      r[j] = rv;
+      rhat[j] = rv;
+      p[j] = rv;
+      s[k] = fma(bv, bv, s[k]);
+      s[K + k] = fma(rv, rv, s[K + k]);
     }
-    stk<K>(r + i * KP, rv);
-    stk<K>(rhat + i * KP, rv);
-    stk<K>(p + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_INIT, st, total);
@@ -693,87 +643,80 @@ k_bcgs_init(int64_t n, const double* __restrict__ b, const double* __restrict__ 
 // s = r - alpha v   (in place in r)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_bcgs_s(int64_t n, const double* __restrict__ v, double* __restrict__ r, const KryState* st) {
-  constexpr int KP = Pad<K>::KP;
+k_bcgs_s(int64_t n, int ld, const double* __restrict__ v, double* __restrict__ r, const KryState* st) {
   if (st->done) return;
-  double alpha[KP];
+  double alpha[K];
+  bool act[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) alpha[k] = (k < K && st->active[k]) ? st->alpha[k] : 0.0;
+  for (int k = 0; k < K; ++k) {
+    act[k] = st->active[k];
+    alpha[k] = st->alpha[k];
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double vv[KP], rv[KP];
-    ldk_nc<K>(v + i * KP, vv);
-    ldk<K>(r + i * KP, rv);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) rv[k] = fma(-alpha[k], vv[k], rv[k]);
-    stk<K>(r + i * KP, rv);
+    for (int k = 0; k < K; ++k) {
+      if (!act[k]) continue;
+      const size_t j = (size_t)k * ld + i;
+      r[j] = fma(-alpha[k], v[j], r[j]);
+    }
   }
 }
 
 // x += alpha p + omega s ; r = s - omega t ; sums rr, rho' = rhat . r
 template <int K>
 __global__ void __launch_bounds__(256)
-k_bcgs_update(int64_t n, const double* __restrict__ p, const double* __restrict__ t,
+k_bcgs_update(int64_t n, int ld, const double* __restrict__ p, const double* __restrict__ t,
               const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
               KryState* st, double* partials, unsigned* counter) {
-  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double alpha[KP], omega[KP];
+  double alpha[K], omega[K];
+  bool act[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    const bool a = k < K && st->active[k];
-    alpha[k] = a ? st->alpha[k] : 0.0;
-    omega[k] = a ? st->omega[k] : 0.0;
+  for (int k = 0; k < K; ++k) {
+    act[k] = st->active[k];
+    alpha[k] = st->alpha[k];
+    omega[k] = st->omega[k];
   }
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double pv[KP], tv[KP], hv[KP], xv[KP], rv[KP];
-    ldk_nc<K>(p + i * KP, pv);
-    ldk_nc<K>(t + i * KP, tv);
-    ldk_nc<K>(rhat + i * KP, hv);
-    ldk<K>(x + i * KP, xv);
-    ldk<K>(r + i * KP, rv);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      xv[k] = fma(alpha[k], pv[k], fma(omega[k], rv[k], xv[k]));
-      rv[k] = fma(-omega[k], tv[k], rv[k]);
-    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      s[k] = fma(rv[k], rv[k], s[k]);
-      s[K + k] = fma(hv[k], rv[k], s[K + k]);
+      if (!act[k]) continue;
+      const size_t j = (size_t)k * ld + i;
+      const double sv = r[j];
+      x[j] = fma(alpha[k], p[j], fma(omega[k], sv, x[j]));
+      const double rv = fma(-omega[k], t[j], sv);
+      r[j] = rv;
+      s[k] = fma(rv, rv, s[k]);
+      s[K + k] = fma(rhat[j], rv, s[K + k]);
     }
-    stk<K>(x + i * KP, xv);
-    stk<K>(r + i * KP, rv);
   }
   double total[2 * K];
   if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_UPDATE, st, total);
 }
 
-// p = r + beta (p - omega v)   (frozen for converged components)
+// p = r + beta (p - omega v)
 template <int K>
 __global__ void __launch_bounds__(256)
-k_bcgs_p(int64_t n, const double* __restrict__ r, const double* __restrict__ v,
+k_bcgs_p(int64_t n, int ld, const double* __restrict__ r, const double* __restrict__ v,
          double* __restrict__ p, const KryState* st) {
-  constexpr int KP = Pad<K>::KP;
   if (st->done) return;
-  double beta[KP], omega[KP];
-  bool act[KP];
+  double beta[K], omega[K];
+  bool act[K];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    act[k] = k < K && st->active[k];
-    beta[k] = act[k] ? st->beta[k] : 0.0;
-    omega[k] = act[k] ? st->omega[k] : 0.0;
+  for (int k = 0; k < K; ++k) {
+    act[k] = st->active[k];
+    beta[k] = st->beta[k];
+    omega[k] = st->omega[k];
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double rv[KP], vv[KP], pv[KP];
-    ldk_nc<K>(r + i * KP, rv);
-    ldk_nc<K>(v + i * KP, vv);
-    ldk<K>(p + i * KP, pv);
 #pragma unroll
-    for (int k = 0; k < KP; ++k)
-      if (act[k]) pv[k] = fma(beta[k], fma(-omega[k], vv[k], pv[k]), rv[k]);
-    stk<K>(p + i * KP, pv);
+    for (int k = 0; k < K; ++k) {
+      if (!act[k]) continue;
+      const size_t j = (size_t)k * ld + i;
+      p[j] = fma(beta[k], fma(-omega[k], v[j], p[j]), r[j]);
+    }
   }
 }

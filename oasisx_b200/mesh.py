@@ -208,7 +208,9 @@ def create_rectangle(comm, points, n, cell_type=CellType.triangle) -> Mesh:
     cells = np.empty((nx * ny, 2, 3), dtype=np.int64)
     cells[:, 0] = np.stack([v0, v1, v3], axis=1)
     cells[:, 1] = np.stack([v0, v2, v3], axis=1)
-    return Mesh(x, cells.reshape(-1, 3), 2, comm)
+    msh = Mesh(x, cells.reshape(-1, 3), 2, comm)
+    msh._lattice = (np.array([x0, y0, 0.0]), np.array([(x1 - x0) / nx, (y1 - y0) / ny, 1.0]))
+    return msh
 
 
 def create_unit_square(comm, nx, ny, cell_type=CellType.triangle) -> Mesh:
@@ -232,7 +234,9 @@ def create_box(comm, points, n, cell_type=CellType.tetrahedron) -> Mesh:
     cells = np.empty((len(v0), 6, 4), dtype=np.int64)
     for t, tet in enumerate(tets):
         cells[:, t] = np.stack([v[a] for a in tet], axis=1)
-    return Mesh(x, cells.reshape(-1, 4), 3, comm)
+    msh = Mesh(x, cells.reshape(-1, 4), 3, comm)
+    msh._lattice = (p0.copy(), (p1 - p0) / np.array([nx, ny, nz], dtype=np.float64))
+    return msh
 
 
 def create_unit_cube(comm, nx, ny, nz, cell_type=CellType.tetrahedron) -> Mesh:
