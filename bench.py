@@ -37,9 +37,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
 DT, NU = 0.005, 0.01
 KRYLOV = {
-    "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10},
-    "pressure": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
-    "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10},
+    "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "pressure": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
 }
 
 

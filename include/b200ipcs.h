@@ -122,6 +122,11 @@ int b2_set_global_sizes(b2_ctx* ctx, int64_t n_global_v, int64_t n_global_q);
 /* ---- sparsity (create_matrix, fracstep.py:293,294,300,315,324,336,352) ---------------- */
 int b2_build_patterns(b2_ctx* ctx);
 int64_t b2_pattern_nnz(b2_ctx* ctx, int pattern);
+/* Optional schedule for the sliced-ELL kernels on a square pattern: a permutation of the 32-row slices
+ * that lists them spatial tile by spatial tile, so that one thread block gathers from one
+ * neighbourhood of the vector (host-side analogue of DOLFINx's graph reordering [ext]).  Results do
+ * not depend on it. */
+int b2_set_slice_order(b2_ctx* ctx, int pattern, int64_t n_slices, const int32_t* order);
 /* copies indptr (n_rows+1) and indices (nnz) back: the bit-exact CSR check of north_star */
 int b2_get_pattern(b2_ctx* ctx, int pattern, int32_t* indptr, int32_t* indices);
 
@@ -179,6 +184,9 @@ int b2_get_stats(b2_ctx* ctx, b2_stats* out);
  * 2 = SpMV Ap*dp, 3 = SpMM M*u.  Returns average ms per launch and the algorithmic bytes moved. */
 int b2_bench_kernel(b2_ctx* ctx, int kernel, int reps, double* ms_per_launch, double* bytes_per_launch);
 int b2_synchronize(b2_ctx* ctx);
+/* Launch-shape knobs for the hot kernels ("spmm_blocks_per_sm", "spmm_unroll"; "spmm_mode" != 0 selects
+ * a diagnostic half-kernel and makes results meaningless). */
+int b2_set_tuning(b2_ctx* ctx, const char* key, int value);
 /* CUDA events on the context's stream (slots 0..7) for callers that time a region of stage calls. */
 int b2_event_record(b2_ctx* ctx, int slot);
 int b2_event_elapsed_ms(b2_ctx* ctx, int slot_start, int slot_stop, double* ms);

@@ -26,12 +26,12 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_build_patterns", "b2_pattern_nnz", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_set_slice_order", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
     "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
-    "b2_event_record", "b2_event_elapsed_ms",
+    "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
         "b2_set_global_sizes": (i32, [vp, i64, i64]),
         "b2_build_patterns": (i32, [vp]),
         "b2_pattern_nnz": (i64, [vp, i32]),
+        "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
         "b2_get_pattern": (i32, [vp, i32, vp, vp]),
         "b2_set_velocity_bc_dofs": (i32, [vp, i32, i64, vp]),
         "b2_set_velocity_bc_values": (i32, [vp, i32, i64, vp]),
@@ -110,6 +111,7 @@ def load_library() -> C.CDLL:
         "b2_get_stats": (i32, [vp, vp]),
         "b2_bench_kernel": (i32, [vp, i32, i32, vp, vp]),
         "b2_synchronize": (i32, [vp]),
+        "b2_set_tuning": (i32, [vp, C.c_char_p, i32]),
         "b2_event_record": (i32, [vp, i32]),
         "b2_event_elapsed_ms": (i32, [vp, i32, i32, vp]),
     }
@@ -179,6 +181,10 @@ class Context:
 
     def build_patterns(self):
         self._check(self.lib.b2_build_patterns(self._h), "b2_build_patterns")
+
+    def set_slice_order(self, which: int, order):
+        o = _i32(order)
+        self._check(self.lib.b2_set_slice_order(self._h, which, o.size, _ptr(o)), "b2_set_slice_order")
 
     def pattern(self, which: int, n_rows: int):
         nnz = self.lib.b2_pattern_nnz(self._h, which)
@@ -297,6 +303,9 @@ class Context:
         ms, nbytes = C.c_double(0.0), C.c_double(0.0)
         self._check(self.lib.b2_bench_kernel(self._h, kernel, reps, C.byref(ms), C.byref(nbytes)), "b2_bench_kernel")
         return ms.value, nbytes.value
+
+    def set_tuning(self, key: str, value: int):
+        self._check(self.lib.b2_set_tuning(self._h, key.encode(), int(value)), "b2_set_tuning")
 
     def event_record(self, slot: int):
         self._check(self.lib.b2_event_record(self._h, slot), "b2_event_record")

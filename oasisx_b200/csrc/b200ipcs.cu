@@ -25,7 +25,7 @@ struct CSR {
   int64_t nnz = 0;
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
-  DBuf<int> slice_ptr, scols, diag_t;
+  DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
 };
@@ -58,7 +58,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8;
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -237,12 +237,40 @@ void dispatch_elem(const b2_ctx* c, F&& f) {
   else throw B2Error(-3, "unsupported (gdim, degree)");
 }
 
+template <int K, int DOT, int UNROLL, int BLOCK>
+void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
+                   KryState* st, int fin) {
+  const int n_slices = (pat.n_rows + 31) / 32;
+  const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
+  const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
+  B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x,
+            ld, y, w, st, fin, c->partials.p, c->d_counter);
+}
+
 template <int K, int DOT>
 void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
-  int grid = pgrid(c, (int64_t)pat.n_rows, 256, c->spmm_blocks_per_sm);
-  B2_LAUNCH(c, (k_spmm<K, DOT>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y, w, st, fin,
-            c->partials.p, c->d_counter);
+  if (c->spmm_mode != 0) {
+    int grid = pgrid(c, (int64_t)pat.n_rows, 256, 8);
+    if (c->spmm_mode == 1) B2_LAUNCH(c, (k_spmm_diag<K, 1>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
+    else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
+    return;
+  }
+  const bool u8 = c->spmm_unroll >= 8;
+  switch (c->spmm_block) {
+    case 256:
+      if (u8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin);
+      else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin);
+      break;
+    case 512:
+      if (u8) launch_spmm_u<K, DOT, 8, 512>(c, pat, vals, x, ld, y, w, st, fin);
+      else launch_spmm_u<K, DOT, 4, 512>(c, pat, vals, x, ld, y, w, st, fin);
+      break;
+    default:
+      if (u8) launch_spmm_u<K, DOT, 8, 1024>(c, pat, vals, x, ld, y, w, st, fin);
+      else launch_spmm_u<K, DOT, 4, 1024>(c, pat, vals, x, ld, y, w, st, fin);
+      break;
+  }
 }
 
 template <int K>
@@ -389,7 +417,7 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   auto comb = [&](auto kc) {
     constexpr int KK = decltype(kc)::value;
     B2_LAUNCH(c, (k_combine_first<KK>), pgrid(c, vv.n_rows), 256, vv.n_rows, vv.slice_ptr.p, vv.scols.p, vv.diag_t.p,
-              c->A.p, c->M.p, c->Kst.p, 1.0 / dt, 0.5 * nu, u1, ld, c->vec(B2_VEC_B0), psurf, c->is_bc_row_v.p, scale,
+              c->A.p, c->M.p, c->Kst.p, vv.order.p, 1.0 / dt, 0.5 * nu, u1, ld, c->vec(B2_VEC_B0), psurf, c->is_bc_row_v.p, scale,
               c->vec(B2_VEC_BFIRST), c->dinvA.p);
   };
   if (K == 2) comb(std::integral_constant<int, 2>{});
@@ -817,6 +845,17 @@ int b2_set_global_sizes(b2_ctx* c, int64_t nv, int64_t nq) {
   });
 }
 
+int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order) {
+  return guarded(c, [&] {
+    B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "slice order: square patterns, after b2_build_patterns");
+    CSR& pat = c->pat[pattern];
+    B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
+    pat.order.alloc(n_slices);
+    B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 int b2_build_patterns(b2_ctx* c) {
   return guarded(c, [&] {
     Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
@@ -1098,6 +1137,17 @@ int b2_get_stats(b2_ctx* c, b2_stats* out) {
 
 int b2_synchronize(b2_ctx* c) {
   return guarded(c, [&] { B2_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int b2_set_tuning(b2_ctx* c, const char* key, int value) {
+  return guarded(c, [&] {
+    std::string k(key);
+    if (k == "spmm_blocks_per_sm") c->spmm_blocks_per_sm = std::max(1, std::min(value, 32));
+    else if (k == "spmm_unroll") c->spmm_unroll = value;
+    else if (k == "spmm_mode") c->spmm_mode = value;
+    else if (k == "spmm_block") c->spmm_block = value;
+    else throw B2Error(-2, "unknown tuning key " + k);
+  });
 }
 
 int b2_event_record(b2_ctx* c, int slot) {

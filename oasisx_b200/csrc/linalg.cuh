@@ -212,21 +212,27 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // Persistent grid: warp w of the grid walks slices w, w + nwarps, ...  The t-loop is unrolled by 4:
 // four independent (column -> gather) chains per thread keep enough loads in flight to cover HBM
 // latency at < 100% occupancy.
-template <int K, int DOT>
-__global__ void __launch_bounds__(256)
+// Scheduling: `order` lists the slices tile by tile (all stencil classes of one small spatial tile
+// are adjacent in the list, fem.slice_order); a block takes blockDim/32 consecutive list entries at
+// a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
+// those lines in L1 instead of each pulling them through the L2 fabric.
+template <int K, int DOT, int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
-       const double* __restrict__ vals, const double* __restrict__ x, int ld, double* __restrict__ y,
-       const double* __restrict__ w, KryState* st, int fin, double* partials, unsigned* counter) {
+       const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
+       double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
+       unsigned* counter) {
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int wib = threadIdx.x >> 5;
+  constexpr int WPB = BLOCK / 32;
   const int n_slices = (n_rows + 31) >> 5;
   constexpr int ND = DOT == 0 ? 1 : DOT * K;
   double dots[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) dots[i] = 0.0;
-  for (int s = warp; s < n_slices; s += nwarps) {
+  for (int i = blockIdx.x * WPB + wib; i < n_slices; i += gridDim.x * WPB) {
+    const int s = order != nullptr ? __ldg(order + i) : i;
     const int base = __ldg(slice_ptr + s);
     const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
     const int row = (s << 5) + lane;
@@ -236,18 +242,23 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     int t = 0;
-    for (; t + 4 <= len; t += 4) {
-      int c[4];
-      double v[4];
+    for (; t + UNROLL <= len; t += UNROLL) {
+      int c[UNROLL];
+      double v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         c[u] = __ldg(cp + ((t + u) << 5));
         v[u] = __ldg(vp + ((t + u) << 5));
       }
+      double xv[UNROLL][K];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = fma(v[u], __ldg(x + (size_t)k * ld + c[u]), acc[k]);
+        for (int k = 0; k < K; ++k) xv[u][k] = __ldg(x + (size_t)k * ld + c[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fma(v[u], xv[u][k], acc[k]);
     }
     for (; t < len; ++t) {
       const int c = __ldg(cp + (t << 5));
@@ -274,6 +285,42 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
 }
 
+// Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
+// gather), 2 = gather only (values taken as 1).  Results are meaningless; they time the two halves.
+template <int K, int MODE>
+__global__ void __launch_bounds__(256)
+k_spmm_diag(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+            const double* __restrict__ vals, const double* __restrict__ x, int ld, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  for (int s = warp; s < n_slices; s += nwarps) {
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) {
+      const int c = __ldg(cols + base + lane + (t << 5));
+      if constexpr (MODE == 1) {
+        const double v = __ldg(vals + base + lane + (t << 5));
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fma(v, (double)(c + k), acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += __ldg(x + (size_t)k * ld + c);
+      }
+    }
+    if (row < n_rows) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
+    }
+  }
+}
+
 // ---- fused "matrix-vector strategy" of assemble_first (fracstep.py:438-472) ------------------
 // In:  A = C(uab) (just assembled), M, Kst, all in SELL slots.   Out, in ONE pass over the slots:
 //   b_first[row] = (M/dt - nu/2 K - 1/2 C) u1 + b0 (+ p_surf)        (:438-465)
@@ -286,15 +333,15 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
                 const int* __restrict__ diag_t, double* __restrict__ A, const double* __restrict__ M,
-                const double* __restrict__ Kst, double inv_dt, double half_nu,
-                const double* __restrict__ u1, int ld, const double* __restrict__ b0,
+                const double* __restrict__ Kst, const int* __restrict__ order, double inv_dt,
+                double half_nu, const double* __restrict__ u1, int ld, const double* __restrict__ b0,
                 const double* __restrict__ psurf, const uint8_t* __restrict__ is_bc_row, int scale,
                 double* __restrict__ bfirst, double* __restrict__ dinv) {
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n_slices = (n_rows + 31) >> 5;
-  for (int s = warp; s < n_slices; s += nwarps) {
+  for (int i = blockIdx.x * wpb + wib; i < n_slices; i += gridDim.x * wpb) {
+    const int s = order != nullptr ? __ldg(order + i) : i;
     const int base = __ldg(slice_ptr + s);
     const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
     const int row = (s << 5) + lane;

@@ -169,6 +169,25 @@ class _SubSpace:
         return Vi, np.arange(n, dtype=np.int32) * self.parent.bs + self.i
 
 
+def slice_order(x: np.ndarray, n_rows: int, lattice=None, tile=(4, 4), rows_per_slice: int = 32) -> np.ndarray:
+    """Schedule of the 32-row slices of the sliced-ELL operators: slices sorted by the spatial tile of
+    their first row, so that all slices of one tile (every stencil class) are adjacent.  A tile spans
+    one slice (32 dofs) in x and `tile` x-lines in y and z; on meshes without lattice information the
+    tile edge is taken from the bounding box and the dof count."""
+    n_slices = (n_rows + rows_per_slice - 1) // rows_per_slice
+    first = x[np.arange(n_slices) * rows_per_slice]
+    if lattice is not None:
+        p0, h = lattice
+    else:
+        p0 = x.min(axis=0)
+        ext = np.maximum(x.max(axis=0) - p0, 1e-300)
+        dim = int(np.count_nonzero(ext > 1e-12 * ext.max()))
+        h = np.where(ext > 1e-12 * ext.max(), ext / max(n_rows ** (1.0 / max(dim, 1)) / 2.0, 1.0), 1.0)
+    q = np.floor((first - p0) / h + 1e-9).astype(np.int64)
+    key = (q[:, 2] // tile[1], q[:, 1] // tile[0], q[:, 0] // rows_per_slice)
+    return np.lexsort((np.arange(n_slices), key[2], key[1], key[0])).astype(np.int32)
+
+
 def functionspace(mesh: Mesh, element) -> FunctionSpace:
     """``functionspace(mesh, ("Lagrange", k))`` or ``("Lagrange", k, (gdim,))``.  Scalar spaces of
     equal degree on one mesh share a dof map (one ``A`` serves every velocity component)."""

@@ -152,6 +152,10 @@ class FractionalStep_AB_CN:
         ctx.set_space(L.SPACE_Q, deg_p, self._Q.num_dofs, 0, self._Q.dofmap.list)
         ctx.set_global_sizes(Vs.num_dofs, self._Q.num_dofs)
         ctx.build_patterns()
+        if deg_u == 2:  # tile-major schedule of the SELL slices (L1 reuse of the gathered vector)
+            ctx.set_slice_order(
+                L.PAT_VV, _fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, getattr(mesh, "_lattice", None))
+            )
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
         for i in range(gdim):

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Sweep SpMM launch shapes / diagnostic modes on the GPU.  Usage: python tools/sweep_spmm.py [mesh]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+from problems import TaylorGreen, make_mesh, make_solver  # noqa: E402
+from oasisx_b200 import _lib as L, fem  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+dt, nu = 0.005, 0.01
+tg = TaylorGreen(nu, 3)
+opts = {k: {"ksp_type": t, "pc_type": "jacobi", "ksp_rtol": 1e-10}
+        for k, t in (("tentative", "bcgs"), ("pressure", "cg"), ("scalar", "cg"))}
+msh = make_mesh(3, N)
+s = make_solver(msh, 2, tg, dt, solver_options=opts)
+ctx = s._ctx
+tg.t_u, tg.t_p = dt, dt / 2
+s.solve(dt, nu, max_iter=1)
+Vs = s._Vi[0][0]
+n_slices = (Vs.num_dofs + 31) // 32
+for tile in (None, (1, 1), (2, 1), (2, 2), (4, 2), (4, 4)):
+    if tile is None:
+        ctx.set_slice_order(L.PAT_VV, np.arange(n_slices, dtype=np.int32))
+    else:
+        ctx.set_slice_order(L.PAT_VV, fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, msh._lattice, tile=tile))
+    for block in (256, 512, 1024):
+        ctx.set_tuning("spmm_block", block)
+        for unroll in (4, 8):
+            ctx.set_tuning("spmm_unroll", unroll)
+            for bps in (1, 2, 4, 8):
+                if block * bps > 2048:
+                    continue
+                ctx.set_tuning("spmm_blocks_per_sm", bps)
+                ms, nbytes = ctx.bench_kernel(3, 10)
+                print(f"tile {tile} block {block:4d} unroll {unroll} blocks/SM {bps}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
