@@ -103,10 +103,12 @@ def bc_series(solver, tg, t_first: float, n_steps: int):
     out = []
     for i, bcl in enumerate(solver._bcs_u):
         bc = bcl[0]
-        vals = np.empty((n_steps, len(bc._dofs)))
+        own = bc._dofs < solver._nV_owned  # the device list holds the owned BC dofs only
+        xT = np.ascontiguousarray(bc._xT[:, own])
+        vals = np.empty((n_steps, int(own.sum())))
         for s in range(n_steps):
             tg.t_u = t_first + s * DT
-            vals[s] = bc._value(bc._xT)
+            vals[s] = bc._value(xT)
         out.append(vals)
     return out
 
@@ -162,23 +164,23 @@ def run_reference(args):
 
 
 def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 or args.gpus > 1:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "n_gpus": args.gpus, "unavailable":
-                              "multi-GPU partitioning (slab halo + NCCL allreduce) is not built yet"}))
-        return
+    from oasisx_b200.comm import HostComm
     from problems import TaylorGreen, make_mesh, make_solver
+
+    comm = HostComm.from_env()
+    rank, world = comm.rank, comm.size
+    if world != args.gpus and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    device = int(os.environ.get("LOCAL_RANK", "0"))
 
     N, K, W = args.mesh, args.steps, max(args.warmup, 3)
     t_setup = time.perf_counter()
     tg = TaylorGreen(NU, 3)
-    msh = make_mesh(3, N)
-    solver = make_solver(msh, 2, tg, DT, solver_options=KRYLOV)
+    msh = make_mesh(3, N, comm if world > 1 else None)
+    solver = make_solver(msh, 2, tg, DT, solver_options=KRYLOV, device=device)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
-    nbc = sum(len(b[0]._dofs) for b in solver._bcs_u)
+    nbc = comm.allreduce(sum(len(d) for d in solver._bc_dofs))
 
     # ---- device-timed region: state and the BC values of every step already in HBM -------------
     series = bc_series(solver, tg, DT, W + K)
@@ -189,10 +191,10 @@ def run_ours(args):
         ctx.select_bc_step(s)
         ctx.step(DT, NU, 1e-12, 1)
     st0 = ctx.stats()
-    launches0 = st0.kernel_launches
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(device)
     sampler.start()
     ctx.synchronize()
+    comm.Barrier()
     ctx.event_record(0)
     its = []
     stage_ms = np.zeros(4)
@@ -204,9 +206,11 @@ def run_ours(args):
         stage_ms += [st.ms_assemble_first, st.ms_tentative, st.ms_pressure, st.ms_update]
     ctx.event_record(1)
     ctx.synchronize()
-    ms_total = ctx.event_elapsed_ms(0, 1)
+    ms_total = comm.allreduce(ctx.event_elapsed_ms(0, 1), "max")  # max over ranks of the device time
+    comm.Barrier()
     clocks = sampler.stop()
-    launches = ctx.stats().kernel_launches - launches0
+    st1 = ctx.stats()
+    launches = comm.allreduce(int(st1.kernel_launches - st0.kernel_launches))
     ms_per_step = ms_total / K
     value = 1000.0 / ms_per_step
 
@@ -216,60 +220,69 @@ def run_ours(args):
     ctx.select_bc_step(-1)
     stA = ctx.stats()
     ctx.synchronize()
+    comm.Barrier()
     t0 = time.perf_counter()
     for s in range(K):
         tg.t_u += DT
         tg.t_p += DT
         solver.solve(DT, NU, max_iter=1)
     ctx.synchronize()
-    e2e_s = (time.perf_counter() - t0) / K
+    e2e_s = comm.allreduce((time.perf_counter() - t0) / K, "max")
     stB = ctx.stats()
     e2e = {"value": 1.0 / e2e_s, "unit": "steps/s",
-           "h2d_bytes_per_step": (stB.bytes_h2d - stA.bytes_h2d) // K,
-           "d2h_bytes_per_step": (stB.bytes_d2h - stA.bytes_d2h) // K}
+           "h2d_bytes_per_step": comm.allreduce(int(stB.bytes_h2d - stA.bytes_h2d)) // K,
+           "d2h_bytes_per_step": comm.allreduce(int(stB.bytes_d2h - stA.bytes_d2h)) // K}
 
-    # ---- roofline of the dominant kernel, measured live ----------------------------------------
+    # ---- roofline of the dominant kernel, measured live (rank 0's share of the rows) ------------
     peak, peak_kind = measured_peaks()
-    ms_k, bytes_k = ctx.bench_kernel(0, 20)
+    comm.Barrier()
+    ms_k, bytes_k = ctx.bench_kernel(3, 20)   # k_spmm on the P2xP2 pattern (mass operator), gdim RHS
     achieved = bytes_k / (ms_k * 1e-3) / 1e9
-    ms_m, bytes_m = ctx.bench_kernel(3, 20)
     ms_a, bytes_a = ctx.bench_kernel(1, 5)
     ms_q, bytes_q = ctx.bench_kernel(2, 50)
-    roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 CSR, 3 RHS)", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
+    comm.Barrier()
+    roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 SELL-32 operator, 3 right-hand sides)",
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
                 "other_kernels": {
-                    "spmm_mass_GBs": bytes_m / (ms_m * 1e-3) / 1e9,
                     "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
                     "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
+    halos = int(st1.halo_exchanges - st0.halo_exchanges) // K
+    allred = int(st1.allreduces - st0.allreduces) // K
+    if rank != 0:
+        comm.Barrier()
+        return
 
-    # ---- CPU restatement on the host cores, bounded sample -------------------------------------
+    # ---- CPU restatement on the host cores, bounded sample (rank 0, N = 1 only) -----------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         sec, cells = cpu_sample(args.cpu_mesh, 2)
         sps = (1.0 / sec) * cells / msh.num_cells
         cpu = {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port",
                "sample": f"numpy/SuperLU restatement, 2 steps on a {args.cpu_mesh}^3 box ({sec:.2f} s/step), "
                          f"scaled linearly by cell count to {N}^3", "host_cpus": os.cpu_count()}
 
-    V, Q = solver._Vi[0][0], solver._Q
+    nV = solver._lp.V.n_global if world > 1 else solver._nV_owned
+    nQ = solver._lp.Q.n_global if world > 1 else solver._nQ_owned
     line = {
-        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D Taylor-Green P2-P1 {N}^3 box (z-extruded exact solution), dt={DT}, nu={NU}, "
                                "max_iter=1, rtol=1e-10", "mesh": N, "cells": msh.num_cells,
-                   "dofs": 3 * V.num_dofs + Q.num_dofs, "nnz_vv": ctx.pattern_nnz(0),
-                   "l2": "working set per step >> 126 MB L2 (matrices alone "
-                         f"{(3 * 8 + 4) * ctx.pattern_nnz(0) / 1e9:.2f} GB); no flush needed",
+                   "dofs": 3 * nV + nQ, "partition": f"{world} z-slab(s), NCCL halo + all-reduce" if world > 1 else "single GPU",
+                   "l2": "working set per step >> 126 MB L2 (P2xP2 operators alone "
+                         f"{3 * 12 * (230 * N**3) / 1e9:.2f} GB over all ranks); no flush needed",
                    "krylov": KRYLOV, "setup_s": t_setup},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
                        "update": int(np.median([i[2] for i in its]))},
         "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
+        "nccl_per_step": {"halo_exchanges": halos, "allreduces": allred},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "bc_dofs": nbc,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    comm.Barrier()
 
 
 def main():

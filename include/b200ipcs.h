@@ -85,6 +85,7 @@ typedef struct b2_stats {
   double ms_assemble_first, ms_tentative, ms_pressure, ms_update; /* CUDA-event times, last step */
   double ms_step;
   int64_t bytes_h2d, bytes_d2h; /* cumulative host<->device traffic through this ABI */
+  int64_t halo_exchanges, allreduces; /* NCCL operations enqueued since creation (multi rank) */
 } b2_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -49,6 +49,8 @@ class Stats(C.Structure):
         ("ms_step", C.c_double),
         ("bytes_h2d", C.c_int64),
         ("bytes_d2h", C.c_int64),
+        ("halo_exchanges", C.c_int64),
+        ("allreduces", C.c_int64),
     ]
 
 
@@ -135,6 +137,15 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.b2_nccl_unique_id(buf)
+    if rc != 0:
+        raise B200Error(f"b2_nccl_unique_id failed ({rc}): {lib.b2_last_error(None).decode()}")
+    return buf.raw
+
+
 class Context:
     """One ``b2_ctx`` (one rank / one GPU)."""
 
@@ -175,6 +186,13 @@ class Context:
         cd = _i32(cell_dofs)
         self.n[space] = n_owned + n_ghost
         self._check(self.lib.b2_set_space(self._h, space, degree, n_owned, n_ghost, _ptr(cd)), "b2_set_space")
+
+    def set_halo(self, space: int, plan):
+        nb = _i32(plan.neighbors)
+        so = np.ascontiguousarray(plan.send_off, dtype=np.int64)
+        si = _i32(plan.send_idx)
+        ro = np.ascontiguousarray(plan.recv_off, dtype=np.int64)
+        self._check(self.lib.b2_set_halo(self._h, space, len(nb), _ptr(nb), _ptr(so), _ptr(si), _ptr(ro)), "b2_set_halo")
 
     def set_global_sizes(self, nv: int, nq: int):
         self._check(self.lib.b2_set_global_sizes(self._h, nv, nq), "b2_set_global_sizes")

@@ -3,6 +3,8 @@
 #include "../../include/b200ipcs.h"
 
 #include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen'ed when a multi-rank context is created
 
 #include <algorithm>
 #include <cmath>
@@ -48,6 +50,58 @@ struct KSPOpts {
   int expected_its = 0;  // iterations of the previous solve: first batch enqueued without a host sync
 };
 
+// NCCL entry points resolved at run time (no link-time dependency; single-rank runs never load it)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  void load() {
+    if (lib) return;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) throw B2Error(-30, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+      void* p = dlsym(lib, n);
+      if (!p) throw B2Error(-30, std::string("NCCL symbol missing: ") + n);
+      return p;
+    };
+    GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+    GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+    Send = (decltype(Send))sym("ncclSend");
+    Recv = (decltype(Recv))sym("ncclRecv");
+    AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+  }
+};
+NcclApi g_nccl;
+
+#define B2_NCCL(expr)                                                                               \
+  do {                                                                                              \
+    ncclResult_t _r = (expr);                                                                       \
+    if (_r != ncclSuccess) throw B2Error(-31, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+  } while (0)
+
+struct Halo {
+  int n_neighbors = 0;
+  std::vector<int> ranks;
+  std::vector<int64_t> send_off, recv_off;  // host copies
+  DBuf<int64_t> d_send_off, d_recv_off;
+  DBuf<int> send_idx;
+  DBuf<double> sendbuf, recvbuf;
+};
+
 struct DVec {
   DBuf<double> buf;
   int K = 1;
@@ -67,6 +121,9 @@ struct b2_ctx {
   DBuf<int> cell_nodes;
   Space sp[2];
   CSR pat[4];
+  Halo halo[2];
+  ncclComm_t comm = nullptr;
+  double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank)
   bool patterns_built = false, preassembled = false;
   bool low_memory = false, rotational = false;
   // matrices (values in pattern order)
@@ -237,6 +294,45 @@ void dispatch_elem(const b2_ctx* c, F&& f) {
   else throw B2Error(-3, "unsupported (gdim, degree)");
 }
 
+// Owner -> ghost exchange of a component-major vector before it is gathered by columns
+// (Vector.scatter_forward / the implicit MatMult gather): pack kernel, grouped
+// ncclSend/ncclRecv with every neighbour, unpack kernel.  Single rank: nothing to do.
+void halo_forward(b2_ctx* c, int space, double* v, int K) {
+  if (c->nranks == 1) return;
+  Halo& h = c->halo[space];
+  if (h.n_neighbors == 0) return;
+  const Space& S = c->sp[space];
+  const int ld = (int)S.n_local();
+  const int64_t ns = h.send_off.back(), nr = h.recv_off.back();
+  if (ns > 0)
+    B2_LAUNCH(c, k_halo_pack, pgrid(c, ns * K), 256, h.n_neighbors, h.d_send_off.p, h.send_idx.p, K, ld, v, h.sendbuf.p);
+  B2_NCCL(g_nccl.GroupStart());
+  for (int j = 0; j < h.n_neighbors; ++j) {
+    const int64_t sc = h.send_off[j + 1] - h.send_off[j], rc = h.recv_off[j + 1] - h.recv_off[j];
+    if (sc > 0) B2_NCCL(g_nccl.Send(h.sendbuf.p + K * h.send_off[j], (size_t)(K * sc), ncclDouble, h.ranks[j], c->comm, c->stream));
+    if (rc > 0) B2_NCCL(g_nccl.Recv(h.recvbuf.p + K * h.recv_off[j], (size_t)(K * rc), ncclDouble, h.ranks[j], c->comm, c->stream));
+  }
+  B2_NCCL(g_nccl.GroupEnd());
+  if (nr > 0)
+    B2_LAUNCH(c, k_halo_unpack, pgrid(c, nr * K), 256, h.n_neighbors, h.d_recv_off.p, K, ld, (int)S.n_owned, h.recvbuf.p, v);
+  c->stats.halo_exchanges++;
+}
+
+// sum over ranks of n doubles on the device (KSP reductions / comm.allreduce)
+void allreduce_sum(b2_ctx* c, double* d, int n) {
+  if (c->nranks == 1) return;
+  B2_NCCL(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+  c->stats.allreduces++;
+}
+
+// after a reducing Krylov kernel: (multi rank) all-reduce the raw totals and run the scalar update
+void reduce_finish_host(b2_ctx* c, int fin, int n, bool is_init = false) {
+  if (c->nranks == 1) return;
+  allreduce_sum(c, c->d_red, n);
+  B2_LAUNCH(c, k_kry_finalize, 1, 1, fin, c->d_st, c->d_red, (int)is_init);
+}
+inline double* red_ptr(b2_ctx* c) { return c->nranks > 1 ? c->d_red : nullptr; }
+
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
@@ -244,7 +340,8 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x,
-            ld, y, w, st, fin, c->partials.p, c->d_counter);
+            ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
+  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
 template <int K, int DOT>
@@ -281,14 +378,6 @@ void launch_spmm_k(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   else launch_spmm_t<K, 2>(c, pat, vals, x, ld, y, w, st, fin);
 }
 
-// Owner -> ghost exchange of an interleaved vector before it is gathered by columns
-// (Vector.scatter_forward / the implicit MatMult gather).  Single rank: nothing to do.
-void halo_forward(b2_ctx* c, int space, double* v, int K) {
-  (void)space; (void)v; (void)K;
-  if (c->nranks == 1) return;
-  throw B2Error(-4, "multi-rank halo exchange not built in this library version");
-}
-
 void spmm(b2_ctx* c, const CSR& pat, const double* vals, int K, double* x, double* y, const double* w = nullptr,
           KryState* st = nullptr, int fin = FIN_NONE, int dot = 0, int xspace = -1) {
   B2_REQUIRE(pat.has_sell(), "SpMM needs the SELL layout of the pattern");
@@ -313,13 +402,15 @@ void krylov_iterations(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double
   for (int it = 0; it < n_iter; ++it) {
     if (o.type == 0) {
       spmm(c, pat, vals, K, p, q, p, st, FIN_CG_PQ, 1, space);
-      B2_LAUNCH(c, k_cg_update<K>, g, 256, n, ld, p, q, dinv, x, r, st, c->partials.p, c->d_counter);
+      B2_LAUNCH(c, k_cg_update<K>, g, 256, n, ld, p, q, dinv, x, r, st, c->partials.p, c->d_counter, red_ptr(c));
+      reduce_finish_host(c, FIN_CG_UPDATE, 2 * K);
       B2_LAUNCH(c, k_cg_p<K>, g, 256, n, ld, r, dinv, p, st);
     } else {
       spmm(c, pat, vals, K, p, q, rhat, st, FIN_BCGS_V, 1, space);                // v = A p
       B2_LAUNCH(c, k_bcgs_s<K>, g, 256, n, ld, q, r, st);                            // s = r - alpha v
       spmm(c, pat, vals, K, r, t, r, st, FIN_BCGS_T, 2, space);                   // t = A s
-      B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, ld, p, t, rhat, x, r, st, c->partials.p, c->d_counter);
+      B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, ld, p, t, rhat, x, r, st, c->partials.p, c->d_counter, red_ptr(c));
+      reduce_finish_host(c, FIN_BCGS_UPDATE, 2 * K);
       B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, ld, r, q, p, st);
     }
   }
@@ -336,10 +427,13 @@ void krylov_init(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals
     spmm(c, pat, vals, K, x, q, nullptr, nullptr, FIN_NONE, 0, space);
     q0 = q;
   }
-  if (o.type == 0)
-    B2_LAUNCH(c, k_cg_init<K>, g, 256, n, ld, b, q0, dinv, x, r, p, c->d_st, c->partials.p, c->d_counter);
-  else
-    B2_LAUNCH(c, k_bcgs_init<K>, g, 256, n, ld, b, q0, dinv, x, r, rhat, p, c->d_st, c->partials.p, c->d_counter);
+  if (o.type == 0) {
+    B2_LAUNCH(c, k_cg_init<K>, g, 256, n, ld, b, q0, dinv, x, r, p, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+    reduce_finish_host(c, FIN_CG_INIT, 3 * K, true);
+  } else {
+    B2_LAUNCH(c, k_bcgs_init<K>, g, 256, n, ld, b, q0, dinv, x, r, rhat, p, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+    reduce_finish_host(c, FIN_BCGS_INIT, 2 * K, true);
+  }
 }
 
 // Solves K systems  A x_k = b_k  (interleaved storage) with the options of solver `which`.
@@ -461,6 +555,7 @@ void apply_velocity_bcs(b2_ctx* c, double* v) {
 template <int K>
 void sqdiff(b2_ctx* c, int64_t n, int ld, const double* a, const double* b, double* out_dev) {
   B2_LAUNCH(c, k_sqdiff<K>, pgrid(c, n), 256, n, ld, a, b, out_dev, c->partials.p, c->d_counter);
+  allreduce_sum(c, out_dev, K);
 }
 
 void read_sums(b2_ctx* c, int n) {
@@ -509,6 +604,7 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
   const int64_t n = Q.n_owned;
   if (!c->has_pbc) {  // MatNullSpaceRemove: subtract the arithmetic mean of the entries (:573-574)
     B2_LAUNCH(c, k_sums, pgrid(c, n), 256, n, b2, (const double*)nullptr, c->d_sums, c->partials.p, c->d_counter);
+    allreduce_sum(c, c->d_sums, 2);
     B2_LAUNCH(c, k_shift, pgrid(c, n), 256, n, b2, c->d_sums, 0, 1.0 / (double)Q.n_global, (const double*)nullptr, (double*)nullptr);
   }
   int32_t its = 0;
@@ -516,6 +612,7 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
   c->stats.its_pressure = its;
   if (!c->has_pbc) {  // dp -= int dp / int 1  (:579-591), then ps = p + dp (:604)
     B2_LAUNCH(c, k_sums, pgrid(c, n), 256, n, dp, c->vec(B2_VEC_MQ), c->d_sums, c->partials.p, c->d_counter);
+    allreduce_sum(c, c->d_sums, 2);
     B2_LAUNCH(c, k_shift, pgrid(c, n), 256, n, dp, c->d_sums, 1, 1.0 / c->vol, c->rotational ? nullptr : p,
               c->rotational ? nullptr : ps);
   } else if (!c->rotational) {
@@ -680,6 +777,7 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
   }
   // measure of the domain = sum mQ  (:581-584)
   B2_LAUNCH(c, k_sums, pgrid(c, Q.n_owned), 256, Q.n_owned, c->vec(B2_VEC_MQ), (const double*)nullptr, c->d_sums, c->partials.p, c->d_counter);
+  allreduce_sum(c, c->d_sums, 2);
   read_sums(c, 1);
   c->vol = c->h_sums[0];
   if (Q.n_global == 0) c->sp[B2_SPACE_Q].n_global = Q.n_owned;
@@ -735,13 +833,16 @@ int b2_device_count(void) {
 }
 
 int b2_nccl_unique_id(void* uid) {
-  (void)uid;
-  g_last_error = "NCCL support not built in this library version";
-  return -4;
+  return guarded(nullptr, [&] {
+    g_nccl.load();
+    static_assert(sizeof(ncclUniqueId) == B2_NCCL_UID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    B2_NCCL(g_nccl.GetUniqueId(&id));
+    std::memcpy(uid, &id, sizeof(id));
+  });
 }
 
 int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_uid) {
-  (void)nccl_uid;
   *out = nullptr;
   b2_ctx* c = nullptr;
   int rc = guarded(nullptr, [&] {
@@ -749,7 +850,8 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     B2_CUDA(cudaGetDeviceCount(&ndev));
     B2_REQUIRE(ndev > 0, "no CUDA device visible: libb200ipcs has no CPU fallback");
     B2_REQUIRE(device >= 0 && device < ndev, "device index out of range");
-    B2_REQUIRE(nranks == 1, "multi-rank contexts are not built in this library version");
+    B2_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    B2_REQUIRE(nranks == 1 || nccl_uid != nullptr, "multi-rank contexts need the NCCL unique id of rank 0");
     B2_CUDA(cudaSetDevice(device));
     c = new b2_ctx();
     c->device = device;
@@ -769,7 +871,14 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     for (auto& e : c->ev) B2_CUDA(cudaEventCreate(&e));
     for (auto& e : c->user_ev) B2_CUDA(cudaEventCreate(&e));
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
+    B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (nranks > 1) {
+      g_nccl.load();
+      ncclUniqueId id;
+      std::memcpy(&id, nccl_uid, sizeof(id));
+      B2_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    }
   });
   if (rc != 0) { delete c; return rc; }
   *out = c;
@@ -785,6 +894,8 @@ void b2_destroy(b2_ctx* c) {
   cudaFree(c->d_sums);
   cudaFreeHost(c->h_sums);
   cudaFree(c->d_counter);
+  cudaFree(c->d_red);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->user_ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
@@ -834,8 +945,28 @@ int b2_set_space(b2_ctx* c, int space, int degree, int64_t n_owned, int64_t n_gh
   });
 }
 
-int b2_set_halo(b2_ctx* c, int, int n_neighbors, const int32_t*, const int64_t*, const int32_t*, const int64_t*) {
-  return guarded(c, [&] { B2_REQUIRE(n_neighbors == 0, "multi-rank halo exchange not built in this library version"); });
+int b2_set_halo(b2_ctx* c, int space, int n_neighbors, const int32_t* neighbor_ranks, const int64_t* send_off,
+                const int32_t* send_idx, const int64_t* recv_off) {
+  return guarded(c, [&] {
+    B2_REQUIRE(space == B2_SPACE_V || space == B2_SPACE_Q, "bad space id");
+    B2_REQUIRE(n_neighbors == 0 || c->nranks > 1, "halo plan on a single-rank context");
+    Halo& h = c->halo[space];
+    h.n_neighbors = n_neighbors;
+    h.ranks.assign(neighbor_ranks, neighbor_ranks + n_neighbors);
+    h.send_off.assign(send_off, send_off + n_neighbors + 1);
+    h.recv_off.assign(recv_off, recv_off + n_neighbors + 1);
+    B2_REQUIRE(h.recv_off.back() == c->sp[space].n_ghost, "halo plan does not cover the ghost block");
+    h.d_send_off.alloc(n_neighbors + 1);
+    h.d_recv_off.alloc(n_neighbors + 1);
+    B2_CUDA(cudaMemcpyAsync(h.d_send_off.p, send_off, sizeof(int64_t) * (n_neighbors + 1), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(h.d_recv_off.p, recv_off, sizeof(int64_t) * (n_neighbors + 1), cudaMemcpyHostToDevice, c->stream));
+    const int64_t ns = h.send_off.back(), nr = h.recv_off.back();
+    h.send_idx.alloc(ns);
+    if (ns) B2_CUDA(cudaMemcpyAsync(h.send_idx.p, send_idx, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    h.sendbuf.alloc(ns * B2_MAXK);
+    h.recvbuf.alloc(nr * B2_MAXK);
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
 }
 
 int b2_set_global_sizes(b2_ctx* c, int64_t nv, int64_t nq) {
@@ -968,6 +1099,7 @@ int b2_get_vector(b2_ctx* c, int vec, int comp, double* host, int64_t n) {
     B2_REQUIRE(it != c->vecs.end(), "unknown vector id");
     DVec& v = it->second;
     const int64_t nl = c->sp[v.space].n_local();
+    halo_forward(c, v.space, v.buf.p, v.K);  // ghost copies are refreshed lazily: do it before handing them out
     if (v.K > 1 && comp < 0) {
       B2_REQUIRE(n == nl * v.K, "size mismatch in b2_get_vector");
       B2_LAUNCH(c, k_to_blocked, pgrid(c, n), 256, nl, v.K, (int)nl, v.buf.p, c->stage.p);
@@ -1126,6 +1258,7 @@ int b2_l2_diff_sq(b2_ctx* c, int vec, const double* exact, int64_t n, double* ou
     B2_LAUNCH(c, k_lincomb2, pgrid(c, n), 256, n, 1.0, v.buf.p, -1.0, e, e);
     spmm(c, c->pat[B2_PAT_VV], c->M.p, v.K, e, me, nullptr, nullptr, FIN_NONE, 0, B2_SPACE_V);
     B2_LAUNCH(c, k_dot_all, pgrid(c, S.n_owned), 256, S.n_owned, v.K, (int)nl, me, e, c->d_sums, c->partials.p, c->d_counter);
+    allreduce_sum(c, c->d_sums, 1);
     read_sums(c, 1);
     *out = c->h_sums[0];
   });

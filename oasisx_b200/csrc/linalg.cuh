@@ -151,6 +151,54 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
   }
 }
 
+// Grid-wide sum of N per-thread values followed by either the fused scalar update (single rank) or a
+// store of the raw totals (multi rank: the host enqueues ncclAllReduce + k_kry_finalize next).
+template <int N>
+__device__ __forceinline__ void reduce_finish(double (&v)[N], double* partials, unsigned* counter, int fin,
+                                              KryState* st, double* red_out) {
+  double total[N];
+  if (grid_reduce<N>(v, partials, counter, total) && threadIdx.x == 0) {
+    if (red_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) red_out[i] = total[i];
+    } else {
+      kry_finalize(fin, st, total);
+    }
+  }
+}
+
+__global__ void k_kry_finalize(int fin, KryState* st, const double* __restrict__ totals, int is_init) {
+  if (!is_init && st->done) return;
+  kry_finalize(fin, st, totals);
+}
+
+// ---- halo exchange helpers (multi rank): pack owned entries per neighbour, unpack into ghost slots --
+// send buffer layout: neighbour j owns [K*send_off[j], K*send_off[j+1]) as [k][i]
+__global__ void k_halo_pack(int n_neighbors, const int64_t* __restrict__ send_off, const int* __restrict__ send_idx,
+                            int K, int ld, const double* __restrict__ v, double* __restrict__ buf) {
+  const int64_t total = send_off[n_neighbors];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total * K; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / total);
+    const int64_t i = t - (int64_t)k * total;
+    int j = 0;
+    while (j + 1 < n_neighbors && i >= send_off[j + 1]) ++j;
+    const int64_t cnt = send_off[j + 1] - send_off[j];
+    buf[K * send_off[j] + k * cnt + (i - send_off[j])] = v[(size_t)k * ld + send_idx[i]];
+  }
+}
+__global__ void k_halo_unpack(int n_neighbors, const int64_t* __restrict__ recv_off, int K, int ld, int n_owned,
+                              const double* __restrict__ buf, double* __restrict__ v) {
+  const int64_t total = recv_off[n_neighbors];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total * K; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / total);
+    const int64_t i = t - (int64_t)k * total;
+    int j = 0;
+    while (j + 1 < n_neighbors && i >= recv_off[j + 1]) ++j;
+    const int64_t cnt = recv_off[j + 1] - recv_off[j];
+    v[(size_t)k * ld + n_owned + i] = buf[K * recv_off[j] + k * cnt + (i - recv_off[j])];
+  }
+}
+
 // ---- storage ------------------------------------------------------------------------------------
 // Vectors: component-major (SoA): component k of a velocity-space vector lives at v + k*ld, ld = dofs
 // of the space incl. ghosts.  Square operators (M, K, A on VxV; Ap, MQ on QxQ): sliced ELLPACK with
@@ -221,7 +269,7 @@ __global__ void __launch_bounds__(BLOCK)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
        double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
-       unsigned* counter) {
+       unsigned* counter, double* red_out) {
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -279,10 +327,7 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       }
     }
   }
-  if constexpr (DOT > 0) {
-    double total[ND];
-    if (grid_reduce<ND>(dots, partials, counter, total) && threadIdx.x == 0) kry_finalize(fin, st, total);
-  }
+  if constexpr (DOT > 0) reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
 }
 
 // Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
@@ -573,7 +618,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_cg_init(int64_t n, int ld, const double* __restrict__ b, const double* __restrict__ q,
           const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-          double* __restrict__ p, KryState* st, double* partials, unsigned* counter) {
+          double* __restrict__ p, KryState* st, double* partials, unsigned* counter, double* red_out) {
   double s[3 * K];
 #pragma unroll
   for (int i = 0; i < 3 * K; ++i) s[i] = 0.0;
@@ -594,8 +639,7 @@ k_cg_init(int64_t n, int ld, const double* __restrict__ b, const double* __restr
       s[2 * K + k] = fma(rv, rv, s[2 * K + k]);
     }
   }
-  double total[3 * K];
-  if (grid_reduce<3 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_INIT, st, total);
+  reduce_finish<3 * K>(s, partials, counter, FIN_CG_INIT, st, red_out);
 }
 
 // x += alpha p ; r -= alpha q ; sums rz' = r.dinv r , rr = r.r
@@ -603,7 +647,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_cg_update(int64_t n, int ld, const double* __restrict__ p, const double* __restrict__ q,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-            KryState* st, double* partials, unsigned* counter) {
+            KryState* st, double* partials, unsigned* counter, double* red_out) {
   if (st->done) return;
   double alpha[K];
   bool act[K];
@@ -628,8 +672,7 @@ k_cg_update(int64_t n, int ld, const double* __restrict__ p, const double* __res
       s[K + k] = fma(rv, rv, s[K + k]);
     }
   }
-  double total[2 * K];
-  if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_CG_UPDATE, st, total);
+  reduce_finish<2 * K>(s, partials, counter, FIN_CG_UPDATE, st, red_out);
 }
 
 // p = dinv r + beta p
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(256)
 k_bcgs_init(int64_t n, int ld, const double* __restrict__ b, const double* __restrict__ q,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             double* __restrict__ rhat, double* __restrict__ p, KryState* st, double* partials,
-            unsigned* counter) {
+            unsigned* counter, double* red_out) {
   double s[2 * K];
 #pragma unroll
   for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
@@ -683,8 +726,7 @@ k_bcgs_init(int64_t n, int ld, const double* __restrict__ b, const double* __res
       s[K + k] = fma(rv, rv, s[K + k]);
     }
   }
-  double total[2 * K];
-  if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_INIT, st, total);
+  reduce_finish<2 * K>(s, partials, counter, FIN_BCGS_INIT, st, red_out);
 }
 
 // s = r - alpha v   (in place in r)
@@ -714,7 +756,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_update(int64_t n, int ld, const double* __restrict__ p, const double* __restrict__ t,
               const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
-              KryState* st, double* partials, unsigned* counter) {
+              KryState* st, double* partials, unsigned* counter, double* red_out) {
   if (st->done) return;
   double alpha[K], omega[K];
   bool act[K];
@@ -740,8 +782,7 @@ k_bcgs_update(int64_t n, int ld, const double* __restrict__ p, const double* __r
       s[K + k] = fma(rhat[j], rv, s[K + k]);
     }
   }
-  double total[2 * K];
-  if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) kry_finalize(FIN_BCGS_UPDATE, st, total);
+  reduce_finish<2 * K>(s, partials, counter, FIN_BCGS_UPDATE, st, red_out);
 }
 
 // p = r + beta (p - omega v)

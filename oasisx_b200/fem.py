@@ -158,6 +158,25 @@ class FunctionSpace:
         return np.unique(np.concatenate(dofs)).astype(np.int32)
 
 
+class LocalFunctionSpace(FunctionSpace):
+    """The part of a scalar space one rank holds in a multi-GPU run: owned dofs first, then ghosts
+    (``oasisx_b200.partition.LocalSpace``); same surface as :class:`FunctionSpace`."""
+
+    def __init__(self, gspace: FunctionSpace, lsp, bs: int = 1):
+        self.mesh = gspace.mesh
+        self.degree = gspace.degree
+        self.bs = bs
+        self.element = gspace.element
+        self._g, self._l = gspace._scalar, lsp
+        self._x = lsp.x
+        self._scalar = self if bs == 1 else LocalFunctionSpace(gspace, lsp, 1)
+        self.dofmap = DofMap(lsp.cell_dofs, IndexMap(lsp.n_owned, ghosts=lsp.l2g[lsp.n_owned:], size_global=lsp.n_global), bs)
+
+    def entity_closure_dofs(self, edim: int, entities: np.ndarray) -> np.ndarray:
+        loc = self._l.g2l[self._g.entity_closure_dofs(edim, entities)]
+        return np.sort(loc[loc >= 0]).astype(np.int32)
+
+
 class _SubSpace:
     def __init__(self, parent: FunctionSpace, i: int):
         self.parent, self.i = parent, i

@@ -103,12 +103,25 @@ class FractionalStep_AB_CN:
         if deg_p != 1:
             raise NotImplementedError("pressure element must be P1 on the B200 hot path")
 
-        # spaces (fracstep.py:187-190,212)
-        self._V = _fem.functionspace(mesh, ("Lagrange", deg_u, (gdim,)))
+        # spaces (fracstep.py:187-190,212); with more than one rank every rank keeps the slab of the
+        # mesh it owns plus a ghost layer (oasisx_b200.partition)
+        comm = mesh.comm
+        self._nranks, self._rank = int(getattr(comm, "size", 1)), int(getattr(comm, "rank", 0))
+        gV = _fem.functionspace(mesh, ("Lagrange", deg_u))
+        gQ = _fem.functionspace(mesh, ("Lagrange", deg_p))
+        if self._nranks > 1:
+            from . import partition as _part
+
+            self._lp = lp = _part.partition(mesh, gV, gQ, self._nranks, self._rank)
+            self._V = _fem.LocalFunctionSpace(gV, lp.V, gdim)
+            self._Q = _fem.LocalFunctionSpace(gQ, lp.Q, 1)
+        else:
+            self._lp = None
+            self._V = _fem.functionspace(mesh, ("Lagrange", deg_u, (gdim,)))
+            self._Q = gQ
         self._sol_u = _fem.Function(self._V, name="u")
         self._Vi = [self._V.sub(i).collapse() for i in range(self._V.num_sub_spaces)]
         Vs = self._Vi[0][0]
-        self._Q = _fem.functionspace(mesh, ("Lagrange", deg_p))
         mk = lambda space, name: _fem.Function(space, name=name)
         self._u = [mk(Vs, f"u{i}") for i in range(gdim)]
         self._u1 = [mk(Vs, f"u_{i}1") for i in range(gdim)]
@@ -146,15 +159,29 @@ class FractionalStep_AB_CN:
         body_force = [float(f.value) if isinstance(f, _fem.Constant) else float(f) for f in body_force]
 
         # ---- device context: upload mesh + dof maps, build patterns, preassemble (:265-268) ----
-        self._ctx = ctx = L.Context(device=device)
-        ctx.set_mesh(gdim, mesh.geometry.x, mesh.geometry.dofmap)
-        ctx.set_space(L.SPACE_V, deg_u, Vs.num_dofs, 0, Vs.dofmap.list)
-        ctx.set_space(L.SPACE_Q, deg_p, self._Q.num_dofs, 0, self._Q.dofmap.list)
-        ctx.set_global_sizes(Vs.num_dofs, self._Q.num_dofs)
+        if self._nranks > 1:
+            uid = comm.bcast(L.nccl_unique_id() if self._rank == 0 else None)
+            self._ctx = ctx = L.Context(device=device, nranks=self._nranks, rank=self._rank, nccl_uid=uid)
+            lp = self._lp
+            ctx.set_mesh(gdim, mesh.geometry.x, lp.cell_nodes)
+            ctx.set_space(L.SPACE_V, deg_u, lp.V.n_owned, lp.V.n_ghost, lp.V.cell_dofs)
+            ctx.set_space(L.SPACE_Q, deg_p, lp.Q.n_owned, lp.Q.n_ghost, lp.Q.cell_dofs)
+            ctx.set_global_sizes(lp.V.n_global, lp.Q.n_global)
+            ctx.set_halo(L.SPACE_V, lp.V.halo)
+            ctx.set_halo(L.SPACE_Q, lp.Q.halo)
+            self._nV_owned, self._nQ_owned = lp.V.n_owned, lp.Q.n_owned
+        else:
+            self._ctx = ctx = L.Context(device=device)
+            ctx.set_mesh(gdim, mesh.geometry.x, mesh.geometry.dofmap)
+            ctx.set_space(L.SPACE_V, deg_u, Vs.num_dofs, 0, Vs.dofmap.list)
+            ctx.set_space(L.SPACE_Q, deg_p, self._Q.num_dofs, 0, self._Q.dofmap.list)
+            ctx.set_global_sizes(Vs.num_dofs, self._Q.num_dofs)
+            self._nV_owned, self._nQ_owned = Vs.num_dofs, self._Q.num_dofs
         ctx.build_patterns()
         if deg_u == 2:  # tile-major schedule of the SELL slices (L1 reuse of the gathered vector)
             ctx.set_slice_order(
-                L.PAT_VV, _fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, getattr(mesh, "_lattice", None))
+                L.PAT_VV,
+                _fem.slice_order(Vs.tabulate_dof_coordinates()[: self._nV_owned], self._nV_owned, getattr(mesh, "_lattice", None)),
             )
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
@@ -165,12 +192,11 @@ class FractionalStep_AB_CN:
         pdofs = (
             np.unique(np.concatenate([b.bc.dofs for b in self._bcs_p])) if self._bcs_p else np.zeros(0, np.int32)
         )
-        ctx.set_pressure_bc_dofs(pdofs)
+        ctx.set_pressure_bc_dofs(pdofs[pdofs < self._nQ_owned])
         ctx.preassemble(body_force, False, self._rotational)
 
         # solvers (fracstep.py:230-255)
         solver_options = {} if solver_options is None else solver_options
-        comm = mesh.comm
         self._solver_u = KSPSolver(comm, solver_options.get("tentative"), prefix="tentative_velocity")
         self._solver_p = KSPSolver(comm, solver_options.get("pressure"), prefix="pressure_correction")
         self._solver_c = KSPSolver(comm, solver_options.get("scalar"), prefix="velocity_update")
@@ -186,14 +212,15 @@ class FractionalStep_AB_CN:
             self._solver_p.updateOptions({"ksp_type": "preonly", "pc_type": "lu"})
 
         # matrices visible to callers (test/test_tentative_velocity.py:175)
-        nV, nQ = Vs.num_dofs, self._Q.num_dofs
-        self._A = DeviceMatrix(ctx, L.MAT_A, L.PAT_VV, (nV, nV))
-        self._M = DeviceMatrix(ctx, L.MAT_M, L.PAT_VV, (nV, nV))
-        self._K = DeviceMatrix(ctx, L.MAT_K, L.PAT_VV, (nV, nV))
-        self._Ap = DeviceMatrix(ctx, L.MAT_AP, L.PAT_QQ, (nQ, nQ))
-        self._p_vdxi_Mat = [DeviceMatrix(ctx, L.MAT_P, L.PAT_VQ, (nV, nQ), i) for i in range(gdim)]
-        self._grad_p_Mat = [DeviceMatrix(ctx, L.MAT_G, L.PAT_VQ, (nV, nQ), i) for i in range(gdim)]
-        self._divu_Mat = [DeviceMatrix(ctx, L.MAT_D, L.PAT_QV, (nQ, nV), i) for i in range(gdim)]
+        # (owned rows, local columns = owned + ghosts), like the local part of a PETSc MPIAIJ matrix
+        nV, nQ, cV, cQ = self._nV_owned, self._nQ_owned, Vs.num_dofs, self._Q.num_dofs
+        self._A = DeviceMatrix(ctx, L.MAT_A, L.PAT_VV, (nV, cV))
+        self._M = DeviceMatrix(ctx, L.MAT_M, L.PAT_VV, (nV, cV))
+        self._K = DeviceMatrix(ctx, L.MAT_K, L.PAT_VV, (nV, cV))
+        self._Ap = DeviceMatrix(ctx, L.MAT_AP, L.PAT_QQ, (nQ, cQ))
+        self._p_vdxi_Mat = [DeviceMatrix(ctx, L.MAT_P, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
+        self._grad_p_Mat = [DeviceMatrix(ctx, L.MAT_G, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
+        self._divu_Mat = [DeviceMatrix(ctx, L.MAT_D, L.PAT_QV, (nQ, cV), i) for i in range(gdim)]
         self._solver_p.setOperators(self._Ap)
         self._solver_c.setOperators(self._M)
         self._solver_u.setOperators(self._A)
@@ -229,9 +256,11 @@ class FractionalStep_AB_CN:
                 f.x.mark_device_written()
 
     def _merged_bc_dofs(self, i: int) -> np.ndarray:
+        """Sorted union of the OWNED dofs of all BCs of component i (ghost copies follow by halo)."""
         if not self._bcs_u[i]:
             return np.zeros(0, dtype=np.int32)
-        return np.unique(np.concatenate([bc._dofs for bc in self._bcs_u[i]])).astype(np.int32)
+        d = np.unique(np.concatenate([bc._dofs for bc in self._bcs_u[i]]))
+        return d[d < self._nV_owned].astype(np.int32)
 
     def _upload_bcs(self):
         """Send g_i on the merged BC dof list of each component; later BCs in the list win on shared
@@ -243,14 +272,13 @@ class FractionalStep_AB_CN:
             version = tuple(bc._version for bc in bcl)
             if version == self._bc_versions[i]:
                 continue
-            if len(bcl) == 1:
-                merged = vals[0] if len(vals[0]) == len(self._bc_dofs[i]) else None
+            if len(bcl) == 1 and len(vals[0]) == len(self._bc_dofs[i]):
+                merged = vals[0]
             else:
-                merged = None
-            if merged is None:
                 merged = np.zeros(len(self._bc_dofs[i]))
                 for bc, v in zip(bcl, vals):
-                    merged[np.searchsorted(self._bc_dofs[i], bc._dofs)] = v
+                    own = bc._dofs < self._nV_owned
+                    merged[np.searchsorted(self._bc_dofs[i], bc._dofs[own])] = v[own]
             self._ctx.set_velocity_bc_values(i, merged)
             self._bc_versions[i] = version
 

@@ -1,0 +1,50 @@
+"""Worker of the multi-rank GPU parity test: launched with torch.distributed.run, one rank per GPU.
+Each rank advances the 3D Taylor-Green problem on its slab and compares its local fields with the
+single-process CPU oracle at the same global dofs."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+from oasisx_b200.comm import HostComm  # noqa: E402
+from problems import TaylorGreen, make_mesh, make_oracle, make_solver, relerr, vscale  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+krylov = len(sys.argv) > 3 and sys.argv[3] == "krylov"
+comm = HostComm.from_env()
+dt, nu = 0.005, 0.01
+tg = TaylorGreen(nu, 3)
+msh = make_mesh(3, N, comm)
+opts = None
+if krylov:
+    opts = {k: {"ksp_type": t, "pc_type": "jacobi", "ksp_rtol": 1e-11}
+            for k, t in (("tentative", "bcgs"), ("pressure", "cg"), ("scalar", "cg"))}
+s = make_solver(msh, 2, tg, dt, solver_options=opts, device=int(os.environ.get("LOCAL_RANK", "0")))
+tg2 = TaylorGreen(nu, 3)
+o = make_oracle(make_mesh(3, N), 2, tg2, dt)
+lp = s._lp
+tg.t_u = tg2.t_u = 0.0
+tg.t_p = tg2.t_p = -dt / 2
+worst = 0.0
+for n in range(steps):
+    for t in (tg, tg2):
+        t.t_u += dt
+        t.t_p += dt
+    d1 = s.solve(dt, nu, max_iter=1)
+    d2 = o.solve(dt, nu, max_iter=1)
+    for i in range(3):
+        worst = max(worst, relerr(s._u[i].x.array_ro(), o.u[i][lp.V.l2g], vscale(o.u)))
+        worst = max(worst, relerr(s._u1[i].x.array_ro(), o.u1[i][lp.V.l2g], vscale(o.u1)))
+    worst = max(worst, relerr(s._p.x.array_ro(), o.p[lp.Q.l2g]))
+    assert abs(d1 - d2) <= 1e-6 * d2, (d1, d2)
+st = s.stats()
+worst = comm.allreduce(worst, "max")
+print(f"rank {comm.rank}/{comm.size}: max rel err {worst:.2e} halos {st.halo_exchanges} allreduces {st.allreduces} "
+      f"owned V {lp.V.n_owned} ghosts {lp.V.n_ghost}", flush=True)
+assert worst <= (1e-7 if krylov else 1e-8), worst
+assert st.halo_exchanges > 0 and st.allreduces > 0
+comm.Barrier()
+print("MR_OK", comm.rank, flush=True)

@@ -31,10 +31,10 @@ class TaylorGreen:
         return [self.eval_x, self.eval_y, self.eval_z][: self.gdim]
 
 
-def make_mesh(gdim: int, N: int):
+def make_mesh(gdim: int, N: int, comm=None):
     if gdim == 2:
-        return bmesh.create_rectangle(None, [[-1.0, -1.0], [1.0, 1.0]], [N, N])
-    return bmesh.create_box(None, [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], [N, N, N])
+        return bmesh.create_rectangle(comm, [[-1.0, -1.0], [1.0, 1.0]], [N, N])
+    return bmesh.create_box(comm, [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], [N, N, N])
 
 
 def boundary_facets(msh):
