@@ -1,0 +1,576 @@
+// CPU ORACLE / CPU BASELINE (test + measurement infrastructure -- never linked into the product).
+//
+// C++17/OpenMP restatement of the reference's IPCS fractional step
+// (/root/reference/src/oasisx/fracstep.py:277-705; algebra in SURVEY.md Appendix A) for problem
+// sizes the numpy/SuperLU oracle (oracle/ipcs_oracle.py) cannot reach.  It follows the reference's
+// own structure: per-component solves with one shared matrix (fracstep.py:516-524,613-656), the
+// "matrix-vector" RHS strategy A.scale/axpy/axpy/mult (fracstep.py:438-469), CSR (int32/FP64)
+// storage, BiCGStab+Jacobi for the tentative velocity, CG+Jacobi for the pressure (null space
+// projected, fracstep.py:573-591) and for the mass solves -- the Krylov choices of SURVEY.md 8(d),
+// because the reference's DOLFINx/PETSc/MUMPS stack cannot be installed here.
+//
+// PARITY UNPINNED for the same reason as oracle/ipcs_oracle.py; it is pinned against that numpy
+// oracle in tests/test_cpu_port.py.  Only tests/ and bench.py's cpu_baseline / --impl reference legs
+// load this library.  Build: oracle/build_cpu.py  (g++ -O3 -march=native -fopenmp).
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#define B2_TABLE_QUAL static const
+#include "../oasisx_b200/csrc/ref_tables.h"
+
+namespace {
+
+struct Tables {
+  int d, nv, nq;
+  const double *MV, *SV, *T, *PX, *GX, *SQ, *MQ, *LV, *LQ;
+};
+
+#define TBL(DD, PP)                                                                                          \
+  Tables { DD, (int)(sizeof(REF_D##DD##P##PP##_LV) / sizeof(double)), DD + 1, &REF_D##DD##P##PP##_MV[0][0],          \
+           &REF_D##DD##P##PP##_SV[0][0][0][0], &REF_D##DD##P##PP##_T[0][0][0][0], &REF_D##DD##P##PP##_PX[0][0][0], \
+           &REF_D##DD##P##PP##_GX[0][0][0], &REF_D##DD##P##PP##_SQ[0][0][0][0], &REF_D##DD##P##PP##_MQ[0][0],      \
+           &REF_D##DD##P##PP##_LV[0], &REF_D##DD##P##PP##_LQ[0] }
+
+Tables tables_for(int d, int deg) {
+  if (d == 2 && deg == 1) return TBL(2, 1);
+  if (d == 2 && deg == 2) return TBL(2, 2);
+  if (d == 3 && deg == 1) return TBL(3, 1);
+  return TBL(3, 2);
+}
+
+struct Csr {
+  int n_rows = 0, n_cols = 0;
+  std::vector<int> ptr, col;
+  int find(int r, int c) const {
+    const int* b = col.data() + ptr[r];
+    const int* e = col.data() + ptr[r + 1];
+    return (int)(std::lower_bound(b, e, c) - col.data());
+  }
+};
+
+struct Geo {
+  double Kinv[3][3];
+  double detJ;
+};
+
+struct Ctx {
+  int d, degv;
+  Tables t;
+  int64_t n_nodes, n_cells, nV, nQ;
+  std::vector<double> x;
+  std::vector<int> cn, vd, qd;
+  // dof -> (cell, local index) adjacency
+  std::vector<int> vadj_ptr, vadj_cell, vadj_loc, qadj_ptr, qadj_cell, qadj_loc;
+  Csr vv, vq, qv, qq;
+  std::vector<double> M, K, A, Ap, P[3], G[3], D[3];
+  std::vector<double> u[3], u1[3], u2[3], uab[3], rhs1[3], bfirst[3], b0[3], wrk, b3;
+  std::vector<double> ps, p, dp, b2, mQ;
+  std::vector<int> bc_dofs[3];
+  std::vector<double> bc_vals[3];
+  std::vector<char> is_bc;
+  std::vector<double> dinvA, dinvM, dinvAp;
+  double vol = 0, rtol = 1e-10;
+  int maxit = 10000, nonzero = 0;
+  int its_t = 0, its_p = 0, its_u = 0;
+};
+
+Geo geometry(const Ctx& c, int64_t cell) {
+  Geo g;
+  const int d = c.d;
+  double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const int* nodes = &c.cn[cell * (d + 1)];
+  for (int k = 0; k < d; ++k)
+    for (int dl = 0; dl < d; ++dl) J[k][dl] = c.x[3 * (size_t)nodes[dl + 1] + k] - c.x[3 * (size_t)nodes[0] + k];
+  if (d == 2) {
+    double det = J[0][0] * J[1][1] - J[0][1] * J[1][0], id = 1.0 / det;
+    g.Kinv[0][0] = J[1][1] * id; g.Kinv[0][1] = -J[0][1] * id;
+    g.Kinv[1][0] = -J[1][0] * id; g.Kinv[1][1] = J[0][0] * id;
+    g.detJ = std::fabs(det);
+  } else {
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+           c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
+    g.Kinv[0][0] = c00 * id; g.Kinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    g.Kinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    g.Kinv[1][0] = c01 * id; g.Kinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    g.Kinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    g.Kinv[2][0] = c02 * id; g.Kinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    g.Kinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    g.detJ = std::fabs(det);
+  }
+  return g;
+}
+
+void build_adj(int64_t n_dofs, int64_t n_cells, int nd, const std::vector<int>& cd, std::vector<int>& ptr,
+               std::vector<int>& cell, std::vector<int>& loc) {
+  ptr.assign(n_dofs + 1, 0);
+  for (int64_t i = 0; i < n_cells * nd; ++i) ptr[cd[i] + 1]++;
+  for (int64_t i = 0; i < n_dofs; ++i) ptr[i + 1] += ptr[i];
+  cell.resize(ptr[n_dofs]);
+  loc.resize(ptr[n_dofs]);
+  std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+  for (int64_t c = 0; c < n_cells; ++c)
+    for (int i = 0; i < nd; ++i) {
+      int p = fill[cd[c * nd + i]]++;
+      cell[p] = (int)c;
+      loc[p] = i;
+    }
+}
+
+// create_matrix: row r couples to every column dof of every cell containing r; sorted columns
+void build_pattern(int64_t n_rows, int64_t n_cols, const std::vector<int>& adj_ptr, const std::vector<int>& adj_cell,
+                   int ncd, const std::vector<int>& coldofs, Csr& out) {
+  out.n_rows = (int)n_rows;
+  out.n_cols = (int)n_cols;
+  out.ptr.assign(n_rows + 1, 0);
+  std::vector<int> cnt(n_rows);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t r = 0; r < n_rows; ++r) {
+      tmp.clear();
+      for (int a = adj_ptr[r]; a < adj_ptr[r + 1]; ++a)
+        for (int j = 0; j < ncd; ++j) tmp.push_back(coldofs[(size_t)adj_cell[a] * ncd + j]);
+      std::sort(tmp.begin(), tmp.end());
+      cnt[r] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    }
+  }
+  for (int64_t r = 0; r < n_rows; ++r) out.ptr[r + 1] = out.ptr[r] + cnt[r];
+  out.col.resize(out.ptr[n_rows]);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t r = 0; r < n_rows; ++r) {
+      tmp.clear();
+      for (int a = adj_ptr[r]; a < adj_ptr[r + 1]; ++a)
+        for (int j = 0; j < ncd; ++j) tmp.push_back(coldofs[(size_t)adj_cell[a] * ncd + j]);
+      std::sort(tmp.begin(), tmp.end());
+      auto e = std::unique(tmp.begin(), tmp.end());
+      std::copy(tmp.begin(), e, out.col.begin() + out.ptr[r]);
+    }
+  }
+}
+
+void spmv(const Csr& m, const std::vector<double>& v, const double* x, double* y) {
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < m.n_rows; ++r) {
+    double s = 0;
+    for (int p = m.ptr[r]; p < m.ptr[r + 1]; ++p) s += v[p] * x[m.col[p]];
+    y[r] = s;
+  }
+}
+
+double dot(int64_t n, const double* a, const double* b) {
+  double s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+// PCG with Jacobi; returns iterations (negative: not converged)
+int cg(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::vector<double>& dinv, const double* b,
+       double* x) {
+  const int64_t n = m.n_rows;
+  std::vector<double> r(n), z(n), p(n), q(n);
+  if (c.nonzero) {
+    spmv(m, vals, x, q.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) r[i] = b[i] - q[i];
+  } else {
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) { r[i] = b[i]; x[i] = 0; }
+  }
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) { z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+  double rz = dot(n, r.data(), z.data()), bb = dot(n, b, b), rr = dot(n, r.data(), r.data());
+  const double tol2 = std::max(c.rtol * c.rtol * bb, 1e-100);
+  int it = 0;
+  while (rr > tol2 && it < c.maxit) {
+    spmv(m, vals, p.data(), q.data());
+    const double alpha = rz / dot(n, p.data(), q.data());
+    double rz2 = 0, rr2 = 0;
+#pragma omp parallel for reduction(+ : rz2, rr2)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
+      z[i] = dinv[i] * r[i];
+      rz2 += r[i] * z[i];
+      rr2 += r[i] * r[i];
+    }
+    const double beta = rz2 / rz;
+    rz = rz2;
+    rr = rr2;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    ++it;
+  }
+  return rr <= tol2 ? it : -it;
+}
+
+// BiCGStab, left Jacobi (PETSc's default side for bcgs [ext]); convergence on |D^-1 r| <= rtol |D^-1 b|
+int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::vector<double>& dinv,
+             const double* b, double* x) {
+  const int64_t n = m.n_rows;
+  std::vector<double> r(n), rh(n), p(n), v(n), t(n), tmp(n);
+  auto apply = [&](const double* in, double* out) {  // out = D^-1 A in
+    spmv(m, vals, in, out);
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) out[i] *= dinv[i];
+  };
+  double bb = 0;
+  if (c.nonzero) apply(x, tmp.data());
+#pragma omp parallel for reduction(+ : bb)
+  for (int64_t i = 0; i < n; ++i) {
+    const double bi = dinv[i] * b[i];
+    bb += bi * bi;
+    if (c.nonzero) r[i] = bi - tmp[i];
+    else { r[i] = bi; x[i] = 0; }
+    rh[i] = r[i];
+    p[i] = r[i];
+  }
+  double rr = dot(n, r.data(), r.data()), rho = rr;
+  const double tol2 = std::max(c.rtol * c.rtol * bb, 1e-100);
+  int it = 0;
+  while (rr > tol2 && it < c.maxit) {
+    apply(p.data(), v.data());
+    const double alpha = rho / dot(n, rh.data(), v.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) r[i] -= alpha * v[i];  // s
+    apply(r.data(), t.data());
+    const double tt = dot(n, t.data(), t.data());
+    const double omega = tt > 0 ? dot(n, t.data(), r.data()) / tt : 0.0;
+    double rr2 = 0, rho2 = 0;
+#pragma omp parallel for reduction(+ : rr2, rho2)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * p[i] + omega * r[i];
+      r[i] -= omega * t[i];
+      rr2 += r[i] * r[i];
+      rho2 += rh[i] * r[i];
+    }
+    rr = rr2;
+    ++it;
+    if (rr <= tol2) break;
+    const double beta = (rho2 / rho) * (alpha / omega);
+    rho = rho2;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+  }
+  return rr <= tol2 ? it : -it;
+}
+
+// row-wise (gather) assembly of a square operator on V or Q: kind 0 mass, 1 stiffness, 2 convection
+void assemble_square(Ctx& c, bool onV, int kind, std::vector<double>& vals) {
+  const Tables& t = c.t;
+  const int d = c.d, nd = onV ? t.nv : t.nq;
+  const Csr& pat = onV ? c.vv : c.qq;
+  const std::vector<int>& cd = onV ? c.vd : c.qd;
+  const auto& aptr = onV ? c.vadj_ptr : c.qadj_ptr;
+  const auto& acell = onV ? c.vadj_cell : c.qadj_cell;
+  const auto& aloc = onV ? c.vadj_loc : c.qadj_loc;
+  const double* Mref = onV ? t.MV : t.MQ;
+  const double* Sref = onV ? t.SV : t.SQ;
+  vals.assign(pat.col.size(), 0.0);
+#pragma omp parallel for schedule(dynamic, 512)
+  for (int r = 0; r < pat.n_rows; ++r) {
+    for (int a = aptr[r]; a < aptr[r + 1]; ++a) {
+      const int64_t cell = acell[a];
+      const int i = aloc[a];
+      const Geo g = geometry(c, cell);
+      const int* dofs = &cd[cell * nd];
+      double row[10];
+      if (kind == 0) {
+        for (int j = 0; j < nd; ++j) row[j] = g.detJ * Mref[i * nd + j];
+      } else if (kind == 1) {
+        double G[3][3];
+        for (int a2 = 0; a2 < d; ++a2)
+          for (int b2 = 0; b2 < d; ++b2) {
+            double s = 0;
+            for (int k = 0; k < d; ++k) s += g.Kinv[a2][k] * g.Kinv[b2][k];
+            G[a2][b2] = s * g.detJ;
+          }
+        for (int j = 0; j < nd; ++j) {
+          double s = 0;
+          for (int a2 = 0; a2 < d; ++a2)
+            for (int b2 = 0; b2 < d; ++b2) s += G[a2][b2] * Sref[((a2 * d + b2) * nd + i) * nd + j];
+          row[j] = s;
+        }
+      } else {  // C[i,j] = |detJ| sum_{a,dl} w[a][dl] T[a][dl][i][j]   (fracstep.py:355-358)
+        for (int j = 0; j < nd; ++j) row[j] = 0;
+        for (int a2 = 0; a2 < nd; ++a2)
+          for (int dl = 0; dl < d; ++dl) {
+            double w = 0;
+            for (int k = 0; k < d; ++k) w += g.Kinv[dl][k] * c.uab[k][dofs[a2]];
+            w *= g.detJ;
+            const double* Trow = &t.T[(((size_t)a2 * d + dl) * nd + i) * nd];
+            for (int j = 0; j < nd; ++j) row[j] += w * Trow[j];
+          }
+      }
+      for (int j = 0; j < nd; ++j) vals[pat.find(r, dofs[j])] += row[j];
+    }
+  }
+}
+
+void assemble_rect(Ctx& c) {
+  const Tables& t = c.t;
+  const int d = c.d;
+  for (int k = 0; k < d; ++k) {
+    c.P[k].assign(c.vq.col.size(), 0.0);
+    c.G[k].assign(c.vq.col.size(), 0.0);
+    c.D[k].assign(c.qv.col.size(), 0.0);
+  }
+#pragma omp parallel for schedule(dynamic, 512)
+  for (int r = 0; r < c.vq.n_rows; ++r)
+    for (int a = c.vadj_ptr[r]; a < c.vadj_ptr[r + 1]; ++a) {
+      const int64_t cell = c.vadj_cell[a];
+      const int j = c.vadj_loc[a];
+      const Geo g = geometry(c, cell);
+      for (int q = 0; q < t.nq; ++q) {
+        const int pos = c.vq.find(r, c.qd[cell * t.nq + q]);
+        for (int k = 0; k < d; ++k) {
+          double pv = 0, gv = 0;
+          for (int dl = 0; dl < d; ++dl) {
+            pv += g.Kinv[dl][k] * t.PX[(dl * t.nv + j) * t.nq + q];
+            gv += g.Kinv[dl][k] * t.GX[(dl * t.nv + j) * t.nq + q];
+          }
+          c.P[k][pos] += g.detJ * pv;
+          c.G[k][pos] += g.detJ * gv;
+        }
+      }
+    }
+#pragma omp parallel for schedule(dynamic, 512)
+  for (int r = 0; r < c.qv.n_rows; ++r)
+    for (int a = c.qadj_ptr[r]; a < c.qadj_ptr[r + 1]; ++a) {
+      const int64_t cell = c.qadj_cell[a];
+      const int q = c.qadj_loc[a];
+      const Geo g = geometry(c, cell);
+      for (int j = 0; j < t.nv; ++j) {
+        const int pos = c.qv.find(r, c.vd[cell * t.nv + j]);
+        for (int k = 0; k < d; ++k) {
+          double pv = 0;
+          for (int dl = 0; dl < d; ++dl) pv += g.Kinv[dl][k] * t.PX[(dl * t.nv + j) * t.nq + q];
+          c.D[k][pos] += g.detJ * pv;
+        }
+      }
+    }
+}
+
+void inv_diag(const Csr& m, const std::vector<double>& v, std::vector<double>& dinv) {
+  dinv.assign(m.n_rows, 1.0);
+#pragma omp parallel for
+  for (int r = 0; r < m.n_rows; ++r) dinv[r] = 1.0 / v[m.find(r, r)];
+}
+
+}  // namespace
+
+extern "C" {
+
+int ipcs_cpu_threads(void) { return omp_get_max_threads(); }
+
+void* ipcs_cpu_create(int gdim, int deg_v, int64_t n_nodes, const double* x, int64_t n_cells, const int* cell_nodes,
+                      int64_t nV, const int* vdofs, int64_t nQ, const int* qdofs) {
+  Ctx* c = new Ctx();
+  c->d = gdim;
+  c->degv = deg_v;
+  c->t = tables_for(gdim, deg_v);
+  c->n_nodes = n_nodes;
+  c->n_cells = n_cells;
+  c->nV = nV;
+  c->nQ = nQ;
+  c->x.assign(x, x + 3 * n_nodes);
+  c->cn.assign(cell_nodes, cell_nodes + n_cells * (gdim + 1));
+  c->vd.assign(vdofs, vdofs + n_cells * c->t.nv);
+  c->qd.assign(qdofs, qdofs + n_cells * c->t.nq);
+  build_adj(nV, n_cells, c->t.nv, c->vd, c->vadj_ptr, c->vadj_cell, c->vadj_loc);
+  build_adj(nQ, n_cells, c->t.nq, c->qd, c->qadj_ptr, c->qadj_cell, c->qadj_loc);
+  build_pattern(nV, nV, c->vadj_ptr, c->vadj_cell, c->t.nv, c->vd, c->vv);
+  build_pattern(nV, nQ, c->vadj_ptr, c->vadj_cell, c->t.nq, c->qd, c->vq);
+  build_pattern(nQ, nV, c->qadj_ptr, c->qadj_cell, c->t.nv, c->vd, c->qv);
+  build_pattern(nQ, nQ, c->qadj_ptr, c->qadj_cell, c->t.nq, c->qd, c->qq);
+  for (int k = 0; k < gdim; ++k)
+    for (auto* v : {&c->u[k], &c->u1[k], &c->u2[k], &c->uab[k], &c->rhs1[k], &c->bfirst[k], &c->b0[k]}) v->assign(nV, 0.0);
+  c->wrk.assign(nV, 0.0);
+  c->b3.assign(nV, 0.0);
+  for (auto* v : {&c->ps, &c->p, &c->dp, &c->b2, &c->mQ}) v->assign(nQ, 0.0);
+  c->is_bc.assign(nV, 0);
+  return c;
+}
+
+void ipcs_cpu_destroy(void* h) { delete (Ctx*)h; }
+
+int64_t ipcs_cpu_nnz(void* h, int which) {
+  Ctx* c = (Ctx*)h;
+  const Csr* p[4] = {&c->vv, &c->vq, &c->qv, &c->qq};
+  return (int64_t)p[which]->col.size();
+}
+
+void ipcs_cpu_get_pattern(void* h, int which, int* indptr, int* indices) {
+  Ctx* c = (Ctx*)h;
+  const Csr* p[4] = {&c->vv, &c->vq, &c->qv, &c->qq};
+  std::copy(p[which]->ptr.begin(), p[which]->ptr.end(), indptr);
+  std::copy(p[which]->col.begin(), p[which]->col.end(), indices);
+}
+
+void ipcs_cpu_set_bc(void* h, int comp, int64_t n, const int* dofs) {
+  Ctx* c = (Ctx*)h;
+  c->bc_dofs[comp].assign(dofs, dofs + n);
+  c->bc_vals[comp].assign(n, 0.0);
+  if (comp == 0)  // the shared matrix takes component 0's dof set (fracstep.py:470-472)
+    for (int64_t i = 0; i < n; ++i) c->is_bc[dofs[i]] = 1;
+}
+
+void ipcs_cpu_set_bc_values(void* h, int comp, const double* vals) {
+  Ctx* c = (Ctx*)h;
+  std::copy(vals, vals + c->bc_vals[comp].size(), c->bc_vals[comp].begin());
+}
+
+void ipcs_cpu_set_options(void* h, double rtol, int maxit, int nonzero_guess) {
+  Ctx* c = (Ctx*)h;
+  c->rtol = rtol;
+  c->maxit = maxit;
+  c->nonzero = nonzero_guess;
+}
+
+// _preassemble (fracstep.py:360-409), no pressure BCs (the Taylor-Green / cavity configuration)
+void ipcs_cpu_preassemble(void* h, const double* f) {
+  Ctx* c = (Ctx*)h;
+  assemble_square(*c, true, 0, c->M);
+  assemble_square(*c, true, 1, c->K);
+  assemble_square(*c, false, 1, c->Ap);
+  assemble_rect(*c);
+  c->A.assign(c->vv.col.size(), 0.0);
+  const Tables& t = c->t;
+  for (int64_t cell = 0; cell < c->n_cells; ++cell) {
+    const Geo g = geometry(*c, cell);
+    for (int j = 0; j < t.nv; ++j)
+      for (int k = 0; k < c->d; ++k) c->b0[k][c->vd[cell * t.nv + j]] += (f ? f[k] : 0.0) * g.detJ * t.LV[j];
+    for (int q = 0; q < t.nq; ++q) c->mQ[c->qd[cell * t.nq + q]] += g.detJ * t.LQ[q];
+  }
+  c->vol = 0;
+  for (double v : c->mQ) c->vol += v;
+  inv_diag(c->vv, c->M, c->dinvM);
+  inv_diag(c->qq, c->Ap, c->dinvAp);
+}
+
+static std::vector<double>* vec_of(Ctx* c, int which, int comp) {
+  switch (which) {
+    case 0: return &c->u[comp];
+    case 1: return &c->u1[comp];
+    case 2: return &c->u2[comp];
+    case 3: return &c->p;
+    case 4: return &c->ps;
+    case 5: return &c->dp;
+    case 6: return &c->rhs1[comp];
+    case 7: return &c->bfirst[comp];
+    case 8: return &c->b2;
+    default: return nullptr;
+  }
+}
+void ipcs_cpu_set_vec(void* h, int which, int comp, const double* v) {
+  auto* d = vec_of((Ctx*)h, which, comp);
+  std::copy(v, v + d->size(), d->begin());
+}
+void ipcs_cpu_get_vec(void* h, int which, int comp, double* v) {
+  auto* d = vec_of((Ctx*)h, which, comp);
+  std::copy(d->begin(), d->end(), v);
+}
+void ipcs_cpu_get_matrix(void* h, int which, int comp, double* v) {
+  Ctx* c = (Ctx*)h;
+  const std::vector<double>* m[7] = {&c->M, &c->K, &c->A, &c->Ap, &c->P[comp], &c->G[comp], &c->D[comp]};
+  std::copy(m[which]->begin(), m[which]->end(), v);
+}
+
+// one time step, fracstep.py:660-696 with max_iter = 1; returns 0 or a negative stage id on divergence
+int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
+  Ctx* c = (Ctx*)h;
+  const int d = c->d;
+  const int64_t nV = c->nV, nQ = c->nQ;
+  c->ps = c->p;  // :673
+  // ---- assemble_first (:411-472)
+  for (int k = 0; k < d; ++k) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < nV; ++i) c->uab[k][i] = 1.5 * c->u1[k][i] - 0.5 * c->u2[k][i];
+  }
+  assemble_square(*c, true, 2, c->A);  // A = C(uab)
+  const int64_t nnz = (int64_t)c->A.size();
+#pragma omp parallel for
+  for (int64_t p = 0; p < nnz; ++p) c->A[p] = -0.5 * c->A[p] + (1.0 / dt) * c->M[p] + (-0.5 * nu) * c->K[p];  // :438-442
+  for (int k = 0; k < d; ++k) {
+    spmv(c->vv, c->A, c->u1[k].data(), c->wrk.data());  // :452
+#pragma omp parallel for
+    for (int64_t i = 0; i < nV; ++i) c->bfirst[k][i] = c->wrk[i] + c->b0[k][i];
+  }
+#pragma omp parallel for
+  for (int64_t p = 0; p < nnz; ++p) c->A[p] = -c->A[p] + (2.0 / dt) * c->M[p];  // :468-469
+#pragma omp parallel for
+  for (int r = 0; r < c->vv.n_rows; ++r)
+    if (c->is_bc[r])
+      for (int p = c->vv.ptr[r]; p < c->vv.ptr[r + 1]; ++p) c->A[p] = (c->vv.col[p] == r) ? 1.0 : 0.0;  // :471-472
+  inv_diag(c->vv, c->A, c->dinvA);
+  // ---- tentative velocity (:474-525)
+  c->its_t = 0;
+  for (int k = 0; k < d; ++k) {
+    spmv(c->vq, c->P[k], c->ps.data(), c->wrk.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < nV; ++i) c->rhs1[k][i] = c->bfirst[k][i] + c->wrk[i];
+    for (size_t i = 0; i < c->bc_dofs[k].size(); ++i) c->rhs1[k][c->bc_dofs[k][i]] = c->bc_vals[k][i];
+    int it = bicgstab(*c, c->vv, c->A, c->dinvA, c->rhs1[k].data(), c->u[k].data());
+    if (it < 0) return -1;
+    c->its_t = std::max(c->its_t, it);
+  }
+  // ---- pressure correction (:527-605)
+  std::fill(c->b2.begin(), c->b2.end(), 0.0);
+  std::vector<double> wq(nQ);
+  for (int k = 0; k < d; ++k) {
+    spmv(c->qv, c->D[k], c->u[k].data(), wq.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < nQ; ++i) c->b2[i] += wq[i];
+  }
+  double mean = 0;
+#pragma omp parallel for reduction(+ : mean)
+  for (int64_t i = 0; i < nQ; ++i) {
+    c->b2[i] *= -1.0 / dt;
+    mean += c->b2[i];
+  }
+  mean /= (double)nQ;
+#pragma omp parallel for
+  for (int64_t i = 0; i < nQ; ++i) c->b2[i] -= mean;  // nullspace.remove, :573-574
+  c->its_p = cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
+  if (c->its_p < 0) return -2;
+  const double avg = dot(nQ, c->mQ.data(), c->dp.data()) / c->vol;  // :579-591
+#pragma omp parallel for
+  for (int64_t i = 0; i < nQ; ++i) {
+    c->dp[i] -= avg;
+    c->ps[i] = c->p[i] + c->dp[i];  // :604
+  }
+  // ---- velocity update (:607-658)
+  c->its_u = 0;
+  for (int k = 0; k < d; ++k) {
+    spmv(c->vv, c->M, c->u[k].data(), c->b3.data());
+    spmv(c->vq, c->G[k], c->dp.data(), c->wrk.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < nV; ++i) c->b3[i] -= dt * c->wrk[i];
+    int it = cg(*c, c->vv, c->M, c->dinvM, c->b3.data(), c->u[k].data());
+    if (it < 0) return -3;
+    c->its_u = std::max(c->its_u, it);
+  }
+  for (int k = 0; k < d; ++k) {  // :689-693
+    c->u2[k] = c->u1[k];
+    c->u1[k] = c->u[k];
+  }
+  c->p = c->ps;
+  if (its) {
+    its[0] = c->its_t;
+    its[1] = c->its_p;
+    its[2] = c->its_u;
+  }
+  return 0;
+}
+
+}  // extern "C"

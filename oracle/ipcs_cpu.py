@@ -1,0 +1,108 @@
+"""ctypes wrapper of oracle/libipcs_cpu.so (C++/OpenMP CPU restatement; test + baseline infrastructure,
+never imported by the product path)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build_cpu import LIB, build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        L = C.CDLL(LIB)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.ipcs_cpu_threads.restype = i32
+        L.ipcs_cpu_create.restype = vp
+        L.ipcs_cpu_create.argtypes = [i32, i32, i64, vp, i64, vp, i64, vp, i64, vp]
+        L.ipcs_cpu_destroy.argtypes = [vp]
+        L.ipcs_cpu_nnz.restype = i64
+        L.ipcs_cpu_nnz.argtypes = [vp, i32]
+        L.ipcs_cpu_get_pattern.argtypes = [vp, i32, vp, vp]
+        L.ipcs_cpu_set_bc.argtypes = [vp, i32, i64, vp]
+        L.ipcs_cpu_set_bc_values.argtypes = [vp, i32, vp]
+        L.ipcs_cpu_set_options.argtypes = [vp, dbl, i32, i32]
+        L.ipcs_cpu_preassemble.argtypes = [vp, vp]
+        L.ipcs_cpu_set_vec.argtypes = [vp, i32, i32, vp]
+        L.ipcs_cpu_get_vec.argtypes = [vp, i32, i32, vp]
+        L.ipcs_cpu_get_matrix.argtypes = [vp, i32, i32, vp]
+        L.ipcs_cpu_step.restype = i32
+        L.ipcs_cpu_step.argtypes = [vp, dbl, dbl, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+U, U1, U2, P, PS, DP, RHS1, BFIRST, B2 = range(9)
+
+
+class CpuIPCS:
+    """Same problem description as ``OracleIPCS`` (one BC per component: (dofs, callable))."""
+
+    def __init__(self, x, cells, d, vdofs, qdofs, xV, xQ, deg_v, bcs_u, rtol=1e-10, nonzero_guess=False, body_force=None):
+        L = lib()
+        self.L, self.d = L, d
+        x = np.ascontiguousarray(x, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32)
+        vdofs = np.ascontiguousarray(vdofs, np.int32)
+        qdofs = np.ascontiguousarray(qdofs, np.int32)
+        self.nV, self.nQ, self.xV, self.xQ = xV.shape[0], xQ.shape[0], xV, xQ
+        self.h = C.c_void_p(L.ipcs_cpu_create(d, deg_v, x.shape[0], _p(x), cells.shape[0], _p(cells), self.nV, _p(vdofs),
+                                              self.nQ, _p(qdofs)))
+        self.bcs_u = bcs_u
+        for i, bcl in enumerate(bcs_u):
+            dofs = np.ascontiguousarray(bcl[0][0], np.int32)
+            L.ipcs_cpu_set_bc(self.h, i, len(dofs), _p(dofs))
+        L.ipcs_cpu_set_options(self.h, rtol, 10000, int(nonzero_guess))
+        f = np.ascontiguousarray(list(body_force or [0.0] * d) + [0.0] * (3 - d), np.float64)
+        L.ipcs_cpu_preassemble(self.h, _p(f))
+        self.its = np.zeros(3, np.int32)
+
+    def __del__(self):
+        try:
+            self.L.ipcs_cpu_destroy(self.h)
+        except Exception:
+            pass
+
+    def update_bcs(self):
+        for i, bcl in enumerate(self.bcs_u):
+            dofs, val = bcl[0]
+            v = np.ascontiguousarray(val(self.xV[dofs].T), np.float64)
+            self.L.ipcs_cpu_set_bc_values(self.h, i, _p(v))
+
+    def set(self, which, comp, v):
+        v = np.ascontiguousarray(v, np.float64)
+        self.L.ipcs_cpu_set_vec(self.h, which, comp, _p(v))
+
+    def get(self, which, comp=0):
+        out = np.empty(self.nQ if which in (P, PS, DP, B2) else self.nV)
+        self.L.ipcs_cpu_get_vec(self.h, which, comp, _p(out))
+        return out
+
+    def pattern(self, which, n_rows):
+        nnz = self.L.ipcs_cpu_nnz(self.h, which)
+        ip, ix = np.empty(n_rows + 1, np.int32), np.empty(nnz, np.int32)
+        self.L.ipcs_cpu_get_pattern(self.h, which, _p(ip), _p(ix))
+        return ip, ix
+
+    def matrix(self, which, comp, nnz):
+        out = np.empty(nnz)
+        self.L.ipcs_cpu_get_matrix(self.h, which, comp, _p(out))
+        return out
+
+    def solve(self, dt, nu):
+        self.update_bcs()
+        rc = self.L.ipcs_cpu_step(self.h, dt, nu, _p(self.its))
+        if rc != 0:
+            raise RuntimeError(f"CPU restatement: Krylov solve diverged in stage {rc}")
+        return rc
