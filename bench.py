@@ -38,7 +38,7 @@ METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
 DT, NU = 0.005, 0.01
 KRYLOV = {
     "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
-    "pressure": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
     "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
 }
 
@@ -313,7 +313,9 @@ def main():
     ap.add_argument("--mesh", type=int, default=96, help="cubes per direction (BASELINE: 96; 48 = configs[2])")
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 64))")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
     args = ap.parse_args()
+    KRYLOV["pressure"]["pc_type"] = args.pressure_pc
     if args.impl == "reference":
         run_reference(args)
     else:

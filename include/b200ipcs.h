@@ -144,6 +144,18 @@ int b2_select_bc_step(b2_ctx* ctx, int step);
 /* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253) */
 int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
 
+/* ---- pressure multigrid hierarchy (optional; selected with pc_type=mg on B2_SOLVER_PRESSURE) --------
+ * The reference forces a direct (MUMPS) solve of the singular pressure system (fracstep.py:562-578); at
+ * 10^6 unknowns the device equivalent is PCG preconditioned by a geometric multigrid V-cycle (damped
+ * Jacobi smoothing).  The host supplies, coarser level by coarser level, the level's P1 mesh (dofs = mesh
+ * nodes) and the transfer operators as CSR: P (rows = OWNED dofs of the previous level, cols = this
+ * level) and R = P^T (rows = this level, cols = local dofs of the previous level).  Coarse levels are
+ * replicated on every rank; only the restriction to level 1 is all-reduced.  Call after b2_preassemble. */
+int b2_pressure_mg_add_level(b2_ctx* ctx, int64_t n_nodes, const double* x, int64_t n_cells, const int32_t* cell_nodes,
+                             int64_t n_fine_rows, const int32_t* P_indptr, const int32_t* P_indices, const double* P_vals,
+                             const int32_t* R_indptr, const int32_t* R_indices, const double* R_vals);
+int b2_pressure_mg_configure(b2_ctx* ctx, int nu_pre, int nu_post, int coarse_sweeps, double omega);
+
 /* ---- _preassemble (fracstep.py:360-409) ----------------------------------------------- */
 int b2_preassemble(b2_ctx* ctx, const double* body_force, int low_memory, int rotational);
 

@@ -26,7 +26,7 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_build_patterns", "b2_pattern_nnz", "b2_set_slice_order", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
@@ -89,6 +89,8 @@ def load_library() -> C.CDLL:
         "b2_build_patterns": (i32, [vp]),
         "b2_pattern_nnz": (i64, [vp, i32]),
         "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
+        "b2_pressure_mg_add_level": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
+        "b2_pressure_mg_configure": (i32, [vp, i32, i32, i32, dbl]),
         "b2_get_pattern": (i32, [vp, i32, vp, vp]),
         "b2_set_velocity_bc_dofs": (i32, [vp, i32, i64, vp]),
         "b2_set_velocity_bc_values": (i32, [vp, i32, i64, vp]),
@@ -203,6 +205,18 @@ class Context:
     def set_slice_order(self, which: int, order):
         o = _i32(order)
         self._check(self.lib.b2_set_slice_order(self._h, which, o.size, _ptr(o)), "b2_set_slice_order")
+
+    def pressure_mg_add_level(self, x, cell_nodes, P, R):
+        """P, R: scipy CSR (fine-owned x coarse, coarse x fine-local)."""
+        x, cn = _f64(x), _i32(cell_nodes)
+        Pi, Px, Pv = _i32(P.indptr), _i32(P.indices), _f64(P.data)
+        Ri, Rx, Rv = _i32(R.indptr), _i32(R.indices), _f64(R.data)
+        self._check(self.lib.b2_pressure_mg_add_level(self._h, x.shape[0], _ptr(x), cn.shape[0], _ptr(cn), P.shape[0],
+                                                      _ptr(Pi), _ptr(Px), _ptr(Pv), _ptr(Ri), _ptr(Rx), _ptr(Rv)),
+                    "b2_pressure_mg_add_level")
+
+    def pressure_mg_configure(self, nu_pre=2, nu_post=2, coarse_sweeps=40, omega=0.7):
+        self._check(self.lib.b2_pressure_mg_configure(self._h, nu_pre, nu_post, coarse_sweeps, omega), "b2_pressure_mg_configure")
 
     def pattern(self, which: int, n_rows: int):
         nnz = self.lib.b2_pattern_nnz(self._h, which)

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "elem.cuh"
 #include "linalg.cuh"
+#include "mg.cuh"
 
 namespace {
 
@@ -42,7 +43,7 @@ struct Space {
 
 struct KSPOpts {
   int type = 0;  // 0 = cg, 1 = bcgs
-  int pc = 0;    // 0 = jacobi, 1 = none
+  int pc = 0;    // 0 = jacobi, 1 = none, 2 = multigrid (pressure only, needs b2_pressure_mg_add_level)
   double rtol = 1e-5, atol = 1e-50;
   int maxit = 10000;
   bool nonzero_guess = false;
@@ -102,6 +103,16 @@ struct Halo {
   DBuf<double> sendbuf, recvbuf;
 };
 
+// one replicated coarse level of the pressure multigrid (level 0 is the distributed fine space)
+struct MgLevel {
+  int n = 0;  // dofs (P1: = nodes of the level's mesh)
+  CSR pat;
+  DBuf<double> A, dinv, x, b, r, tmp;
+  // transfer operators to/from the previous (finer) level, CSR with scalar values
+  CSR P, R;  // P: rows = owned dofs of the finer level, cols = this level;  R = P^T
+  DBuf<double> Pv, Rv;
+};
+
 struct DVec {
   DBuf<double> buf;
   int K = 1;
@@ -122,6 +133,10 @@ struct b2_ctx {
   Space sp[2];
   CSR pat[4];
   Halo halo[2];
+  std::vector<MgLevel> mg;  // coarse levels 1..L of the pressure hierarchy
+  int mg_pre = 2, mg_post = 2, mg_coarse = 40;
+  double mg_omega = 0.7;
+  DBuf<double> mg_x0, mg_t0;  // fine-level work vectors (n_local of Q)
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank)
   bool patterns_built = false, preassembled = false;
@@ -215,14 +230,20 @@ __global__ void k_keys_to_csr(int64_t n_keys, const unsigned long long* __restri
   if (i < n_keys && r < n_rows) cols[i] = (int)(keys[i] & 0xffffffffull);
 }
 
+void build_pattern_raw(b2_ctx* c, int64_t n_cells, const int* rdofs, int nr, const int* cdofs, int nc, int n_rows,
+                       int n_cols, CSR& out);
+
 void build_pattern(b2_ctx* c, const Space& rs, const Space& cs, CSR& out) {
-  const int nr = rs.nd, nc = cs.nd;
-  const int64_t n_pairs = c->n_cells * nr * nc;
-  const int n_rows = (int)rs.n_owned;
+  build_pattern_raw(c, c->n_cells, rs.cell_dofs.p, rs.nd, cs.cell_dofs.p, cs.nd, (int)rs.n_owned, (int)cs.n_local(), out);
+}
+
+void build_pattern_raw(b2_ctx* c, int64_t n_cells, const int* rdofs, int nr, const int* cdofs, int nc, int n_rows,
+                       int n_cols, CSR& out) {
+  const int64_t n_pairs = n_cells * nr * nc;
   DBuf<unsigned long long> k0, k1;
   k0.alloc(n_pairs);
   k1.alloc(n_pairs);
-  B2_LAUNCH(c, k_gen_keys, blocks_for(n_pairs, 256), 256, c->n_cells, rs.cell_dofs.p, nr, cs.cell_dofs.p, nc, n_rows, k0.p);
+  B2_LAUNCH(c, k_gen_keys, blocks_for(n_pairs, 256), 256, n_cells, rdofs, nr, cdofs, nc, n_rows, k0.p);
   int row_bits = 1;
   while ((1ll << row_bits) <= (int64_t)n_rows + 1) ++row_bits;
   size_t tmp_bytes = 0;
@@ -241,7 +262,7 @@ void build_pattern(b2_ctx* c, const Space& rs, const Space& cs, CSR& out) {
   B2_CUDA(cudaStreamSynchronize(c->stream));
   B2_REQUIRE(n_unique < (1ll << 31), "pattern too large for int32 indptr");
   out.n_rows = n_rows;
-  out.n_cols = (int)cs.n_local();
+  out.n_cols = n_cols;
   out.rowptr.alloc(n_rows + 1);
   DBuf<int> cols_tmp;
   cols_tmp.alloc(n_unique);
@@ -443,7 +464,7 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
   DBuf<double>* w = space == B2_SPACE_V ? c->wv : c->wq;
   // CG: Jacobi through dinv in the vector kernels.  BiCGStab: the operator is already row-scaled
   // (k_combine_first), dinv only scales the right-hand side in k_bcgs_init.
-  const double* dinv = (o.pc == 0 || o.type == 1) ? dinv_jacobi : (space == B2_SPACE_V ? c->onesV.p : c->onesQ.p);
+  const double* dinv = (o.pc != 1 || o.type == 1) ? dinv_jacobi : (space == B2_SPACE_V ? c->onesV.p : c->onesQ.p);
   double *r = w[0].p, *p = w[1].p, *q = w[2].p, *t = nullptr, *rhat = nullptr;
   if (o.type == 1) {
     B2_REQUIRE(space == B2_SPACE_V, "BiCGStab work vectors exist for the velocity space only");
@@ -484,6 +505,108 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
     mx = std::max(mx, c->h_st->its[k]);
   }
   o.expected_its = mx;
+}
+
+// ---- multigrid V-cycle on the pressure hierarchy ---------------------------------------------------
+// level 0: distributed fine operator Ap (halo before every gather); levels >= 1 replicated.
+struct MgView {
+  int n, ld;
+  const CSR* pat;
+  const double *A, *dinv;
+};
+
+void mg_sweeps(b2_ctx* c, const MgView& L, bool fine, const double* b, double*& x, double*& tmp, int n_sweeps, bool from_zero) {
+  const int g = pgrid(c, L.n, 256, 8);
+  int s = 0;
+  if (from_zero && n_sweeps > 0) {
+    B2_LAUNCH(c, k_mg_first, pgrid(c, L.n), 256, (int64_t)L.n, L.dinv, b, c->mg_omega, x);
+    s = 1;
+  }
+  for (; s < n_sweeps; ++s) {
+    if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
+    B2_LAUNCH(c, k_mg_sweep<false>, g, 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, c->mg_omega, tmp);
+    std::swap(x, tmp);
+  }
+}
+
+// x_l <- V-cycle(b_l), zero initial guess.  Returns the buffer that holds the result.
+double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
+  const bool fine = (l == 0);
+  MgView L;
+  if (fine) {
+    const CSR& qq = c->pat[B2_PAT_QQ];
+    L = {qq.n_rows, qq.n_cols, &qq, c->Ap.p, c->dinvAp.p};
+  } else {
+    MgLevel& M = c->mg[l - 1];
+    L = {M.n, M.n, &M.pat, M.A.p, M.dinv.p};
+  }
+  const bool coarsest = (l == (int)c->mg.size());
+  if (coarsest) {
+    mg_sweeps(c, L, fine, b, x, tmp, c->mg_coarse, true);
+    return x;
+  }
+  mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
+  // residual and restriction
+  MgLevel& C = c->mg[l];
+  if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
+  B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
+  B2_LAUNCH(c, (k_rect_vq<1, 8>), blocks_for((int64_t)C.n * 8, 256), 256, C.n, C.R.rowptr.p, C.R.cols.p, C.Rv.p, tmp,
+            (const double*)nullptr, C.n, 1.0, C.b.p);
+  if (fine && c->nranks > 1) allreduce_sum(c, C.b.p, C.n);  // coarse levels are replicated: sum the partial restrictions
+  double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p);
+  // x += P xc   (rows: owned dofs of this level)
+  B2_LAUNCH(c, (k_rect_vq<1, 4>), blocks_for((int64_t)L.n * 4, 256), 256, L.n, C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, x, L.ld, 1.0, x);
+  mg_sweeps(c, L, fine, b, x, tmp, c->mg_post, false);
+  return x;
+}
+
+void cgz_finish(b2_ctx* c, int fin, int n) {
+  if (c->nranks == 1) return;
+  allreduce_sum(c, c->d_red, n);
+  B2_LAUNCH(c, k_cgz_finalize, 1, 1, fin, c->d_st, c->d_red);
+}
+
+// PCG on the pressure system with the V-cycle as preconditioner (K = 1)
+void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_t* its) {
+  KSPOpts& o = c->ksp[B2_SOLVER_PRESSURE];
+  const CSR& qq = c->pat[B2_PAT_QQ];
+  const int64_t n = qq.n_rows;
+  const int g = pgrid(c, n, 256, 8);
+  double *r = c->wq[0].p, *p = c->wq[1].p, *q = c->wq[2].p;
+  std::memset(c->h_st, 0, sizeof(KryState));
+  c->h_st->K = 1;
+  c->h_st->maxit = o.maxit;
+  c->h_st->rtol = o.rtol;
+  c->h_st->atol = o.atol;
+  B2_CUDA(cudaMemcpyAsync(c->d_st, c->h_st, sizeof(KryState), cudaMemcpyHostToDevice, c->stream));
+  const double* q0 = nullptr;
+  if (o.nonzero_guess) {
+    spmm(c, qq, c->Ap.p, 1, x, q, nullptr, nullptr, FIN_NONE, 0, B2_SPACE_Q);
+    q0 = q;
+  }
+  B2_LAUNCH(c, k_cgz_init, g, 256, n, b, q0, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+  cgz_finish(c, FIN_CGZ_INIT, 2);
+  for (int it = 0; it <= o.maxit; ++it) {
+    if (it % 2 == 0 || it < 4) {  // poll the device state (iteration counts are small with multigrid)
+      B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
+      B2_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.bytes_d2h += sizeof(KryState);
+      if (c->h_st->done) break;
+    }
+    double* z = mg_vcycle(c, 0, r, c->mg_x0.p, c->mg_t0.p);
+    B2_LAUNCH(c, k_cgz_rz, g, 256, n, r, z, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+    cgz_finish(c, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, 1);
+    B2_LAUNCH(c, k_cgz_p, g, 256, n, z, p, c->d_st);
+    spmm(c, qq, c->Ap.p, 1, p, q, p, c->d_st, FIN_CG_PQ, 1, B2_SPACE_Q);
+    B2_LAUNCH(c, k_cgz_update, g, 256, n, p, q, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+    cgz_finish(c, FIN_CGZ_UPDATE, 1);
+  }
+  if (!c->h_st->done) {
+    B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  *reason = c->h_st->reason[0] != 0 ? c->h_st->reason[0] : -3;
+  *its = c->h_st->its[0];
 }
 
 void require_ready(b2_ctx* c) { B2_REQUIRE(c->preassembled, "b2_preassemble has not been called"); }
@@ -608,7 +731,10 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
     B2_LAUNCH(c, k_shift, pgrid(c, n), 256, n, b2, c->d_sums, 0, 1.0 / (double)Q.n_global, (const double*)nullptr, (double*)nullptr);
   }
   int32_t its = 0;
-  krylov_solve(c, B2_SOLVER_PRESSURE, c->pat[B2_PAT_QQ], c->Ap.p, c->dinvAp.p, B2_SPACE_Q, 1, b2, dp, reason, &its);  // :578
+  if (c->ksp[B2_SOLVER_PRESSURE].pc == 2 && !c->mg.empty() && !c->has_pbc)
+    pcg_mg_solve(c, b2, dp, reason, &its);
+  else
+    krylov_solve(c, B2_SOLVER_PRESSURE, c->pat[B2_PAT_QQ], c->Ap.p, c->dinvAp.p, B2_SPACE_Q, 1, b2, dp, reason, &its);  // :578
   c->stats.its_pressure = its;
   if (!c->has_pbc) {  // dp -= int dp / int 1  (:579-591), then ps = p + dp (:604)
     B2_LAUNCH(c, k_sums, pgrid(c, n), 256, n, dp, c->vec(B2_VEC_MQ), c->d_sums, c->partials.p, c->d_counter);
@@ -976,6 +1102,68 @@ int b2_set_global_sizes(b2_ctx* c, int64_t nv, int64_t nq) {
   });
 }
 
+int b2_pressure_mg_add_level(b2_ctx* c, int64_t n_nodes, const double* x, int64_t n_cells, const int32_t* cell_nodes,
+                             int64_t n_fine_rows, const int32_t* P_indptr, const int32_t* P_indices, const double* P_vals,
+                             const int32_t* R_indptr, const int32_t* R_indices, const double* R_vals) {
+  return guarded(c, [&] {
+    B2_REQUIRE(c->preassembled, "add multigrid levels after b2_preassemble");
+    const int d = c->gdim;
+    const int64_t fine_n = c->mg.empty() ? c->sp[B2_SPACE_Q].n_owned : c->mg.back().n;
+    const int64_t fine_cols = c->mg.empty() ? c->sp[B2_SPACE_Q].n_local() : c->mg.back().n;
+    B2_REQUIRE(n_fine_rows == fine_n, "prolongation rows must equal the owned dofs of the previous level");
+    c->mg.emplace_back();
+    MgLevel& L = c->mg.back();
+    L.n = (int)n_nodes;
+    // mesh of the level: P1 dofs are the mesh nodes
+    DBuf<double> dx;
+    DBuf<int> dcells;
+    dx.alloc(n_nodes * 3);
+    dcells.alloc(n_cells * (d + 1));
+    B2_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * n_nodes * 3, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(dcells.p, cell_nodes, sizeof(int) * n_cells * (d + 1), cudaMemcpyHostToDevice, c->stream));
+    build_pattern_raw(c, n_cells, dcells.p, d + 1, dcells.p, d + 1, L.n, L.n, L.pat);
+    build_sell(c, L.pat);
+    L.A.alloc(L.pat.slots);
+    L.A.zero(c->stream);
+    if (d == 2)
+      B2_LAUNCH(c, (k_assemble_square<2, 1, B2_FORM_STIFF_Q>), blocks_for(n_cells * 3, 128), 128, n_cells, dx.p, dcells.p, dcells.p,
+                L.n, L.pat.rowptr.p, L.pat.cols.p, L.pat.slice_ptr.p, L.A.p);
+    else
+      B2_LAUNCH(c, (k_assemble_square<3, 1, B2_FORM_STIFF_Q>), blocks_for(n_cells * 4, 128), 128, n_cells, dx.p, dcells.p, dcells.p,
+                L.n, L.pat.rowptr.p, L.pat.cols.p, L.pat.slice_ptr.p, L.A.p);
+    L.dinv.alloc(L.n);
+    B2_LAUNCH(c, k_inv_diag, blocks_for(L.n, 256), 256, L.n, L.pat.slice_ptr.p, L.pat.diag_t.p, L.A.p, L.dinv.p);
+    for (auto* v : {&L.x, &L.b, &L.r, &L.tmp}) { v->alloc(L.n); v->zero(c->stream); }
+    auto upload_csr = [&](CSR& m, DBuf<double>& vals, int rows, int cols, const int32_t* ip, const int32_t* ix, const double* vv) {
+      int nnz = ip[rows];
+      m.n_rows = rows; m.n_cols = cols; m.nnz = nnz;
+      m.rowptr.alloc(rows + 1); m.cols.alloc(nnz); vals.alloc(nnz);
+      B2_CUDA(cudaMemcpyAsync(m.rowptr.p, ip, sizeof(int) * (rows + 1), cudaMemcpyHostToDevice, c->stream));
+      if (nnz) {
+        B2_CUDA(cudaMemcpyAsync(m.cols.p, ix, sizeof(int) * nnz, cudaMemcpyHostToDevice, c->stream));
+        B2_CUDA(cudaMemcpyAsync(vals.p, vv, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
+      }
+    };
+    upload_csr(L.P, L.Pv, (int)fine_n, L.n, P_indptr, P_indices, P_vals);
+    upload_csr(L.R, L.Rv, L.n, (int)fine_cols, R_indptr, R_indices, R_vals);
+    if (c->mg.size() == 1) {
+      c->mg_x0.alloc(c->sp[B2_SPACE_Q].n_local()); c->mg_x0.zero(c->stream);
+      c->mg_t0.alloc(c->sp[B2_SPACE_Q].n_local()); c->mg_t0.zero(c->stream);
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int b2_pressure_mg_configure(b2_ctx* c, int nu_pre, int nu_post, int coarse_sweeps, double omega) {
+  return guarded(c, [&] {
+    B2_REQUIRE(nu_pre >= 1 && nu_post >= 0 && coarse_sweeps >= 1 && omega > 0 && omega < 2, "bad multigrid parameters");
+    c->mg_pre = nu_pre;
+    c->mg_post = nu_post;
+    c->mg_coarse = coarse_sweeps;
+    c->mg_omega = omega;
+  });
+}
+
 int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order) {
   return guarded(c, [&] {
     B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "slice order: square patterns, after b2_build_patterns");
@@ -1192,6 +1380,7 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
     } else if (k == "pc_type") {
       if (v == "jacobi") o.pc = 0;
       else if (v == "none") o.pc = 1;
+      else if (v == "mg" || v == "gamg" || v == "hypre") o.pc = (solver == B2_SOLVER_PRESSURE) ? 2 : 0;
       else if (v == "lu" || v == "cholesky") { o.pc = 0; o.rtol = 1e-12; o.atol = 1e-50; }  // "exact" solve (Appendix G)
       else o.pc = 0;  // unknown preconditioners fall back to Jacobi, silently like PETSc's options DB
     } else if (k == "ksp_rtol") o.rtol = std::stod(v);

@@ -1,0 +1,143 @@
+// mg.cuh -- kernels of the geometric multigrid preconditioner for the pressure Poisson problem
+// (the device-side answer to the reference's forced direct solve of the singular system,
+// /root/reference/src/oasisx/fracstep.py:562-578, which cannot scale to 10^6 unknowns), and the
+// PCG recurrences with an explicit preconditioned residual z = V(r).
+#pragma once
+#include "linalg.cuh"
+
+// one damped-Jacobi sweep on a SELL-32 operator: x_out = x_in + omega * dinv * (b - A x_in);
+// RESID: r_out = b - A x_in instead (x_out unused)
+template <bool RESID>
+__global__ void __launch_bounds__(256)
+k_mg_sweep(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+           const double* __restrict__ vals, const double* __restrict__ dinv, const double* __restrict__ b,
+           const double* __restrict__ x_in, double omega, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  for (int s = warp; s < n_slices; s += nwarps) {
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) {
+      const int c = __ldg(cols + base + lane + (t << 5));
+      acc = fma(__ldg(vals + base + lane + (t << 5)), __ldg(x_in + c), acc);
+    }
+    if (row < n_rows) {
+      const double r = b[row] - acc;
+      out[row] = RESID ? r : fma(omega * dinv[row], r, x_in[row]);
+    }
+  }
+}
+
+// x = omega * dinv * b  (first sweep from a zero initial guess)
+__global__ void k_mg_first(int64_t n, const double* __restrict__ dinv, const double* __restrict__ b, double omega,
+                           double* __restrict__ x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = omega * dinv[i] * b[i];
+}
+
+// ---- PCG with explicit z (K = 1) ----------------------------------------------------------------
+enum { FIN_CGZ_INIT = 32, FIN_CGZ_RZ0, FIN_CGZ_RZ, FIN_CGZ_UPDATE };
+
+__device__ inline void cgz_finalize(int fin, KryState* st, const double* t) {
+  switch (fin) {
+    case FIN_CGZ_INIT: {  // t = bb, rr
+      st->bb[0] = t[0];
+      st->rr[0] = t[1];
+      double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * st->bb[0];
+      st->tol2[0] = r2 > a2 ? r2 : a2;
+      st->its[0] = 0;
+      st->reason[0] = 0;
+      st->active[0] = 1;
+      st->beta[0] = 0.0;
+      kry_converge_test(st, 0);
+      kry_check_done(st);
+    } break;
+    case FIN_CGZ_RZ0:
+      st->rz[0] = t[0];
+      st->beta[0] = 0.0;
+      break;
+    case FIN_CGZ_RZ:
+      st->beta[0] = t[0] / st->rz[0];
+      st->rz[0] = t[0];
+      break;
+    case FIN_CGZ_UPDATE:  // t = rr
+      if (st->active[0]) {
+        st->rr[0] = t[0];
+        st->its[0] += 1;
+        kry_converge_test(st, 0);
+      }
+      kry_check_done(st);
+      break;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void cgz_reduce_finish(double (&v)[N], double* partials, unsigned* counter, int fin,
+                                                  KryState* st, double* red_out) {
+  double total[N];
+  if (grid_reduce<N>(v, partials, counter, total) && threadIdx.x == 0) {
+    if (red_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) red_out[i] = total[i];
+    } else {
+      cgz_finalize(fin, st, total);
+    }
+  }
+}
+
+__global__ void k_cgz_finalize(int fin, KryState* st, const double* __restrict__ totals) { cgz_finalize(fin, st, totals); }
+
+// r = b - q (or r = b, x = 0); sums bb, rr
+__global__ void __launch_bounds__(256)
+k_cgz_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ x,
+           double* __restrict__ r, KryState* st, double* partials, unsigned* counter, double* red_out) {
+  double s[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bv = b[i];
+    double rv = bv;
+    if (q != nullptr) rv -= q[i];
+    else x[i] = 0.0;
+    r[i] = rv;
+    s[0] = fma(bv, bv, s[0]);
+    s[1] = fma(rv, rv, s[1]);
+  }
+  cgz_reduce_finish<2>(s, partials, counter, FIN_CGZ_INIT, st, red_out);
+}
+
+// sum r.z -> rz (first: beta = 0) / beta = rz'/rz
+__global__ void __launch_bounds__(256)
+k_cgz_rz(int64_t n, const double* __restrict__ r, const double* __restrict__ z, int fin, KryState* st,
+         double* partials, unsigned* counter, double* red_out) {
+  double s[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s[0] = fma(r[i], z[i], s[0]);
+  cgz_reduce_finish<1>(s, partials, counter, fin, st, red_out);
+}
+
+// p = z + beta p
+__global__ void k_cgz_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const KryState* st) {
+  const double beta = st->beta[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+// x += alpha p ; r -= alpha q ; sum rr
+__global__ void __launch_bounds__(256)
+k_cgz_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+             double* __restrict__ r, KryState* st, double* partials, unsigned* counter, double* red_out) {
+  if (st->done) return;
+  const double alpha = st->alpha[0];
+  double s[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double rv = fma(-alpha, q[i], r[i]);
+    r[i] = rv;
+    s[0] = fma(rv, rv, s[0]);
+  }
+  cgz_reduce_finish<1>(s, partials, counter, FIN_CGZ_UPDATE, st, red_out);
+}

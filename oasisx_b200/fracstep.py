@@ -211,6 +211,17 @@ class FractionalStep_AB_CN:
             # equivalent is the null-space-projected CG run to the "exact" tolerance
             self._solver_p.updateOptions({"ksp_type": "preonly", "pc_type": "lu"})
 
+        # optional geometric multigrid for the pressure ("pc_type": "mg"): hierarchy from the provider
+        self._mg_levels = 0
+        if (solver_options.get("pressure") or {}).get("pc_type") in ("mg", "gamg", "hypre") and not self._bcs_p:
+            from . import multigrid as _mg
+
+            self._mg_levels = _mg.attach_pressure_multigrid(
+                ctx, mesh, self._Q.tabulate_dof_coordinates(), self._nQ_owned, **(options.get("multigrid") or {})
+            )
+            if self._mg_levels == 0:
+                logger.warning("pc_type=mg requested but the mesh carries no nested hierarchy: using Jacobi")
+
         # matrices visible to callers (test/test_tentative_velocity.py:175)
         # (owned rows, local columns = owned + ghosts), like the local part of a PETSc MPIAIJ matrix
         nV, nQ, cV, cQ = self._nV_owned, self._nQ_owned, Vs.num_dofs, self._Q.num_dofs

@@ -210,6 +210,8 @@ def create_rectangle(comm, points, n, cell_type=CellType.triangle) -> Mesh:
     cells[:, 1] = np.stack([v0, v2, v3], axis=1)
     msh = Mesh(x, cells.reshape(-1, 3), 2, comm)
     msh._lattice = (np.array([x0, y0, 0.0]), np.array([(x1 - x0) / nx, (y1 - y0) / ny, 1.0]))
+    msh._shape = (nx, ny)
+    msh._box = (np.array([x0, y0]), np.array([x1, y1]))
     return msh
 
 
@@ -236,6 +238,8 @@ def create_box(comm, points, n, cell_type=CellType.tetrahedron) -> Mesh:
         cells[:, t] = np.stack([v[a] for a in tet], axis=1)
     msh = Mesh(x, cells.reshape(-1, 4), 3, comm)
     msh._lattice = (p0.copy(), (p1 - p0) / np.array([nx, ny, nz], dtype=np.float64))
+    msh._shape = (nx, ny, nz)
+    msh._box = (p0.copy(), p1.copy())
     return msh
 
 
