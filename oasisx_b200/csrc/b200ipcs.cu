@@ -151,6 +151,7 @@ struct b2_ctx {
   int bc_series_steps[B2_MAXK] = {0, 0, 0};
   int bc_step = -1;                 // >= 0: apply bc_series[.][bc_step] instead of bc_vals
   DBuf<uint8_t> is_bc_row_v, is_bc_q;
+  DBuf<uint8_t> pos8;  // per-cell scatter table of the convection assembly (elem.cuh)
   DBuf<int> pbc_dofs;
   bool has_pbc = false;
   double vol = 0.0;  // sum of mQ over all ranks
@@ -374,21 +375,8 @@ void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* 
     else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     return;
   }
-  const bool u8 = c->spmm_unroll >= 8;
-  switch (c->spmm_block) {
-    case 256:
-      if (u8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin);
-      else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin);
-      break;
-    case 512:
-      if (u8) launch_spmm_u<K, DOT, 8, 512>(c, pat, vals, x, ld, y, w, st, fin);
-      else launch_spmm_u<K, DOT, 4, 512>(c, pat, vals, x, ld, y, w, st, fin);
-      break;
-    default:
-      if (u8) launch_spmm_u<K, DOT, 8, 1024>(c, pat, vals, x, ld, y, w, st, fin);
-      else launch_spmm_u<K, DOT, 4, 1024>(c, pat, vals, x, ld, y, w, st, fin);
-      break;
-  }
+  if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin);
+  else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin);
 }
 
 template <int K>
@@ -627,7 +615,7 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   dispatch_elem(c, [&](auto e) {
     using E = decltype(e);
     B2_LAUNCH(c, (k_convection<E::D, E::DEG>), blocks_for(c->n_cells, 128), 128, c->n_cells, c->x.p, c->cell_nodes.p,
-              V.cell_dofs.p, (int)V.n_owned, uab, ld, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->A.p);
+              V.cell_dofs.p, (int)V.n_owned, uab, ld, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->pos8.p, c->A.p);
   });
   const double* psurf = c->vecs.count(B2_VEC_PSURF) ? c->vec(B2_VEC_PSURF) : nullptr;
   const int scale = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
@@ -886,6 +874,23 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
     B2_LAUNCH(c, (k_assemble_loads<D, DEG>), blocks_for(nc, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
               (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), f[0], f[1], f[2], c->vec(B2_VEC_B0), c->vec(B2_VEC_MQ));  // :387-390
   });
+  // scatter table for the per-step convection assembly (needs rows shorter than 256 entries)
+  {
+    std::vector<int> sp((size_t)(vv.n_rows + 31) / 32 + 1);
+    B2_CUDA(cudaMemcpyAsync(sp.data(), vv.slice_ptr.p, sizeof(int) * sp.size(), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    int maxlen = 0;
+    for (size_t i = 0; i + 1 < sp.size(); ++i) maxlen = std::max(maxlen, (sp[i + 1] - sp[i]) / 32);
+    if (maxlen < 256) {
+      dispatch_elem(c, [&](auto e) {
+        using E = decltype(e);
+        constexpr int NVP = (E::NV + 3) / 4 * 4;
+        c->pos8.alloc(c->n_cells * E::NV * NVP);
+        B2_LAUNCH(c, (k_build_pos8<E::NV>), blocks_for(c->n_cells * E::NV, 128), 128, c->n_cells, V.cell_dofs.p, (int)V.n_owned,
+                  vv.rowptr.p, vv.cols.p, c->pos8.p);
+      });
+    }
+  }
   // Dirichlet masks
   c->is_bc_row_v.alloc(V.n_local()); c->is_bc_row_v.zero(c->stream);
   c->is_bc_q.alloc(Q.n_local()); c->is_bc_q.zero(c->stream);
@@ -1467,7 +1472,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     if (k == "spmm_blocks_per_sm") c->spmm_blocks_per_sm = std::max(1, std::min(value, 32));
     else if (k == "spmm_unroll") c->spmm_unroll = value;
     else if (k == "spmm_mode") c->spmm_mode = value;
-    else if (k == "spmm_block") c->spmm_block = value;
+    else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });
 }

@@ -265,7 +265,7 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
 // those lines in L1 instead of each pulling them through the L2 fabric.
 template <int K, int DOT, int UNROLL, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
        double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
@@ -276,9 +276,14 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   constexpr int WPB = BLOCK / 32;
   const int n_slices = (n_rows + 31) >> 5;
   constexpr int ND = DOT == 0 ? 1 : DOT * K;
-  double dots[ND];
+  // the running dot products live in shared memory between slices: keeping them in registers across
+  // the gather loop costs 8-16 registers, i.e. one to three resident blocks per SM on a kernel whose
+  // speed is set by the number of loads in flight
+  __shared__ double sdots[DOT == 0 ? 1 : ND][DOT == 0 ? 1 : BLOCK];
+  if constexpr (DOT > 0) {
 #pragma unroll
-  for (int i = 0; i < ND; ++i) dots[i] = 0.0;
+    for (int i = 0; i < ND; ++i) sdots[i][threadIdx.x] = 0.0;
+  }
   for (int i = blockIdx.x * WPB + wib; i < n_slices; i += gridDim.x * WPB) {
     const int s = order != nullptr ? __ldg(order + i) : i;
     const int base = __ldg(slice_ptr + s);
@@ -319,15 +324,20 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
       if constexpr (DOT >= 1) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], w[(size_t)k * ld + row], dots[k]);
+        for (int k = 0; k < K; ++k) sdots[k][threadIdx.x] = fma(acc[k], w[(size_t)k * ld + row], sdots[k][threadIdx.x]);
       }
       if constexpr (DOT == 2) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) dots[K + k] = fma(acc[k], acc[k], dots[K + k]);
+        for (int k = 0; k < K; ++k) sdots[K + k][threadIdx.x] = fma(acc[k], acc[k], sdots[K + k][threadIdx.x]);
       }
     }
   }
-  if constexpr (DOT > 0) reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+  if constexpr (DOT > 0) {
+    double dots[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) dots[i] = sdots[i][threadIdx.x];
+    reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+  }
 }
 
 // Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
