@@ -123,7 +123,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256;  // sweep: tools/sweep_spmm.py
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -361,8 +361,12 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
-  B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x,
-            ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
+  if (c->spmm_stream)
+    B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
+              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
+  else
+    B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, false>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
+              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
@@ -1472,6 +1476,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     if (k == "spmm_blocks_per_sm") c->spmm_blocks_per_sm = std::max(1, std::min(value, 32));
     else if (k == "spmm_unroll") c->spmm_unroll = value;
     else if (k == "spmm_mode") c->spmm_mode = value;
+    else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });

@@ -209,6 +209,19 @@ __global__ void k_halo_unpack(int n_neighbors, const int64_t* __restrict__ recv_
 // entries are (nearly) consecutive too.  No cross-lane reduction is needed.  The CSR pattern of
 // create_matrix stays the public face (b2_get_pattern); CSR position p of row r maps to the SELL
 // slot slice_ptr[r/32] + 32*(p - rowptr[r]) + r%32.
+// streaming loads for the matrix stream (values, columns): read-only path, do not allocate in L1, so that
+// the lines of the gathered vector are what stays resident there
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ size_t sell_slot(const int* __restrict__ slice_ptr, int row, int t) {
   return (size_t)__ldg(slice_ptr + (row >> 5)) + ((size_t)t << 5) + (row & 31);
 }
@@ -264,7 +277,7 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // are adjacent in the list, fem.slice_order); a block takes blockDim/32 consecutive list entries at
 // a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
 // those lines in L1 instead of each pulling them through the L2 fabric.
-template <int K, int DOT, int UNROLL, int BLOCK>
+template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM>
 __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
@@ -300,8 +313,8 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       double v[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        c[u] = __ldg(cp + ((t + u) << 5));
-        v[u] = __ldg(vp + ((t + u) << 5));
+        c[u] = STREAM ? ld_stream(cp + ((t + u) << 5)) : __ldg(cp + ((t + u) << 5));
+        v[u] = STREAM ? ld_stream(vp + ((t + u) << 5)) : __ldg(vp + ((t + u) << 5));
       }
       double xv[UNROLL][K];
 #pragma unroll
@@ -314,8 +327,8 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
         for (int k = 0; k < K; ++k) acc[k] = fma(v[u], xv[u][k], acc[k]);
     }
     for (; t < len; ++t) {
-      const int c = __ldg(cp + (t << 5));
-      const double v = __ldg(vp + (t << 5));
+      const int c = STREAM ? ld_stream(cp + (t << 5)) : __ldg(cp + (t << 5));
+      const double v = STREAM ? ld_stream(vp + (t << 5)) : __ldg(vp + (t << 5));
 #pragma unroll
       for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
     }
@@ -412,9 +425,9 @@ k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __rest
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     for (int t = 0; t < len; ++t) {
       const size_t p = (size_t)base + ((size_t)t << 5) + lane;
-      const int c = __ldg(cols + p);
-      const double m = inv_dt * __ldg(M + p);
-      const double kk = half_nu * __ldg(Kst + p);
+      const int c = ld_stream(cols + p);
+      const double m = inv_dt * ld_stream(M + p);
+      const double kk = half_nu * ld_stream(Kst + p);
       const double cv = 0.5 * A[p];
       const double r = (m - cv) - kk;
       double a = ((m + cv) + kk) * invd;

@@ -23,8 +23,8 @@ k_mg_sweep(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict_
     double acc = 0.0;
 #pragma unroll 4
     for (int t = 0; t < len; ++t) {
-      const int c = __ldg(cols + base + lane + (t << 5));
-      acc = fma(__ldg(vals + base + lane + (t << 5)), __ldg(x_in + c), acc);
+      const int c = ld_stream(cols + base + lane + (t << 5));
+      acc = fma(ld_stream(vals + base + lane + (t << 5)), __ldg(x_in + c), acc);
     }
     if (row < n_rows) {
       const double r = b[row] - acc;

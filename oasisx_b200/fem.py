@@ -188,7 +188,7 @@ class _SubSpace:
         return Vi, np.arange(n, dtype=np.int32) * self.parent.bs + self.i
 
 
-def slice_order(x: np.ndarray, n_rows: int, lattice=None, tile=(4, 4), rows_per_slice: int = 32) -> np.ndarray:
+def slice_order(x: np.ndarray, n_rows: int, lattice=None, tile=(8, 8), rows_per_slice: int = 32) -> np.ndarray:
     """Schedule of the 32-row slices of the sliced-ELL operators: slices sorted by the spatial tile of
     their first row, so that all slices of one tile (every stencil class) are adjacent.  A tile spans
     one slice (32 dofs) in x and `tile` x-lines in y and z; on meshes without lattice information the

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Sweep SpMM launch shapes / diagnostic modes on the GPU.  Usage: python tools/sweep_spmm.py [mesh]"""
+"""Sweep SpMM launch shapes / cache policies / schedules on the GPU.  Usage: python tools/sweep_spmm.py [mesh]"""
 import os
 import sys
 
@@ -22,18 +22,16 @@ tg.t_u, tg.t_p = dt, dt / 2
 s.solve(dt, nu, max_iter=1)
 Vs = s._Vi[0][0]
 n_slices = (Vs.num_dofs + 31) // 32
-for tile in (None, (1, 1), (2, 1), (2, 2), (4, 2), (4, 4)):
+for tile in ((8, 8), (6, 6), (12, 12), (16, 16), (8, 16), (16, 8), (24, 24), (32, 32)):
     if tile is None:
         ctx.set_slice_order(L.PAT_VV, np.arange(n_slices, dtype=np.int32))
     else:
         ctx.set_slice_order(L.PAT_VV, fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, msh._lattice, tile=tile))
-    for block in (256, 512, 1024):
-        ctx.set_tuning("spmm_block", block)
-        for unroll in (4, 8):
+    for stream in (1,):
+        ctx.set_tuning("spmm_stream", stream)
+        for unroll in (8,):
             ctx.set_tuning("spmm_unroll", unroll)
-            for bps in (1, 2, 4, 8):
-                if block * bps > 2048:
-                    continue
+            for bps in (8,):
                 ctx.set_tuning("spmm_blocks_per_sm", bps)
                 ms, nbytes = ctx.bench_kernel(3, 10)
-                print(f"tile {tile} block {block:4d} unroll {unroll} blocks/SM {bps}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
+                print(f"tile {tile} stream {stream} unroll {unroll} blocks/SM {bps}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
