@@ -37,9 +37,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
 DT, NU = 0.005, 0.01
 KRYLOV = {
-    "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
+                  "b200_guess": "extrapolate"},
     "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
-    "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
+               "b200_guess": "extrapolate"},
 }
 
 

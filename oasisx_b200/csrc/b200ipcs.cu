@@ -47,6 +47,7 @@ struct KSPOpts {
   double rtol = 1e-5, atol = 1e-50;
   int maxit = 10000;
   bool nonzero_guess = false;
+  bool extrapolate_guess = false;  // "b200_guess": "extrapolate" -- start from a time-extrapolated state (implies nonzero guess)
   bool scaled_operator = false;  // the matrix is stored row-scaled by its diagonal (tentative velocity)
   int expected_its = 0;  // iterations of the previous solve: first batch enqueued without a host sync
 };
@@ -159,6 +160,8 @@ struct b2_ctx {
   // Krylov work space
   DBuf<double> wv[5], wq[4];
   DBuf<double> stage;  // staging for strided host copies
+  DBuf<double> delta_prev;  // previous velocity correction u - u* (initial guess of the next mass solve)
+  int steps_done = 0;
   KryState* d_st = nullptr;
   KryState* h_st = nullptr;  // pinned
   double* d_sums = nullptr;  // small device scratch for reductions (16 doubles)
@@ -687,6 +690,11 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
   apply_velocity_bcs(c, rhs1);                                                                  // :517-518
   B2_CUDA(cudaMemcpyAsync(wrk, u, sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));  // :520
   int32_t its[B2_MAXK] = {0, 0, 0};
+  if (c->ksp[B2_SOLVER_TENTATIVE].extrapolate_guess && c->steps_done >= 1) {
+    // initial guess 2 u^n - u^{n-1}: the converged solution does not depend on it, the iteration count does
+    const int64_t nl = V.n_local() * K;
+    B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 2.0, c->vec(B2_VEC_U1), -1.0, c->vec(B2_VEC_U2), u);
+  }
   krylov_solve(c, B2_SOLVER_TENTATIVE, c->pat[B2_PAT_VV], c->A.p, c->dinvA.p, B2_SPACE_V, K, rhs1, u, reasons, its);  // :521
   for (int k = 0; k < K; ++k) c->stats.its_tentative[k] = its[k];
   if (K == 2) sqdiff<2>(c, V.n_owned, (int)V.n_local(), wrk, u, c->d_sums);
@@ -772,7 +780,16 @@ void stage_velocity_update(b2_ctx* c, double dt, int32_t* reasons) {
   if (K == 2) rect_vq<2>(c, c->G.p, dp, b3, -dt, b3);  // :642-645
   else rect_vq<3>(c, c->G.p, dp, b3, -dt, b3);
   int32_t its[B2_MAXK] = {0, 0, 0};
+  const bool extrap = c->ksp[B2_SOLVER_SCALAR].extrapolate_guess;
+  const int64_t nl = c->sp[B2_SPACE_V].n_local() * K;
+  double* ustar = c->vec(B2_VEC_WRK);  // free after the tentative solve's diff
+  if (extrap) {
+    if (c->delta_prev.p == nullptr) { c->delta_prev.alloc(nl); c->delta_prev.zero(c->stream); }
+    B2_CUDA(cudaMemcpyAsync(ustar, u, sizeof(double) * nl, cudaMemcpyDeviceToDevice, c->stream));
+    B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, 1.0, c->delta_prev.p, u);  // guess u* + (u - u*)_previous step
+  }
   krylov_solve(c, B2_SOLVER_SCALAR, c->pat[B2_PAT_VV], c->M.p, c->dinvM.p, B2_SPACE_V, K, b3, u, reasons, its);  // :656
+  if (extrap) B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, -1.0, ustar, c->delta_prev.p);
   for (int k = 0; k < K; ++k) c->stats.its_update[k] = its[k];
 }
 
@@ -823,6 +840,7 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
   c->stats.ms_pressure = ms_p;
   c->stats.ms_update = ev_ms(c->ev[4], c->ev[5]);
   c->stats.ms_step = ev_ms(c->ev[0], c->ev[5]);
+  c->steps_done++;
   *diff_out = diff;
 }
 
@@ -1396,6 +1414,10 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
     else if (k == "ksp_atol") o.atol = std::stod(v);
     else if (k == "ksp_max_it") o.maxit = std::stoi(v);
     else if (k == "ksp_initial_guess_nonzero") o.nonzero_guess = (v == "1" || v == "true" || v == "True");
+    else if (k == "b200_guess") {
+      o.extrapolate_guess = (v == "extrapolate");
+      if (o.extrapolate_guess) o.nonzero_guess = true;
+    }
     // anything else: ignored (PETSc leaves unused options in the database without error)
   });
 }

@@ -11,7 +11,7 @@ import logging
 
 logger = logging.getLogger("oasisx")
 
-_UNDERSTOOD = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_max_it", "ksp_initial_guess_nonzero"}
+_UNDERSTOOD = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_max_it", "ksp_initial_guess_nonzero", "b200_guess"}
 
 
 class KSPSolver:

@@ -215,3 +215,26 @@ def test_pressure_multigrid_matches_oracle(gdim, N):
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8
     assert max(its) <= 40, its  # mesh-independent convergence (Jacobi-PCG needs hundreds at scale)
+
+
+def test_extrapolated_initial_guesses_do_not_change_the_solution():
+    """b200_guess=extrapolate only changes the Krylov starting point: fields still match the oracle."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(3, 6)
+    tg = TaylorGreen(nu, 3)
+    opts = {
+        "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate"},
+        "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-12, "ksp_initial_guess_nonzero": True},
+        "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate"},
+    }
+    s = make_solver(msh, 2, tg, dt, solver_options=opts)
+    o = make_oracle(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(5):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(3):
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, n
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
