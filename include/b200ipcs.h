@@ -182,6 +182,13 @@ int b2_velocity_update(b2_ctx* ctx, double dt, int32_t* reasons);/* fracstep.py:
 /* whole step (fracstep.py:660-696) with the BC values already uploaded */
 int b2_step(b2_ctx* ctx, double dt, double nu, double max_error, int max_iter, double* diff);
 
+/* Natural pressure boundary term of PressureBC (bcs.py:233-242, assembled at fracstep.py:461-465):
+ * B2_VEC_PSURF_i[j] (+)= int h n_i d(phi_j)/dx_i ds over the given exterior facets (local cell index,
+ * local facet index = index of the opposite vertex), h nodal in Q.  Call before b2_assemble_first;
+ * accumulate = 0 zeroes the vector first (one call per PressureBC). */
+int b2_assemble_pressure_surface(b2_ctx* ctx, int64_t n_facets, const int32_t* facet_cells, const int32_t* facet_local,
+                                 const double* h_nodal, int accumulate);
+
 /* ---- Projector (function.py:108-133) on Q: solve MQ x = rhs ---------------------------- */
 int b2_project_q(b2_ctx* ctx, const double* rhs, double* x, int32_t* reason);
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
-    "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
@@ -110,6 +110,7 @@ def load_library() -> C.CDLL:
         "b2_pressure_solve": (i32, [vp, dbl, vp]),
         "b2_velocity_update": (i32, [vp, dbl, vp]),
         "b2_step": (i32, [vp, dbl, dbl, dbl, i32, vp]),
+        "b2_assemble_pressure_surface": (i32, [vp, i64, vp, vp, vp, i32]),
         "b2_project_q": (i32, [vp, vp, vp, vp]),
         "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
         "b2_get_stats": (i32, [vp, vp]),
@@ -312,6 +313,11 @@ class Context:
         diff = C.c_double(0.0)
         self._check(self.lib.b2_step(self._h, dt, nu, max_error, max_iter, C.byref(diff)), "b2_step")
         return diff.value
+
+    def assemble_pressure_surface(self, facet_cells, facet_local, h_nodal, accumulate: bool):
+        fc, fl, h = _i32(facet_cells), _i32(facet_local), _f64(h_nodal)
+        self._check(self.lib.b2_assemble_pressure_surface(self._h, fc.size, _ptr(fc), _ptr(fl), _ptr(h), int(accumulate)),
+                    "b2_assemble_pressure_surface")
 
     def project_q(self, rhs: np.ndarray):
         rhs = _f64(rhs)

@@ -130,6 +130,11 @@ class PressureBC:
         mesh.topology.create_connectivity(fdim, mesh.topology.dim)
         dofs = _fem.locate_dofs_topological(Q, fdim, self._facets)
         self._bc = _DofBC(dofs, np.zeros(len(dofs)))  # bcs.py:245-253
+        # (cell, local facet index) of every tagged facet: what the ds-integral kernel iterates over
+        cf = mesh.topology.cell_entities(fdim)
+        mask = np.isin(cf, self._facets)
+        cells, local = np.nonzero(mask)
+        self._facet_cells, self._facet_local = cells.astype(np.int32), local.astype(np.int32)
         self._is_callable = callable(self._value)
         self._h = np.zeros(Q.num_dofs)  # nodal values of the boundary pressure in Q
         self._version = 0

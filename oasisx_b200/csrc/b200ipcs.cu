@@ -1444,6 +1444,34 @@ int b2_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter, dou
   return guarded(c, [&] { stage_step(c, dt, nu, max_error, max_iter, diff); });
 }
 
+int b2_assemble_pressure_surface(b2_ctx* c, int64_t n_facets, const int32_t* facet_cells, const int32_t* facet_local,
+                                 const double* h_nodal, int accumulate) {
+  return guarded(c, [&] {
+    require_ready(c);
+    const Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
+    if (!c->vecs.count(B2_VEC_PSURF)) alloc_vec(c, B2_VEC_PSURF, B2_SPACE_V, c->gdim);
+    double* ps = c->vec(B2_VEC_PSURF);
+    if (!accumulate) B2_CUDA(cudaMemsetAsync(ps, 0, sizeof(double) * V.n_local() * c->gdim, c->stream));
+    if (n_facets > 0) {
+      DBuf<int> fc, fl;
+      DBuf<double> h;
+      fc.alloc(n_facets);
+      fl.alloc(n_facets);
+      h.alloc(Q.n_local());
+      B2_CUDA(cudaMemcpyAsync(fc.p, facet_cells, sizeof(int) * n_facets, cudaMemcpyHostToDevice, c->stream));
+      B2_CUDA(cudaMemcpyAsync(fl.p, facet_local, sizeof(int) * n_facets, cudaMemcpyHostToDevice, c->stream));
+      B2_CUDA(cudaMemcpyAsync(h.p, h_nodal, sizeof(double) * Q.n_local(), cudaMemcpyHostToDevice, c->stream));
+      dispatch_elem(c, [&](auto e) {
+        using E = decltype(e);
+        B2_LAUNCH(c, (k_pressure_surface<E::D, E::DEG>), blocks_for(n_facets, 128), 128, n_facets, fc.p, fl.p, c->x.p,
+                  c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p, (int)V.n_owned, (int)V.n_local(), h.p, ps);
+      });
+      B2_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.bytes_h2d += sizeof(int) * 2 * n_facets + sizeof(double) * Q.n_local();
+    }
+  });
+}
+
 int b2_project_q(b2_ctx* c, const double* rhs, double* x, int32_t* reason) {
   return guarded(c, [&] {
     require_ready(c);

@@ -336,3 +336,98 @@ k_convection(int64_t n_cells, const double* __restrict__ x, const int* __restric
     }
   }
 }
+
+// ---- natural pressure boundary term (PressureBC, bcs.py:233-242; fracstep.py:461-465) --------------
+// psurf_i[j] += int_F h n_i d(phi_j)/dx_i ds over the tagged exterior facets F (one thread per facet).
+// h is a P1 function (nodal values in Q); the integrand is at most quadratic on the facet: 2-point
+// Gauss on edges, the 3-point degree-2 rule on triangles.
+template <int D, int DEG>
+__global__ void k_pressure_surface(int64_t n_facets, const int* __restrict__ facet_cells,
+                                   const int* __restrict__ facet_local, const double* __restrict__ x,
+                                   const int* __restrict__ cell_nodes, const int* __restrict__ vdofs,
+                                   const int* __restrict__ qdofs, int nV_owned, int ld,
+                                   const double* __restrict__ h, double* __restrict__ psurf) {
+  using E = El<D, DEG>;
+  constexpr int NV = E::NV;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_facets) return;
+  const int64_t c = facet_cells[t];
+  const int f = facet_local[t];
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  // reference gradients of the barycentrics and their physical images
+  double dl[D + 1][D], gl[D + 1][D];
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int k = 0; k < D; ++k) dl[a][k] = a == 0 ? -1.0 : (a - 1 == k ? 1.0 : 0.0);
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double s = 0;
+#pragma unroll
+      for (int d2 = 0; d2 < D; ++d2) s += g.Kinv[d2][k] * dl[a][d2];
+      gl[a][k] = s;
+    }
+  // outward normal times facet measure: -grad(lambda_f) * detJ / (D-1)!
+  double nA[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) nA[k] = -gl[f][k] * g.detJ / (D == 3 ? 2.0 : 1.0);
+  double hq[D + 1];
+#pragma unroll
+  for (int a = 0; a <= D; ++a) hq[a] = h[qdofs[c * (D + 1) + a]];
+  constexpr int NQP = D == 3 ? 3 : 2;
+  double acc[NV][D];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[j][k] = 0.0;
+  for (int q = 0; q < NQP; ++q) {
+    // barycentric coordinates of the quadrature point in the cell: zero on vertex f
+    double lam[D + 1];
+    int m = 0;
+#pragma unroll
+    for (int a = 0; a <= D; ++a) {
+      if (a == f) { lam[a] = 0.0; continue; }
+      if (D == 3) lam[a] = (m == q) ? 2.0 / 3.0 : 1.0 / 6.0;
+      else lam[a] = (m == q) ? 0.5 + 0.28867513459481287 : 0.5 - 0.28867513459481287;
+      ++m;
+    }
+    const double wq = 1.0 / NQP;
+    double hv = 0;
+#pragma unroll
+    for (int a = 0; a <= D; ++a) hv += lam[a] * hq[a];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      double gphi[D];
+      if (DEG == 1 || j <= D) {
+        const double cf = DEG == 1 ? 1.0 : 4.0 * lam[j] - 1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) gphi[k] = cf * gl[j][k];
+      } else {
+        // edge dof: basix order e0=(2,3), e1=(1,3), e2=(1,2), e3=(0,3), e4=(0,2), e5=(0,1) / e0=(1,2), e1=(0,2), e2=(0,1)
+        const int e = j - (D + 1);
+        int a, b;
+        if (D == 3) {
+          const int ea[6] = {2, 1, 1, 0, 0, 0}, eb[6] = {3, 3, 2, 3, 2, 1};
+          a = ea[e];
+          b = eb[e];
+        } else {
+          const int ea[3] = {1, 0, 0}, eb[3] = {2, 2, 1};
+          a = ea[e];
+          b = eb[e];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) gphi[k] = 4.0 * (lam[a] * gl[b][k] + lam[b] * gl[a][k]);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc[j][k] = fma(wq * hv * nA[k], gphi[k], acc[j][k]);
+    }
+  }
+  for (int j = 0; j < NV; ++j) {
+    const int row = vdofs[c * NV + j];
+    if (row >= nV_owned) continue;
+#pragma unroll
+    for (int k = 0; k < D; ++k) atomicAdd(psurf + (size_t)k * ld + row, acc[j][k]);
+  }
+}

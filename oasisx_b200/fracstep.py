@@ -141,10 +141,8 @@ class FractionalStep_AB_CN:
         self._bcs_p = bcs_p
         for bcp in self._bcs_p:
             bcp.create_bcs(Vs, self._Q)
-        if len(self._bcs_p) > 0:
-            raise NotImplementedError(
-                "PressureBC surface terms are not on the device yet (SURVEY.md 8f-2); use bcs_p=[]"
-            )
+        if len(self._bcs_p) > 0 and self._nranks > 1:
+            raise NotImplementedError("PressureBC on more than one rank is not wired up yet")
 
         options = {} if options is None else options
         self._low_memory = bool(options.get("low_memory_version", True))
@@ -293,11 +291,18 @@ class FractionalStep_AB_CN:
             self._ctx.set_velocity_bc_values(i, merged)
             self._bc_versions[i] = version
 
+    def _assemble_pressure_surface(self):
+        """``fracstep.py:445-446,461-465``: refresh the PressureBC values and assemble their ds-terms."""
+        for k, bcp in enumerate(self._bcs_p):
+            bcp.update_bc()
+            self._ctx.assemble_pressure_surface(bcp._facet_cells, bcp._facet_local, bcp._h, accumulate=k > 0)
+
     # ---- stages (same names and meaning as the reference) ---------------------------------
     def assemble_first(self, dt: float, nu: float):
         """``fracstep.py:411-472``: A = M/dt + C/2 + nu K/2 (Dirichlet rows -> identity) and
         b_k = (M/dt - C/2 - nu K/2) u_k^{n-1} + f_k."""
         self._flush()
+        self._assemble_pressure_surface()
         self._ctx.assemble_first(float(dt), float(nu))
         self._written(self._uab, self._b_first)
 
@@ -343,6 +348,7 @@ class FractionalStep_AB_CN:
         [[bc.update_bc() for bc in bcu] for bcu in self._bcs_u]
         self._upload_bcs()
         self._flush()
+        self._assemble_pressure_surface()
         diff = self._ctx.step(float(dt), float(nu), float(max_error), int(max_iter))
         self._written(self._u, self._u1, self._u2, self._uab, self._rhs1, self._b_first, self._ps, self._p,
                       self._dp, self._b2)

@@ -37,6 +37,9 @@ EDGES = {
 def simplex_quadrature(d: int, degree: int):
     """Collapsed-coordinate Gauss-Jacobi rule exact for polynomials of total degree <= degree."""
     n = degree // 2 + 1
+    if d == 1:
+        x0, w0 = roots_jacobi(n, 0, 0)
+        return ((x0 + 1) / 2)[:, None], w0 / 2
     if d == 2:
         x0, w0 = roots_jacobi(n, 0, 0)
         x1, w1 = roots_jacobi(n, 1, 0)
@@ -187,6 +190,37 @@ class Forms:
         return err
 
 
+FACET_VERTS = {
+    2: [(1, 2), (0, 2), (0, 1)],
+    3: [(1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)],
+}
+
+
+def pressure_surface_vector(F: "Forms", i: int, facet_cells, facet_local, h_nodal):
+    """int_Gamma h n_i dv/dx_i ds  (``bcs.py:233-242``: rhs(i) = value * n_i * v.dx(i) * ds), h given
+    nodally in Q, on the exterior facets (cell, local facet index); numerical facet quadrature."""
+    d = F.d
+    fpts, fw = simplex_quadrature(d - 1, 3)
+    fw = fw / fw.sum()  # weights relative to the facet measure
+    ref_verts = np.vstack([np.zeros(d), np.eye(d)])
+    b = np.zeros(F.nV)
+    for c, f in zip(np.asarray(facet_cells), np.asarray(facet_local)):
+        fv = ref_verts[list(FACET_VERTS[d][f])]  # (d, d) facet vertices in cell reference coordinates
+        mu = np.hstack([1 - fpts.sum(axis=1, keepdims=True), fpts])  # barycentrics on the facet
+        pts = mu @ fv
+        phi, dphi = tabulate(d, F.deg_v, pts)
+        psi, _ = tabulate(d, F.deg_q, pts)
+        Kinv, detJ = F.g.Kinv[c], F.g.detJ[c]
+        glam = Kinv.T @ np.concatenate([[-np.ones(d)], np.eye(d)])[f]  # physical grad of lambda_f (inward)
+        area = detJ * np.linalg.norm(glam) / (2.0 if d == 3 else 1.0)
+        n = -glam / np.linalg.norm(glam)
+        gphys = np.einsum("dk,qjd->qjk", Kinv, dphi)  # (q, j, k)
+        hq = psi @ h_nodal[F.qdofs[c]]
+        contrib = area * np.einsum("q,q,qj->j", fw, hq, gphys[:, :, i]) * n[i]
+        np.add.at(b, F.vdofs[c], contrib)
+    return b
+
+
 def zero_rows(A: sp.csr_matrix, rows: np.ndarray, diag: float) -> sp.csr_matrix:
     """``Mat.zeroRowsLocal(rows, diag)``: zero the rows, keep the pattern, put `diag` on the diagonal."""
     A = A.tocsr(copy=True)
@@ -216,7 +250,7 @@ class OracleIPCS:
     optionally with surface vectors ``p_surf[i]`` (``fracstep.py:461-465``)."""
 
     def __init__(self, x, cells, d, vdofs, qdofs, xV, xQ, deg_v, bcs_u, bcs_p=(), body_force=None,
-                 low_memory=False, rotational=False, p_surf=None):
+                 low_memory=False, rotational=False, p_surf=None, pressure_facets=()):
         self.d = d
         self.nV, self.nQ = xV.shape[0], xQ.shape[0]
         self.xV, self.xQ = xV, xQ
@@ -225,6 +259,8 @@ class OracleIPCS:
         self.bcs_u = bcs_u
         self.bcs_p = [np.asarray(b, dtype=np.int64) for b in bcs_p]
         self.p_surf = p_surf
+        # natural pressure BCs: list of (facet_cells, facet_local, value) with value float or callable(x)
+        self.pressure_facets = list(pressure_facets)
         self.rotational = rotational
         z = lambda n: np.zeros(n)
         self.u = [z(self.nV) for _ in range(d)]
@@ -267,6 +303,12 @@ class OracleIPCS:
 
     # ---- stages --------------------------------------------------------------------------
     def assemble_first(self, dt, nu):
+        if self.pressure_facets:  # :445-446 update, :461-465 surface vector
+            self.p_surf = [np.zeros(self.nV) for _ in range(self.d)]
+            for fc, fl, val in self.pressure_facets:
+                h = np.asarray(val(self.xQ.T), dtype=np.float64) if callable(val) else np.full(self.nQ, float(val))
+                for i in range(self.d):
+                    self.p_surf[i] += pressure_surface_vector(self.F, i, fc, fl, h)
         uab = [1.5 * a - 0.5 * b for a, b in zip(self.u1, self.u2)]  # :432-434
         C = self.F.convection(uab)  # :435-437
         R = (-0.5) * C + (1.0 / dt) * self.M + (-0.5 * nu) * self.K  # :438-442

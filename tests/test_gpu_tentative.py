@@ -1,0 +1,113 @@
+"""Mirror of /root/reference/test/test_tentative_velocity.py:87-242: unit square 10x10, inlet callable
+BC + walls + outlet PressureBC(4.0), +/- body force; `assemble_first`, `velocity_tentative_assemble`,
+`velocity_tentative_solve` through oasisx_b200, compared with the direct statement of the equation (the
+CPU oracle) -- RHS vectors (the reference's assertion, :235), the matrix (the reference's dead check,
+:227-229, made live) and the solution; then whole time steps incl. the pressure Dirichlet rows."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oasisx_b200 import DirichletBC, FractionalStep_AB_CN, LocatorMethod, PressureBC, fem, mesh as bmesh
+from problems import relerr, vscale
+
+pytestmark = pytest.mark.gpu
+
+
+class Inlet:
+    def __init__(self, t):
+        self.t = t
+
+    def eval(self, x):
+        return (1 + self.t) * np.sin(np.pi * x[1])
+
+
+def build(deg_u, body_force, solver_options=None):
+    from oracle.ipcs_oracle import OracleIPCS
+
+    msh = bmesh.create_unit_square(None, 10, 10)
+    dim = msh.topology.dim - 1
+    left = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 0))
+    tb = bmesh.locate_entities_boundary(msh, dim, lambda x: np.logical_or(np.isclose(x[1], 0), np.isclose(x[1], 1)))
+    right = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 1))
+    facets = np.hstack([left, tb, right])
+    values = np.hstack([np.full_like(left, 1), np.full_like(tb, 2), np.full_like(right, 3)])
+    order = np.argsort(facets)
+    tags = bmesh.meshtags(msh, dim, facets[order], values[order])
+    inlet = Inlet(0)
+    bc_tb = DirichletBC(0.0, LocatorMethod.TOPOLOGICAL, (tags, 2))
+    bc_inlet_x = DirichletBC(inlet.eval, LocatorMethod.TOPOLOGICAL, (tags, 1))
+    bc_inlet_y = DirichletBC(0.0, LocatorMethod.TOPOLOGICAL, (tags, 1))
+    bcs_u = [[bc_inlet_x, bc_tb], [bc_inlet_y, bc_tb]]
+    bcs_p = [PressureBC(4.0, (tags, 3))]
+    f = np.array([0.3, -0.1]) if body_force else None
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    s = FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=bcs_p,
+                             solver_options=solver_options or {"tentative": lu, "pressure": lu, "scalar": lu},
+                             options={"low_memory_version": False}, body_force=f)
+    V, Q = fem.functionspace(msh, ("Lagrange", deg_u)), fem.functionspace(msh, ("Lagrange", 1))
+    dl, dtb = fem.locate_dofs_topological(V, dim, left), fem.locate_dofs_topological(V, dim, tb)
+    pdofs = fem.locate_dofs_topological(Q, dim, right)
+    o = OracleIPCS(msh.geometry.x, msh.geometry.dofmap, 2, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                   Q.tabulate_dof_coordinates(), deg_u,
+                   bcs_u=[[(dl, inlet.eval), (dtb, 0.0)], [(dl, 0.0), (dtb, 0.0)]], bcs_p=[pdofs], body_force=f,
+                   pressure_facets=[(bcs_p[0]._facet_cells, bcs_p[0]._facet_local, 4.0)])
+    return s, o, inlet, bc_inlet_x
+
+
+@pytest.mark.parametrize("body_force", [True, False])
+@pytest.mark.parametrize("deg_u", [1, 2])
+def test_tentative(deg_u, body_force):
+    s, o, inlet, bc_inlet_x = build(deg_u, body_force)
+    dt, nu = 0.1, 0.5
+    xV = o.xV.T
+    inlet.t = -2 * dt
+    for i in range(2):
+        s._u2[i].interpolate(inlet.eval)
+        o.u2[i] = inlet.eval(xV)
+    inlet.t = -dt
+    for i in range(2):
+        s._u1[i].interpolate(inlet.eval)
+        o.u1[i] = inlet.eval(xV)
+    inlet.t = dt
+    bc_inlet_x.update_bc()
+    o.update_bcs()
+    s._ps.interpolate(lambda x: x[1])
+    o.ps = o.xQ[:, 1].copy()
+    s.assemble_first(dt, nu)
+    s.velocity_tentative_assemble()
+    diff, reasons = s.velocity_tentative_solve()
+    o.assemble_first(dt, nu)
+    o.velocity_tentative_assemble()
+    o.velocity_tentative_solve()
+    # the natural pressure term is there and matters
+    assert max(np.abs(p).max() for p in o.p_surf) > 1e-3
+    ip, ix, v = s._A.getValuesCSR()
+    A = sp.csr_matrix((v, ix, ip), shape=s._A.getSize())
+    assert abs(A - o.A).max() <= 1e-12 * abs(o.A).max()  # test_tentative_velocity.py:227-229
+    assert (reasons > 0).all()  # :234
+    for i in range(2):
+        assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i], vscale(o.rhs1)) <= 1e-12  # :235
+        assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-9
+    # the stages the reference leaves commented out (:237-240)
+    s.pressure_assemble(dt)
+    assert s.pressure_solve(nu) > 0
+    assert (s.velocity_update(dt) > 0).all()
+    o.pressure_assemble(dt)
+    o.pressure_solve(nu)
+    o.velocity_update(dt)
+    assert relerr(s._dp.x.array_ro(), o.dp) <= 1e-8
+    for i in range(2):
+        assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
+
+
+def test_channel_time_steps_with_pressure_bc():
+    s, o, inlet, _ = build(2, False)
+    dt, nu = 0.01, 0.5
+    inlet.t = 0.0
+    for n in range(3):
+        inlet.t += dt
+        s.solve(dt, nu, max_iter=2, max_error=1e-30)
+        o.solve(dt, nu, max_iter=2, max_error=1e-30)
+        for i in range(2):
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, n
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
