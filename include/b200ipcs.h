@@ -196,6 +196,11 @@ int b2_project_q(b2_ctx* ctx, const double* rhs, double* x, int32_t* reason);
 /* sum_k int (u_h,k - e_k)^2 dx where e is given nodally in a P2 (or P1 for Q) space of the same
  * mesh: `exact` has the layout of the vector it is compared with. */
 int b2_l2_diff_sq(b2_ctx* ctx, int vec, const double* exact, int64_t n, double* out);
+/* The reference's own error functional: sum_k int (u_h,k - e_k)^2 dx by quadrature on the first `n_cells`
+ * local cells (the owned ones), e evaluated by the caller at the physical images of the n_q reference
+ * points (`exact` is [n_cells][n_q][K]); summed over ranks. */
+int b2_l2_error_quadrature(b2_ctx* ctx, int vec, int64_t n_cells, int n_q, const double* ref_points,
+                           const double* weights, const double* exact, double* out);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 int b2_get_stats(b2_ctx* ctx, b2_stats* out);

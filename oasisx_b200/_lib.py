@@ -30,7 +30,7 @@ SYMBOLS = [
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
-    "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "b2_assemble_pressure_surface": (i32, [vp, i64, vp, vp, vp, i32]),
         "b2_project_q": (i32, [vp, vp, vp, vp]),
         "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
+        "b2_l2_error_quadrature": (i32, [vp, i32, i64, i32, vp, vp, vp, vp]),
         "b2_get_stats": (i32, [vp, vp]),
         "b2_bench_kernel": (i32, [vp, i32, i32, vp, vp]),
         "b2_synchronize": (i32, [vp]),
@@ -330,6 +331,13 @@ class Context:
         e = _f64(exact)
         out = C.c_double(0.0)
         self._check(self.lib.b2_l2_diff_sq(self._h, vec, _ptr(e), e.size, C.byref(out)), "b2_l2_diff_sq")
+        return out.value
+
+    def l2_error_quadrature(self, vec: int, n_cells: int, ref_points, weights, exact) -> float:
+        p, w, e = _f64(ref_points), _f64(weights), _f64(exact)
+        out = C.c_double(0.0)
+        self._check(self.lib.b2_l2_error_quadrature(self._h, vec, n_cells, len(w), _ptr(p), _ptr(w), _ptr(e), C.byref(out)),
+                    "b2_l2_error_quadrature")
         return out.value
 
     def stats(self) -> Stats:

@@ -431,3 +431,60 @@ __global__ void k_pressure_surface(int64_t n_facets, const int* __restrict__ fac
     for (int k = 0; k < D; ++k) atomicAdd(psurf + (size_t)k * ld + row, acc[j][k]);
   }
 }
+
+// ---- functionals (assemble_scalar, demo/taylor_green.py:186-207) ----------------------------------
+// out += sum over cells, quadrature points and components of |detJ| w_q (u_h,k(x_q) - exact[c][q][k])^2.
+// The exact field is evaluated by the host at the physical quadrature points (it is a Python callable).
+// SPACE_V: vec is component-major with K comps of the velocity element; !SPACE_V: P1, K = 1.
+template <int D, int DEG, bool SPACE_V>
+__global__ void __launch_bounds__(128)
+k_l2_error(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
+           const int* __restrict__ cdofs, int K, int ld, const double* __restrict__ vec, int n_q,
+           const double* __restrict__ ref_pts, const double* __restrict__ weights,
+           const double* __restrict__ exact, double* out, double* partials, unsigned* counter) {
+  using E = El<D, DEG>;
+  constexpr int ND = SPACE_V ? E::NV : E::NQ;
+  constexpr bool P2 = SPACE_V && DEG == 2;
+  double s[1] = {0.0};
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+    int dofs[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) dofs[j] = cdofs[c * ND + j];
+    for (int q = 0; q < n_q; ++q) {
+      double lam[D + 1];
+      lam[0] = 1.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        lam[k + 1] = ref_pts[q * D + k];
+        lam[0] -= lam[k + 1];
+      }
+      double phi[ND];
+      if (!P2) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) phi[j] = lam[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j <= D; ++j) phi[j] = lam[j] * (2.0 * lam[j] - 1.0);
+        if (D == 3) {
+          const int ea[6] = {2, 1, 1, 0, 0, 0}, eb[6] = {3, 3, 2, 3, 2, 1};
+#pragma unroll
+          for (int e = 0; e < 6; ++e) phi[(D + 1 + e) < ND ? (D + 1 + e) : 0] = 4.0 * lam[ea[e]] * lam[eb[e]];
+        } else {
+          const int ea[3] = {1, 0, 0}, eb[3] = {2, 2, 1};
+#pragma unroll
+          for (int e = 0; e < 3; ++e) phi[(D + 1 + e) < ND ? (D + 1 + e) : 0] = 4.0 * lam[ea[e]] * lam[eb[e]];
+        }
+      }
+      for (int k = 0; k < K; ++k) {
+        double uh = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) uh = fma(phi[j], vec[(size_t)k * ld + dofs[j]], uh);
+        const double e = uh - exact[((size_t)c * n_q + q) * K + k];
+        s[0] = fma(g.detJ * weights[q], e * e, s[0]);
+      }
+    }
+  }
+  double total[1];
+  if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
+}

@@ -363,5 +363,28 @@ class FractionalStep_AB_CN:
         self._sol_u.x._host_touched = False
         return self._sol_u
 
+    def assemble_l2_error_sq(self, which: str, exact, degree: int = 8) -> float:
+        """``assemble_scalar(inner(u_h - u_ex, u_h - u_ex) * dx)`` summed over ranks
+        (``demo/taylor_green.py:186-207``).  which: "u" (the velocity, `exact` = one callable per
+        component) or "p" (the pressure `_p`, `exact` = one callable).  The exact field is sampled by the
+        host at the quadrature points of a degree-`degree` rule; the integration runs on the device."""
+        from .quadrature import simplex_rule
+
+        mesh, d = self._mesh, self._mesh.geometry.dim
+        pts, w = simplex_rule(d, degree)
+        if self._lp is not None:
+            cells = self._lp.cell_nodes[: self._lp.n_cells_owned]
+        else:
+            cells = mesh.geometry.dofmap
+        X = mesh.geometry.x[cells]  # (nc, d+1, 3)
+        lam = np.hstack([1.0 - pts.sum(axis=1, keepdims=True), pts])  # (nq, d+1)
+        xq = np.einsum("qa,cak->kcq", lam, X)  # (3, nc, nq)
+        flat = xq.reshape(3, -1)
+        fs = list(exact) if which == "u" else [exact]
+        ex = np.stack([np.asarray(f(flat), dtype=np.float64).reshape(len(cells), len(w)) for f in fs], axis=2)
+        self._flush()
+        vec = L.VEC_U if which == "u" else L.VEC_P
+        return self._ctx.l2_error_quadrature(vec, len(cells), pts, w, np.ascontiguousarray(ex))
+
     def stats(self):
         return self._ctx.stats()

@@ -238,3 +238,21 @@ def test_extrapolated_initial_guesses_do_not_change_the_solution():
         for i in range(3):
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, n
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
+
+
+@pytest.mark.parametrize("gdim,N", [(2, 8), (3, 4)])
+def test_l2_error_functional_matches_oracle(gdim, N):
+    """assemble_scalar of |u_h - u_ex|^2 and |p_h - p_ex|^2 (demo/taylor_green.py:186-207) <= 1e-10 rel."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    s = make_solver(msh, 2, tg, dt)
+    o = make_oracle(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = dt, dt / 2
+    s.solve(dt, nu, max_iter=1)
+    o.solve(dt, nu, max_iter=1)
+    eu = s.assemble_l2_error_sq("u", tg.components, degree=10)
+    ep = s.assemble_l2_error_sq("p", tg.eval_p, degree=10)
+    ou = o.F.l2_error_sq(o.u, o.vdofs, tg.components, degree=10)
+    op = o.F.l2_error_sq([o.p], o.qdofs, [tg.eval_p], degree=10, space="Q")
+    assert abs(eu - ou) <= 1e-8 * ou and abs(ep - op) <= 1e-8 * op
