@@ -138,6 +138,10 @@ struct b2_ctx {
   int mg_pre = 2, mg_post = 2, mg_coarse = 40;
   double mg_omega = 0.7;
   DBuf<double> mg_x0, mg_t0;  // fine-level work vectors (n_local of Q)
+  DBuf<MgDev> mg_dev;         // device descriptors of the coarse levels (index = level - 1)
+  int mg_dev_levels = 0;      // number of levels the descriptor array was built for
+  int mg_small_from = 1 << 30; // first level (>= 1) handled by the single-block kernel
+  double** d_mg_result = nullptr; double** h_mg_result = nullptr;
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank)
   bool patterns_built = false, preassembled = false;
@@ -524,8 +528,39 @@ void mg_sweeps(b2_ctx* c, const MgView& L, bool fine, const double* b, double*& 
   }
 }
 
+void mg_build_descriptors(b2_ctx* c) {
+  const int nl = (int)c->mg.size();
+  std::vector<MgDev> h(nl);
+  c->mg_small_from = 1 << 30;
+  for (int i = 0; i < nl; ++i) {
+    MgLevel& M = c->mg[i];
+    h[i] = {M.n, M.P.n_rows, M.pat.slice_ptr.p, M.pat.scols.p, M.A.p, M.dinv.p, M.x.p, M.b.p, M.tmp.p,
+            M.P.rowptr.p, M.P.cols.p, M.Pv.p, M.R.rowptr.p, M.R.cols.p, M.Rv.p};
+    if (M.n <= 8192 && c->mg_small_from == (1 << 30)) c->mg_small_from = i + 1;
+  }
+  if (nl - (c->mg_small_from - 1) > 15) c->mg_small_from = 1 << 30;  // shared pointer tables hold 16 levels
+  c->mg_dev.alloc(nl);
+  B2_CUDA(cudaMemcpyAsync(c->mg_dev.p, h.data(), sizeof(MgDev) * nl, cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->d_mg_result) {
+    B2_CUDA(cudaMalloc(&c->d_mg_result, sizeof(double*)));
+    B2_CUDA(cudaMallocHost(&c->h_mg_result, sizeof(double*)));
+  }
+  c->mg_dev_levels = nl;
+}
+
 // x_l <- V-cycle(b_l), zero initial guess.  Returns the buffer that holds the result.
 double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
+  if (c->mg_dev_levels != (int)c->mg.size()) mg_build_descriptors(c);
+  if (l >= c->mg_small_from) {
+    // the rest of the hierarchy in one single-block kernel; b is c->mg[l-1].b by construction
+    B2_LAUNCH(c, k_mg_small_cycle, 1, 1024, c->mg_dev.p, l - 1, (int)c->mg.size() - 1, c->mg_pre, c->mg_post, c->mg_coarse,
+              c->mg_omega, c->d_mg_result);
+    // the result lives in x or tmp of that level depending on the parity of the sweep counts
+    const int last = (int)c->mg.size();
+    const int sweeps = (l == last ? c->mg_coarse : c->mg_pre) - 1 + (l == last ? 0 : c->mg_post);
+    return (sweeps % 2 == 0) ? c->mg[l - 1].x.p : c->mg[l - 1].tmp.p;
+  }
   const bool fine = (l == 0);
   MgView L;
   if (fine) {

@@ -40,6 +40,94 @@ __global__ void k_mg_first(int64_t n, const double* __restrict__ dinv, const dou
     x[i] = omega * dinv[i] * b[i];
 }
 
+// ---- the small end of the hierarchy in one kernel ------------------------------------------------
+// Levels with a few thousand unknowns are pure launch latency when every sweep is its own kernel
+// (~60 launches per cycle).  One 1024-thread block runs the whole sub-cycle from level l0 down to the
+// coarsest level and back, with block barriers between the phases.
+struct MgDev {
+  int n, n_fine;
+  const int *slice_ptr, *cols;
+  const double *A, *dinv;
+  double *x, *b, *tmp;
+  const int *Pptr, *Pcol;
+  const double* Pval;  // rows: dofs of the finer level, cols: this level
+  const int *Rptr, *Rcol;
+  const double* Rval;  // rows: this level, cols: dofs of the finer level
+};
+
+__device__ __forceinline__ double mg_row_dot(const MgDev& L, int row, const double* x) {
+  const int s = row >> 5;
+  const int base = L.slice_ptr[s];
+  const int len = (L.slice_ptr[s + 1] - base) >> 5;
+  double acc = 0.0;
+  for (int t = 0; t < len; ++t) {
+    const size_t p = (size_t)base + ((size_t)t << 5) + (row & 31);
+    acc = fma(L.A[p], x[L.cols[p]], acc);
+  }
+  return acc;
+}
+
+// n_sweeps damped-Jacobi sweeps on level L for L.b, result pointer returned (x and tmp ping-pong)
+__device__ double* mg_block_sweeps(const MgDev& L, double* x, double* tmp, int n_sweeps, bool from_zero, double omega) {
+  int s = 0;
+  if (from_zero && n_sweeps > 0) {
+    for (int r = threadIdx.x; r < L.n; r += blockDim.x) x[r] = omega * L.dinv[r] * L.b[r];
+    __syncthreads();
+    s = 1;
+  }
+  for (; s < n_sweeps; ++s) {
+    for (int r = threadIdx.x; r < L.n; r += blockDim.x) tmp[r] = fma(omega * L.dinv[r], L.b[r] - mg_row_dot(L, r, x), x[r]);
+    __syncthreads();
+    double* t = x;
+    x = tmp;
+    tmp = t;
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(1024)
+k_mg_small_cycle(const MgDev* __restrict__ lv, int l0, int l_last, int pre, int post, int coarse, double omega,
+                 double** result) {
+  __shared__ double* xs[16];
+  __shared__ double* ts[16];
+  // down
+  for (int l = l0; l <= l_last; ++l) {
+    const MgDev L = lv[l];
+    double* x = mg_block_sweeps(L, L.x, L.tmp, l == l_last ? coarse : pre, true, omega);
+    double* tmp = (x == L.x) ? L.tmp : L.x;
+    if (threadIdx.x == 0) { xs[l - l0] = x; ts[l - l0] = tmp; }
+    if (l < l_last) {
+      for (int r = threadIdx.x; r < L.n; r += blockDim.x) tmp[r] = L.b[r] - mg_row_dot(L, r, x);  // residual
+      __syncthreads();
+      const MgDev C = lv[l + 1];
+      for (int r = threadIdx.x; r < C.n; r += blockDim.x) {  // b_{l+1} = R r
+        double acc = 0.0;
+        for (int p = C.Rptr[r]; p < C.Rptr[r + 1]; ++p) acc = fma(C.Rval[p], tmp[C.Rcol[p]], acc);
+        C.b[r] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  // up
+  for (int l = l_last - 1; l >= l0; --l) {
+    const MgDev L = lv[l];
+    const MgDev C = lv[l + 1];
+    double* x = xs[l - l0];
+    double* tmp = ts[l - l0];
+    const double* xc = xs[l + 1 - l0];
+    for (int r = threadIdx.x; r < L.n; r += blockDim.x) {  // x += P xc
+      double acc = x[r];
+      for (int p = C.Pptr[r]; p < C.Pptr[r + 1]; ++p) acc = fma(C.Pval[p], xc[C.Pcol[p]], acc);
+      x[r] = acc;
+    }
+    __syncthreads();
+    x = mg_block_sweeps(L, x, tmp, post, false, omega);
+    if (threadIdx.x == 0) xs[l - l0] = x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *result = xs[0];
+}
+
 // ---- PCG with explicit z (K = 1) ----------------------------------------------------------------
 enum { FIN_CGZ_INIT = 32, FIN_CGZ_RZ0, FIN_CGZ_RZ, FIN_CGZ_UPDATE };
 
