@@ -682,11 +682,39 @@ void rect_vq(b2_ctx* c, const double* vals, const double* xq, const double* add,
     B2_LAUNCH(c, (k_rect_vq<K, 4>), blocks_for((int64_t)vq.n_rows * 4, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, ld, scale, out);
 }
 
+// matrix-free element vectors of the low-memory strategy (elem.cuh: k_lowmem_vector)
+void lowmem_vector(b2_ctx* c, int mode, const double* in, double scale, double* out) {
+  const Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
+  dispatch_elem(c, [&](auto e) {
+    using E = decltype(e);
+    const int grid = blocks_for(c->n_cells, 128);
+    if (mode == 0)
+      B2_LAUNCH(c, (k_lowmem_vector<E::D, E::DEG, 0>), grid, 128, c->n_cells, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
+                (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), in, scale, out);
+    else if (mode == 1)
+      B2_LAUNCH(c, (k_lowmem_vector<E::D, E::DEG, 1>), grid, 128, c->n_cells, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
+                (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), in, scale, out);
+    else
+      B2_LAUNCH(c, (k_lowmem_vector<E::D, E::DEG, 2>), grid, 128, c->n_cells, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
+                (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), in, scale, out);
+  });
+}
+
+__global__ void k_zero_rows_q(int64_t n, const uint8_t* __restrict__ zero_row, double* __restrict__ v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && zero_row[i]) v[i] = 0.0;
+}
+
 void stage_tentative_assemble(b2_ctx* c) {
   require_ready(c);
-  B2_REQUIRE(!c->low_memory, "low_memory_version=True is not built yet (SURVEY.md 8f-1)");
   double* ps = c->vec(B2_VEC_PS);
   halo_forward(c, B2_SPACE_Q, ps, 1);
+  if (c->low_memory) {  // :485-497: assemble int p* dv/dx_i directly; rhs1 = b_first + that (:505-506)
+    const int64_t nl = c->sp[B2_SPACE_V].n_local() * c->gdim;
+    B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_RHS1), c->vec(B2_VEC_BFIRST), sizeof(double) * nl, cudaMemcpyDeviceToDevice, c->stream));
+    lowmem_vector(c, 0, ps, 1.0, c->vec(B2_VEC_RHS1));
+    return;
+  }
   if (c->gdim == 2) rect_vq<2>(c, c->P.p, ps, c->vec(B2_VEC_BFIRST), 1.0, c->vec(B2_VEC_RHS1));
   else rect_vq<3>(c, c->P.p, ps, c->vec(B2_VEC_BFIRST), 1.0, c->vec(B2_VEC_RHS1));
 }
@@ -742,11 +770,17 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
 
 void stage_pressure_assemble(b2_ctx* c, double dt) {
   require_ready(c);
-  B2_REQUIRE(!c->low_memory, "low_memory_version=True is not built yet (SURVEY.md 8f-1)");
   const CSR& qv = c->pat[B2_PAT_QV];
   double* u = c->vec(B2_VEC_U);
   halo_forward(c, B2_SPACE_V, u, c->gdim);
   const uint8_t* zr = c->has_pbc ? c->is_bc_q.p : nullptr;
+  if (c->low_memory) {  // :537-538: b2 = -(1/dt) int div(u) q, Dirichlet rows zeroed (:549-550)
+    const Space& Q = c->sp[B2_SPACE_Q];
+    B2_CUDA(cudaMemsetAsync(c->vec(B2_VEC_B2), 0, sizeof(double) * Q.n_local(), c->stream));
+    lowmem_vector(c, 2, u, -1.0 / dt, c->vec(B2_VEC_B2));
+    if (zr) B2_LAUNCH(c, k_zero_rows_q, blocks_for(Q.n_owned, 256), 256, Q.n_owned, zr, c->vec(B2_VEC_B2));
+    return;
+  }
   const int grid = blocks_for((int64_t)qv.n_rows * 16, 256);
   const int ld = (int)c->sp[B2_SPACE_V].n_local();
   if (c->gdim == 2)
@@ -790,7 +824,10 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
     const int grid = blocks_for((int64_t)qv.n_rows * 16, 256);
     // rhs <- -0.5 nu sum_i D_i u_i (reusing b2 as scratch: it is rebuilt by the next pressure_assemble)
     const int ldv = (int)c->sp[B2_SPACE_V].n_local();
-    if (c->gdim == 2)
+    if (c->low_memory) {
+      B2_CUDA(cudaMemsetAsync(rhs, 0, sizeof(double) * Q.n_local(), c->stream));
+      lowmem_vector(c, 2, u, -0.5 * nu, rhs);
+    } else if (c->gdim == 2)
       B2_LAUNCH(c, (k_rect_qv<2, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ldv, -0.5 * nu, (const uint8_t*)nullptr, rhs);
     else
       B2_LAUNCH(c, (k_rect_qv<3, 16>), grid, 256, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p, u, ldv, -0.5 * nu, (const uint8_t*)nullptr, rhs);
@@ -807,12 +844,12 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
 
 void stage_velocity_update(b2_ctx* c, double dt, int32_t* reasons) {
   require_ready(c);
-  B2_REQUIRE(!c->low_memory, "low_memory_version=True is not built yet (SURVEY.md 8f-1)");
   const int K = c->gdim;
   double *u = c->vec(B2_VEC_U), *b3 = c->vec(B2_VEC_B3), *dp = c->vec(B2_VEC_DP);
   spmm(c, c->pat[B2_PAT_VV], c->M.p, K, u, b3, nullptr, nullptr, FIN_NONE, 0, B2_SPACE_V);  // :638
   halo_forward(c, B2_SPACE_Q, dp, 1);
-  if (K == 2) rect_vq<2>(c, c->G.p, dp, b3, -dt, b3);  // :642-645
+  if (c->low_memory) lowmem_vector(c, 1, dp, -dt, b3);  // :617-622: b3 -= dt int d(dp)/dx_i v
+  else if (K == 2) rect_vq<2>(c, c->G.p, dp, b3, -dt, b3);  // :642-645
   else rect_vq<3>(c, c->G.p, dp, b3, -dt, b3);
   int32_t its[B2_MAXK] = {0, 0, 0};
   const bool extrap = c->ksp[B2_SOLVER_SCALAR].extrapolate_guess;
@@ -899,9 +936,11 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
   c->Kst.alloc(vv.slots); c->Kst.zero(c->stream);
   c->A.alloc(vv.slots); c->A.zero(c->stream);
   c->Ap.alloc(qq.slots); c->Ap.zero(c->stream);
-  c->P.alloc(vq.nnz * K); c->P.zero(c->stream);
-  c->G.alloc(vq.nnz * K); c->G.zero(c->stream);
-  c->D.alloc(qv.nnz * K); c->D.zero(c->stream);
+  if (!c->low_memory) {  // the 3d rectangular operator families exist only in the matrix-vector strategy (:392-404)
+    c->P.alloc(vq.nnz * K); c->P.zero(c->stream);
+    c->G.alloc(vq.nnz * K); c->G.zero(c->stream);
+    c->D.alloc(qv.nnz * K); c->D.zero(c->stream);
+  }
   if (c->rotational) { c->MQ.alloc(qq.slots); c->MQ.zero(c->stream); }
   c->dinvA.alloc(V.n_local()); c->dinvM.alloc(V.n_local()); c->dinvAp.alloc(Q.n_local());
   c->onesV.alloc(V.n_local()); c->onesQ.alloc(Q.n_local());
@@ -924,10 +963,12 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
     if (c->rotational)
       B2_LAUNCH(c, (k_assemble_square<D, DEG, B2_FORM_MASS_Q>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p,
                 Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, qq.slice_ptr.p, c->MQ.p);                    // function.py:63-71
-    B2_LAUNCH(c, (k_assemble_PG<D, DEG>), blocks_for(nc * E::NV, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
-              Q.cell_dofs.p, vq.n_rows, vq.rowptr.p, vq.cols.p, c->P.p, c->G.p);              // :395,399
-    B2_LAUNCH(c, (k_assemble_D<D, DEG>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
-              Q.cell_dofs.p, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p);                      // :403
+    if (!c->low_memory) {
+      B2_LAUNCH(c, (k_assemble_PG<D, DEG>), blocks_for(nc * E::NV, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
+                Q.cell_dofs.p, vq.n_rows, vq.rowptr.p, vq.cols.p, c->P.p, c->G.p);              // :395,399
+      B2_LAUNCH(c, (k_assemble_D<D, DEG>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
+                Q.cell_dofs.p, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p);                      // :403
+    }
     B2_LAUNCH(c, (k_assemble_loads<D, DEG>), blocks_for(nc, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
               (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), f[0], f[1], f[2], c->vec(B2_VEC_B0), c->vec(B2_VEC_MQ));  // :387-390
   });

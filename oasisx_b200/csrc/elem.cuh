@@ -488,3 +488,72 @@ k_l2_error(int64_t n_cells, const double* __restrict__ x, const int* __restrict_
   double total[1];
   if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
 }
+
+// ---- low_memory_version=True: matrix-free element vectors (fracstep.py:305-309,327-330,342-346) -----
+// MODE 0: out_k[j] += int s dphi_j/dx_k          (s in Q: p* for :485-497, out = rhs1 preloaded with b_first)
+// MODE 1: out_k[j] += int ds/dx_k phi_j          (s in Q: dp for :612-622)
+// MODE 2: outq[q]  += int (sum_k du_k/dx_k) psi_q (u in V: div(u) q for :537-538)
+// One thread per local cell; rows beyond the owned range are skipped (the ghost-cell layer makes owned
+// rows complete, so no reverse scatter is needed).
+template <int D, int DEG, int MODE>
+__global__ void __launch_bounds__(128)
+k_lowmem_vector(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
+                const int* __restrict__ vdofs, const int* __restrict__ qdofs, int nV_owned, int nQ_owned, int ld,
+                const double* __restrict__ in, double scale, double* __restrict__ out) {
+  using E = El<D, DEG>;
+  constexpr int NV = E::NV, NQ = E::NQ;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  const double f = scale * g.detJ;
+  if constexpr (MODE == 0 || MODE == 1) {
+    double sq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sq[q] = __ldg(in + qdofs[c * NQ + q]);
+    for (int j = 0; j < NV; ++j) {
+      const int row = vdofs[c * NV + j];
+      if (row >= nV_owned) continue;
+      double gr[D];  // reference-direction sums  sum_q T[dl][j][q] s_q
+#pragma unroll
+      for (int dl = 0; dl < D; ++dl) {
+        double a = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) a = fma(MODE == 0 ? E::PX(dl, j, q) : E::GX(dl, j, q), sq[q], a);
+        gr[dl] = a;
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double v = 0;
+#pragma unroll
+        for (int dl = 0; dl < D; ++dl) v = fma(g.Kinv[dl][k], gr[dl], v);
+        atomicAdd(out + (size_t)k * ld + row, f * v);
+      }
+    }
+  } else {
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    for (int j = 0; j < NV; ++j) {
+      const int dof = vdofs[c * NV + j];
+      // w[dl] = sum_k Kinv[dl][k] u_k[dof]
+      double w[D];
+#pragma unroll
+      for (int dl = 0; dl < D; ++dl) w[dl] = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double uk = __ldg(in + (size_t)k * ld + dof);
+#pragma unroll
+        for (int dl = 0; dl < D; ++dl) w[dl] = fma(g.Kinv[dl][k], uk, w[dl]);
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int dl = 0; dl < D; ++dl) acc[q] = fma(w[dl], E::PX(dl, j, q), acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int row = qdofs[c * NQ + q];
+      if (row < nQ_owned) atomicAdd(out + row, f * acc[q]);
+    }
+  }
+}

@@ -146,11 +146,6 @@ class FractionalStep_AB_CN:
 
         options = {} if options is None else options
         self._low_memory = bool(options.get("low_memory_version", True))
-        if self._low_memory:
-            logger.debug(
-                "low_memory_version=True: the matrix-free vector kernels are not built yet; "
-                "using the (algebraically identical) matrix-vector strategy"
-            )
         self._rotational = bool(rotational)
         if body_force is None:
             body_force = (0.0,) * gdim
@@ -191,7 +186,7 @@ class FractionalStep_AB_CN:
             np.unique(np.concatenate([b.bc.dofs for b in self._bcs_p])) if self._bcs_p else np.zeros(0, np.int32)
         )
         ctx.set_pressure_bc_dofs(pdofs[pdofs < self._nQ_owned])
-        ctx.preassemble(body_force, False, self._rotational)
+        ctx.preassemble(body_force, self._low_memory, self._rotational)
 
         # solvers (fracstep.py:230-255)
         solver_options = {} if solver_options is None else solver_options
@@ -227,9 +222,10 @@ class FractionalStep_AB_CN:
         self._M = DeviceMatrix(ctx, L.MAT_M, L.PAT_VV, (nV, cV))
         self._K = DeviceMatrix(ctx, L.MAT_K, L.PAT_VV, (nV, cV))
         self._Ap = DeviceMatrix(ctx, L.MAT_AP, L.PAT_QQ, (nQ, cQ))
-        self._p_vdxi_Mat = [DeviceMatrix(ctx, L.MAT_P, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
-        self._grad_p_Mat = [DeviceMatrix(ctx, L.MAT_G, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
-        self._divu_Mat = [DeviceMatrix(ctx, L.MAT_D, L.PAT_QV, (nQ, cV), i) for i in range(gdim)]
+        if not self._low_memory:  # fracstep.py:315,336,352: these exist only in the matrix-vector strategy
+            self._p_vdxi_Mat = [DeviceMatrix(ctx, L.MAT_P, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
+            self._grad_p_Mat = [DeviceMatrix(ctx, L.MAT_G, L.PAT_VQ, (nV, cQ), i) for i in range(gdim)]
+            self._divu_Mat = [DeviceMatrix(ctx, L.MAT_D, L.PAT_QV, (nQ, cV), i) for i in range(gdim)]
         self._solver_p.setOperators(self._Ap)
         self._solver_c.setOperators(self._M)
         self._solver_u.setOperators(self._A)

@@ -256,3 +256,26 @@ def test_l2_error_functional_matches_oracle(gdim, N):
     ou = o.F.l2_error_sq(o.u, o.vdofs, tg.components, degree=10)
     op = o.F.l2_error_sq([o.p], o.qdofs, [tg.eval_p], degree=10, space="Q")
     assert abs(eu - ou) <= 1e-8 * ou and abs(ep - op) <= 1e-8 * op
+
+
+@pytest.mark.parametrize("gdim,N,deg", [(2, 8, 2), (3, 4, 2), (2, 8, 1)])
+@pytest.mark.parametrize("rotational", [False, True])
+def test_low_memory_version_matches_oracle(gdim, N, deg, rotational):
+    """options={"low_memory_version": True} (the reference's class default, fracstep.py:259): the
+    matrix-free element-vector kernels give the same steps as the oracle (and as the matrix strategy)."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    s = make_solver(msh, deg, tg, dt, low_memory=True, rotational=rotational)
+    assert not hasattr(s, "_p_vdxi_Mat")
+    o = make_oracle(msh, deg, tg, dt, rotational=rotational)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(3):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(gdim):
+            assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i], vscale(o.rhs1)) <= 1e-11
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8

@@ -21,7 +21,7 @@ class Inlet:
         return (1 + self.t) * np.sin(np.pi * x[1])
 
 
-def build(deg_u, body_force, solver_options=None):
+def build(deg_u, body_force, solver_options=None, low_memory=False):
     from oracle.ipcs_oracle import OracleIPCS
 
     msh = bmesh.create_unit_square(None, 10, 10)
@@ -43,7 +43,7 @@ def build(deg_u, body_force, solver_options=None):
     lu = {"ksp_type": "preonly", "pc_type": "lu"}
     s = FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=bcs_p,
                              solver_options=solver_options or {"tentative": lu, "pressure": lu, "scalar": lu},
-                             options={"low_memory_version": False}, body_force=f)
+                             options={"low_memory_version": low_memory}, body_force=f)
     V, Q = fem.functionspace(msh, ("Lagrange", deg_u)), fem.functionspace(msh, ("Lagrange", 1))
     dl, dtb = fem.locate_dofs_topological(V, dim, left), fem.locate_dofs_topological(V, dim, tb)
     pdofs = fem.locate_dofs_topological(Q, dim, right)
@@ -55,9 +55,10 @@ def build(deg_u, body_force, solver_options=None):
 
 
 @pytest.mark.parametrize("body_force", [True, False])
+@pytest.mark.parametrize("low_memory", [True, False])
 @pytest.mark.parametrize("deg_u", [1, 2])
-def test_tentative(deg_u, body_force):
-    s, o, inlet, bc_inlet_x = build(deg_u, body_force)
+def test_tentative(deg_u, low_memory, body_force):
+    s, o, inlet, bc_inlet_x = build(deg_u, body_force, low_memory=low_memory)
     dt, nu = 0.1, 0.5
     xV = o.xV.T
     inlet.t = -2 * dt
