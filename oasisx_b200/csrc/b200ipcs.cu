@@ -431,7 +431,7 @@ void krylov_iterations(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double
       spmm(c, pat, vals, K, r, t, r, st, FIN_BCGS_T, 2, space);                   // t = A s
       B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, ld, p, t, rhat, x, r, st, c->partials.p, c->d_counter, red_ptr(c));
       reduce_finish_host(c, FIN_BCGS_UPDATE, 2 * K);
-      B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, ld, r, q, p, st);
+      B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, ld, r, q, p, rhat, st);
     }
   }
 }

@@ -12,6 +12,8 @@ struct KryState {
   double rho[B2_MAXK], alpha[B2_MAXK], beta[B2_MAXK], omega[B2_MAXK];
   double rz[B2_MAXK], bb[B2_MAXK], rr[B2_MAXK], tol2[B2_MAXK];
   int active[B2_MAXK], reason[B2_MAXK], its[B2_MAXK];
+  int restart[B2_MAXK];  // BiCGStab: shadow residual became orthogonal to r -> restart with rhat = r
+  double rh2[B2_MAXK];   // |rhat|^2
   int done, maxit, K, pad;
   double rtol, atol;
 };
@@ -98,6 +100,8 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
         st->bb[k] = t[k];
         st->rr[k] = t[K + k];
         st->rho[k] = t[K + k];  // rhat = r0
+        st->rh2[k] = t[K + k];
+        st->restart[k] = 0;
         st->alpha[k] = 1.0;
         st->omega[k] = 1.0;
         st->beta[k] = 0.0;
@@ -135,11 +139,21 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
         kry_converge_test(st, k);
         if (!st->active[k]) continue;
         double rn = t[K + k];
-        if (st->omega[k] == 0.0 || st->rho[k] == 0.0 || rn == 0.0) {
-          st->reason[k] = -5;
+        if (b2_bad(rn)) {
+          st->reason[k] = -9;
           st->active[k] = 0;
           continue;
         }
+        // (near) breakdown: rhat orthogonal to r, or a vanishing omega -- restart from the current
+        // residual (rhat = p = r) instead of giving up (PETSc would return KSP_DIVERGED_BREAKDOWN)
+        if (st->omega[k] == 0.0 || st->rho[k] == 0.0 || rn * rn <= 1e-24 * st->rr[k] * st->rh2[k]) {
+          st->restart[k] = 1;
+          st->rho[k] = st->rr[k];
+          st->rh2[k] = st->rr[k];
+          st->beta[k] = 0.0;
+          continue;
+        }
+        st->restart[k] = 0;
         st->beta[k] = (rn / st->rho[k]) * (st->alpha[k] / st->omega[k]);
         st->rho[k] = rn;
       }
@@ -808,17 +822,18 @@ k_bcgs_update(int64_t n, int ld, const double* __restrict__ p, const double* __r
   reduce_finish<2 * K>(s, partials, counter, FIN_BCGS_UPDATE, st, red_out);
 }
 
-// p = r + beta (p - omega v)
+// p = r + beta (p - omega v);  on a restart: rhat = p = r
 template <int K>
 __global__ void __launch_bounds__(256)
 k_bcgs_p(int64_t n, int ld, const double* __restrict__ r, const double* __restrict__ v,
-         double* __restrict__ p, const KryState* st) {
+         double* __restrict__ p, double* __restrict__ rhat, const KryState* st) {
   if (st->done) return;
   double beta[K], omega[K];
-  bool act[K];
+  bool act[K], rst[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     act[k] = st->active[k];
+    rst[k] = st->restart[k];
     beta[k] = st->beta[k];
     omega[k] = st->omega[k];
   }
@@ -827,7 +842,13 @@ k_bcgs_p(int64_t n, int ld, const double* __restrict__ r, const double* __restri
     for (int k = 0; k < K; ++k) {
       if (!act[k]) continue;
       const size_t j = (size_t)k * ld + i;
-      p[j] = fma(beta[k], fma(-omega[k], v[j], p[j]), r[j]);
+      if (rst[k]) {
+        const double rv = r[j];
+        rhat[j] = rv;
+        p[j] = rv;
+      } else {
+        p[j] = fma(beta[k], fma(-omega[k], v[j], p[j]), r[j]);
+      }
     }
   }
 }

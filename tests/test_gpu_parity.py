@@ -279,3 +279,35 @@ def test_low_memory_version_matches_oracle(gdim, N, deg, rotational):
             assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i], vscale(o.rhs1)) <= 1e-11
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8
+
+
+def test_lid_driven_cavity_matches_oracle():
+    """BASELINE config 5 in miniature: 3D lid-driven cavity (u = (1,0,0) on the lid z = 1, no-slip elsewhere,
+    no pressure BC), constant-value DirichletBCs, Re = 100, a few steps against the oracle."""
+    import oasisx_b200 as oasisx
+    from oasisx_b200 import fem, mesh as bmesh
+    from oracle.ipcs_oracle import OracleIPCS
+
+    N, dt, nu = 6, 0.01, 0.01
+    msh = bmesh.create_unit_cube(None, N, N, N)
+    lid = lambda x: np.isclose(x[2], 1.0)
+    walls = lambda x: np.isclose(x[0], 0) | np.isclose(x[0], 1) | np.isclose(x[1], 0) | np.isclose(x[1], 1) | np.isclose(x[2], 0)
+    G = oasisx.LocatorMethod.GEOMETRICAL
+    bcs_u = [[oasisx.DirichletBC(0.0, G, walls), oasisx.DirichletBC(1.0, G, lid)],
+             [oasisx.DirichletBC(0.0, G, walls), oasisx.DirichletBC(0.0, G, lid)],
+             [oasisx.DirichletBC(0.0, G, walls), oasisx.DirichletBC(0.0, G, lid)]]
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[],
+                                    solver_options={"tentative": lu, "pressure": lu, "scalar": lu})
+    V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    dw, dl = fem.locate_dofs_geometrical(V, walls), fem.locate_dofs_geometrical(V, lid)
+    o = OracleIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                   Q.tabulate_dof_coordinates(), 2,
+                   bcs_u=[[(dw, 0.0), (dl, 1.0)], [(dw, 0.0), (dl, 0.0)], [(dw, 0.0), (dl, 0.0)]])
+    for n in range(4):
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(3):
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, (n, i)
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
+    assert np.abs(s._u[0].x.array_ro()).max() > 0.5  # the lid drives the flow
