@@ -45,6 +45,22 @@ KRYLOV = {
 }
 
 
+def ncu_traffic(mesh: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_spmm launch from the committed `ncu --set full`
+    capture (profiles/r01_ncu_spmm_final_96cube.txt); only valid for the mesh it was taken on."""
+    if mesh != 96:
+        return None
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_spmm_final_96cube.txt")):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -151,9 +167,10 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1):
 
 
 def cpu_mesh_for(args) -> int:
-    """Bounded CPU sample: the full step on a box of at most 64^3 cubes (about 10 s per step on 16 cores);
-    steps/s are scaled to the benchmark mesh by the cell count (conservative: pressure iterations grow with N)."""
-    return args.cpu_mesh if args.cpu_mesh > 0 else min(args.mesh, 64)
+    """Bounded CPU sample: full IPCS steps on the benchmark mesh itself up to 96^3 (about 9 s per step on 16
+    cores); larger meshes are sampled at 96^3 and scaled by the cell count (conservative: pressure
+    iterations grow with N)."""
+    return args.cpu_mesh if args.cpu_mesh > 0 else min(args.mesh, 96)
 
 
 def run_reference(args):
@@ -162,7 +179,8 @@ def run_reference(args):
         return
     n_cpu = cpu_mesh_for(args)
     W, K = max(args.warmup, 0), max(args.steps, 1)
-    sec, cells, threads, its = cpu_sample(n_cpu, K, W)
+    K_run, W_run = (K, W) if n_cpu < 96 else (min(K, 5), min(W, 1))  # keep the whole run within a few minutes
+    sec, cells, threads, its = cpu_sample(n_cpu, K_run, W_run)
     target_cells = 6 * args.mesh**3
     sps = (1.0 / sec) * cells / target_cells
     line = {
@@ -172,8 +190,9 @@ def run_reference(args):
         "config": {"workload": f"3D Taylor-Green P2-P1 {args.mesh}^3 box (z-extruded exact solution), dt={DT}, nu={NU}, "
                                "max_iter=1, rtol=1e-10", "mesh": args.mesh, "krylov": KRYLOV},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp), {K} full IPCS steps after {W} warm-up on a "
-                                   f"{n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {its}), scaled by cell count to {args.mesh}^3",
+                         "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp), {K_run} full IPCS steps after {W_run} warm-up on a "
+                                   f"{n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {its})"
+                                   + ("" if n_cpu == args.mesh else f", scaled by cell count to {args.mesh}^3"),
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference algorithm on the host cores; the DOLFINx/PETSc/MUMPS reference itself "
@@ -262,7 +281,7 @@ def run_ours(args):
     comm.Barrier()
     roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 SELL-32 operator, 3 right-hand sides)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
+                "traffic": ncu_traffic(N) if world == 1 else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
                 "other_kernels": {
                     "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
                     "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
@@ -276,11 +295,12 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu and world == 1:
         n_cpu = cpu_mesh_for(args)
-        sec, cells, threads, cits = cpu_sample(n_cpu, 2, 1)
+        sec, cells, threads, cits = cpu_sample(n_cpu, 2 if n_cpu < 96 else 1, 1)
         sps = (1.0 / sec) * cells / msh.num_cells
         cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-               "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp), 2 full IPCS steps after 1 warm-up on a {n_cpu}^3 box "
-                         f"({sec:.2f} s/step, Krylov its u/p/m {cits}), scaled by cell count to {N}^3",
+               "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp), {2 if n_cpu < 96 else 1} full IPCS step(s) after 1 warm-up on "
+                         f"a {n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {cits})"
+                         + ("" if n_cpu == N else f", scaled by cell count to {N}^3"),
                "host_cpus": os.cpu_count()}
 
     nV = solver._lp.V.n_global if world > 1 else solver._nV_owned
@@ -313,7 +333,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", type=int, default=96, help="cubes per direction (BASELINE: 96; 48 = configs[2])")
-    ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 64))")
+    ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
     args = ap.parse_args()
