@@ -336,8 +336,12 @@ def main():
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
+    ap.add_argument("--scalar-ksp", default="auto", choices=["auto", "cg", "chebyshev"],
+                    help="mass-solve method: auto = cg, except reduction-free chebyshev on 8+ GPUs (latency-bound there)")
     args = ap.parse_args()
     KRYLOV["pressure"]["pc_type"] = args.pressure_pc
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    KRYLOV["scalar"]["ksp_type"] = args.scalar_ksp if args.scalar_ksp != "auto" else ("chebyshev" if world >= 8 else "cg")
     if args.impl == "reference":
         run_reference(args)
     else:

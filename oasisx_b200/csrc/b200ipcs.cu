@@ -42,7 +42,8 @@ struct Space {
 };
 
 struct KSPOpts {
-  int type = 0;  // 0 = cg, 1 = bcgs
+  int type = 0;  // 0 = cg, 1 = bcgs, 2 = chebyshev (mass solves: needs eig bounds, b2_set_solver_option ksp_chebyshev_eigenvalues)
+  double eig_lo = 0.0, eig_hi = 0.0;  // bounds of the spectrum of D^-1 A for type 2
   int pc = 0;    // 0 = jacobi, 1 = none, 2 = multigrid (pressure only, needs b2_pressure_mg_add_level)
   double rtol = 1e-5, atol = 1e-50;
   int maxit = 10000;
@@ -457,9 +458,16 @@ void krylov_init(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals
 }
 
 // Solves K systems  A x_k = b_k  (interleaved storage) with the options of solver `which`.
+void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, const double* dinv, int space, int K,
+                     const double* b, double* x, int32_t* reasons, int32_t* its);
+
 void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, const double* dinv_jacobi, int space,
                   int K, const double* b, double* x, int32_t* reasons, int32_t* its) {
   KSPOpts& o = c->ksp[which];
+  if (o.type == 2) {
+    chebyshev_solve(c, which, pat, vals, dinv_jacobi, space, K, b, x, reasons, its);
+    return;
+  }
   DBuf<double>* w = space == B2_SPACE_V ? c->wv : c->wq;
   // CG: Jacobi through dinv in the vector kernels.  BiCGStab: the operator is already row-scaled
   // (k_combine_first), dinv only scales the right-hand side in k_bcgs_init.
@@ -637,6 +645,85 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   }
   *reason = c->h_st->reason[0] != 0 ? c->h_st->reason[0] : -3;
   *its = c->h_st->its[0];
+}
+
+void read_sums(b2_ctx* c, int n);
+
+// Chebyshev iteration for K SPD systems sharing `vals` (mass matrix), Jacobi-scaled, spectrum of D^-1 A in
+// [eig_lo, eig_hi].  No reductions inside the iteration; the residual norm is checked after the predicted
+// number of iterations and then every 4.
+void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, const double* dinv, int space, int K,
+                     const double* b, double* x, int32_t* reasons, int32_t* its) {
+  KSPOpts& o = c->ksp[which];
+  B2_REQUIRE(o.eig_hi > o.eig_lo && o.eig_lo > 0.0, "ksp_type chebyshev needs ksp_chebyshev_eigenvalues lo,hi");
+  DBuf<double>* w = space == B2_SPACE_V ? c->wv : c->wq;
+  double *r = w[0].p, *d = w[1].p, *q = w[2].p;
+  const int64_t n = pat.n_rows;
+  const int ld = pat.n_cols;
+  const int g = pgrid(c, n, 256, 8);
+  const double theta = 0.5 * (o.eig_hi + o.eig_lo), delta = 0.5 * (o.eig_hi - o.eig_lo), sigma1 = theta / delta;
+  const double* q0 = nullptr;
+  if (o.nonzero_guess) {
+    spmm(c, pat, vals, K, x, q, nullptr, nullptr, FIN_NONE, 0, space);
+    q0 = q;
+  }
+  auto init = [&](auto kc) {
+    constexpr int KK = decltype(kc)::value;
+    B2_LAUNCH(c, k_cheb_init<KK>, g, 256, n, ld, b, q0, dinv, 1.0 / theta, x, r, d, c->d_sums, c->partials.p, c->d_counter);
+  };
+  auto update = [&](auto kc, bool norm, double c1, double c2) {
+    constexpr int KK = decltype(kc)::value;
+    if (norm)
+      B2_LAUNCH(c, (k_cheb_update<KK, true>), g, 256, n, ld, q, dinv, c1, c2, x, r, d, c->d_sums, c->partials.p, c->d_counter);
+    else
+      B2_LAUNCH(c, (k_cheb_update<KK, false>), g, 256, n, ld, q, dinv, c1, c2, x, r, d, c->d_sums, c->partials.p, c->d_counter);
+  };
+  auto dispatch = [&](auto&& f) {
+    if (K == 1) f(std::integral_constant<int, 1>{});
+    else if (K == 2) f(std::integral_constant<int, 2>{});
+    else f(std::integral_constant<int, 3>{});
+  };
+  dispatch([&](auto kc) { init(kc); });
+  allreduce_sum(c, c->d_sums, 2 * K);
+  read_sums(c, 2 * K);
+  double tol2[B2_MAXK], need = 0.0;
+  bool conv = true;
+  for (int k = 0; k < K; ++k) {
+    const double bb = c->h_sums[k], rr = c->h_sums[K + k];
+    tol2[k] = std::max(o.rtol * o.rtol * bb, o.atol * o.atol);
+    if (rr > tol2[k]) {
+      conv = false;
+      need = std::max(need, 0.5 * std::log(rr / tol2[k]));  // ln(|r0| / tol)
+    }
+  }
+  int it = 0;
+  if (!conv) {
+    const double kappa = o.eig_hi / o.eig_lo;
+    const double rate = (std::sqrt(kappa) - 1.0) / (std::sqrt(kappa) + 1.0);
+    int next_check = std::max(1, (int)std::ceil((need + std::log(2.0)) / -std::log(rate)));
+    double rho = 1.0 / sigma1;
+    while (it < o.maxit) {
+      spmm(c, pat, vals, K, d, q, nullptr, nullptr, FIN_NONE, 0, space);
+      const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+      const bool check = (it + 1 >= next_check);
+      dispatch([&](auto kc) { update(kc, check, rho_new * rho, 2.0 * rho_new / delta); });
+      rho = rho_new;
+      ++it;
+      if (check) {
+        allreduce_sum(c, c->d_sums, K);
+        read_sums(c, K);
+        conv = true;
+        for (int k = 0; k < K; ++k) conv = conv && (c->h_sums[k] <= tol2[k]);
+        if (conv) break;
+        next_check = it + 4;
+      }
+    }
+    // the last update already prepared the next direction; x holds the iterate of `it` steps
+  }
+  for (int k = 0; k < K; ++k) {
+    reasons[k] = conv ? 2 : -3;
+    its[k] = it;
+  }
 }
 
 void require_ready(b2_ctx* c) { B2_REQUIRE(c->preassembled, "b2_preassemble has not been called"); }
@@ -1478,6 +1565,10 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
       else if (v == "bcgs" || v == "bicgstab") o.type = 1;
       else if (v == "preonly") { /* direct solve requested: keep the Krylov default, tighten below */ }
       else if (v == "gmres") o.type = 1;  // nonsymmetric Krylov available here is BiCGStab
+      else if (v == "chebyshev") {
+        B2_REQUIRE(solver == B2_SOLVER_SCALAR || solver == B2_SOLVER_PROJECTOR, "chebyshev is for the SPD mass solves");
+        o.type = 2;
+      }
       else throw B2Error(-5, "unsupported ksp_type " + v);
       if (o.type == 1) B2_REQUIRE(solver == B2_SOLVER_TENTATIVE || solver == B2_SOLVER_SCALAR, "bcgs only on the velocity space");
     } else if (k == "pc_type") {
@@ -1489,7 +1580,12 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
     } else if (k == "ksp_rtol") o.rtol = std::stod(v);
     else if (k == "ksp_atol") o.atol = std::stod(v);
     else if (k == "ksp_max_it") o.maxit = std::stoi(v);
-    else if (k == "ksp_initial_guess_nonzero") o.nonzero_guess = (v == "1" || v == "true" || v == "True");
+    else if (k == "ksp_chebyshev_eigenvalues") {  // "lo,hi" of D^-1 A (PETSc: -ksp_chebyshev_eigenvalues)
+      const size_t comma = v.find(',');
+      B2_REQUIRE(comma != std::string::npos, "ksp_chebyshev_eigenvalues expects lo,hi");
+      o.eig_lo = std::stod(v.substr(0, comma));
+      o.eig_hi = std::stod(v.substr(comma + 1));
+    } else if (k == "ksp_initial_guess_nonzero") o.nonzero_guess = (v == "1" || v == "true" || v == "True");
     else if (k == "b200_guess") {
       o.extrapolate_guess = (v == "extrapolate");
       if (o.extrapolate_guess) o.nonzero_guess = true;

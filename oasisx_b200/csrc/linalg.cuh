@@ -852,3 +852,69 @@ k_bcgs_p(int64_t n, int ld, const double* __restrict__ r, const double* __restri
     }
   }
 }
+
+// ---- Chebyshev iteration (Jacobi-preconditioned) on K systems sharing one SPD matrix -----------------
+// The spectrum of D^-1 M of a mass matrix is bounded by the element-level generalised eigenvalues
+// (Wathen 1987), which the host computes once from the reference tables: the recurrence scalars are
+// data independent, so an iteration needs NO reduction (multi-GPU: no all-reduce).
+// init: r = b - q (or b), d = dinv r / theta ; sums bb, rr (stored to out[0..2K))
+template <int K>
+__global__ void __launch_bounds__(256)
+k_cheb_init(int64_t n, int ld, const double* __restrict__ b, const double* __restrict__ q,
+            const double* __restrict__ dinv, double inv_theta, double* __restrict__ x, double* __restrict__ r,
+            double* __restrict__ d, double* out, double* partials, unsigned* counter) {
+  double s[2 * K];
+#pragma unroll
+  for (int i = 0; i < 2 * K; ++i) s[i] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = dinv[i] * inv_theta;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const size_t j = (size_t)k * ld + i;
+      const double bv = b[j];
+      double rv = bv;
+      if (q != nullptr) rv -= q[j];
+      else x[j] = 0.0;
+      r[j] = rv;
+      d[j] = di * rv;
+      s[k] = fma(bv, bv, s[k]);
+      s[K + k] = fma(rv, rv, s[K + k]);
+    }
+  }
+  double total[2 * K];
+  if (grid_reduce<2 * K>(s, partials, counter, total) && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 2 * K; ++i) out[i] = total[i];
+  }
+}
+
+// x += d ; r -= q ; d = c1 d + c2 dinv r ; NORM: out[k] = |r_k|^2
+template <int K, bool NORM>
+__global__ void __launch_bounds__(256)
+k_cheb_update(int64_t n, int ld, const double* __restrict__ q, const double* __restrict__ dinv, double c1, double c2,
+              double* __restrict__ x, double* __restrict__ r, double* __restrict__ d, double* out, double* partials,
+              unsigned* counter) {
+  double s[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) s[k] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = c2 * dinv[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const size_t j = (size_t)k * ld + i;
+      const double dv = d[j];
+      x[j] += dv;
+      const double rv = r[j] - q[j];
+      r[j] = rv;
+      d[j] = fma(c1, dv, di * rv);
+      if (NORM) s[k] = fma(rv, rv, s[k]);
+    }
+  }
+  if constexpr (NORM) {
+    double total[K];
+    if (grid_reduce<K>(s, partials, counter, total) && threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) out[k] = total[k];
+    }
+  }
+}

@@ -207,6 +207,18 @@ def slice_order(x: np.ndarray, n_rows: int, lattice=None, tile=(8, 8), rows_per_
     return np.lexsort((np.arange(n_slices), key[2], key[1], key[0])).astype(np.int32)
 
 
+def mass_jacobi_bounds(gdim: int, degree: int) -> tuple[float, float]:
+    """[lambda_min, lambda_max] of diag(M_e)^-1 M_e on the reference simplex: bounds of the spectrum of the
+    Jacobi-scaled assembled mass matrix on any affine mesh (element-by-element bound)."""
+    import os
+
+    t = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref_tables.npz"))
+    M = t[f"D{gdim}P{degree}_MV"]
+    d = np.sqrt(np.diag(M))
+    w = np.linalg.eigvalsh(M / np.outer(d, d))
+    return float(w[0]), float(w[-1])
+
+
 def functionspace(mesh: Mesh, element) -> FunctionSpace:
     """``functionspace(mesh, ("Lagrange", k))`` or ``("Lagrange", k, (gdim,))``.  Scalar spaces of
     equal degree on one mesh share a dof map (one ``A`` serves every velocity component)."""

@@ -193,6 +193,11 @@ class FractionalStep_AB_CN:
         self._solver_u = KSPSolver(comm, solver_options.get("tentative"), prefix="tentative_velocity")
         self._solver_p = KSPSolver(comm, solver_options.get("pressure"), prefix="pressure_correction")
         self._solver_c = KSPSolver(comm, solver_options.get("scalar"), prefix="velocity_update")
+        if (solver_options.get("scalar") or {}).get("ksp_type") == "chebyshev" and "ksp_chebyshev_eigenvalues" not in solver_options["scalar"]:
+            # rigorous bounds of spec(D^-1 M): extreme generalised eigenvalues of the reference element mass
+            # matrix against its own diagonal (Wathen 1987) -- mesh independent for affine simplices
+            lo, hi = _fem.mass_jacobi_bounds(gdim, deg_u)
+            self._solver_c.updateOptions({"ksp_chebyshev_eigenvalues": f"{lo!r},{hi!r}"})
         self._solver_u.bind(ctx, L.SOLVER_TENTATIVE)
         self._solver_p.bind(ctx, L.SOLVER_PRESSURE)
         self._solver_c.bind(ctx, L.SOLVER_SCALAR)

@@ -11,7 +11,8 @@ import logging
 
 logger = logging.getLogger("oasisx")
 
-_UNDERSTOOD = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_max_it", "ksp_initial_guess_nonzero", "b200_guess"}
+_UNDERSTOOD = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_max_it", "ksp_initial_guess_nonzero", "b200_guess",
+               "ksp_chebyshev_eigenvalues"}
 
 
 class KSPSolver:

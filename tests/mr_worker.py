@@ -25,6 +25,7 @@ if krylov:
             for k, t in (("tentative", "bcgs"), ("pressure", "cg"), ("scalar", "cg"))}
     if use_mg:
         opts["pressure"]["pc_type"] = "mg"
+        opts["scalar"]["ksp_type"] = "chebyshev"  # reduction-free mass solves
 s = make_solver(msh, 2, tg, dt, solver_options=opts, device=int(os.environ.get("LOCAL_RANK", "0")))
 tg2 = TaylorGreen(nu, 3)
 o = make_oracle(make_mesh(3, N), 2, tg2, dt)

@@ -311,3 +311,24 @@ def test_lid_driven_cavity_matches_oracle():
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, (n, i)
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
     assert np.abs(s._u[0].x.array_ro()).max() > 0.5  # the lid drives the flow
+
+
+@pytest.mark.parametrize("gdim,N,deg", [(3, 6, 2), (2, 12, 2), (2, 10, 1)])
+def test_chebyshev_mass_solve_matches_oracle(gdim, N, deg):
+    """ksp_type=chebyshev on the velocity update (reduction-free, element-level eigenvalue bounds)."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    opts = {"tentative": lu, "pressure": lu, "scalar": {"ksp_type": "chebyshev", "pc_type": "jacobi", "ksp_rtol": 1e-12}}
+    s = make_solver(msh, deg, tg, dt, solver_options=opts)
+    o = make_oracle(msh, deg, tg, dt)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(3):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(gdim):
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
+    assert 0 < max(s.stats().its_update) < 80
