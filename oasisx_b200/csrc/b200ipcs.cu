@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -125,7 +126,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -378,9 +379,42 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
+template <int K, int DOT, int CH, int STAGES>
+void launch_spmm_tma(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
+                     KryState* st, int fin) {
+  constexpr int BLOCK = 256, WPB = BLOCK / 32;
+  constexpr int ND = DOT == 0 ? 0 : DOT * K;
+  const size_t smem = (size_t)WPB * STAGES * CH * 32 * 12 + WPB * STAGES * 8 + (size_t)ND * BLOCK * 8;
+  auto kern = k_spmm_tma<K, DOT, CH, STAGES, BLOCK>;
+  static bool configured = false;
+  if (!configured) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int per_sm = std::max(1, std::min(8, (int)(220 * 1024 / (smem + 1024))));
+  const int n_slices = (pat.n_rows + 31) / 32;
+  const int need = (n_slices + WPB - 1) / WPB;
+  const int grid = std::max(1, std::min(need, c->sm * per_sm));
+  kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x, ld, y, w, st, fin,
+                                         c->partials.p, c->d_counter, red_ptr(c));
+  c->stats.kernel_launches++;
+  B2_CUDA(cudaGetLastError());
+  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
+}
+
 template <int K, int DOT>
 void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
+  switch (c->spmm_tma) {
+    case 82: launch_spmm_tma<K, DOT, 8, 2>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 83: launch_spmm_tma<K, DOT, 8, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 43: launch_spmm_tma<K, DOT, 4, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 44: launch_spmm_tma<K, DOT, 4, 4>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 42: launch_spmm_tma<K, DOT, 4, 2>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 24: launch_spmm_tma<K, DOT, 2, 4>(c, pat, vals, x, ld, y, w, st, fin); return;
+    case 33: launch_spmm_tma<K, DOT, 3, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
+    default: break;
+  }
   if (c->spmm_mode != 0) {
     int grid = pgrid(c, (int64_t)pat.n_rows, 256, 8);
     if (c->spmm_mode == 1) B2_LAUNCH(c, (k_spmm_diag<K, 1>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
@@ -1187,6 +1221,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     for (auto& e : c->ev) B2_CUDA(cudaEventCreate(&e));
     for (auto& e : c->user_ev) B2_CUDA(cudaEventCreate(&e));
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
+    if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -1734,6 +1769,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_unroll") c->spmm_unroll = value;
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
+    else if (k == "spmm_tma") c->spmm_tma = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });

@@ -367,6 +367,164 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
 }
 
+// ---- TMA-fed variant of the SpMM ---------------------------------------------------------------
+// The matrix stream (values + columns of one slice, contiguous in SELL storage) is moved by the TMA
+// unit: one elected lane per warp issues 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) of
+// the next CH steps of its slice into a per-warp ring in shared memory while the warp gathers and
+// multiplies the current chunk.  The stream then costs no registers and no LSU load instructions, so
+// all of the thread's load slots go to the gathers (CH*K of them in flight).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int K, int DOT, int CH, int STAGES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_spmm_tma(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+           const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
+           double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
+           unsigned* counter, double* red_out) {
+  constexpr int WPB = BLOCK / 32;
+  constexpr int ND = DOT == 0 ? 1 : DOT * K;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [WPB][STAGES] value chunks (CH*32 doubles), then column chunks (CH*32 ints), then barriers
+  double* svals_all = reinterpret_cast<double*>(smem_raw);
+  int* scols_all = reinterpret_cast<int*>(smem_raw + (size_t)WPB * STAGES * CH * 32 * sizeof(double));
+  unsigned long long* bars_all =
+      reinterpret_cast<unsigned long long*>(smem_raw + (size_t)WPB * STAGES * CH * 32 * (sizeof(double) + sizeof(int)));
+  double* sdots = reinterpret_cast<double*>(bars_all + WPB * STAGES);  // [ND][BLOCK] when DOT > 0
+  if (st != nullptr && st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  double* svals = svals_all + (size_t)wib * STAGES * CH * 32;
+  int* scols = scols_all + (size_t)wib * STAGES * CH * 32;
+  unsigned long long* bars = bars_all + wib * STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (DOT > 0) {
+#pragma unroll
+    for (int i = 0; i < ND; ++i) sdots[i * BLOCK + threadIdx.x] = 0.0;
+  }
+  __syncwarp();
+  const int n_slices = (n_rows + 31) >> 5;
+  const int stride = gridDim.x * WPB;
+  // producer cursor (slice list index pi, step pt) runs STAGES-1 chunks ahead of the consumer
+  int pi = blockIdx.x * WPB + wib, pt = 0, pbase = 0, plen = 0;
+  auto load_slice = [&](int i, int& base, int& len) {
+    if (i < n_slices) {
+      const int s = order != nullptr ? __ldg(order + i) : i;
+      base = __ldg(slice_ptr + s);
+      len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    } else {
+      base = 0;
+      len = 0;
+    }
+  };
+  load_slice(pi, pbase, plen);
+  int issued = 0;
+  auto issue = [&]() {  // enqueue the next chunk of this warp's stream, if any
+    while (pi < n_slices && pt >= plen) {
+      pi += stride;
+      pt = 0;
+      load_slice(pi, pbase, plen);
+    }
+    if (pi >= n_slices) return;
+    const int tn = min(CH, plen - pt);
+    const int stg = issued % STAGES;
+    if (lane == 0) {
+      mbar_expect_tx(bars + stg, (unsigned)(tn * 32 * 12));
+      bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
+      bulk_g2s(scols + (size_t)stg * CH * 32, cols + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 4), bars + stg);
+    }
+    pt += tn;
+    ++issued;
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue();
+  int consumed = 0;
+  for (int i = blockIdx.x * WPB + wib; i < n_slices; i += stride) {
+    int base, len;
+    load_slice(i, base, len);
+    const int s = order != nullptr ? __ldg(order + i) : i;
+    const int row = (s << 5) + lane;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int t = 0; t < len; t += CH) {
+      issue();  // refill the stage consumed in the previous round
+      const int tn = min(CH, len - t);
+      const int stg = consumed % STAGES;
+      mbar_wait(bars + stg, (unsigned)((consumed / STAGES) & 1));
+      const double* sv = svals + (size_t)stg * CH * 32 + lane;
+      const int* sc = scols + (size_t)stg * CH * 32 + lane;
+      if (tn == CH) {
+        double xv[CH][K];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int c = sc[u << 5];
+#pragma unroll
+          for (int k = 0; k < K; ++k) xv[u][k] = __ldg(x + (size_t)k * ld + c);
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const double v = sv[u << 5];
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] = fma(v, xv[u][k], acc[k]);
+        }
+      } else {
+        for (int u = 0; u < tn; ++u) {
+          const int c = sc[u << 5];
+          const double v = sv[u << 5];
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
+        }
+      }
+      __syncwarp();  // every lane is done reading this stage before lane 0 lets the TMA overwrite it
+      ++consumed;
+    }
+    if (row < n_rows) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
+      if constexpr (DOT >= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          sdots[k * BLOCK + threadIdx.x] = fma(acc[k], w[(size_t)k * ld + row], sdots[k * BLOCK + threadIdx.x]);
+      }
+      if constexpr (DOT == 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sdots[(K + k) * BLOCK + threadIdx.x] = fma(acc[k], acc[k], sdots[(K + k) * BLOCK + threadIdx.x]);
+      }
+    }
+  }
+  if constexpr (DOT > 0) {
+    double dots[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) dots[i] = sdots[i * BLOCK + threadIdx.x];
+    reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+  }
+}
+
 // Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
 // gather), 2 = gather only (values taken as 1).  Results are meaningless; they time the two halves.
 template <int K, int MODE>

@@ -22,16 +22,9 @@ tg.t_u, tg.t_p = dt, dt / 2
 s.solve(dt, nu, max_iter=1)
 Vs = s._Vi[0][0]
 n_slices = (Vs.num_dofs + 31) // 32
-for tile in ((8, 8), (6, 6), (12, 12), (16, 16), (8, 16), (16, 8), (24, 24), (32, 32)):
-    if tile is None:
-        ctx.set_slice_order(L.PAT_VV, np.arange(n_slices, dtype=np.int32))
-    else:
-        ctx.set_slice_order(L.PAT_VV, fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, msh._lattice, tile=tile))
-    for stream in (1,):
-        ctx.set_tuning("spmm_stream", stream)
-        for unroll in (8,):
-            ctx.set_tuning("spmm_unroll", unroll)
-            for bps in (8,):
-                ctx.set_tuning("spmm_blocks_per_sm", bps)
-                ms, nbytes = ctx.bench_kernel(3, 10)
-                print(f"tile {tile} stream {stream} unroll {unroll} blocks/SM {bps}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
+ctx.set_slice_order(L.PAT_VV, fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, msh._lattice, tile=(8, 8)))
+for tma in (0, 43, 42, 24, 33):
+    ctx.set_tuning("spmm_tma", tma)
+    for kern in (3, 0):
+        ms, nbytes = ctx.bench_kernel(kern, 10)
+        print(f"tma {tma:2d} kernel {kern}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
