@@ -30,6 +30,7 @@ struct CSR {
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
+  DBuf<int> sm_range;                          // k_spmm_sm: schedule ranges per SM, balanced by slots
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
 };
@@ -126,7 +127,9 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel  // sweep: tools/sweep_spmm.py
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues
+  DBuf<int> sm_dense, sm_next;  // %smid -> dense SM index; per-range work counters
+  int n_sm_dense = 0;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -402,9 +405,64 @@ void launch_spmm_tma(b2_ctx* c, const CSR& pat, const double* vals, const double
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
+void build_sm_ranges(b2_ctx* c, CSR& pat) {
+  const int n_slices = (pat.n_rows + 31) / 32;
+  std::vector<int> sp(n_slices + 1), ord(n_slices);
+  B2_CUDA(cudaMemcpyAsync(sp.data(), pat.slice_ptr.p, sizeof(int) * (n_slices + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (pat.order.p) B2_CUDA(cudaMemcpyAsync(ord.data(), pat.order.p, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (!pat.order.p) for (int i = 0; i < n_slices; ++i) ord[i] = i;
+  const int nr = c->n_sm_dense;
+  std::vector<int> range(nr + 1, n_slices);
+  range[0] = 0;
+  const double total = (double)sp[n_slices] + 64.0 * n_slices;  // slots + a per-slice overhead
+  double acc = 0;
+  int r = 1;
+  for (int i = 0; i < n_slices && r < nr; ++i) {
+    acc += (sp[ord[i] + 1] - sp[ord[i]]) + 64.0;
+    if (acc >= total * r / nr) range[r++] = i + 1;
+  }
+  pat.sm_range.alloc(nr + 1);
+  B2_CUDA(cudaMemcpyAsync(pat.sm_range.p, range.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+template <int K, int DOT>
+void launch_spmm_sm(b2_ctx* c, CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
+                    KryState* st, int fin) {
+  if (c->n_sm_dense == 0) {  // one-off: which %smid values exist on this part
+    DBuf<int> seen;
+    seen.alloc(4096);
+    seen.zero(c->stream);
+    k_probe_smid<<<c->sm * 64, 32, 0, c->stream>>>(seen.p);
+    std::vector<int> h(4096);
+    B2_CUDA(cudaMemcpyAsync(h.data(), seen.p, sizeof(int) * 4096, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int> dense(4096, 0);
+    int n = 0;
+    for (int i = 0; i < 4096; ++i) dense[i] = h[i] ? n++ : 0;
+    c->n_sm_dense = std::max(n, 1);
+    c->sm_dense.alloc(4096);
+    B2_CUDA(cudaMemcpyAsync(c->sm_dense.p, dense.data(), sizeof(int) * 4096, cudaMemcpyHostToDevice, c->stream));
+    c->sm_next.alloc(c->n_sm_dense);
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (pat.sm_range.p == nullptr) build_sm_ranges(c, pat);
+  B2_CUDA(cudaMemsetAsync(c->sm_next.p, 0, sizeof(int) * c->n_sm_dense, c->stream));
+  const int grid = c->sm * 8;
+  B2_LAUNCH(c, (k_spmm_sm<K, DOT, 8, 256>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
+            c->sm_dense.p, c->n_sm_dense, pat.sm_range.p, c->sm_next.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter,
+            red_ptr(c));
+  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
+}
+
 template <int K, int DOT>
 void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
+  if (c->spmm_sm && pat.n_rows >= 32 * 8 * c->sm) {
+    launch_spmm_sm<K, DOT>(c, const_cast<CSR&>(pat), vals, x, ld, y, w, st, fin);
+    return;
+  }
   switch (c->spmm_tma) {
     case 82: launch_spmm_tma<K, DOT, 8, 2>(c, pat, vals, x, ld, y, w, st, fin); return;
     case 83: launch_spmm_tma<K, DOT, 8, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
@@ -1222,6 +1280,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     for (auto& e : c->user_ev) B2_CUDA(cudaEventCreate(&e));
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
     if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
+    if (const char* e = std::getenv("B200_SPMM_SM")) c->spmm_sm = std::atoi(e);
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -1395,6 +1454,7 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
     CSR& pat = c->pat[pattern];
     B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
     pat.order.alloc(n_slices);
+    pat.sm_range.release();
     B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -1770,6 +1830,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "spmm_tma") c->spmm_tma = value;
+    else if (k == "spmm_sm") c->spmm_sm = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });

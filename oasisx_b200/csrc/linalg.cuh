@@ -367,6 +367,101 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
 }
 
+// ---- SM-local scheduling variant of the SpMM -----------------------------------------------------
+// The slice schedule is cut into one contiguous range per SM (balanced by slot count, `sm_range`); every
+// warp resident on SM s pulls the next slice of range s with an atomic counter, so all ~64 warps of an
+// SM walk through neighbouring slices together and share the gathered vector lines in that SM's L1.
+// Ranges of SMs that received no block (or are slower) are stolen once a warp's own range is drained,
+// which also makes the result independent of block placement.  `next` must be zero at launch.
+__device__ __forceinline__ unsigned get_smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
+template <int K, int DOT, int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
+k_spmm_sm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
+          const double* __restrict__ vals, const int* __restrict__ order, const int* __restrict__ sm_dense,
+          int n_ranges, const int* __restrict__ sm_range, int* __restrict__ next, const double* __restrict__ x, int ld,
+          double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
+          unsigned* counter, double* red_out) {
+  if (st != nullptr && st->done) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int ND = DOT == 0 ? 1 : DOT * K;
+  __shared__ double sdots[DOT == 0 ? 1 : ND][DOT == 0 ? 1 : BLOCK];
+  if constexpr (DOT > 0) {
+#pragma unroll
+    for (int i = 0; i < ND; ++i) sdots[i][threadIdx.x] = 0.0;
+  }
+  const int home = __ldg(sm_dense + get_smid()) % n_ranges;
+  for (int hop = 0; hop < n_ranges; ++hop) {
+    const int rg = (home + hop) % n_ranges;
+    const int lo = __ldg(sm_range + rg), hi = __ldg(sm_range + rg + 1);
+    if (hop > 0 && *((volatile int*)next + rg) >= hi - lo) continue;  // cheap peek before stealing
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = lo + atomicAdd(next + rg, 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= hi) break;
+      const int s = order != nullptr ? __ldg(order + i) : i;
+      const int base = __ldg(slice_ptr + s);
+      const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+      const int row = (s << 5) + lane;
+      const int* cp = cols + base + lane;
+      const double* vp = vals + base + lane;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.0;
+      int t = 0;
+      for (; t + UNROLL <= len; t += UNROLL) {
+        int c[UNROLL];
+        double v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          c[u] = ld_stream(cp + ((t + u) << 5));
+          v[u] = ld_stream(vp + ((t + u) << 5));
+        }
+        double xv[UNROLL][K];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+          for (int k = 0; k < K; ++k) xv[u][k] = __ldg(x + (size_t)k * ld + c[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] = fma(v[u], xv[u][k], acc[k]);
+      }
+      for (; t < len; ++t) {
+        const int c = ld_stream(cp + (t << 5));
+        const double v = ld_stream(vp + (t << 5));
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
+      }
+      if (row < n_rows) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) sdots[k][threadIdx.x] = fma(acc[k], w[(size_t)k * ld + row], sdots[k][threadIdx.x]);
+        }
+        if constexpr (DOT == 2) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) sdots[K + k][threadIdx.x] = fma(acc[k], acc[k], sdots[K + k][threadIdx.x]);
+        }
+      }
+    }
+  }
+  if constexpr (DOT > 0) {
+    double dots[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) dots[i] = sdots[i][threadIdx.x];
+    reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+  }
+}
+
+__global__ void k_probe_smid(int* seen) { if (threadIdx.x == 0) seen[get_smid()] = 1; }
+
 // ---- TMA-fed variant of the SpMM ---------------------------------------------------------------
 // The matrix stream (values + columns of one slice, contiguous in SELL storage) is moved by the TMA
 // unit: one elected lane per warp issues 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) of
