@@ -86,6 +86,7 @@ typedef struct b2_stats {
   double ms_step;
   int64_t bytes_h2d, bytes_d2h; /* cumulative host<->device traffic through this ABI */
   int64_t halo_exchanges, allreduces; /* NCCL operations enqueued since creation (multi rank) */
+  double res0_tentative, res0_pressure, res0_update; /* |r0|/|b| of the last solves (max over components) */
 } b2_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -51,6 +51,9 @@ class Stats(C.Structure):
         ("bytes_d2h", C.c_int64),
         ("halo_exchanges", C.c_int64),
         ("allreduces", C.c_int64),
+        ("res0_tentative", C.c_double),
+        ("res0_pressure", C.c_double),
+        ("res0_update", C.c_double),
     ]
 
 

@@ -50,6 +50,7 @@ struct KSPOpts {
   double rtol = 1e-5, atol = 1e-50;
   int maxit = 10000;
   bool nonzero_guess = false;
+  bool block_rtol = false;  // "b200_block_rtol": rtol relative to max over the components' |b_k|
   bool extrapolate_guess = false;  // "b200_guess": "extrapolate" -- start from a time-extrapolated state (implies nonzero guess)
   bool scaled_operator = false;  // the matrix is stored row-scaled by its diagonal (tentative velocity)
   int expected_its = 0;  // iterations of the previous solve: first batch enqueued without a host sync
@@ -575,6 +576,7 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
   c->h_st->maxit = o.maxit;
   c->h_st->rtol = o.rtol;
   c->h_st->atol = o.atol;
+  c->h_st->block_rtol = o.block_rtol ? 1 : 0;
   B2_CUDA(cudaMemcpyAsync(c->d_st, c->h_st, sizeof(KryState), cudaMemcpyHostToDevice, c->stream));
   auto run = [&](auto kc) {
     constexpr int KK = decltype(kc)::value;
@@ -598,12 +600,17 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
     default: throw B2Error(-3, "K must be 1..3");
   }
   int mx = 0;
+  double res0 = 0.0;
   for (int k = 0; k < K; ++k) {
     reasons[k] = c->h_st->reason[k];
     its[k] = c->h_st->its[k];
     mx = std::max(mx, c->h_st->its[k]);
+    if (c->h_st->bb[k] > 0) res0 = std::max(res0, std::sqrt(c->h_st->rr0[k] / c->h_st->bb[k]));
   }
   o.expected_its = mx;
+  if (which == B2_SOLVER_TENTATIVE) c->stats.res0_tentative = res0;
+  else if (which == B2_SOLVER_PRESSURE) c->stats.res0_pressure = res0;
+  else if (which == B2_SOLVER_SCALAR) c->stats.res0_update = res0;
 }
 
 // ---- multigrid V-cycle on the pressure hierarchy ---------------------------------------------------
@@ -737,6 +744,7 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   }
   *reason = c->h_st->reason[0] != 0 ? c->h_st->reason[0] : -3;
   *its = c->h_st->its[0];
+  if (c->h_st->bb[0] > 0) c->stats.res0_pressure = std::sqrt(c->h_st->rr0[0] / c->h_st->bb[0]);
 }
 
 void read_sums(b2_ctx* c, int n);
@@ -778,10 +786,11 @@ void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, c
   dispatch([&](auto kc) { init(kc); });
   allreduce_sum(c, c->d_sums, 2 * K);
   read_sums(c, 2 * K);
-  double tol2[B2_MAXK], need = 0.0;
+  double tol2[B2_MAXK], need = 0.0, bbmax = 0.0;
   bool conv = true;
+  for (int k = 0; k < K; ++k) bbmax = std::max(bbmax, c->h_sums[k]);
   for (int k = 0; k < K; ++k) {
-    const double bb = c->h_sums[k], rr = c->h_sums[K + k];
+    const double bb = o.block_rtol ? bbmax : c->h_sums[k], rr = c->h_sums[K + k];
     tol2[k] = std::max(o.rtol * o.rtol * bb, o.atol * o.atol);
     if (rr > tol2[k]) {
       conv = false;
@@ -1681,6 +1690,7 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
       o.eig_lo = std::stod(v.substr(0, comma));
       o.eig_hi = std::stod(v.substr(comma + 1));
     } else if (k == "ksp_initial_guess_nonzero") o.nonzero_guess = (v == "1" || v == "true" || v == "True");
+    else if (k == "b200_block_rtol") o.block_rtol = (v == "1" || v == "true" || v == "True");
     else if (k == "b200_guess") {
       o.extrapolate_guess = (v == "extrapolate");
       if (o.extrapolate_guess) o.nonzero_guess = true;

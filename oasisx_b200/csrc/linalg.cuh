@@ -14,7 +14,8 @@ struct KryState {
   int active[B2_MAXK], reason[B2_MAXK], its[B2_MAXK];
   int restart[B2_MAXK];  // BiCGStab: shadow residual became orthogonal to r -> restart with rhat = r
   double rh2[B2_MAXK];   // |rhat|^2
-  int done, maxit, K, pad;
+  double rr0[B2_MAXK];   // initial |r|^2 (diagnostics: quality of the initial guess)
+  int done, maxit, K, block_rtol;  // block_rtol: tolerance relative to max_k |b_k| (one vector system)
   double rtol, atol;
 };
 
@@ -63,7 +64,13 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
         st->rz[k] = t[k];
         st->bb[k] = t[K + k];
         st->rr[k] = t[2 * K + k];
-        double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * st->bb[k];
+        st->rr0[k] = t[2 * K + k];
+      }
+      for (int k = 0; k < K; ++k) {
+        double bref = st->bb[k];
+        if (st->block_rtol)
+          for (int j = 0; j < K; ++j) bref = bref > t[K + j] ? bref : t[K + j];
+        double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * bref;
         st->tol2[k] = r2 > a2 ? r2 : a2;
         st->its[k] = 0;
         st->reason[k] = 0;
@@ -99,13 +106,19 @@ __device__ inline void kry_finalize(int fin, KryState* st, const double* t) {
       for (int k = 0; k < K; ++k) {
         st->bb[k] = t[k];
         st->rr[k] = t[K + k];
+        st->rr0[k] = t[K + k];
         st->rho[k] = t[K + k];  // rhat = r0
         st->rh2[k] = t[K + k];
         st->restart[k] = 0;
         st->alpha[k] = 1.0;
         st->omega[k] = 1.0;
         st->beta[k] = 0.0;
-        double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * st->bb[k];
+      }
+      for (int k = 0; k < K; ++k) {
+        double bref = st->bb[k];
+        if (st->block_rtol)
+          for (int j = 0; j < K; ++j) bref = bref > t[j] ? bref : t[j];
+        double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * bref;
         st->tol2[k] = r2 > a2 ? r2 : a2;
         st->its[k] = 0;
         st->reason[k] = 0;

@@ -136,6 +136,7 @@ __device__ inline void cgz_finalize(int fin, KryState* st, const double* t) {
     case FIN_CGZ_INIT: {  // t = bb, rr
       st->bb[0] = t[0];
       st->rr[0] = t[1];
+      st->rr0[0] = t[1];
       double a2 = st->atol * st->atol, r2 = st->rtol * st->rtol * st->bb[0];
       st->tol2[0] = r2 > a2 ? r2 : a2;
       st->its[0] = 0;

@@ -12,7 +12,7 @@ import logging
 logger = logging.getLogger("oasisx")
 
 _UNDERSTOOD = {"ksp_type", "pc_type", "ksp_rtol", "ksp_atol", "ksp_max_it", "ksp_initial_guess_nonzero", "b200_guess",
-               "ksp_chebyshev_eigenvalues"}
+               "ksp_chebyshev_eigenvalues", "b200_block_rtol"}
 
 
 class KSPSolver:

@@ -75,7 +75,9 @@ struct Ctx {
   std::vector<char> is_bc;
   std::vector<double> dinvA, dinvM, dinvAp;
   double vol = 0, rtol = 1e-10;
-  int maxit = 10000, nonzero = 0;
+  int maxit = 10000, nonzero = 0, block_rtol = 0, extrapolate = 0, steps_done = 0;
+  std::vector<double> delta_prev[3];
+  double bref2 = 0;  // block_rtol: max_k |b_k|^2 of the current vector solve
   int its_t = 0, its_p = 0, its_u = 0;
 };
 
@@ -190,7 +192,7 @@ int cg(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::v
 #pragma omp parallel for
   for (int64_t i = 0; i < n; ++i) { z[i] = dinv[i] * r[i]; p[i] = z[i]; }
   double rz = dot(n, r.data(), z.data()), bb = dot(n, b, b), rr = dot(n, r.data(), r.data());
-  const double tol2 = std::max(c.rtol * c.rtol * bb, 1e-100);
+  const double tol2 = std::max(c.rtol * c.rtol * (c.block_rtol && c.bref2 > bb ? c.bref2 : bb), 1e-100);
   int it = 0;
   while (rr > tol2 && it < c.maxit) {
     spmv(m, vals, p.data(), q.data());
@@ -236,7 +238,7 @@ int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const 
     p[i] = r[i];
   }
   double rr = dot(n, r.data(), r.data()), rho = rr;
-  const double tol2 = std::max(c.rtol * c.rtol * bb, 1e-100);
+  const double tol2 = std::max(c.rtol * c.rtol * (c.block_rtol && c.bref2 > bb ? c.bref2 : bb), 1e-100);
   int it = 0;
   while (rr > tol2 && it < c.maxit) {
     apply(p.data(), v.data());
@@ -436,6 +438,10 @@ void ipcs_cpu_set_options(void* h, double rtol, int maxit, int nonzero_guess) {
   c->maxit = maxit;
   c->nonzero = nonzero_guess;
 }
+// tolerance of the velocity solves relative to max_k |b_k| (same option as the GPU arm's b200_block_rtol)
+void ipcs_cpu_set_block_rtol(void* h, int on) { ((Ctx*)h)->block_rtol = on; }
+// same initial guesses as the GPU arm's b200_guess=extrapolate: 2u^n - u^{n-1} / u* + (u - u*)^{n-1}
+void ipcs_cpu_set_extrapolate(void* h, int on) { ((Ctx*)h)->extrapolate = on; }
 
 // _preassemble (fracstep.py:360-409), no pressure BCs (the Taylor-Green / cavity configuration)
 void ipcs_cpu_preassemble(void* h, const double* f) {
@@ -520,6 +526,19 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
 #pragma omp parallel for
     for (int64_t i = 0; i < nV; ++i) c->rhs1[k][i] = c->bfirst[k][i] + c->wrk[i];
     for (size_t i = 0; i < c->bc_dofs[k].size(); ++i) c->rhs1[k][c->bc_dofs[k][i]] = c->bc_vals[k][i];
+  }
+  c->bref2 = 0;
+  for (int k = 0; k < d; ++k) {
+    double s2 = 0;
+#pragma omp parallel for reduction(+ : s2)
+    for (int64_t i = 0; i < nV; ++i) s2 += (c->dinvA[i] * c->rhs1[k][i]) * (c->dinvA[i] * c->rhs1[k][i]);
+    c->bref2 = std::max(c->bref2, s2);
+  }
+  for (int k = 0; k < d; ++k) {
+    if (c->extrapolate && c->nonzero && c->steps_done >= 1) {
+#pragma omp parallel for
+      for (int64_t i = 0; i < nV; ++i) c->u[k][i] = 2.0 * c->u1[k][i] - c->u2[k][i];
+    }
     int it = bicgstab(*c, c->vv, c->A, c->dinvA, c->rhs1[k].data(), c->u[k].data());
     if (it < 0) return -1;
     c->its_t = std::max(c->its_t, it);
@@ -541,6 +560,7 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   mean /= (double)nQ;
 #pragma omp parallel for
   for (int64_t i = 0; i < nQ; ++i) c->b2[i] -= mean;  // nullspace.remove, :573-574
+  c->bref2 = 0;
   c->its_p = cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
   if (c->its_p < 0) return -2;
   const double avg = dot(nQ, c->mQ.data(), c->dp.data()) / c->vol;  // :579-591
@@ -551,12 +571,29 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   }
   // ---- velocity update (:607-658)
   c->its_u = 0;
+  std::vector<std::vector<double>> b3s(d, std::vector<double>(nV));
+  c->bref2 = 0;
   for (int k = 0; k < d; ++k) {
-    spmv(c->vv, c->M, c->u[k].data(), c->b3.data());
+    spmv(c->vv, c->M, c->u[k].data(), b3s[k].data());
     spmv(c->vq, c->G[k], c->dp.data(), c->wrk.data());
 #pragma omp parallel for
-    for (int64_t i = 0; i < nV; ++i) c->b3[i] -= dt * c->wrk[i];
+    for (int64_t i = 0; i < nV; ++i) b3s[k][i] -= dt * c->wrk[i];
+    c->bref2 = std::max(c->bref2, dot(nV, b3s[k].data(), b3s[k].data()));
+  }
+  for (int k = 0; k < d; ++k) {
+    c->b3 = b3s[k];
+    std::vector<double> ustar;
+    if (c->extrapolate && c->nonzero) {
+      if (c->delta_prev[k].empty()) c->delta_prev[k].assign(nV, 0.0);
+      ustar = c->u[k];
+#pragma omp parallel for
+      for (int64_t i = 0; i < nV; ++i) c->u[k][i] += c->delta_prev[k][i];
+    }
     int it = cg(*c, c->vv, c->M, c->dinvM, c->b3.data(), c->u[k].data());
+    if (!ustar.empty()) {
+#pragma omp parallel for
+      for (int64_t i = 0; i < nV; ++i) c->delta_prev[k][i] = c->u[k][i] - ustar[i];
+    }
     if (it < 0) return -3;
     c->its_u = std::max(c->its_u, it);
   }
@@ -565,6 +602,7 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
     c->u1[k] = c->u[k];
   }
   c->p = c->ps;
+  c->steps_done++;
   if (its) {
     its[0] = c->its_t;
     its[1] = c->its_p;

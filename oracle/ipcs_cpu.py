@@ -29,6 +29,8 @@ def lib():
         L.ipcs_cpu_set_bc.argtypes = [vp, i32, i64, vp]
         L.ipcs_cpu_set_bc_values.argtypes = [vp, i32, vp]
         L.ipcs_cpu_set_options.argtypes = [vp, dbl, i32, i32]
+        L.ipcs_cpu_set_block_rtol.argtypes = [vp, i32]
+        L.ipcs_cpu_set_extrapolate.argtypes = [vp, i32]
         L.ipcs_cpu_preassemble.argtypes = [vp, vp]
         L.ipcs_cpu_set_vec.argtypes = [vp, i32, i32, vp]
         L.ipcs_cpu_get_vec.argtypes = [vp, i32, i32, vp]
@@ -49,7 +51,8 @@ U, U1, U2, P, PS, DP, RHS1, BFIRST, B2 = range(9)
 class CpuIPCS:
     """Same problem description as ``OracleIPCS`` (one BC per component: (dofs, callable))."""
 
-    def __init__(self, x, cells, d, vdofs, qdofs, xV, xQ, deg_v, bcs_u, rtol=1e-10, nonzero_guess=False, body_force=None):
+    def __init__(self, x, cells, d, vdofs, qdofs, xV, xQ, deg_v, bcs_u, rtol=1e-10, nonzero_guess=False, body_force=None,
+                 block_rtol=False, extrapolate=False):
         L = lib()
         self.L, self.d = L, d
         x = np.ascontiguousarray(x, np.float64)
@@ -64,6 +67,8 @@ class CpuIPCS:
             dofs = np.ascontiguousarray(bcl[0][0], np.int32)
             L.ipcs_cpu_set_bc(self.h, i, len(dofs), _p(dofs))
         L.ipcs_cpu_set_options(self.h, rtol, 10000, int(nonzero_guess))
+        L.ipcs_cpu_set_block_rtol(self.h, int(block_rtol))
+        L.ipcs_cpu_set_extrapolate(self.h, int(extrapolate))
         f = np.ascontiguousarray(list(body_force or [0.0] * d) + [0.0] * (3 - d), np.float64)
         L.ipcs_cpu_preassemble(self.h, _p(f))
         self.its = np.zeros(3, np.int32)

@@ -60,3 +60,23 @@ def test_cpu_port_matches_numpy_oracle(gdim, N, deg):
             assert relerr(c.get(cpu.U, i), o.u[i], vscale(o.u)) <= 1e-8
         assert relerr(c.get(cpu.P), o.p) <= 1e-8
     assert (c.its > 0).all()
+
+
+def test_cpu_port_bench_options_do_not_change_the_solution():
+    """block-relative tolerance + extrapolated guesses (the bench settings): same fields as the oracle."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(3, 4)
+    tg, tg2 = TaylorGreen(nu, 3), TaylorGreen(nu, 3)
+    c = make_cpu(msh, 2, tg, dt, rtol=1e-12, nonzero_guess=True, block_rtol=True, extrapolate=True)
+    o = make_oracle(msh, 2, tg2, dt)
+    for t in (tg, tg2):
+        t.t_u, t.t_p = 0.0, -dt / 2
+    for n in range(5):
+        for t in (tg, tg2):
+            t.t_u += dt
+            t.t_p += dt
+        c.solve(dt, nu)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(3):
+            assert relerr(c.get(cpu.U, i), o.u[i], vscale(o.u)) <= 1e-8
+        assert relerr(c.get(cpu.P), o.p) <= 1e-8

@@ -218,14 +218,18 @@ def test_pressure_multigrid_matches_oracle(gdim, N):
 
 
 def test_extrapolated_initial_guesses_do_not_change_the_solution():
-    """b200_guess=extrapolate only changes the Krylov starting point: fields still match the oracle."""
+    """b200_guess=extrapolate only changes the Krylov starting point and b200_block_rtol only stops the solver
+    from polishing a component whose right-hand side is round-off (w = 0 in the z-extruded field): fields still
+    match the oracle, and the zero component needs no more iterations than the others."""
     dt, nu = 0.005, 0.01
     msh = make_mesh(3, 6)
     tg = TaylorGreen(nu, 3)
     opts = {
-        "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate"},
+        "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate",
+                      "b200_block_rtol": True},
         "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-12, "ksp_initial_guess_nonzero": True},
-        "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate"},
+        "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate",
+                   "b200_block_rtol": True},
     }
     s = make_solver(msh, 2, tg, dt, solver_options=opts)
     o = make_oracle(msh, 2, tg, dt)
@@ -238,6 +242,8 @@ def test_extrapolated_initial_guesses_do_not_change_the_solution():
         for i in range(3):
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, n
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
+    st = s.stats()
+    assert st.its_update[2] <= max(st.its_update[0], st.its_update[1])
 
 
 @pytest.mark.parametrize("gdim,N", [(2, 8), (3, 4)])
