@@ -180,6 +180,10 @@ int b2_tentative_solve(b2_ctx* ctx, double* diff, int32_t* reasons); /* fracstep
 int b2_pressure_assemble(b2_ctx* ctx, double dt);                /* fracstep.py:527-551 */
 int b2_pressure_solve(b2_ctx* ctx, double nu, int32_t* reason);  /* fracstep.py:553-605 */
 int b2_velocity_update(b2_ctx* ctx, double dt, int32_t* reasons);/* fracstep.py:607-658 */
+/* Optional first half of a step: p* <- p and assemble_first (fracstep.py:673,676), enqueued without waiting,
+ * so that the caller can evaluate this step's Dirichlet callables on the host meanwhile; b2_step then
+ * continues from there.  (The velocity BC values are first read by the tentative solve, :517-518.) */
+int b2_step_begin(b2_ctx* ctx, double dt, double nu);
 /* whole step (fracstep.py:660-696) with the BC values already uploaded */
 int b2_step(b2_ctx* ctx, double dt, double nu, double max_error, int max_iter, double* diff);
 

@@ -29,7 +29,7 @@ SYMBOLS = [
     "b2_build_patterns", "b2_pattern_nnz", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
-    "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step",
+    "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
     "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
         "b2_pressure_assemble": (i32, [vp, dbl]),
         "b2_pressure_solve": (i32, [vp, dbl, vp]),
         "b2_velocity_update": (i32, [vp, dbl, vp]),
+        "b2_step_begin": (i32, [vp, dbl, dbl]),
         "b2_step": (i32, [vp, dbl, dbl, dbl, i32, vp]),
         "b2_assemble_pressure_surface": (i32, [vp, i64, vp, vp, vp, i32]),
         "b2_project_q": (i32, [vp, vp, vp, vp]),
@@ -220,7 +221,7 @@ class Context:
                                                       _ptr(Pi), _ptr(Px), _ptr(Pv), _ptr(Ri), _ptr(Rx), _ptr(Rv)),
                     "b2_pressure_mg_add_level")
 
-    def pressure_mg_configure(self, nu_pre=2, nu_post=2, coarse_sweeps=40, omega=0.7):
+    def pressure_mg_configure(self, nu_pre=2, nu_post=2, coarse_sweeps=16, omega=0.7):
         self._check(self.lib.b2_pressure_mg_configure(self._h, nu_pre, nu_post, coarse_sweeps, omega), "b2_pressure_mg_configure")
 
     def pattern(self, which: int, n_rows: int):
@@ -312,6 +313,9 @@ class Context:
         reasons = np.zeros(3, dtype=np.int32)
         self._check(self.lib.b2_velocity_update(self._h, dt, _ptr(reasons)), "b2_velocity_update")
         return reasons[: self.gdim].copy()
+
+    def step_begin(self, dt: float, nu: float):
+        self._check(self.lib.b2_step_begin(self._h, dt, nu), "b2_step_begin")
 
     def step(self, dt: float, nu: float, max_error: float, max_iter: int) -> float:
         diff = C.c_double(0.0)

@@ -141,7 +141,7 @@ struct b2_ctx {
   CSR pat[4];
   Halo halo[2];
   std::vector<MgLevel> mg;  // coarse levels 1..L of the pressure hierarchy
-  int mg_pre = 2, mg_post = 2, mg_coarse = 40;
+  int mg_pre = 2, mg_post = 2, mg_coarse = 16;
   double mg_omega = 0.7;
   DBuf<double> mg_x0, mg_t0;  // fine-level work vectors (n_local of Q)
   DBuf<MgDev> mg_dev;         // device descriptors of the coarse levels (index = level - 1)
@@ -172,6 +172,7 @@ struct b2_ctx {
   DBuf<double> stage;  // staging for strided host copies
   DBuf<double> delta_prev;  // previous velocity correction u - u* (initial guess of the next mass solve)
   int steps_done = 0;
+  bool step_begun = false;  // b2_step_begin was called for the step b2_step is about to finish
   KryState* d_st = nullptr;
   KryState* h_st = nullptr;  // pinned
   double* d_sums = nullptr;  // small device scratch for reductions (16 doubles)
@@ -942,9 +943,12 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
   B2_CUDA(cudaMemcpyAsync(wrk, u, sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));  // :520
   int32_t its[B2_MAXK] = {0, 0, 0};
   if (c->ksp[B2_SOLVER_TENTATIVE].extrapolate_guess && c->steps_done >= 1) {
-    // initial guess 2 u^n - u^{n-1}: the converged solution does not depend on it, the iteration count does
+    // initial guess 2 u^n - u^{n-1} - (u - u*)^n, i.e. the extrapolated velocity minus the last pressure
+    // correction (the tentative velocity lacks it): the converged solution does not depend on the guess, the
+    // iteration count does
     const int64_t nl = V.n_local() * K;
     B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 2.0, c->vec(B2_VEC_U1), -1.0, c->vec(B2_VEC_U2), u);
+    if (c->delta_prev.p != nullptr) B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, -1.0, c->delta_prev.p, u);
   }
   krylov_solve(c, B2_SOLVER_TENTATIVE, c->pat[B2_PAT_VV], c->A.p, c->dinvA.p, B2_SPACE_V, K, rhs1, u, reasons, its);  // :521
   for (int k = 0; k < K; ++k) c->stats.its_tentative[k] = its[k];
@@ -1059,14 +1063,24 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter, double* diff_out) {
+// first half of a step: everything that does not need this step's Dirichlet values.  Only enqueues work,
+// so the host can evaluate time-dependent boundary callables while the GPU assembles.
+void stage_step_begin(b2_ctx* c, double dt, double nu) {
   require_ready(c);
-  const int K = c->gdim;
-  const Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
+  const Space& Q = c->sp[B2_SPACE_Q];
   B2_CUDA(cudaEventRecord(c->ev[0], c->stream));
   B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_PS), c->vec(B2_VEC_P), sizeof(double) * Q.n_local(), cudaMemcpyDeviceToDevice, c->stream));  // :673
   stage_assemble_first(c, dt, nu);
   B2_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  c->step_begun = true;
+}
+
+void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter, double* diff_out) {
+  require_ready(c);
+  const int K = c->gdim;
+  const Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
+  if (!c->step_begun) stage_step_begin(c, dt, nu);
+  c->step_begun = false;
   int inner = 0;
   double diff = 1e8;
   float ms_t = 0, ms_p = 0;
@@ -1290,6 +1304,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
     if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
     if (const char* e = std::getenv("B200_SPMM_SM")) c->spmm_sm = std::atoi(e);
+    if (const char* e = std::getenv("B200_MG_COARSE")) c->mg_coarse = std::max(1, std::atoi(e));
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -1716,6 +1731,9 @@ int b2_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
 }
 int b2_velocity_update(b2_ctx* c, double dt, int32_t* reasons) {
   return guarded(c, [&] { stage_velocity_update(c, dt, reasons); });
+}
+int b2_step_begin(b2_ctx* c, double dt, double nu) {
+  return guarded(c, [&] { stage_step_begin(c, dt, nu); });
 }
 int b2_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter, double* diff) {
   return guarded(c, [&] { stage_step(c, dt, nu, max_error, max_iter, diff); });

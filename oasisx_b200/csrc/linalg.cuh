@@ -703,18 +703,44 @@ k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __rest
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
-    for (int t = 0; t < len; ++t) {
-      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
-      const int c = ld_stream(cols + p);
-      const double m = inv_dt * ld_stream(M + p);
-      const double kk = half_nu * ld_stream(Kst + p);
-      const double cv = 0.5 * A[p];
+    const int dt_row = live ? __ldg(diag_t + row) : -1;
+    auto body = [&](int t, int c, double mv, double kv, double av, const double (&xu)[K]) {
+      const double m = inv_dt * mv;
+      const double kk = half_nu * kv;
+      const double cv = 0.5 * av;
       const double r = (m - cv) - kk;
       double a = ((m + cv) + kk) * invd;
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] = fma(r, __ldg(u1 + (size_t)k * ld + c), acc[k]);
-      if (bc) a = (live && c == row && t == __ldg(diag_t + row)) ? 1.0 : 0.0;
-      A[p] = a;
+      for (int k = 0; k < K; ++k) acc[k] = fma(r, xu[k], acc[k]);
+      if (bc) a = (t == dt_row) ? 1.0 : 0.0;
+      A[(size_t)base + ((size_t)t << 5) + lane] = a;
+    };
+    int t = 0;
+    for (; t + 4 <= len; t += 4) {  // four independent (stream -> gather) chains in flight
+      int cc[4];
+      double mv[4], kv[4], av[4], xu[4][K];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t p = (size_t)base + ((size_t)(t + u) << 5) + lane;
+        cc[u] = ld_stream(cols + p);
+        mv[u] = ld_stream(M + p);
+        kv[u] = ld_stream(Kst + p);
+        av[u] = A[p];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) xu[u][k] = __ldg(u1 + (size_t)k * ld + cc[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(t + u, cc[u], mv[u], kv[u], av[u], xu[u]);
+    }
+    for (; t < len; ++t) {
+      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
+      const int c = ld_stream(cols + p);
+      double xu[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) xu[k] = __ldg(u1 + (size_t)k * ld + c);
+      body(t, c, ld_stream(M + p), ld_stream(Kst + p), A[p], xu);
     }
     if (live) {
 #pragma unroll

@@ -346,10 +346,13 @@ class FractionalStep_AB_CN:
 
     def solve(self, dt: float, nu: float, max_error: float = 1e-12, max_iter: int = 10):
         """Propagate the splitting scheme one time step (``fracstep.py:660-696``)."""
-        [[bc.update_bc() for bc in bcu] for bcu in self._bcs_u]
-        self._upload_bcs()
+        # enqueue p* <- p and assemble_first first: they do not read the velocity Dirichlet values, so the host
+        # evaluates the boundary callables (the reference does it up front, :675) while the GPU assembles
         self._flush()
         self._assemble_pressure_surface()
+        self._ctx.step_begin(float(dt), float(nu))
+        [[bc.update_bc() for bc in bcu] for bcu in self._bcs_u]
+        self._upload_bcs()
         diff = self._ctx.step(float(dt), float(nu), float(max_error), int(max_iter))
         self._written(self._u, self._u1, self._u2, self._uab, self._rhs1, self._b_first, self._ps, self._p,
                       self._dp, self._b2)

@@ -537,7 +537,8 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   for (int k = 0; k < d; ++k) {
     if (c->extrapolate && c->nonzero && c->steps_done >= 1) {
 #pragma omp parallel for
-      for (int64_t i = 0; i < nV; ++i) c->u[k][i] = 2.0 * c->u1[k][i] - c->u2[k][i];
+      for (int64_t i = 0; i < nV; ++i)
+        c->u[k][i] = 2.0 * c->u1[k][i] - c->u2[k][i] - (c->delta_prev[k].empty() ? 0.0 : c->delta_prev[k][i]);
     }
     int it = bicgstab(*c, c->vv, c->A, c->dinvA, c->rhs1[k].data(), c->u[k].data());
     if (it < 0) return -1;
