@@ -39,7 +39,8 @@ DT, NU = 0.005, 0.01
 KRYLOV = {
     "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
                   "b200_guess": "extrapolate", "b200_block_rtol": True},
-    "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True},
+    "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
+                 "b200_guess": "extrapolate"},
     "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
                "b200_guess": "extrapolate", "b200_block_rtol": True},
 }

@@ -170,6 +170,8 @@ struct b2_ctx {
   // Krylov work space
   DBuf<double> wv[5], wq[4];
   DBuf<double> stage;  // staging for strided host copies
+  DBuf<double> dp_old;      // pressure correction of the step before the previous one (extrapolated guess)
+  int dp_hist = 0;
   DBuf<double> delta_prev;  // previous velocity correction u - u* (initial guess of the next mass solve)
   int steps_done = 0;
   bool step_begun = false;  // b2_step_begin was called for the step b2_step is about to finish
@@ -992,6 +994,15 @@ void stage_pressure_solve(b2_ctx* c, double nu, int32_t* reason) {
     B2_LAUNCH(c, k_shift, pgrid(c, n), 256, n, b2, c->d_sums, 0, 1.0 / (double)Q.n_global, (const double*)nullptr, (double*)nullptr);
   }
   int32_t its = 0;
+  if (c->ksp[B2_SOLVER_PRESSURE].extrapolate_guess) {  // start from 2 dp^{n-1} - dp^{n-2}
+    const int64_t nq = Q.n_local();
+    if (c->dp_old.p == nullptr) { c->dp_old.alloc(nq); c->dp_old.zero(c->stream); }
+    double* t3 = c->wq[3].p;
+    if (c->dp_hist >= 2) B2_LAUNCH(c, k_lincomb2, pgrid(c, nq), 256, nq, 2.0, dp, -1.0, c->dp_old.p, t3);
+    B2_CUDA(cudaMemcpyAsync(c->dp_old.p, dp, sizeof(double) * nq, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->dp_hist >= 2) B2_CUDA(cudaMemcpyAsync(dp, t3, sizeof(double) * nq, cudaMemcpyDeviceToDevice, c->stream));
+    c->dp_hist++;
+  }
   if (c->ksp[B2_SOLVER_PRESSURE].pc == 2 && !c->mg.empty() && !c->has_pbc)
     pcg_mg_solve(c, b2, dp, reason, &its);
   else

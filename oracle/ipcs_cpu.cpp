@@ -76,7 +76,8 @@ struct Ctx {
   std::vector<double> dinvA, dinvM, dinvAp;
   double vol = 0, rtol = 1e-10;
   int maxit = 10000, nonzero = 0, block_rtol = 0, extrapolate = 0, steps_done = 0;
-  std::vector<double> delta_prev[3];
+  std::vector<double> delta_prev[3], dp_old;
+  int dp_hist = 0;
   double bref2 = 0;  // block_rtol: max_k |b_k|^2 of the current vector solve
   int its_t = 0, its_p = 0, its_u = 0;
 };
@@ -562,6 +563,16 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
 #pragma omp parallel for
   for (int64_t i = 0; i < nQ; ++i) c->b2[i] -= mean;  // nullspace.remove, :573-574
   c->bref2 = 0;
+  if (c->extrapolate && c->nonzero) {  // start from 2 dp^{n-1} - dp^{n-2}
+    if (c->dp_old.empty()) c->dp_old.assign(nQ, 0.0);
+    std::vector<double> prev = c->dp;
+    if (c->dp_hist >= 2) {
+#pragma omp parallel for
+      for (int64_t i = 0; i < nQ; ++i) c->dp[i] = 2.0 * prev[i] - c->dp_old[i];
+    }
+    c->dp_old = prev;
+    c->dp_hist++;
+  }
   c->its_p = cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
   if (c->its_p < 0) return -2;
   const double avg = dot(nQ, c->mQ.data(), c->dp.data()) / c->vol;  // :579-591

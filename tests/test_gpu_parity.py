@@ -227,7 +227,7 @@ def test_extrapolated_initial_guesses_do_not_change_the_solution():
     opts = {
         "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate",
                       "b200_block_rtol": True},
-        "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-12, "ksp_initial_guess_nonzero": True},
+        "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-12, "b200_guess": "extrapolate"},
         "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12, "b200_guess": "extrapolate",
                    "b200_block_rtol": True},
     }
