@@ -342,11 +342,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
     ap.add_argument("--scalar-ksp", default="auto", choices=["auto", "cg", "chebyshev"],
-                    help="mass-solve method: auto = cg, except reduction-free chebyshev on 8+ GPUs (latency-bound there)")
+                    help="mass-solve method (auto = cg; chebyshev is reduction-free but needs ~3x the iterations once the "
+                         "initial guesses are good)")
     args = ap.parse_args()
     KRYLOV["pressure"]["pc_type"] = args.pressure_pc
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    KRYLOV["scalar"]["ksp_type"] = args.scalar_ksp if args.scalar_ksp != "auto" else ("chebyshev" if world >= 8 else "cg")
+    KRYLOV["scalar"]["ksp_type"] = args.scalar_ksp if args.scalar_ksp != "auto" else "cg"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1316,6 +1316,8 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
     if (const char* e = std::getenv("B200_SPMM_SM")) c->spmm_sm = std::atoi(e);
     if (const char* e = std::getenv("B200_MG_COARSE")) c->mg_coarse = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("B200_MG_SWEEPS")) c->mg_pre = c->mg_post = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("B200_MG_OMEGA")) c->mg_omega = std::atof(e);
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
