@@ -38,11 +38,11 @@ METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
 DT, NU = 0.005, 0.01
 KRYLOV = {
     "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
-                  "b200_guess": "extrapolate", "b200_block_rtol": True},
+                  "b200_guess": "extrapolate2", "b200_block_rtol": True},
     "pressure": {"ksp_type": "cg", "pc_type": "mg", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
                  "b200_guess": "extrapolate"},
     "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
-               "b200_guess": "extrapolate", "b200_block_rtol": True},
+               "b200_guess": "extrapolate2", "b200_block_rtol": True},
 }
 
 
@@ -148,7 +148,7 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1):
                     Q.tabulate_dof_coordinates(), 2, bcs_u=[[(bd, f)] for f in tg.components],
                     rtol=KRYLOV["tentative"]["ksp_rtol"], nonzero_guess=KRYLOV["tentative"]["ksp_initial_guess_nonzero"],
                     block_rtol=KRYLOV["tentative"]["b200_block_rtol"],
-                    extrapolate=KRYLOV["tentative"].get("b200_guess") == "extrapolate")
+                    extrapolate={"extrapolate": 1, "extrapolate2": 2}.get(KRYLOV["tentative"].get("b200_guess"), 0))
     xV, xQ = V.tabulate_dof_coordinates().T, Q.tabulate_dof_coordinates().T
     tg.t_u = -DT
     for i, f in enumerate(tg.components):

@@ -124,6 +124,10 @@ int b2_set_global_sizes(b2_ctx* ctx, int64_t n_global_v, int64_t n_global_q);
 /* ---- sparsity (create_matrix, fracstep.py:293,294,300,315,324,336,352) ---------------- */
 int b2_build_patterns(b2_ctx* ctx);
 int64_t b2_pattern_nnz(b2_ctx* ctx, int pattern);
+/* Layout statistics of a square pattern's sliced-ELL form: slots (padded entries) and the number of 32-entry slice
+ * columns whose column indices form a run c0..c0+31 (their index loads are skipped by the SpMM).  -1 if unavailable. */
+int64_t b2_pattern_sell_slots(b2_ctx* ctx, int pattern);
+int64_t b2_pattern_sell_runs(b2_ctx* ctx, int pattern);
 /* Optional schedule for the sliced-ELL kernels on a square pattern: a permutation of the 32-row slices
  * that lists them spatial tile by spatial tile, so that one thread block gathers from one
  * neighbourhood of the vector (host-side analogue of DOLFINx's graph reordering [ext]).  Results do

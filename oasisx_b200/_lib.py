@@ -26,7 +26,7 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_build_patterns", "b2_pattern_nnz", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_pattern_sell_runs", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
         "b2_set_global_sizes": (i32, [vp, i64, i64]),
         "b2_build_patterns": (i32, [vp]),
         "b2_pattern_nnz": (i64, [vp, i32]),
+        "b2_pattern_sell_slots": (i64, [vp, i32]),
+        "b2_pattern_sell_runs": (i64, [vp, i32]),
         "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
         "b2_pressure_mg_add_level": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
         "b2_pressure_mg_configure": (i32, [vp, i32, i32, i32, dbl]),
@@ -235,6 +237,10 @@ class Context:
 
     def pattern_nnz(self, which: int) -> int:
         return int(self.lib.b2_pattern_nnz(self._h, which))
+
+    def pattern_sell(self, which: int) -> tuple[int, int]:
+        """(slots, run slice columns) of the sliced-ELL form of a square pattern."""
+        return int(self.lib.b2_pattern_sell_slots(self._h, which)), int(self.lib.b2_pattern_sell_runs(self._h, which))
 
     def set_velocity_bc_dofs(self, comp: int, dofs):
         d = _i32(dofs)

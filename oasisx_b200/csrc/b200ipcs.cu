@@ -30,6 +30,8 @@ struct CSR {
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
+  DBuf<int> cbase;                             // run-compressed columns, one entry per slice column (k_sell_cbase)
+  int64_t runs = 0;                            // number of slice columns that are runs (their column loads are skipped)
   DBuf<int> sm_range;                          // k_spmm_sm: schedule ranges per SM, balanced by slots
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
@@ -52,6 +54,7 @@ struct KSPOpts {
   bool nonzero_guess = false;
   bool block_rtol = false;  // "b200_block_rtol": rtol relative to max over the components' |b_k|
   bool extrapolate_guess = false;  // "b200_guess": "extrapolate" -- start from a time-extrapolated state (implies nonzero guess)
+  int guess_order = 1;             // "extrapolate2": quadratic extrapolation of the solver's own solution history (u*, u - u*)
   bool scaled_operator = false;  // the matrix is stored row-scaled by its diagonal (tentative velocity)
   int expected_its = 0;  // iterations of the previous solve: first batch enqueued without a host sync
 };
@@ -128,7 +131,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0, spmm_comp = 1;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues
   DBuf<int> sm_dense, sm_next;  // %smid -> dense SM index; per-range work counters
   int n_sm_dense = 0;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
@@ -147,6 +150,10 @@ struct b2_ctx {
   DBuf<MgDev> mg_dev;         // device descriptors of the coarse levels (index = level - 1)
   int mg_dev_levels = 0;      // number of levels the descriptor array was built for
   int mg_small_from = 1 << 30; // first level (>= 1) handled by the single-block kernel
+  int mg_dense_max = 5000;     // the first coarse level with at most this many dofs is solved exactly (dense inverse); 0 = off
+  int mg_dense_level = -1;     // index into mg (level - 1) of that level, -1: none
+  int mg_dense_on = 1;         // tuning "mg_dense": 0 falls back to smoothing all the way down (A/B comparisons)
+  DBuf<double> mg_dense;       // (A_l + alpha e e^T)^-1, row-major
   double** d_mg_result = nullptr; double** h_mg_result = nullptr;
   ncclComm_t comm = nullptr;
   double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank)
@@ -173,6 +180,10 @@ struct b2_ctx {
   DBuf<double> dp_old;      // pressure correction of the step before the previous one (extrapolated guess)
   int dp_hist = 0;
   DBuf<double> delta_prev;  // previous velocity correction u - u* (initial guess of the next mass solve)
+  // "extrapolate2": the last three tentative velocities u* and corrections u - u* (index 0 = newest)
+  DBuf<double> ustar_hist[3], delta_hist[3];
+  int n_ustar_hist = 0, n_delta_hist = 0;
+  bool fresh_step = true;  // assemble_first ran since the last tentative solve: its solution opens a new history entry
   int steps_done = 0;
   bool step_begun = false;  // b2_step_begin was called for the step b2_step is about to finish
   KryState* d_st = nullptr;
@@ -295,6 +306,13 @@ void build_pattern_raw(b2_ctx* c, int64_t n_cells, const int* rdofs, int nr, con
   out.lpr = avg >= 48 ? 16 : (avg >= 20 ? 8 : 4);
 }
 
+__global__ void k_count_nonneg(int64_t n, const int* __restrict__ v, int64_t* __restrict__ out) {
+  int64_t cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cnt += v[i] >= 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)out, (unsigned long long)cnt);
+}
+
 // SELL-32 companion of a square CSR pattern: slice offsets (in slots), padded column indices,
 // position of the diagonal in each row.
 void build_sell(b2_ctx* c, CSR& pat) {
@@ -318,6 +336,17 @@ void build_sell(b2_ctx* c, CSR& pat) {
   pat.scols.zero(c->stream);
   pat.diag_t.alloc(n_rows);
   B2_LAUNCH(c, k_sell_fill_cols, blocks_for(n_rows, 256), 256, n_rows, pat.rowptr.p, pat.cols.p, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p);
+  const int64_t n_sc = slots / 32;
+  pat.cbase.alloc(std::max<int64_t>(n_sc, 1));
+  pat.runs = 0;
+  if (n_sc > 0) {
+    B2_LAUNCH(c, k_sell_cbase, blocks_for(n_sc * 32, 256), 256, n_rows, n_sc, pat.slice_ptr.p, pat.scols.p, pat.cbase.p);
+    DBuf<int64_t> cnt;
+    cnt.alloc(1);
+    cnt.zero(c->stream);
+    B2_LAUNCH(c, k_count_nonneg, pgrid(c, n_sc), 256, n_sc, pat.cbase.p, cnt.p);
+    B2_CUDA(cudaMemcpyAsync(&pat.runs, cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   B2_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -377,7 +406,21 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
-  if (c->spmm_stream)
+  if (UNROLL == 8 && c->spmm_comp && c->spmm_stream && pat.cbase.p != nullptr && (int64_t)K * ld < (1ll << 31)) {
+    // run-compressed columns; spmm_comp selects (unroll, blocks/SM the registers are bounded for): 1 = (8, 8), 2 = (4, 8),
+    // 3 = (8, 6), 4 = (4, 6)
+#define B2_SPMM_COMP(U, MB)                                                                                              \
+    B2_LAUNCH(c, (k_spmm<K, DOT, U, BLOCK, true, true, MB>), std::max(1, std::min(need, c->sm * std::min(c->spmm_blocks_per_sm, MB))), \
+              BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x, ld, y, w, st, fin, c->partials.p,  \
+              c->d_counter, red_ptr(c), pat.cbase.p)
+    switch (c->spmm_comp) {
+      case 2: B2_SPMM_COMP(4, 8); break;
+      case 3: B2_SPMM_COMP(8, 6); break;
+      case 4: B2_SPMM_COMP(4, 6); break;
+      default: B2_SPMM_COMP(8, 8); break;
+    }
+#undef B2_SPMM_COMP
+  } else if (c->spmm_stream)
     B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
               x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
   else
@@ -603,12 +646,15 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
     default: throw B2Error(-3, "K must be 1..3");
   }
   int mx = 0;
-  double res0 = 0.0;
+  double res0 = 0.0, bref = 0.0;
+  for (int k = 0; k < K; ++k) bref = std::max(bref, c->h_st->bb[k]);
   for (int k = 0; k < K; ++k) {
     reasons[k] = c->h_st->reason[k];
     its[k] = c->h_st->its[k];
     mx = std::max(mx, c->h_st->its[k]);
-    if (c->h_st->bb[k] > 0) res0 = std::max(res0, std::sqrt(c->h_st->rr0[k] / c->h_st->bb[k]));
+    // initial residual relative to the norm the tolerance refers to (block_rtol: the largest component)
+    const double ref = o.block_rtol ? bref : c->h_st->bb[k];
+    if (ref > 0) res0 = std::max(res0, std::sqrt(c->h_st->rr0[k] / ref));
   }
   o.expected_its = mx;
   if (which == B2_SOLVER_TENTATIVE) c->stats.res0_tentative = res0;
@@ -659,9 +705,38 @@ void mg_build_descriptors(b2_ctx* c) {
   c->mg_dev_levels = nl;
 }
 
+// dense inverse of (A_l + alpha e e^T) for coarse level index i (mg.cuh); alpha = A_00 / n keeps the shift at the
+// scale of the operator
+void mg_build_dense(b2_ctx* c, int i) {
+  MgLevel& M = c->mg[i];
+  const int n = M.n;
+  c->mg_dense.alloc((int64_t)n * n);
+  DBuf<double> rowk, colk;
+  rowk.alloc(n);
+  colk.alloc(n);
+  double dinv0 = 0.0;
+  B2_CUDA(cudaMemcpyAsync(&dinv0, M.dinv.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  const double alpha = 1.0 / (dinv0 * n);
+  B2_LAUNCH(c, k_dense_from_sell, n, 128, n, M.pat.slice_ptr.p, M.pat.scols.p, M.A.p, alpha, c->mg_dense.p);
+  const dim3 grid((unsigned)blocks_for(n, 256), (unsigned)n);
+  for (int k = 0; k < n; ++k) {
+    B2_LAUNCH(c, k_gj_pivot, blocks_for(n, 256), 256, n, k, c->mg_dense.p, rowk.p, colk.p);
+    B2_LAUNCH(c, k_gj_update, grid, 256, n, k, c->mg_dense.p, rowk.p, colk.p);
+  }
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  c->mg_dense_level = i;
+}
+
 // x_l <- V-cycle(b_l), zero initial guess.  Returns the buffer that holds the result.
 double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
   if (c->mg_dev_levels != (int)c->mg.size()) mg_build_descriptors(c);
+  if (l >= 1 && l - 1 == c->mg_dense_level && c->mg_dense_on) {
+    // exact solve on this level: one dense mat-vec with the precomputed inverse; deeper levels are not visited
+    MgLevel& M = c->mg[l - 1];
+    B2_LAUNCH(c, k_dense_matvec, blocks_for((int64_t)M.n * 32, 256), 256, M.n, c->mg_dense.p, b, x);
+    return x;
+  }
   if (l >= c->mg_small_from) {
     // the rest of the hierarchy in one single-block kernel; b is c->mg[l-1].b by construction
     B2_LAUNCH(c, k_mg_small_cycle, 1, 1024, c->mg_dev.p, l - 1, (int)c->mg.size() - 1, c->mg_pre, c->mg_post, c->mg_coarse,
@@ -726,8 +801,12 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   }
   B2_LAUNCH(c, k_cgz_init, g, 256, n, b, q0, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
   cgz_finish(c, FIN_CGZ_INIT, 2);
+  // The device decides convergence; the host only has to stop enqueueing.  Iteration counts barely change
+  // from one time step to the next, so nothing is polled (no pipeline drain) until one iteration short of
+  // what the previous solve needed; kernels of a surplus iteration leave x untouched (st->done).
+  const int first_poll = o.expected_its > 0 ? o.expected_its - 1 : 0;
   for (int it = 0; it <= o.maxit; ++it) {
-    if (it % 2 == 0 || it < 4) {  // poll the device state (iteration counts are small with multigrid)
+    if (it >= first_poll) {
       B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
       B2_CUDA(cudaStreamSynchronize(c->stream));
       c->stats.bytes_d2h += sizeof(KryState);
@@ -747,6 +826,7 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   }
   *reason = c->h_st->reason[0] != 0 ? c->h_st->reason[0] : -3;
   *its = c->h_st->its[0];
+  o.expected_its = c->h_st->its[0];
   if (c->h_st->bb[0] > 0) c->stats.res0_pressure = std::sqrt(c->h_st->rr0[0] / c->h_st->bb[0]);
 }
 
@@ -861,6 +941,7 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   if (K == 2) comb(std::integral_constant<int, 2>{});
   else comb(std::integral_constant<int, 3>{});
   c->last_dt = dt;
+  c->fresh_step = true;
 }
 
 template <int K>
@@ -936,7 +1017,28 @@ void read_sums(b2_ctx* c, int n) {
   c->stats.bytes_d2h += sizeof(double) * n;
 }
 
-void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
+// out = (add) + time extrapolation of a solution history (h[0] newest): h0 | 2 h0 - h1 | 3 h0 - 3 h1 + h2
+void hist_extrapolate(b2_ctx* c, DBuf<double>* h, int n_avail, int64_t n, const double* add, double* out) {
+  const int g = pgrid(c, n);
+  if (n_avail >= 3) B2_LAUNCH(c, k_lincomb4, g, 256, n, 3.0, h[0].p, -3.0, h[1].p, 1.0, h[2].p, add, out);
+  else if (n_avail == 2) B2_LAUNCH(c, k_lincomb4, g, 256, n, 2.0, h[0].p, -1.0, h[1].p, 0.0, h[0].p, add, out);
+  else B2_LAUNCH(c, k_lincomb4, g, 256, n, 1.0, h[0].p, 0.0, h[0].p, 0.0, h[0].p, add, out);
+}
+
+// newest <- v: rotate the three buffers, copy into slot 0
+void hist_push(b2_ctx* c, DBuf<double>* h, int& n_avail, int64_t n, const double* v, bool replace_newest) {
+  if (!replace_newest || n_avail == 0) {
+    std::swap(h[2], h[1]);
+    std::swap(h[1], h[0]);  // (h0, h1, h2) <- (old h2 = free slot, old h0, old h1)
+    n_avail = std::min(n_avail + 1, 3);
+  }
+  if (h[0].p == nullptr) h[0].alloc(n);
+  B2_CUDA(cudaMemcpyAsync(h[0].p, v, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// defer_diff: leave the squared differences in pinned memory (h_sums[8..8+K), valid after the next stream
+// synchronisation) instead of draining the pipeline for a number only the caller of the whole step needs
+void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons, bool defer_diff = false) {
   require_ready(c);
   const int K = c->gdim;
   const Space& V = c->sp[B2_SPACE_V];
@@ -944,7 +1046,15 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
   apply_velocity_bcs(c, rhs1);                                                                  // :517-518
   B2_CUDA(cudaMemcpyAsync(wrk, u, sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));  // :520
   int32_t its[B2_MAXK] = {0, 0, 0};
-  if (c->ksp[B2_SOLVER_TENTATIVE].extrapolate_guess && c->steps_done >= 1) {
+  const KSPOpts& ot = c->ksp[B2_SOLVER_TENTATIVE];
+  const bool hist2 = ot.extrapolate_guess && ot.guess_order == 2;
+  const bool new_entry = c->fresh_step;
+  c->fresh_step = false;
+  if (hist2) {
+    // quadratic extrapolation of the tentative velocities of the last three steps (the sequence u* is smooth in
+    // time even where u^n - u* is not); a repeated pass of the same step starts from the pass before (u)
+    if (new_entry && c->n_ustar_hist >= 1) hist_extrapolate(c, c->ustar_hist, c->n_ustar_hist, V.n_local() * K, nullptr, u);
+  } else if (ot.extrapolate_guess && c->steps_done >= 1) {
     // initial guess 2 u^n - u^{n-1} - (u - u*)^n, i.e. the extrapolated velocity minus the last pressure
     // correction (the tentative velocity lacks it): the converged solution does not depend on the guess, the
     // iteration count does
@@ -954,8 +1064,15 @@ void stage_tentative_solve(b2_ctx* c, double* diff, int32_t* reasons) {
   }
   krylov_solve(c, B2_SOLVER_TENTATIVE, c->pat[B2_PAT_VV], c->A.p, c->dinvA.p, B2_SPACE_V, K, rhs1, u, reasons, its);  // :521
   for (int k = 0; k < K; ++k) c->stats.its_tentative[k] = its[k];
-  if (K == 2) sqdiff<2>(c, V.n_owned, (int)V.n_local(), wrk, u, c->d_sums);
-  else sqdiff<3>(c, V.n_owned, (int)V.n_local(), wrk, u, c->d_sums);
+  if (hist2) hist_push(c, c->ustar_hist, c->n_ustar_hist, V.n_local() * K, u, !new_entry);
+  double* dsq = c->d_sums + (defer_diff ? 8 : 0);
+  if (K == 2) sqdiff<2>(c, V.n_owned, (int)V.n_local(), wrk, u, dsq);
+  else sqdiff<3>(c, V.n_owned, (int)V.n_local(), wrk, u, dsq);
+  if (defer_diff) {
+    B2_CUDA(cudaMemcpyAsync(c->h_sums + 8, dsq, sizeof(double) * K, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.bytes_d2h += sizeof(double) * K;
+    return;
+  }
   read_sums(c, K);
   double d = 0.0;
   for (int k = 0; k < K; ++k) d += std::sqrt(c->h_sums[k]);  // :523-524 (sum of per-component 2-norms)
@@ -1058,13 +1175,16 @@ void stage_velocity_update(b2_ctx* c, double dt, int32_t* reasons) {
   const bool extrap = c->ksp[B2_SOLVER_SCALAR].extrapolate_guess;
   const int64_t nl = c->sp[B2_SPACE_V].n_local() * K;
   double* ustar = c->vec(B2_VEC_WRK);  // free after the tentative solve's diff
+  const bool hist2m = extrap && c->ksp[B2_SOLVER_SCALAR].guess_order == 2;
   if (extrap) {
     if (c->delta_prev.p == nullptr) { c->delta_prev.alloc(nl); c->delta_prev.zero(c->stream); }
     B2_CUDA(cudaMemcpyAsync(ustar, u, sizeof(double) * nl, cudaMemcpyDeviceToDevice, c->stream));
-    B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, 1.0, c->delta_prev.p, u);  // guess u* + (u - u*)_previous step
+    if (hist2m && c->n_delta_hist >= 1) hist_extrapolate(c, c->delta_hist, c->n_delta_hist, nl, ustar, u);  // u* + extrapolated correction
+    else B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, 1.0, c->delta_prev.p, u);  // guess u* + (u - u*)_previous step
   }
   krylov_solve(c, B2_SOLVER_SCALAR, c->pat[B2_PAT_VV], c->M.p, c->dinvM.p, B2_SPACE_V, K, b3, u, reasons, its);  // :656
   if (extrap) B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.0, u, -1.0, ustar, c->delta_prev.p);
+  if (hist2m) hist_push(c, c->delta_hist, c->n_delta_hist, nl, c->delta_prev.p, false);
   for (int k = 0; k < K; ++k) c->stats.its_update[k] = its[k];
 }
 
@@ -1095,12 +1215,14 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
   int inner = 0;
   double diff = 1e8;
   float ms_t = 0, ms_p = 0;
+  bool pending = false;  // the last pass leaves its diff and stage times to be collected after the step's final sync
   while (inner < max_iter && diff > max_error) {  // :677-684
     ++inner;
+    const bool last_pass = inner >= max_iter;  // diff cannot start another pass: no need to wait for it here
     int32_t reasons[B2_MAXK] = {0, 0, 0}, rp = 0;
     B2_CUDA(cudaEventRecord(c->ev[2], c->stream));
     stage_tentative_assemble(c);
-    stage_tentative_solve(c, &diff, reasons);
+    stage_tentative_solve(c, &diff, reasons, last_pass);
     for (int k = 0; k < K; ++k)
       if (reasons[k] <= 0) throw B2Error(-20, "tentative velocity solve diverged, component " + std::to_string(k) + " reason " + std::to_string(reasons[k]));
     B2_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -1108,6 +1230,7 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
     stage_pressure_solve(c, nu, &rp);
     if (rp <= 0) throw B2Error(-21, "pressure solve diverged, reason " + std::to_string(rp));
     B2_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    if (last_pass) { pending = true; break; }
     B2_CUDA(cudaEventSynchronize(c->ev[4]));
     ms_t += ev_ms(c->ev[2], c->ev[3]);
     ms_p += ev_ms(c->ev[3], c->ev[4]);
@@ -1120,6 +1243,12 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
   B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_P), c->vec(B2_VEC_PS), sizeof(double) * Q.n_local(), cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaEventRecord(c->ev[5], c->stream));
   B2_CUDA(cudaEventSynchronize(c->ev[5]));
+  if (pending) {
+    ms_t += ev_ms(c->ev[2], c->ev[3]);
+    ms_p += ev_ms(c->ev[3], c->ev[4]);
+    diff = 0.0;
+    for (int k = 0; k < K; ++k) diff += std::sqrt(c->h_sums[8 + k]);  // :523-524
+  }
   c->stats.ms_assemble_first = ev_ms(c->ev[0], c->ev[1]);
   c->stats.ms_tentative = ms_t;
   c->stats.ms_pressure = ms_p;
@@ -1315,9 +1444,11 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
     if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
     if (const char* e = std::getenv("B200_SPMM_SM")) c->spmm_sm = std::atoi(e);
+    if (const char* e = std::getenv("B200_SPMM_COMP")) c->spmm_comp = std::atoi(e);
     if (const char* e = std::getenv("B200_MG_COARSE")) c->mg_coarse = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("B200_MG_SWEEPS")) c->mg_pre = c->mg_post = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("B200_MG_OMEGA")) c->mg_omega = std::atof(e);
+    if (const char* e = std::getenv("B200_MG_DENSE")) c->mg_dense_max = std::atoi(e);
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -1467,6 +1598,7 @@ int b2_pressure_mg_add_level(b2_ctx* c, int64_t n_nodes, const double* x, int64_
     };
     upload_csr(L.P, L.Pv, (int)fine_n, L.n, P_indptr, P_indices, P_vals);
     upload_csr(L.R, L.Rv, L.n, (int)fine_cols, R_indptr, R_indices, R_vals);
+    if (c->mg_dense_level < 0 && L.n <= c->mg_dense_max) mg_build_dense(c, (int)c->mg.size() - 1);
     if (c->mg.size() == 1) {
       c->mg_x0.alloc(c->sp[B2_SPACE_Q].n_local()); c->mg_x0.zero(c->stream);
       c->mg_t0.alloc(c->sp[B2_SPACE_Q].n_local()); c->mg_t0.zero(c->stream);
@@ -1514,6 +1646,16 @@ int b2_build_patterns(b2_ctx* c) {
 int64_t b2_pattern_nnz(b2_ctx* c, int pattern) {
   if (!c || pattern < 0 || pattern > 3 || !c->patterns_built) return -1;
   return c->pat[pattern].nnz;
+}
+
+int64_t b2_pattern_sell_slots(b2_ctx* c, int pattern) {
+  if (!c || pattern < 0 || pattern > 3 || !c->patterns_built || !c->pat[pattern].has_sell()) return -1;
+  return c->pat[pattern].slots;
+}
+
+int64_t b2_pattern_sell_runs(b2_ctx* c, int pattern) {
+  if (!c || pattern < 0 || pattern > 3 || !c->patterns_built || !c->pat[pattern].has_sell()) return -1;
+  return c->pat[pattern].runs;
 }
 
 int b2_get_pattern(b2_ctx* c, int pattern, int32_t* indptr, int32_t* indices) {
@@ -1720,7 +1862,9 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
     } else if (k == "ksp_initial_guess_nonzero") o.nonzero_guess = (v == "1" || v == "true" || v == "True");
     else if (k == "b200_block_rtol") o.block_rtol = (v == "1" || v == "true" || v == "True");
     else if (k == "b200_guess") {
-      o.extrapolate_guess = (v == "extrapolate");
+      B2_REQUIRE(v == "extrapolate" || v == "extrapolate2" || v == "none" || v == "", "b200_guess: none | extrapolate | extrapolate2");
+      o.extrapolate_guess = (v == "extrapolate" || v == "extrapolate2");
+      o.guess_order = v == "extrapolate2" ? 2 : 1;
       if (o.extrapolate_guess) o.nonzero_guess = true;
     }
     // anything else: ignored (PETSc leaves unused options in the database without error)
@@ -1872,6 +2016,8 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "spmm_tma") c->spmm_tma = value;
     else if (k == "spmm_sm") c->spmm_sm = value;
+    else if (k == "spmm_comp") c->spmm_comp = value;
+    else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });

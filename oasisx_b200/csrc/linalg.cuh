@@ -279,6 +279,28 @@ __global__ void k_sell_fill_cols(int n_rows, const int* __restrict__ rowptr, con
   if (diag_t != nullptr) diag_t[row] = dt;
 }
 
+// run detection for the compressed SpMM (k_spmm<..., COMP>): one warp per slice column
+__global__ void k_sell_cbase(int n_rows, int64_t n_slice_cols, const int* __restrict__ slice_ptr,
+                             const int* __restrict__ scols, int* __restrict__ cbase) {
+  const int lane = threadIdx.x & 31;
+  const int64_t sc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (sc >= n_slice_cols) return;
+  // slice of this slice column: last s with slice_ptr[s] <= 32 * sc
+  const int n_slices = (n_rows + 31) >> 5;
+  int lo = 0, hi = n_slices - 1;
+  const int64_t slot0 = sc << 5;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int64_t)slice_ptr[mid] <= slot0) lo = mid;
+    else hi = mid - 1;
+  }
+  const int c = scols[slot0 + lane];
+  const int c0 = __shfl_sync(0xffffffffu, c, 0);
+  const bool full = ((lo << 5) + 31) < n_rows;  // rows beyond n_rows have no columns: never a run
+  const bool ok = __all_sync(0xffffffffu, c == c0 + lane) && full;
+  if (lane == 0) cbase[sc] = ok ? c0 : -1;
+}
+
 // values between CSR order and SELL slots (to_sell: pads are left untouched = 0)
 __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr,
                                int to_sell, const double* __restrict__ in, double* __restrict__ out,
@@ -304,12 +326,18 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // are adjacent in the list, fem.slice_order); a block takes blockDim/32 consecutive list entries at
 // a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
 // those lines in L1 instead of each pulling them through the L2 fabric.
-template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM>
-__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK)
+// COMP: run-compressed column indices.  `cbase[slot/32]` holds c0 >= 0 when the 32 columns of that slice
+// column are c0, c0+1, ..., c0+31 (the common case under the stencil-class dof order: 57 % of the slice
+// columns at 64^3, more on larger boxes) and -1 otherwise.  A run needs no column load at all: 4 bytes per
+// nonzero less DRAM traffic and, more importantly for a latency-bound kernel, the gather no longer waits
+// for a column index to arrive from HBM.  The test is warp-uniform (one broadcast load per slice column).
+// MINB: resident blocks per SM the register allocation is bounded for (8 x 256 threads = 32 registers, 6 = 40).
+template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, bool COMP = false, int MINB = 2048 / BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
        double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
-       unsigned* counter, double* red_out) {
+       unsigned* counter, double* red_out, const int* __restrict__ cbase = nullptr) {
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -331,6 +359,7 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
     const int row = (s << 5) + lane;
     const int* cp = cols + base + lane;
     const double* vp = vals + base + lane;
+    const int* cbp = COMP ? cbase + (base >> 5) : nullptr;
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
@@ -338,16 +367,30 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
     for (; t + UNROLL <= len; t += UNROLL) {
       int c[UNROLL];
       double v[UNROLL];
+      if constexpr (COMP) {
+        const int* cb = cbp + t;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) c[u] = __ldg(cb + u);
+        const int e = base + lane + (t << 5);  // 32-bit slot index: one register instead of two pointers
+        const double* ve = vals + e;
+        const int* ce = cols + e;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          v[u] = ld_stream(ve + (u << 5));
+          c[u] = c[u] >= 0 ? c[u] + lane : ld_stream(ce + (u << 5));
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         c[u] = STREAM ? ld_stream(cp + ((t + u) << 5)) : __ldg(cp + ((t + u) << 5));
         v[u] = STREAM ? ld_stream(vp + ((t + u) << 5)) : __ldg(vp + ((t + u) << 5));
       }
+      }
       double xv[UNROLL][K];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-        for (int k = 0; k < K; ++k) xv[u][k] = __ldg(x + (size_t)k * ld + c[u]);
+        for (int k = 0; k < K; ++k) xv[u][k] = COMP ? __ldg(x + (c[u] + k * ld)) : __ldg(x + (size_t)k * ld + c[u]);  // COMP: 32-bit index (K * ld < 2^31, checked by the launcher)
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
@@ -813,6 +856,15 @@ k_rect_qv(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ co
 __global__ void k_lincomb2(int64_t n, double a, const double* x, double b, const double* y, double* out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = a * x[i] + b * y[i];
+}
+
+// out = a x + b y + c z (+ add)
+__global__ void k_lincomb4(int64_t n, double a, const double* x, double b, const double* y, double c, const double* z,
+                           const double* add, double* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = fma(a, x[i], fma(b, y[i], c * z[i]));
+    out[i] = add != nullptr ? v + add[i] : v;
+  }
 }
 
 __global__ void k_fill(int64_t n, double v, double* __restrict__ out) {

@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -80,6 +82,11 @@ struct Ctx {
   int dp_hist = 0;
   double bref2 = 0;  // block_rtol: max_k |b_k|^2 of the current vector solve
   int its_t = 0, its_p = 0, its_u = 0;
+  // experiments (environment IPCS_GUESS_T / _M / _P, IPCS_DEBUG): order of the time extrapolation of the guesses
+  int debug = 0, guess_t = 0, guess_m = 0, guess_p = 1;
+  mutable double dbg_rr0 = 0;
+  std::vector<double> ustar_hist[3][3], delta_hist[3][3], dp_hist3[3];
+  int n_hist = 0, n_dp_hist = 0;
 };
 
 Geo geometry(const Ctx& c, int64_t cell) {
@@ -194,6 +201,7 @@ int cg(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::v
   for (int64_t i = 0; i < n; ++i) { z[i] = dinv[i] * r[i]; p[i] = z[i]; }
   double rz = dot(n, r.data(), z.data()), bb = dot(n, b, b), rr = dot(n, r.data(), r.data());
   const double tol2 = std::max(c.rtol * c.rtol * (c.block_rtol && c.bref2 > bb ? c.bref2 : bb), 1e-100);
+  c.dbg_rr0 = rr;
   int it = 0;
   while (rr > tol2 && it < c.maxit) {
     spmv(m, vals, p.data(), q.data());
@@ -214,6 +222,7 @@ int cg(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::v
     for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
     ++it;
   }
+  if (c.debug) std::fprintf(stderr, "  cg: res0 %.2e (vs tol ref) its %d\n", std::sqrt(c.dbg_rr0 / (tol2 / (c.rtol * c.rtol))), it);
   return rr <= tol2 ? it : -it;
 }
 
@@ -240,6 +249,7 @@ int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const 
   }
   double rr = dot(n, r.data(), r.data()), rho = rr;
   const double tol2 = std::max(c.rtol * c.rtol * (c.block_rtol && c.bref2 > bb ? c.bref2 : bb), 1e-100);
+  const double rr0 = rr;
   int it = 0;
   while (rr > tol2 && it < c.maxit) {
     apply(p.data(), v.data());
@@ -265,6 +275,7 @@ int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const 
 #pragma omp parallel for
     for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
   }
+  if (c.debug) std::fprintf(stderr, "  bcgs: res0 %.2e (vs tol ref) its %d\n", std::sqrt(rr0 / (tol2 / (c.rtol * c.rtol))), it);
   return rr <= tol2 ? it : -it;
 }
 
@@ -379,6 +390,10 @@ int ipcs_cpu_threads(void) { return omp_get_max_threads(); }
 void* ipcs_cpu_create(int gdim, int deg_v, int64_t n_nodes, const double* x, int64_t n_cells, const int* cell_nodes,
                       int64_t nV, const int* vdofs, int64_t nQ, const int* qdofs) {
   Ctx* c = new Ctx();
+  if (const char* e = std::getenv("IPCS_DEBUG")) c->debug = std::atoi(e);
+  if (const char* e = std::getenv("IPCS_GUESS_T")) c->guess_t = std::atoi(e);
+  if (const char* e = std::getenv("IPCS_GUESS_M")) c->guess_m = std::atoi(e);
+  if (const char* e = std::getenv("IPCS_GUESS_P")) c->guess_p = std::atoi(e);
   c->d = gdim;
   c->degv = deg_v;
   c->t = tables_for(gdim, deg_v);
@@ -439,10 +454,36 @@ void ipcs_cpu_set_options(void* h, double rtol, int maxit, int nonzero_guess) {
   c->maxit = maxit;
   c->nonzero = nonzero_guess;
 }
+// time extrapolation of order `order` from a history (h[0] newest): h0 / 2h0 - h1 / 3h0 - 3h1 + h2, limited by
+// the number of stored states
+static void extrap(int order, const std::vector<double>* h, int n_avail, int64_t n, double* out, double scale_add = 0.0,
+                   const double* add = nullptr) {
+  order = std::min(order, n_avail - 1);
+  const double c0 = order == 2 ? 3.0 : (order == 1 ? 2.0 : 1.0), c1 = order == 2 ? -3.0 : (order == 1 ? -1.0 : 0.0),
+               c2 = order == 2 ? 1.0 : 0.0;
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) {
+    double v = c0 * h[0][i];
+    if (order >= 1) v += c1 * h[1][i];
+    if (order >= 2) v += c2 * h[2][i];
+    out[i] = v + (add ? scale_add * add[i] : 0.0);
+  }
+}
+static void push_hist(std::vector<double>* h, const std::vector<double>& v) {
+  h[2].swap(h[1]);
+  h[1].swap(h[0]);
+  h[0] = v;
+}
+
 // tolerance of the velocity solves relative to max_k |b_k| (same option as the GPU arm's b200_block_rtol)
 void ipcs_cpu_set_block_rtol(void* h, int on) { ((Ctx*)h)->block_rtol = on; }
 // same initial guesses as the GPU arm's b200_guess=extrapolate: 2u^n - u^{n-1} / u* + (u - u*)^{n-1}
-void ipcs_cpu_set_extrapolate(void* h, int on) { ((Ctx*)h)->extrapolate = on; }
+// order 2 = the GPU arm's b200_guess=extrapolate2: quadratic extrapolation of the u* and (u - u*) histories
+void ipcs_cpu_set_extrapolate(void* h, int order) {
+  Ctx* c = (Ctx*)h;
+  c->extrapolate = order > 0;
+  if (order >= 2) { c->guess_t = 2; c->guess_m = 2; }
+}
 
 // _preassemble (fracstep.py:360-409), no pressure BCs (the Taylor-Green / cavity configuration)
 void ipcs_cpu_preassemble(void* h, const double* f) {
@@ -537,14 +578,20 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   }
   for (int k = 0; k < d; ++k) {
     if (c->extrapolate && c->nonzero && c->steps_done >= 1) {
+      if (c->guess_t > 0 && c->n_hist >= 1) {
+        extrap(c->guess_t, c->ustar_hist[k], c->n_hist, nV, c->u[k].data());
+      } else {
 #pragma omp parallel for
       for (int64_t i = 0; i < nV; ++i)
         c->u[k][i] = 2.0 * c->u1[k][i] - c->u2[k][i] - (c->delta_prev[k].empty() ? 0.0 : c->delta_prev[k][i]);
+      }
     }
     int it = bicgstab(*c, c->vv, c->A, c->dinvA, c->rhs1[k].data(), c->u[k].data());
     if (it < 0) return -1;
     c->its_t = std::max(c->its_t, it);
+    if (c->guess_t > 0) push_hist(c->ustar_hist[k], c->u[k]);
   }
+  if (c->guess_t > 0) c->n_hist = std::min(c->n_hist + 1, 3);
   // ---- pressure correction (:527-605)
   std::fill(c->b2.begin(), c->b2.end(), 0.0);
   std::vector<double> wq(nQ);
@@ -566,7 +613,9 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   if (c->extrapolate && c->nonzero) {  // start from 2 dp^{n-1} - dp^{n-2}
     if (c->dp_old.empty()) c->dp_old.assign(nQ, 0.0);
     std::vector<double> prev = c->dp;
-    if (c->dp_hist >= 2) {
+    if (c->guess_p != 1 && c->n_dp_hist >= 1) {
+      extrap(c->guess_p, c->dp_hist3, c->n_dp_hist, nQ, c->dp.data());
+    } else if (c->dp_hist >= 2) {
 #pragma omp parallel for
       for (int64_t i = 0; i < nQ; ++i) c->dp[i] = 2.0 * prev[i] - c->dp_old[i];
     }
@@ -575,6 +624,7 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
   }
   c->its_p = cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
   if (c->its_p < 0) return -2;
+  if (c->guess_p != 1) { push_hist(c->dp_hist3, c->dp); c->n_dp_hist = std::min(c->n_dp_hist + 1, 3); }
   const double avg = dot(nQ, c->mQ.data(), c->dp.data()) / c->vol;  // :579-591
 #pragma omp parallel for
   for (int64_t i = 0; i < nQ; ++i) {
@@ -598,13 +648,19 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
     if (c->extrapolate && c->nonzero) {
       if (c->delta_prev[k].empty()) c->delta_prev[k].assign(nV, 0.0);
       ustar = c->u[k];
+      if (c->guess_m > 0 && !c->delta_hist[k][0].empty()) {
+        int avail = 1 + !c->delta_hist[k][1].empty() + (!c->delta_hist[k][1].empty() && !c->delta_hist[k][2].empty());
+        extrap(c->guess_m, c->delta_hist[k], avail, nV, c->u[k].data(), 1.0, ustar.data());
+      } else {
 #pragma omp parallel for
       for (int64_t i = 0; i < nV; ++i) c->u[k][i] += c->delta_prev[k][i];
+      }
     }
     int it = cg(*c, c->vv, c->M, c->dinvM, c->b3.data(), c->u[k].data());
     if (!ustar.empty()) {
 #pragma omp parallel for
       for (int64_t i = 0; i < nV; ++i) c->delta_prev[k][i] = c->u[k][i] - ustar[i];
+      if (c->guess_m > 0) push_hist(c->delta_hist[k], c->delta_prev[k]);
     }
     if (it < 0) return -3;
     c->its_u = std::max(c->its_u, it);

@@ -62,12 +62,14 @@ def test_cpu_port_matches_numpy_oracle(gdim, N, deg):
     assert (c.its > 0).all()
 
 
-def test_cpu_port_bench_options_do_not_change_the_solution():
-    """block-relative tolerance + extrapolated guesses (the bench settings): same fields as the oracle."""
+@pytest.mark.parametrize("order", [1, 2])
+def test_cpu_port_bench_options_do_not_change_the_solution(order):
+    """block-relative tolerance + extrapolated guesses (the bench settings; order 2 = quadratic history
+    extrapolation, b200_guess=extrapolate2 on the GPU arm): same fields as the oracle."""
     dt, nu = 0.005, 0.01
     msh = make_mesh(3, 4)
     tg, tg2 = TaylorGreen(nu, 3), TaylorGreen(nu, 3)
-    c = make_cpu(msh, 2, tg, dt, rtol=1e-12, nonzero_guess=True, block_rtol=True, extrapolate=True)
+    c = make_cpu(msh, 2, tg, dt, rtol=1e-12, nonzero_guess=True, block_rtol=True, extrapolate=order)
     o = make_oracle(msh, 2, tg2, dt)
     for t in (tg, tg2):
         t.t_u, t.t_p = 0.0, -dt / 2
