@@ -146,6 +146,12 @@ int b2_set_velocity_bc_values(b2_ctx* ctx, int comp, int64_t n, const double* va
  * device and keeps the per-step H2D copy out of the step (update_bc, bcs.py:128-133). */
 int b2_set_velocity_bc_series(b2_ctx* ctx, int comp, int n_steps, int64_t n, const double* values);
 int b2_select_bc_step(b2_ctx* ctx, int step);
+/* cudaProfilerStart / cudaProfilerStop after draining the stream: delimits the region `ncu --profile-from-start off`
+ * (or nsys --capture-range=cudaProfilerApi) records, e.g. the timed steps of bench.py without the set-up kernels. */
+int b2_profiler_range(b2_ctx* ctx, int on);
+/* Forget the solution histories behind the extrapolated initial guesses (b200_guess) and the predicted iteration
+ * counts: call when the state vectors are re-initialised to start another run on the same context. */
+int b2_reset_time_history(b2_ctx* ctx);
 /* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253) */
 int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
 
@@ -155,7 +161,11 @@ int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
  * Jacobi smoothing).  The host supplies, coarser level by coarser level, the level's P1 mesh (dofs = mesh
  * nodes) and the transfer operators as CSR: P (rows = OWNED dofs of the previous level, cols = this
  * level) and R = P^T (rows = this level, cols = local dofs of the previous level).  Coarse levels are
- * replicated on every rank; only the restriction to level 1 is all-reduced.  Call after b2_preassemble. */
+ * replicated on every rank; only the restriction to level 1 is all-reduced.  Call after b2_preassemble.
+ * The first coarse level with at most 5000 dofs is solved exactly (dense inverse of the stiffness shifted by the
+ * constant mode, built on the device by Gauss-Jordan); deeper levels, if supplied, are then never visited.
+ * Defaults: V(1,1), damping 0.85, overridden by b2_pressure_mg_configure (coarse_sweeps: Jacobi sweeps on the last
+ * level when no level qualifies for the exact solve). */
 int b2_pressure_mg_add_level(b2_ctx* ctx, int64_t n_nodes, const double* x, int64_t n_cells, const int32_t* cell_nodes,
                              int64_t n_fine_rows, const int32_t* P_indptr, const int32_t* P_indices, const double* P_vals,
                              const int32_t* R_indptr, const int32_t* R_indices, const double* R_vals);

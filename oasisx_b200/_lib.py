@@ -27,7 +27,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
     "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_pattern_sell_runs", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
-    "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
+    "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
     "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
         "b2_set_velocity_bc_values": (i32, [vp, i32, i64, vp]),
         "b2_set_velocity_bc_series": (i32, [vp, i32, i32, i64, vp]),
         "b2_select_bc_step": (i32, [vp, i32]),
+        "b2_reset_time_history": (i32, [vp]),
+        "b2_profiler_range": (i32, [vp, i32]),
         "b2_set_pressure_bc_dofs": (i32, [vp, i64, vp]),
         "b2_preassemble": (i32, [vp, vp, i32, i32]),
         "b2_set_vector": (i32, [vp, i32, i32, vp, i64]),
@@ -223,7 +225,7 @@ class Context:
                                                       _ptr(Pi), _ptr(Px), _ptr(Pv), _ptr(Ri), _ptr(Rx), _ptr(Rv)),
                     "b2_pressure_mg_add_level")
 
-    def pressure_mg_configure(self, nu_pre=2, nu_post=2, coarse_sweeps=16, omega=0.7):
+    def pressure_mg_configure(self, nu_pre=1, nu_post=1, coarse_sweeps=16, omega=0.85):
         self._check(self.lib.b2_pressure_mg_configure(self._h, nu_pre, nu_post, coarse_sweeps, omega), "b2_pressure_mg_configure")
 
     def pattern(self, which: int, n_rows: int):
@@ -258,6 +260,12 @@ class Context:
 
     def select_bc_step(self, step: int):
         self._check(self.lib.b2_select_bc_step(self._h, step), "b2_select_bc_step")
+
+    def profiler_range(self, on: bool):
+        self._check(self.lib.b2_profiler_range(self._h, int(bool(on))), "b2_profiler_range")
+
+    def reset_time_history(self):
+        self._check(self.lib.b2_reset_time_history(self._h), "b2_reset_time_history")
 
     def set_pressure_bc_dofs(self, dofs):
         d = _i32(dofs)

@@ -3,6 +3,7 @@
 #include "../../include/b200ipcs.h"
 
 #include <cub/cub.cuh>
+#include <cuda_profiler_api.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is dlopen'ed when a multi-rank context is created
 
@@ -131,7 +132,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0, spmm_comp = 1;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0, spmm_comp = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues; spmm_comp: run-compressed columns (measured no faster: the kernel is bound by the L2->L1 gather path, not by DRAM bytes)
   DBuf<int> sm_dense, sm_next;  // %smid -> dense SM index; per-range work counters
   int n_sm_dense = 0;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
@@ -144,8 +145,10 @@ struct b2_ctx {
   CSR pat[4];
   Halo halo[2];
   std::vector<MgLevel> mg;  // coarse levels 1..L of the pressure hierarchy
-  int mg_pre = 2, mg_post = 2, mg_coarse = 16;
-  double mg_omega = 0.7;
+  // V(1,1) with omega = 0.85: measured best at 96^3 (9 iterations of 0.33 ms against 7 of 0.46 ms for V(2,2), omega 0.8;
+  // 6/7 is the optimal damping of the 7-point stencil the Kuhn P1 stiffness reduces to); b2_pressure_mg_configure overrides
+  int mg_pre = 1, mg_post = 1, mg_coarse = 16;
+  double mg_omega = 0.85;
   DBuf<double> mg_x0, mg_t0;  // fine-level work vectors (n_local of Q)
   DBuf<MgDev> mg_dev;         // device descriptors of the coarse levels (index = level - 1)
   int mg_dev_levels = 0;      // number of levels the descriptor array was built for
@@ -1708,6 +1711,27 @@ int b2_set_velocity_bc_series(b2_ctx* c, int comp, int n_steps, int64_t n, const
 
 int b2_select_bc_step(b2_ctx* c, int step) {
   return guarded(c, [&] { c->bc_step = step; });
+}
+
+int b2_profiler_range(b2_ctx* c, int on) {
+  return guarded(c, [&] {
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (on) B2_CUDA(cudaProfilerStart());
+    else B2_CUDA(cudaProfilerStop());
+  });
+}
+
+int b2_reset_time_history(b2_ctx* c) {
+  return guarded(c, [&] {
+    c->steps_done = 0;
+    c->dp_hist = 0;
+    c->n_ustar_hist = 0;
+    c->n_delta_hist = 0;
+    c->fresh_step = true;
+    if (c->delta_prev.p) c->delta_prev.zero(c->stream);
+    if (c->dp_old.p) c->dp_old.zero(c->stream);
+    for (auto& o : c->ksp) o.expected_its = 0;
+  });
 }
 
 int b2_set_pressure_bc_dofs(b2_ctx* c, int64_t n, const int32_t* dofs) {
