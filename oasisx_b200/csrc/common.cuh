@@ -55,6 +55,19 @@ struct DBuf {  // owning device buffer
   }
 };
 
+// streaming loads for the matrix stream (values, columns): read-only path, do not allocate in L1, so that
+// the lines of the gathered vector are what stays resident there
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // ---- warp / block reductions ------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

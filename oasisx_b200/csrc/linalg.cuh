@@ -236,18 +236,7 @@ __global__ void k_halo_unpack(int n_neighbors, const int64_t* __restrict__ recv_
 // entries are (nearly) consecutive too.  No cross-lane reduction is needed.  The CSR pattern of
 // create_matrix stays the public face (b2_get_pattern); CSR position p of row r maps to the SELL
 // slot slice_ptr[r/32] + 32*(p - rowptr[r]) + r%32.
-// streaming loads for the matrix stream (values, columns): read-only path, do not allocate in L1, so that
-// the lines of the gathered vector are what stays resident there
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ int ld_stream(const int* p) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
+// ld_stream (common.cuh): streaming loads for the matrix stream (values, columns)
 
 __device__ __forceinline__ size_t sell_slot(const int* __restrict__ slice_ptr, int row, int t) {
   return (size_t)__ldg(slice_ptr + (row >> 5)) + ((size_t)t << 5) + (row & 31);
@@ -720,8 +709,8 @@ k_spmm_diag(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict
 //                   PETSc default side for BiCGStab [ext]): the Krylov kernels then need no
 //                   preconditioner at all.  b2_get_matrix_values undoes the scaling.
 //   dinv[row]    = 1 / D[row]  (1 when !scale)
-template <int K>
-__global__ void __launch_bounds__(256)
+template <int K, int U = 4, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB)
 k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
                 const int* __restrict__ diag_t, double* __restrict__ A, const double* __restrict__ M,
                 const double* __restrict__ Kst, const int* __restrict__ order, double inv_dt,
@@ -759,11 +748,11 @@ k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __rest
       A[(size_t)base + ((size_t)t << 5) + lane] = a;
     };
     int t = 0;
-    for (; t + 4 <= len; t += 4) {  // four independent (stream -> gather) chains in flight
-      int cc[4];
-      double mv[4], kv[4], av[4], xu[4][K];
+    for (; t + U <= len; t += U) {  // U independent (stream -> gather) chains in flight
+      int cc[U];
+      double mv[U], kv[U], av[U], xu[U][K];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const size_t p = (size_t)base + ((size_t)(t + u) << 5) + lane;
         cc[u] = ld_stream(cols + p);
         mv[u] = ld_stream(M + p);
@@ -771,11 +760,11 @@ k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __rest
         av[u] = A[p];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int k = 0; k < K; ++k) xu[u][k] = __ldg(u1 + (size_t)k * ld + cc[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) body(t + u, cc[u], mv[u], kv[u], av[u], xu[u]);
+      for (int u = 0; u < U; ++u) body(t + u, cc[u], mv[u], kv[u], av[u], xu[u]);
     }
     for (; t < len; ++t) {
       const size_t p = (size_t)base + ((size_t)t << 5) + lane;

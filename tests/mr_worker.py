@@ -13,7 +13,8 @@ from problems import TaylorGreen, make_mesh, make_oracle, make_solver, relerr, v
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-krylov = len(sys.argv) > 3 and sys.argv[3] in ("krylov", "mg")
+krylov = len(sys.argv) > 3 and sys.argv[3] in ("krylov", "mg", "bench")
+bench_opts = len(sys.argv) > 3 and sys.argv[3] == "bench"  # the settings bench.py times (extrapolated guesses, multigrid)
 use_mg = len(sys.argv) > 3 and sys.argv[3] == "mg"
 comm = HostComm.from_env()
 dt, nu = 0.005, 0.01
@@ -26,6 +27,14 @@ if krylov:
     if use_mg:
         opts["pressure"]["pc_type"] = "mg"
         opts["scalar"]["ksp_type"] = "chebyshev"  # reduction-free mass solves
+if bench_opts:
+    import copy
+
+    import bench
+
+    opts = copy.deepcopy(bench.KRYLOV)
+    for o_ in opts.values():
+        o_["ksp_rtol"] = 1e-11
 s = make_solver(msh, 2, tg, dt, solver_options=opts, device=int(os.environ.get("LOCAL_RANK", "0")))
 tg2 = TaylorGreen(nu, 3)
 o = make_oracle(make_mesh(3, N), 2, tg2, dt)

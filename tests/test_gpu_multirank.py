@@ -17,13 +17,14 @@ def _ngpu():
     return _lib.load_library().b2_device_count()
 
 
-@pytest.mark.parametrize("nranks,mode", [(2, "lu"), (2, "krylov"), (2, "mg"), (4, "krylov")])
+@pytest.mark.parametrize("nranks,mode", [(2, "lu"), (2, "krylov"), (2, "mg"), (2, "bench"), (4, "krylov")])
 def test_multirank_matches_oracle(nranks, mode):
     if _ngpu() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    port = 29700 + nranks * 10 + {"lu": 0, "krylov": 1, "mg": 2}[mode]
+    port = 29700 + nranks * 10 + {"lu": 0, "krylov": 1, "mg": 2, "bench": 3}[mode]
+    steps = "7" if mode == "bench" else "3"  # long enough for the three-deep solution histories to be in use
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mr_worker.py"), "8", "3", mode]
+           "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mr_worker.py"), "8", steps, mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("MR_OK") == nranks

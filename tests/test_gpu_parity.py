@@ -52,14 +52,17 @@ def test_preassembled_matrices(gdim, N, deg):
 
 @pytest.mark.parametrize("gdim,N,deg", CASES)
 @pytest.mark.parametrize("body_force", [False, True])
-def test_assemble_first_and_tentative_rhs(gdim, N, deg, body_force):
+@pytest.mark.parametrize("rows", [1, 0])
+def test_assemble_first_and_tentative_rhs(gdim, N, deg, body_force, rows):
     """A, b_first and rhs1 after assemble_first + velocity_tentative_assemble
-    (test/test_tentative_velocity.py:172-173,235)."""
+    (test/test_tentative_velocity.py:172-173,235), with the row-wise fused kernel (rows=1, the default) and with
+    the scatter + combine pair it replaces."""
     dt, nu = 0.1, 0.5
     f = [0.3, -0.1, 0.2][:gdim] if body_force else None
     msh = make_mesh(gdim, N)
     tg = TaylorGreen(nu, gdim)
     s = make_solver(msh, deg, tg, dt, body_force=f)
+    s._ctx.set_tuning("assemble_rows", rows)
     o = make_oracle(msh, deg, tg, dt, body_force=f)
     ps = lambda x: x[1] + 0.5 * x[0] ** 2
     s._ps.interpolate(ps)
@@ -84,6 +87,28 @@ def test_assemble_first_and_tentative_rhs(gdim, N, deg, body_force):
         assert relerr(s._rhs1[i].x.array_ro(), o.rhs1[i], vscale(o.rhs1)) <= 1e-12  # now with BC values applied
         assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-9
     assert abs(diff - odiff) <= 1e-8 * odiff
+
+
+@pytest.mark.parametrize("gdim,N", [(3, 20), (2, 96)])
+def test_rowwise_and_scatter_assembly_agree_on_larger_meshes(gdim, N):
+    """Beyond the sizes the LU oracle reaches: the fused row-wise assemble_first and the scatter + combine pair give
+    the same A (<= 1e-13 of its largest entry), b_first and Jacobi scaling on meshes with thousands of slices."""
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(gdim, N)
+    tg = TaylorGreen(nu, gdim)
+    kry = {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10}
+    cg = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-10}
+    s = make_solver(msh, 2, tg, dt, solver_options={"tentative": kry, "pressure": cg, "scalar": cg})
+    tg.t_u = dt
+    out = []
+    for rows in (1, 0):
+        s._ctx.set_tuning("assemble_rows", rows)
+        s.assemble_first(dt, nu)
+        out.append((_csr(s._A), [s._b_first[i].x.array_ro().copy() for i in range(gdim)]))
+    (A1, b1), (A0, b0) = out
+    assert abs(A1 - A0).max() <= 1e-13 * abs(A0).max()
+    for i in range(gdim):
+        assert relerr(b1[i], b0[i], vscale(b0)) <= 1e-13
 
 
 @pytest.mark.parametrize("gdim,N,deg", [(2, 8, 2), (3, 4, 2), (2, 8, 1)])
