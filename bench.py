@@ -132,6 +132,133 @@ def bc_series(solver, tg, t_first: float, n_steps: int):
     return out
 
 
+# ---- second workload: lid-driven cavity (BASELINE.json configs[4]), unit cube, Re = 1000 ---------------------
+CAVITY_NU, CAVITY_DT = 1.0e-3, 0.005
+
+
+def _cavity_markers():
+    lid = lambda x: np.isclose(x[2], 1.0)
+    walls = lambda x: (np.isclose(x[0], 0) | np.isclose(x[0], 1) | np.isclose(x[1], 0) | np.isclose(x[1], 1) | np.isclose(x[2], 0)) & ~lid(x)
+    return lid, walls
+
+
+def make_cavity_solver(N: int, comm, device: int):
+    """Unit cube, u = (1, 0, 0) on the lid z = 1, no slip on the other walls, no pressure BC, start from rest
+    (the set-up of tests/test_gpu_parity.py::test_lid_driven_cavity_matches_oracle at Re = 1000)."""
+    import oasisx_b200 as oasisx
+    from oasisx_b200 import mesh as bmesh
+
+    msh = bmesh.create_unit_cube(comm, N, N, N)
+    lid, walls = _cavity_markers()
+    G = oasisx.LocatorMethod.GEOMETRICAL
+    bcs_u = [[oasisx.DirichletBC(0.0, G, walls), oasisx.DirichletBC(1.0 if k == 0 else 0.0, G, lid)] for k in range(3)]
+    s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[], solver_options=KRYLOV,
+                                    options={"low_memory_version": False}, device=device)
+    return msh, s
+
+
+def cpu_sample_cavity(n_cpu: int, n_steps: int, n_warm: int = 1):
+    from oasisx_b200 import fem, mesh as bmesh
+    from oracle import ipcs_cpu as cpu
+
+    msh = bmesh.create_unit_cube(None, n_cpu, n_cpu, n_cpu)
+    V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    lid, walls = _cavity_markers()
+    bd = fem.locate_dofs_geometrical(V, lambda x: lid(x) | walls(x))
+    vals = [lambda x: np.where(lid(x), 1.0, 0.0), lambda x: np.zeros_like(x[0]), lambda x: np.zeros_like(x[0])]
+    c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                    Q.tabulate_dof_coordinates(), 2, bcs_u=[[(bd, f)] for f in vals],
+                    rtol=KRYLOV["tentative"]["ksp_rtol"], nonzero_guess=True, block_rtol=True,
+                    extrapolate={"extrapolate": 1, "extrapolate2": 2}.get(KRYLOV["tentative"].get("b200_guess"), 0))
+    for _ in range(n_warm):
+        c.solve(CAVITY_DT, CAVITY_NU)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        c.solve(CAVITY_DT, CAVITY_NU)
+    return (time.perf_counter() - t0) / n_steps, msh.num_cells, cpu.lib().ipcs_cpu_threads(), c.its.tolist()
+
+
+def run_cavity(args):
+    """Lid-driven cavity at Re = 1000 on an N^3 unit cube (default 128^3 = 53 M dofs on ONE GPU; with several ranks
+    the same global mesh is split in z-slabs: strong scaling -- BASELINE.json's "weak scaling" would need a global mesh
+    of 128 x 128 x 128 n cubes, which the z-slab provider can build but the host set-up time of this bench does not
+    allow).  Same JSON contract as the Taylor-Green line; constant boundary values, so the end-to-end path moves no
+    boundary data after the first step."""
+    from oasisx_b200.comm import HostComm
+
+    comm = HostComm.from_env()
+    rank, world = comm.rank, comm.size
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    N, K, W = args.mesh, args.steps, max(args.warmup, 3)
+    t_setup = time.perf_counter()
+    msh, solver = make_cavity_solver(N, comm if world > 1 else None, device)
+    ctx = solver._ctx
+    t_setup = time.perf_counter() - t_setup
+    dt, nu = CAVITY_DT, CAVITY_NU
+    for s in range(W):
+        solver.solve(dt, nu, max_iter=1)
+    st0 = ctx.stats()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ctx.synchronize()
+    comm.Barrier()
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    its, stage_ms = [], np.zeros(4)
+    for s in range(K):
+        solver.solve(dt, nu, max_iter=1)  # constant BCs: after the first step this is the device path plus one scalar D2H
+        st = ctx.stats()
+        its.append((max(st.its_tentative), st.its_pressure, max(st.its_update)))
+        stage_ms += [st.ms_assemble_first, st.ms_tentative, st.ms_pressure, st.ms_update]
+    ctx.event_record(1)
+    ctx.synchronize()
+    e2e_s = comm.allreduce((time.perf_counter() - t0) / K, "max")
+    ms_total = comm.allreduce(ctx.event_elapsed_ms(0, 1), "max")
+    comm.Barrier()
+    clocks = sampler.stop()
+    st1 = ctx.stats()
+    launches = comm.allreduce(int(st1.kernel_launches - st0.kernel_launches))
+    umax = comm.allreduce(float(np.abs(solver._u[0].x.array_ro()).max()), "max")
+    peak, peak_kind = measured_peaks()
+    ms_k, bytes_k = ctx.bench_kernel(3, 20)
+    if rank != 0:
+        comm.Barrier()
+        return
+    cpu = None
+    if not args.no_cpu and world == 1:
+        n_cpu = args.cpu_mesh if args.cpu_mesh > 0 else min(N, 64)
+        sec, cells, threads, cits = cpu_sample_cavity(n_cpu, 2, 1)
+        sps = (1.0 / sec) * cells / msh.num_cells
+        cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"C++/OpenMP restatement, 2 cavity steps after 1 warm-up on a {n_cpu}^3 cube ({sec:.2f} s/step, its u/p/m {cits})"
+                         + ("" if n_cpu == N else f", scaled by cell count to {N}^3 (optimistic for the CPU: its Jacobi-PCG pressure iterations grow with N)"),
+               "host_cpus": os.cpu_count()}
+    nV = solver._lp.V.n_global if world > 1 else solver._nV_owned
+    nQ = solver._lp.Q.n_global if world > 1 else solver._nQ_owned
+    line = {
+        "metric": "IPCS steps/s, 3D lid-driven cavity P2-P1 box", "value": 1000.0 * K / ms_total, "unit": "steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D lid-driven cavity P2-P1 {N}^3 unit cube, Re=1000 (nu={nu}, lid speed 1), dt={dt}, from rest, max_iter=1, rtol=1e-10",
+                   "mesh": N, "cells": msh.num_cells, "dofs": 3 * nV + nQ, "krylov": KRYLOV, "setup_s": t_setup,
+                   "l2": "working set per step >> 126 MB L2; no flush needed"},
+        "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
+                       "update": int(np.median([i[2] for i in its]))},
+        "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
+        "max_abs_u_x": umax,
+        "roofline": {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 SELL-32 operator, 3 right-hand sides)", "achieved": bytes_k / (ms_k * 1e-3) / 1e9,
+                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": bytes_k / (ms_k * 1e-3) / 1e9 / peak, "traffic": None,
+                     "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k},
+        "cpu_baseline": cpu,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(st1.bytes_h2d - st0.bytes_h2d) // K,
+                "d2h_bytes_per_step": int(st1.bytes_d2h - st0.bytes_d2h) // K,
+                "note": "the timed loop IS the public-API loop (constant boundary values: nothing to prefetch); value = device events, e2e = wall clock"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    comm.Barrier()
+
+
 def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1):
     """Time the CPU restatement (oracle/ipcs_cpu.cpp: C++/OpenMP, CSR + BiCGStab/CG with Jacobi, the same
     Krylov options as the GPU arm) on an n_cpu^3 box with all host threads.
@@ -366,7 +493,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100, help="timed steps (the reference demo's T/dt = 100, SURVEY.md 8d)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mesh", type=int, default=96, help="cubes per direction (BASELINE: 96; 48 = configs[2])")
+    ap.add_argument("--mesh", type=int, default=0, help="cubes per direction (default 96 = BASELINE's metric, 48 = configs[2]; cavity: 128)")
+    ap.add_argument("--workload", default="taylor-green", choices=["taylor-green", "cavity"],
+                    help="taylor-green = BASELINE.json's metric (the line the driver reads); cavity = configs[4], an extra line")
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
@@ -377,7 +506,13 @@ def main():
     KRYLOV["pressure"]["pc_type"] = args.pressure_pc
     world = int(os.environ.get("WORLD_SIZE", "1"))
     KRYLOV["scalar"]["ksp_type"] = args.scalar_ksp if args.scalar_ksp != "auto" else "cg"
-    if args.impl == "reference":
+    if args.mesh <= 0:
+        args.mesh = 128 if args.workload == "cavity" else 96
+    if args.workload == "cavity":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the Taylor-Green metric; the cavity line carries its own cpu_baseline")
+        run_cavity(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

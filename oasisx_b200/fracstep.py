@@ -178,6 +178,7 @@ class FractionalStep_AB_CN:
             )
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
+        self._bc_merge_maps: dict = {}
         for i in range(gdim):
             dofs = self._merged_bc_dofs(i)
             self._bc_dofs.append(dofs)
@@ -285,10 +286,16 @@ class FractionalStep_AB_CN:
             if len(bcl) == 1 and len(vals[0]) == len(self._bc_dofs[i]):
                 merged = vals[0]
             else:
+                # positions of every BC's owned dofs in the merged list: located once, not every time step
+                maps = self._bc_merge_maps.setdefault(i, {})
                 merged = np.zeros(len(self._bc_dofs[i]))
-                for bc, v in zip(bcl, vals):
-                    own = bc._dofs < self._nV_owned
-                    merged[np.searchsorted(self._bc_dofs[i], bc._dofs[own])] = v[own]
+                for k, (bc, v) in enumerate(zip(bcl, vals)):
+                    m = maps.get(k)
+                    if m is None or m[0] is not bc._dofs:
+                        own = np.flatnonzero(bc._dofs < self._nV_owned)
+                        m = (bc._dofs, own, np.searchsorted(self._bc_dofs[i], bc._dofs[own]))
+                        maps[k] = m
+                    merged[m[2]] = v[m[1]]
             self._ctx.set_velocity_bc_values(i, merged)
             self._bc_versions[i] = version
 

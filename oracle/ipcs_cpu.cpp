@@ -247,7 +247,7 @@ int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const 
     rh[i] = r[i];
     p[i] = r[i];
   }
-  double rr = dot(n, r.data(), r.data()), rho = rr;
+  double rr = dot(n, r.data(), r.data()), rho = rr, rh2 = rr;
   const double tol2 = std::max(c.rtol * c.rtol * (c.block_rtol && c.bref2 > bb ? c.bref2 : bb), 1e-100);
   const double rr0 = rr;
   int it = 0;
@@ -270,6 +270,14 @@ int bicgstab(const Ctx& c, const Csr& m, const std::vector<double>& vals, const 
     rr = rr2;
     ++it;
     if (rr <= tol2) break;
+    // (near) breakdown: restart from the current residual (rhat = p = r), as the GPU arm does (linalg.cuh FIN_BCGS_UPDATE)
+    if (omega == 0.0 || rho == 0.0 || rho2 * rho2 <= 1e-24 * rr * rh2) {
+      rho = rr;
+      rh2 = rr;
+#pragma omp parallel for
+      for (int64_t i = 0; i < n; ++i) { rh[i] = r[i]; p[i] = r[i]; }
+      continue;
+    }
     const double beta = (rho2 / rho) * (alpha / omega);
     rho = rho2;
 #pragma omp parallel for

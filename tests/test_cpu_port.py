@@ -82,3 +82,32 @@ def test_cpu_port_bench_options_do_not_change_the_solution(order):
         for i in range(3):
             assert relerr(c.get(cpu.U, i), o.u[i], vscale(o.u)) <= 1e-8
         assert relerr(c.get(cpu.P), o.p) <= 1e-8
+
+
+def test_cpu_port_lid_driven_cavity_matches_oracle():
+    """bench.py's cavity CPU sample (merged wall + lid dofs, BiCGStab restarting on the start-up breakdown) against
+    the LU oracle with the two constant DirichletBCs of the GPU test."""
+    import bench
+    from oasisx_b200 import mesh as bmesh
+    from oracle.ipcs_oracle import OracleIPCS
+
+    N, dt, nu = 4, 0.01, 0.01
+    msh = bmesh.create_unit_cube(None, N, N, N)
+    V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    lid, walls = bench._cavity_markers()
+    dw, dl = fem.locate_dofs_geometrical(V, walls), fem.locate_dofs_geometrical(V, lid)
+    assert len(np.intersect1d(dw, dl)) == 0
+    bd = fem.locate_dofs_geometrical(V, lambda x: lid(x) | walls(x))
+    vals = [lambda x: np.where(lid(x), 1.0, 0.0), lambda x: np.zeros_like(x[0]), lambda x: np.zeros_like(x[0])]
+    c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                    Q.tabulate_dof_coordinates(), 2, bcs_u=[[(bd, f)] for f in vals], rtol=1e-12, nonzero_guess=True,
+                    block_rtol=True, extrapolate=2)
+    o = OracleIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                   Q.tabulate_dof_coordinates(), 2,
+                   bcs_u=[[(dw, 0.0), (dl, 1.0)], [(dw, 0.0), (dl, 0.0)], [(dw, 0.0), (dl, 0.0)]])
+    for n in range(4):
+        c.solve(dt, nu)
+        o.solve(dt, nu, max_iter=1)
+        for i in range(3):
+            assert relerr(c.get(cpu.U, i), o.u[i], vscale(o.u)) <= 1e-8, (n, i)
+        assert relerr(c.get(cpu.P), o.p) <= 1e-8, n
