@@ -429,6 +429,16 @@ def run_ours(args):
            "d2h_bytes_per_step": comm.allreduce(int(stB.bytes_d2h - stA.bytes_d2h)) // K,
            "iterations": [int(np.median([i[j] for i in e2e_its])) for j in range(3)]}
 
+    # ---- full-size sanity of the state the timed steps produced (not part of any timing) --------
+    # the discrete solution against the analytic Taylor-Green field (nodal interpolant, mass-matrix norm) and the
+    # z-component that must stay at round-off (z-extruded field)
+    xV = solver._Vi[0][0].tabulate_dof_coordinates().T
+    exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][3] at the time of the last step
+    err2 = ctx.l2_diff_sq(L.VEC_U, exact)
+    nrm2 = ctx.l2_diff_sq(L.VEC_U, exact * 0.0)
+    wmax = comm.allreduce(float(np.abs(solver._u[2].x.array_ro()).max()), "max")
+    checks = {"t_end": tg.t_u, "rel_l2_error_u_vs_exact": float(np.sqrt(err2 / nrm2)), "max_abs_w": wmax}
+
     # ---- roofline of the dominant kernel, measured live (rank 0's share of the rows) ------------
     peak, peak_kind = measured_peaks()
     comm.Barrier()
@@ -481,7 +491,7 @@ def run_ours(args):
         "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
         "nccl_per_step": {"halo_exchanges": halos, "allreduces": allred},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "bc_dofs": nbc,
+        "bc_dofs": nbc, "checks": checks,
     }
     print(json.dumps(line), flush=True)
     comm.Barrier()

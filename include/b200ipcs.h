@@ -152,8 +152,13 @@ int b2_profiler_range(b2_ctx* ctx, int on);
 /* Forget the solution histories behind the extrapolated initial guesses (b200_guess) and the predicted iteration
  * counts: call when the state vectors are re-initialised to start another run on the same context. */
 int b2_reset_time_history(b2_ctx* ctx);
-/* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253) */
+/* homogeneous Dirichlet dofs of the pressure correction (bcs.py:245-253): LOCAL dofs, owned and ghost (the ghost ones
+ * are needed to zero the matching columns of the owned rows, fracstep.py:379-380). */
 int b2_set_pressure_bc_dofs(b2_ctx* ctx, int64_t n, const int32_t* dofs);
+/* Multi-rank: whether ANY rank holds pressure Dirichlet dofs (len(bcs_p) > 0 in fracstep.py:381-384,562). A rank whose
+ * slab touches none of them must still skip the null-space handling, collectively with the others. Call before
+ * b2_set_pressure_bc_dofs / b2_preassemble; single-rank callers need not call it. */
+int b2_declare_pressure_bcs(b2_ctx* ctx, int any);
 
 /* ---- pressure multigrid hierarchy (optional; selected with pc_type=mg on B2_SOLVER_PRESSURE) --------
  * The reference forces a direct (MUMPS) solve of the singular pressure system (fracstep.py:562-578); at

@@ -27,7 +27,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
     "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_pattern_sell_runs", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
-    "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
+    "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
     "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
         "b2_set_velocity_bc_series": (i32, [vp, i32, i32, i64, vp]),
         "b2_select_bc_step": (i32, [vp, i32]),
         "b2_reset_time_history": (i32, [vp]),
+        "b2_declare_pressure_bcs": (i32, [vp, i32]),
         "b2_profiler_range": (i32, [vp, i32]),
         "b2_set_pressure_bc_dofs": (i32, [vp, i64, vp]),
         "b2_preassemble": (i32, [vp, vp, i32, i32]),
@@ -266,6 +267,9 @@ class Context:
 
     def reset_time_history(self):
         self._check(self.lib.b2_reset_time_history(self._h), "b2_reset_time_history")
+
+    def declare_pressure_bcs(self, any_bc: bool):
+        self._check(self.lib.b2_declare_pressure_bcs(self._h, int(bool(any_bc))), "b2_declare_pressure_bcs")
 
     def set_pressure_bc_dofs(self, dofs):
         d = _i32(dofs)

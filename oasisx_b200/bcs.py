@@ -134,6 +134,14 @@ class PressureBC:
         cf = mesh.topology.cell_entities(fdim)
         mask = np.isin(cf, self._facets)
         cells, local = np.nonzero(mask)
+        local_cells = getattr(Q, "_local_cells", None)
+        if local_cells is not None:
+            # multi-rank: keep the tagged facets of the cells this rank holds, owned AND ghost (a ghost cell's facet
+            # contributes to dofs owned here; rows of ghost dofs are dropped by the kernel), in local cell numbering
+            g2l = np.full(mesh.geometry.dofmap.shape[0], -1, dtype=np.int64)
+            g2l[local_cells] = np.arange(len(local_cells))
+            keep = g2l[cells] >= 0
+            cells, local = g2l[cells[keep]], local[keep]
         self._facet_cells, self._facet_local = cells.astype(np.int32), local.astype(np.int32)
         self._is_callable = callable(self._value)
         self._h = np.zeros(Q.num_dofs)  # nodal values of the boundary pressure in Q

@@ -1800,11 +1800,18 @@ int b2_reset_time_history(b2_ctx* c) {
   });
 }
 
+int b2_declare_pressure_bcs(b2_ctx* c, int any) {
+  return guarded(c, [&] {
+    B2_REQUIRE(!c->preassembled, "pressure BCs must be declared before b2_preassemble");
+    c->has_pbc = any != 0;
+  });
+}
+
 int b2_set_pressure_bc_dofs(b2_ctx* c, int64_t n, const int32_t* dofs) {
   return guarded(c, [&] {
     B2_REQUIRE(!c->preassembled, "pressure BC dofs must be set before b2_preassemble");
     c->pbc_dofs.alloc(n);
-    c->has_pbc = n > 0;
+    c->has_pbc = c->has_pbc || n > 0;
     if (n) B2_CUDA(cudaMemcpyAsync(c->pbc_dofs.p, dofs, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });

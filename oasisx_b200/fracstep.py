@@ -115,6 +115,8 @@ class FractionalStep_AB_CN:
             self._lp = lp = _part.partition(mesh, gV, gQ, self._nranks, self._rank)
             self._V = _fem.LocalFunctionSpace(gV, lp.V, gdim)
             self._Q = _fem.LocalFunctionSpace(gQ, lp.Q, 1)
+            for sp_ in (self._V, self._V._scalar, self._Q):
+                sp_._local_cells = lp.cells  # global ids of the cells this rank holds (owned first, then ghost cells)
         else:
             self._lp = None
             self._V = _fem.functionspace(mesh, ("Lagrange", deg_u, (gdim,)))
@@ -141,8 +143,6 @@ class FractionalStep_AB_CN:
         self._bcs_p = bcs_p
         for bcp in self._bcs_p:
             bcp.create_bcs(Vs, self._Q)
-        if len(self._bcs_p) > 0 and self._nranks > 1:
-            raise NotImplementedError("PressureBC on more than one rank is not wired up yet")
 
         options = {} if options is None else options
         self._low_memory = bool(options.get("low_memory_version", True))
@@ -186,7 +186,8 @@ class FractionalStep_AB_CN:
         pdofs = (
             np.unique(np.concatenate([b.bc.dofs for b in self._bcs_p])) if self._bcs_p else np.zeros(0, np.int32)
         )
-        ctx.set_pressure_bc_dofs(pdofs[pdofs < self._nQ_owned])
+        ctx.declare_pressure_bcs(len(self._bcs_p) > 0)  # the same on every rank, also on one whose slab has no such dof
+        ctx.set_pressure_bc_dofs(pdofs)  # local dofs, owned and ghost (columns of ghost BC dofs are zeroed too)
         ctx.preassemble(body_force, self._low_memory, self._rotational)
 
         # solvers (fracstep.py:230-255)

@@ -17,6 +17,33 @@ krylov = len(sys.argv) > 3 and sys.argv[3] in ("krylov", "mg", "bench")
 bench_opts = len(sys.argv) > 3 and sys.argv[3] == "bench"  # the settings bench.py times (extrapolated guesses, multigrid)
 use_mg = len(sys.argv) > 3 and sys.argv[3] == "mg"
 comm = HostComm.from_env()
+if len(sys.argv) > 3 and sys.argv[3] == "pbc":
+    # open channel of test/test_tentative_velocity.py on several ranks: inlet callable + walls (two DirichletBCs per
+    # component), outlet PressureBC: natural boundary term, pressure Dirichlet rows/columns across the slab interface
+    from test_gpu_tentative import build
+
+    kry = {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12}
+    cg = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12}
+    s, o, inlet, _ = build(2, True, solver_options={"tentative": kry, "pressure": cg, "scalar": cg}, comm=comm,
+                           device=int(os.environ.get("LOCAL_RANK", "0")))
+    lp = s._lp
+    dt, nu = 0.01, 0.5
+    inlet.t = 0.0
+    worst = 0.0
+    for n in range(steps):
+        inlet.t += dt
+        s.solve(dt, nu, max_iter=2, max_error=1e-30)
+        o.solve(dt, nu, max_iter=2, max_error=1e-30)
+        for i in range(2):
+            worst = max(worst, relerr(s._u[i].x.array_ro(), o.u[i][lp.V.l2g], vscale(o.u)))
+        worst = max(worst, relerr(s._p.x.array_ro(), o.p[lp.Q.l2g]))
+    assert max(np.abs(p).max() for p in o.p_surf) > 1e-3  # the natural pressure term is there and matters
+    worst = comm.allreduce(worst, "max")
+    print(f"rank {comm.rank}/{comm.size}: channel with PressureBC, max rel err {worst:.2e}, local facets {len(s._bcs_p[0]._facet_cells)}", flush=True)
+    assert worst <= 1e-7, worst
+    comm.Barrier()
+    print("MR_OK", comm.rank, flush=True)
+    sys.exit(0)
 dt, nu = 0.005, 0.01
 tg = TaylorGreen(nu, 3)
 msh = make_mesh(3, N, comm)

@@ -112,3 +112,25 @@ def relerr(a, b, scale=None):
 
 def vscale(vs):
     return max(float(np.max(np.abs(v))) for v in vs)
+
+
+def make_cpu_port(msh, deg_u, tg: TaylorGreen, dt, **kw):
+    """The same set-up for the C++/OpenMP CPU restatement (oracle/ipcs_cpu.cpp), which reaches meshes the LU oracle
+    cannot and is itself pinned against that oracle in tests/test_cpu_port.py."""
+    from oracle import ipcs_cpu as cpu
+
+    d = msh.geometry.dim
+    V, Q = fem.functionspace(msh, ("Lagrange", deg_u)), fem.functionspace(msh, ("Lagrange", 1))
+    bd = fem.locate_dofs_topological(V, d - 1, boundary_facets(msh))
+    c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, d, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                    Q.tabulate_dof_coordinates(), deg_u, bcs_u=[[(bd, f)] for f in tg.components], **kw)
+    xV, xQ = V.tabulate_dof_coordinates().T, Q.tabulate_dof_coordinates().T
+    tg.t_u = -dt
+    for i, f in enumerate(tg.components):
+        c.set(cpu.U2, i, f(xV))
+    tg.t_u = 0.0
+    for i, f in enumerate(tg.components):
+        c.set(cpu.U1, i, f(xV))
+    tg.t_p = -dt / 2
+    c.set(cpu.P, 0, tg.eval_p(xQ))
+    return c

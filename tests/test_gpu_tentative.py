@@ -21,10 +21,10 @@ class Inlet:
         return (1 + self.t) * np.sin(np.pi * x[1])
 
 
-def build(deg_u, body_force, solver_options=None, low_memory=False):
+def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, device=0):
     from oracle.ipcs_oracle import OracleIPCS
 
-    msh = bmesh.create_unit_square(None, 10, 10)
+    msh = bmesh.create_unit_square(comm, 10, 10)
     dim = msh.topology.dim - 1
     left = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 0))
     tb = bmesh.locate_entities_boundary(msh, dim, lambda x: np.logical_or(np.isclose(x[1], 0), np.isclose(x[1], 1)))
@@ -43,15 +43,25 @@ def build(deg_u, body_force, solver_options=None, low_memory=False):
     lu = {"ksp_type": "preonly", "pc_type": "lu"}
     s = FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=bcs_p,
                              solver_options=solver_options or {"tentative": lu, "pressure": lu, "scalar": lu},
-                             options={"low_memory_version": low_memory}, body_force=f)
+                             options={"low_memory_version": low_memory}, body_force=f, device=device)
     V, Q = fem.functionspace(msh, ("Lagrange", deg_u)), fem.functionspace(msh, ("Lagrange", 1))
     dl, dtb = fem.locate_dofs_topological(V, dim, left), fem.locate_dofs_topological(V, dim, tb)
     pdofs = fem.locate_dofs_topological(Q, dim, right)
     o = OracleIPCS(msh.geometry.x, msh.geometry.dofmap, 2, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
                    Q.tabulate_dof_coordinates(), deg_u,
                    bcs_u=[[(dl, inlet.eval), (dtb, 0.0)], [(dl, 0.0), (dtb, 0.0)]], bcs_p=[pdofs], body_force=f,
-                   pressure_facets=[(bcs_p[0]._facet_cells, bcs_p[0]._facet_local, 4.0)])
+                   pressure_facets=[_global_pressure_facets(msh, right) + (4.0,)])
     return s, o, inlet, bc_inlet_x
+
+
+def _global_pressure_facets(msh, facets):
+    """(cell, local facet index) of the tagged facets in GLOBAL cell numbering (what the single-process oracle needs;
+    a multi-rank PressureBC holds its slab's share in local numbering)."""
+    fdim = msh.topology.dim - 1
+    msh.topology.create_connectivity(fdim, msh.topology.dim)
+    cf = msh.topology.cell_entities(fdim)
+    cells, local = np.nonzero(np.isin(cf, facets))
+    return cells.astype(np.int32), local.astype(np.int32)
 
 
 @pytest.mark.parametrize("body_force", [True, False])

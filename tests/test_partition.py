@@ -90,3 +90,37 @@ def test_halo_plan_over_gloo_two_ranks(tmp_path):
          "--master-port", "29613", str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("gdim,N", [(2, 10), (3, 4)])
+def test_pressure_bc_facets_split_over_ranks(gdim, N):
+    """PressureBC.create_bcs on the local spaces of a 2-rank partition: every tagged facet of a cell a rank holds
+    (owned or ghost) appears there in local cell numbering, every tagged facet is owned by exactly one rank, and the
+    local pressure Dirichlet dofs are the global ones seen through the rank's index map."""
+    from oasisx_b200 import PressureBC, mesh as bmesh
+
+    msh = make_mesh(gdim, N)
+    fdim = gdim - 1
+    right = bmesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[0], 1.0))
+    tags = bmesh.meshtags(msh, fdim, np.sort(right), np.full(len(right), 3, dtype=np.int32))
+    gV, gQ = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    ref = PressureBC(4.0, (tags, 3))
+    ref.create_bcs(gV, gQ)
+    glob = set(zip(ref._facet_cells.tolist(), ref._facet_local.tolist()))
+    owned_seen = []
+    for rank in range(2):
+        lp = part.partition(msh, gV, gQ, 2, rank)
+        V, Q = fem.LocalFunctionSpace(gV, lp.V, 1), fem.LocalFunctionSpace(gQ, lp.Q, 1)
+        V._local_cells = Q._local_cells = lp.cells
+        bc = PressureBC(4.0, (tags, 3))
+        bc.create_bcs(V, Q)
+        assert (bc._facet_cells >= 0).all() and (bc._facet_cells < len(lp.cells)).all()
+        here = set(zip(lp.cells[bc._facet_cells].tolist(), bc._facet_local.tolist()))
+        assert here <= glob
+        assert here == {(c, f) for (c, f) in glob if c in set(lp.cells.tolist())}
+        owned_seen += [(c, f) for (c, f) in here if c in set(lp.cells[: lp.n_cells_owned].tolist())]
+        assert len(bc._h) == Q.num_dofs and np.all(bc._h == 4.0)
+        gd = ref.bc.dofs
+        expect = np.sort(lp.Q.g2l[gd][lp.Q.g2l[gd] >= 0])
+        np.testing.assert_array_equal(np.sort(bc.bc.dofs), expect)
+    assert sorted(owned_seen) == sorted(glob)
