@@ -1,12 +1,14 @@
 #!/usr/bin/env python3
 """bench.py -- IPCS time steps per second, 3D Taylor-Green P2-P1 on an N^3 box (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh 96]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh 96] [--workload cavity]
 
 One "step" = one ``FractionalStep_AB_CN.solve(dt, nu, max_iter=1)`` (fracstep.py:660-696) on the
 z-extruded Taylor-Green problem of SURVEY.md 8(d): box [-1,1]^3, N^3 x 6 Kuhn tetrahedra, P2-P1,
-nu = 0.01, dt = 0.005, BiCGStab+Jacobi (velocity), CG+Jacobi (pressure, null space projected; mass),
-rtol 1e-10.
+nu = 0.01, dt = 0.005, BiCGStab+Jacobi (tentative velocity), CG+multigrid (pressure, null space projected),
+CG+Jacobi (mass), rtol 1e-10, initial guesses extrapolated from the solution histories (KRYLOV below; the CPU arm uses
+the same options except a Jacobi-preconditioned pressure CG).  Default: the reference demo's 100 steps after 3 warm-up
+steps; the first ~30 steps carry the start-up transient (more Krylov iterations), so short runs report fewer steps/s.
 
   value   device-timed steps/s with every input (state, BC values of all timed steps) resident in HBM;
   e2e     the same steps through the public Python API (host evaluation of the callable BCs, H2D of
