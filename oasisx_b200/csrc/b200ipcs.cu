@@ -179,6 +179,14 @@ struct b2_ctx {
   int assemble_rows = 0;    // tuning "assemble_rows": 1 = row-wise fused kernel (deterministic, no atomics, but 10x redundant
                             // gathers of the cell data: measured 9.3 ms against 5.7 ms for scatter + combine at 96^3)
   int rows_blocks_per_sm = 0;
+  // CUDA graph of one multigrid-preconditioned CG iteration of the pressure solve (single rank): ~21 dependent
+  // launches of a few microseconds each become one graph launch
+  cudaGraphExec_t pcg_graph = nullptr;
+  uint64_t pcg_graph_version = 0, cfg_version = 1;  // cfg_version: bumped by everything the captured body depends on
+  const double* pcg_graph_x = nullptr;
+  const double* pcg_graph_b = nullptr;
+  int pcg_graph_launches = 0;
+  int use_graphs = 1;  // tuning "graphs"
   int combine_variant = 2;  // tuning "combine": launch shape of k_combine_first (2: unroll 8, 64 registers, 4 blocks per SM)
   DBuf<int> pbc_dofs;
   bool has_pbc = false;
@@ -815,13 +823,7 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   // from one time step to the next, so nothing is polled (no pipeline drain) until one iteration short of
   // what the previous solve needed; kernels of a surplus iteration leave x untouched (st->done).
   const int first_poll = o.expected_its > 0 ? o.expected_its - 1 : 0;
-  for (int it = 0; it <= o.maxit; ++it) {
-    if (it >= first_poll) {
-      B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
-      B2_CUDA(cudaStreamSynchronize(c->stream));
-      c->stats.bytes_d2h += sizeof(KryState);
-      if (c->h_st->done) break;
-    }
+  auto body = [&](int it) {
     double* z = mg_vcycle(c, 0, r, c->mg_x0.p, c->mg_t0.p);
     B2_LAUNCH(c, k_cgz_rz, g, 256, n, r, z, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
     cgz_finish(c, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, 1);
@@ -829,6 +831,44 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
     spmm(c, qq, c->Ap.p, 1, p, q, p, c->d_st, FIN_CG_PQ, 1, B2_SPACE_Q);
     B2_LAUNCH(c, k_cgz_update, g, 256, n, p, q, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
     cgz_finish(c, FIN_CGZ_UPDATE, 1);
+  };
+  // Iterations 1, 2, ... are identical streams of small dependent kernels (all scalars live in device memory):
+  // captured once into a CUDA graph and replayed.  Multi-rank contexts keep plain launches (NCCL calls in between).
+  const bool graphs = c->use_graphs && c->nranks == 1;
+  for (int it = 0; it <= o.maxit; ++it) {
+    if (it >= first_poll) {
+      B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
+      B2_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.bytes_d2h += sizeof(KryState);
+      if (c->h_st->done) break;
+    }
+    if (it == 0 || !graphs) {
+      body(it);
+      continue;
+    }
+    if (c->pcg_graph == nullptr || c->pcg_graph_version != c->cfg_version || c->pcg_graph_x != x || c->pcg_graph_b != b) {
+      if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
+      const int64_t before = c->stats.kernel_launches;
+      cudaGraph_t graph = nullptr;
+      B2_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        body(it);
+      } catch (...) {
+        cudaStreamEndCapture(c->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      B2_CUDA(cudaStreamEndCapture(c->stream, &graph));
+      c->pcg_graph_launches = (int)(c->stats.kernel_launches - before);
+      c->stats.kernel_launches = before;  // capturing launched nothing
+      B2_CUDA(cudaGraphInstantiate(&c->pcg_graph, graph, 0));
+      cudaGraphDestroy(graph);
+      c->pcg_graph_version = c->cfg_version;
+      c->pcg_graph_x = x;
+      c->pcg_graph_b = b;
+    }
+    B2_CUDA(cudaGraphLaunch(c->pcg_graph, c->stream));
+    c->stats.kernel_launches += c->pcg_graph_launches;
   }
   if (!c->h_st->done) {
     B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
@@ -1309,6 +1349,7 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
 // ---- preassembly ----------------------------------------------------------------------------------
 void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rotational) {
   B2_REQUIRE(c->patterns_built, "b2_build_patterns has not been called");
+  c->cfg_version++;  // every buffer a captured graph refers to is (re)allocated below
   c->low_memory = low_memory != 0;
   c->rotational = rotational != 0;
   const int K = c->gdim;
@@ -1542,6 +1583,7 @@ void b2_destroy(b2_ctx* c) {
   cudaFreeHost(c->h_sums);
   cudaFree(c->d_counter);
   cudaFree(c->d_red);
+  if (c->pcg_graph) cudaGraphExecDestroy(c->pcg_graph);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->user_ev) cudaEventDestroy(e);
@@ -1628,6 +1670,7 @@ int b2_pressure_mg_add_level(b2_ctx* c, int64_t n_nodes, const double* x, int64_
                              const int32_t* R_indptr, const int32_t* R_indices, const double* R_vals) {
   return guarded(c, [&] {
     B2_REQUIRE(c->preassembled, "add multigrid levels after b2_preassemble");
+    c->cfg_version++;
     const int d = c->gdim;
     const int64_t fine_n = c->mg.empty() ? c->sp[B2_SPACE_Q].n_owned : c->mg.back().n;
     const int64_t fine_cols = c->mg.empty() ? c->sp[B2_SPACE_Q].n_local() : c->mg.back().n;
@@ -1679,6 +1722,7 @@ int b2_pressure_mg_add_level(b2_ctx* c, int64_t n_nodes, const double* x, int64_
 int b2_pressure_mg_configure(b2_ctx* c, int nu_pre, int nu_post, int coarse_sweeps, double omega) {
   return guarded(c, [&] {
     B2_REQUIRE(nu_pre >= 1 && nu_post >= 0 && coarse_sweeps >= 1 && omega > 0 && omega < 2, "bad multigrid parameters");
+    c->cfg_version++;
     c->mg_pre = nu_pre;
     c->mg_post = nu_post;
     c->mg_coarse = coarse_sweeps;
@@ -1691,6 +1735,7 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
     B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "slice order: square patterns, after b2_build_patterns");
     CSR& pat = c->pat[pattern];
     B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
+    c->cfg_version++;
     pat.order.alloc(n_slices);
     pat.sm_range.release();
     B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
@@ -2106,6 +2151,7 @@ int b2_synchronize(b2_ctx* c) {
 
 int b2_set_tuning(b2_ctx* c, const char* key, int value) {
   return guarded(c, [&] {
+    c->cfg_version++;
     std::string k(key);
     if (k == "spmm_blocks_per_sm") c->spmm_blocks_per_sm = std::max(1, std::min(value, 32));
     else if (k == "spmm_unroll") c->spmm_unroll = value;
@@ -2116,6 +2162,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_comp") c->spmm_comp = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "assemble_rows") c->assemble_rows = value;
+    else if (k == "graphs") c->use_graphs = value;
     else if (k == "combine") c->combine_variant = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
