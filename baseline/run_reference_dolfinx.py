@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Time the REAL reference (oasisx on DOLFINx/PETSc) on bench.py's workload -- for a machine that has the FEniCSx stack.
 
-    mpirun -n <cores> python baseline/run_reference_dolfinx.py [--mesh 96] [--steps 100] [--warmup 3] [--direct-pressure]
+    mpirun -n <cores> python baseline/run_reference_dolfinx.py [--mesh 96] [--steps 100] [--warmup 3]
 
 NOT RUN in this repository's environment: neither the build container nor the GPU boxes can install
 fenics-dolfinx / petsc4py / mpi4py, which is why ``bench.py --impl reference`` times the C++/OpenMP
