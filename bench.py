@@ -72,6 +72,23 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
+def step_algorithmic_bytes(n2, n1, nnz22, nnz21, nnz11, gdim, its, bytes_assemble, bytes_spmm, bytes_spmv_q):
+    """Algorithmic bytes of ONE IPCS step with the measured Krylov iteration counts its = (k_u, k_p, k_m): the
+    per-kernel figures of SURVEY.md 8(d) (k-RHS SpMM, CSR-value passes, 8 bytes per vector entry read or written)
+    summed over the kernels a step launches.  An accounting aid for `step_roofline`, not a
+    measurement."""
+    k_u, k_p, k_m = its
+    vec = 8.0 * gdim * n2  # one pass over a velocity-space vector (all components)
+    q = 8.0 * n1           # one pass over a pressure-space vector
+    rect = nnz21 * (8.0 * gdim + 4.0)  # one pass over a rectangular operator family ([nnz][gdim] values + columns)
+    tentative = (rect + 2 * vec + q) + 4 * vec + (bytes_spmm + 5 * vec) + k_u * (2 * bytes_spmm + 14 * vec) + 6 * vec
+    pressure = (rect + vec + q) + 6 * q + k_p * (1.15 * (3 * bytes_spmv_q + 10 * q) + 6 * q) + 4 * q
+    update = (bytes_spmm) + (rect + 2 * vec + q) + 7 * vec + (bytes_spmm + 5 * vec) + k_m * (bytes_spmm + 10 * vec) + 5 * vec
+    state = 2 * vec + 2 * q  # u1 <- u, p <- ps
+    return {"assemble_first": bytes_assemble, "tentative": tentative, "pressure": pressure, "update": update,
+            "total": bytes_assemble + tentative + pressure + update + state}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -455,6 +472,21 @@ def run_ours(args):
                 "other_kernels": {
                     "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
                     "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
+    step_roofline = None
+    try:
+        if world == 1:
+            med = (int(np.median([i[0] for i in its])), int(np.median([i[1] for i in its])), int(np.median([i[2] for i in its])))
+            sb = step_algorithmic_bytes(solver._nV_owned, solver._nQ_owned, ctx.pattern_nnz(L.PAT_VV), ctx.pattern_nnz(L.PAT_VQ),
+                                        ctx.pattern_nnz(L.PAT_QQ), 3, med, bytes_a, bytes_k, bytes_q)
+            gbs = sb["total"] / (ms_per_step * 1e-3) / 1e9
+            step_roofline = {"algorithmic_bytes_per_step": sb["total"], "iterations_assumed": list(med), "achieved": gbs, "peak": peak,
+                             "unit": "GB/s", "frac": gbs / peak,
+                             "stage_frac": {k: sb[k] / (v * 1e-3) / 1e9 / peak for k, v in
+                                            zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).tolist()) if v > 0},
+                             "note": "whole step and stages against the HBM roofline: algorithmic bytes (SURVEY.md 8d formulas, median "
+                                     "iteration counts) / measured time / peak; the pressure stage is latency-bound by construction"}
+    except Exception as exc:  # an accounting aid must never cost the bench line
+        step_roofline = {"error": repr(exc)}
     halos = int(st1.halo_exchanges - st0.halo_exchanges) // K
     allred = int(st1.allreduces - st0.allreduces) // K
     if rank != 0:
@@ -492,7 +524,7 @@ def run_ours(args):
         "initial_rel_residual": dict(zip(["tentative", "pressure", "update"], [float(f"{r:.3e}") for r in res0])),
         "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
         "nccl_per_step": {"halo_exchanges": halos, "allreduces": allred},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "bc_dofs": nbc, "checks": checks,
     }
     print(json.dumps(line), flush=True)
