@@ -5,8 +5,9 @@
 // sizes the numpy/SuperLU oracle (oracle/ipcs_oracle.py) cannot reach.  It follows the reference's
 // own structure: per-component solves with one shared matrix (fracstep.py:516-524,613-656), the
 // "matrix-vector" RHS strategy A.scale/axpy/axpy/mult (fracstep.py:438-469), CSR (int32/FP64)
-// storage, BiCGStab+Jacobi for the tentative velocity, CG+Jacobi for the pressure (null space
-// projected, fracstep.py:573-591) and for the mass solves -- the Krylov choices of SURVEY.md 8(d),
+// storage, BiCGStab+Jacobi for the tentative velocity, CG+Jacobi (or CG + the geometric multigrid of the GPU arm,
+// ipcs_cpu_mg_*) for the pressure (null space projected, fracstep.py:573-591) and CG+Jacobi for the mass solves -- the
+// Krylov choices of SURVEY.md 8(d),
 // because the reference's DOLFINx/PETSc/MUMPS stack cannot be installed here.
 //
 // PARITY UNPINNED for the same reason as oracle/ipcs_oracle.py; it is pinned against that numpy
@@ -82,6 +83,16 @@ struct Ctx {
   int dp_hist = 0;
   double bref2 = 0;  // block_rtol: max_k |b_k|^2 of the current vector solve
   int its_t = 0, its_p = 0, its_u = 0;
+  // pressure multigrid (same algorithm as the GPU arm's pc_type=mg: V(1,1), damped Jacobi, exact dense coarse solve);
+  // the hierarchy (Galerkin operators, transfers, dense inverse) is built by the Python side (oracle/ipcs_cpu.py)
+  struct MgLev {
+    Csr A, P, R;  // P: rows = dofs of the finer level, cols = this level; R = P^T
+    std::vector<double> Av, Pv, Rv, dinv;
+  };
+  std::vector<MgLev> mg;
+  std::vector<double> mg_dense;  // inverse of (A_last + alpha e e^T), row-major
+  double mg_omega = 0.85;
+  int pressure_mg = 0;
   // experiments (environment IPCS_GUESS_T / _M / _P, IPCS_DEBUG): order of the time extrapolation of the guesses
   int debug = 0, guess_t = 0, guess_m = 0, guess_p = 1;
   mutable double dbg_rr0 = 0;
@@ -223,6 +234,85 @@ int cg(const Ctx& c, const Csr& m, const std::vector<double>& vals, const std::v
     ++it;
   }
   if (c.debug) std::fprintf(stderr, "  cg: res0 %.2e (vs tol ref) its %d\n", std::sqrt(c.dbg_rr0 / (tol2 / (c.rtol * c.rtol))), it);
+  return rr <= tol2 ? it : -it;
+}
+
+// z = V(r): V(1,1) cycle on the pressure hierarchy, level 0 = (qq, Ap), levels >= 1 = c.mg[l - 1]; the last level is
+// solved exactly with the dense inverse (k_mg_sweep / k_dense_matvec on the GPU arm)
+static void mg_vcycle(const Ctx& c, size_t l, const std::vector<double>& b, std::vector<double>& x) {
+  const bool fine = (l == 0);
+  const Csr& A = fine ? c.qq : c.mg[l - 1].A;
+  const std::vector<double>& Av = fine ? c.Ap : c.mg[l - 1].Av;
+  const std::vector<double>& dinv = fine ? c.dinvAp : c.mg[l - 1].dinv;
+  const int64_t n = A.n_rows;
+  x.assign(n, 0.0);
+  if (l == c.mg.size()) {  // exact solve
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0;
+      const double* row = c.mg_dense.data() + (size_t)i * n;
+      for (int64_t j = 0; j < n; ++j) s += row[j] * b[j];
+      x[i] = s;
+    }
+    return;
+  }
+  const double w = c.mg_omega;
+  std::vector<double> r(n), t(n);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] = w * dinv[i] * b[i];  // first sweep from zero
+  spmv(A, Av, x.data(), t.data());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) r[i] = b[i] - t[i];
+  const Ctx::MgLev& C = c.mg[l];
+  std::vector<double> bc(C.A.n_rows), xc;
+  spmv(C.R, C.Rv, r.data(), bc.data());
+  mg_vcycle(c, l + 1, bc, xc);
+  spmv(C.P, C.Pv, xc.data(), t.data());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] += t[i];
+  spmv(A, Av, x.data(), t.data());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] += w * dinv[i] * (b[i] - t[i]);  // post-smoothing
+}
+
+// PCG with the V-cycle as preconditioner (the GPU arm's pcg_mg_solve); true-residual test |r| <= rtol |b|
+int cg_mg(const Ctx& c, const double* b, double* x) {
+  const Csr& m = c.qq;
+  const int64_t n = m.n_rows;
+  std::vector<double> r(n), z, p(n), q(n);
+  if (c.nonzero) {
+    spmv(m, c.Ap, x, q.data());
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) r[i] = b[i] - q[i];
+  } else {
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) { r[i] = b[i]; x[i] = 0; }
+  }
+  const double bb = dot(n, b, b);
+  double rr = dot(n, r.data(), r.data()), rz = 0;
+  const double tol2 = std::max(c.rtol * c.rtol * bb, 1e-100);
+  c.dbg_rr0 = rr;
+  int it = 0;
+  while (rr > tol2 && it < c.maxit) {
+    mg_vcycle(c, 0, r, z);
+    const double rz2 = dot(n, r.data(), z.data());
+    const double beta = it == 0 ? 0.0 : rz2 / rz;
+    rz = rz2;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    spmv(m, c.Ap, p.data(), q.data());
+    const double alpha = rz / dot(n, p.data(), q.data());
+    double rr2 = 0;
+#pragma omp parallel for reduction(+ : rr2)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
+      rr2 += r[i] * r[i];
+    }
+    rr = rr2;
+    ++it;
+  }
+  if (c.debug) std::fprintf(stderr, "  cg+mg: res0 %.2e its %d\n", std::sqrt(c.dbg_rr0 / std::max(bb, 1e-300)), it);
   return rr <= tol2 ? it : -it;
 }
 
@@ -483,6 +573,38 @@ static void push_hist(std::vector<double>* h, const std::vector<double>& v) {
   h[0] = v;
 }
 
+// pressure multigrid: one coarser level per call (CSR of its operator, of P from the previous level and of R = P^T),
+// then the dense inverse of the last level's shifted operator; ipcs_cpu_set_pressure_mg switches PCG to it
+void ipcs_cpu_mg_add_level(void* h, int n, const int* Ap, const int* Ai, const double* Av, int n_fine, const int* Pp,
+                           const int* Pi, const double* Pv, const int* Rp, const int* Ri, const double* Rv) {
+  Ctx* c = (Ctx*)h;
+  c->mg.emplace_back();
+  Ctx::MgLev& L = c->mg.back();
+  auto fill = [](Csr& m, std::vector<double>& v, int rows, int cols, const int* p, const int* i, const double* a) {
+    m.n_rows = rows;
+    m.n_cols = cols;
+    m.ptr.assign(p, p + rows + 1);
+    m.col.assign(i, i + p[rows]);
+    v.assign(a, a + p[rows]);
+  };
+  fill(L.A, L.Av, n, n, Ap, Ai, Av);
+  fill(L.P, L.Pv, n_fine, n, Pp, Pi, Pv);
+  fill(L.R, L.Rv, n, n_fine, Rp, Ri, Rv);
+  L.dinv.assign(n, 1.0);
+  for (int r = 0; r < n; ++r)
+    for (int q = L.A.ptr[r]; q < L.A.ptr[r + 1]; ++q)
+      if (L.A.col[q] == r) L.dinv[r] = 1.0 / L.Av[q];
+}
+void ipcs_cpu_mg_set_dense(void* h, int n, const double* inv) {
+  Ctx* c = (Ctx*)h;
+  c->mg_dense.assign(inv, inv + (size_t)n * n);
+}
+void ipcs_cpu_set_pressure_mg(void* h, int on, double omega) {
+  Ctx* c = (Ctx*)h;
+  c->pressure_mg = on;
+  if (omega > 0) c->mg_omega = omega;
+}
+
 // tolerance of the velocity solves relative to max_k |b_k| (same option as the GPU arm's b200_block_rtol)
 void ipcs_cpu_set_block_rtol(void* h, int on) { ((Ctx*)h)->block_rtol = on; }
 // same initial guesses as the GPU arm's b200_guess=extrapolate: 2u^n - u^{n-1} / u* + (u - u*)^{n-1}
@@ -630,7 +752,8 @@ int ipcs_cpu_step(void* h, double dt, double nu, int* its) {
     c->dp_old = prev;
     c->dp_hist++;
   }
-  c->its_p = cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
+  c->its_p = (c->pressure_mg && !c->mg.empty()) ? cg_mg(*c, c->b2.data(), c->dp.data())
+                                                : cg(*c, c->qq, c->Ap, c->dinvAp, c->b2.data(), c->dp.data());
   if (c->its_p < 0) return -2;
   if (c->guess_p != 1) { push_hist(c->dp_hist3, c->dp); c->n_dp_hist = std::min(c->n_dp_hist + 1, 3); }
   const double avg = dot(nQ, c->mQ.data(), c->dp.data()) / c->vol;  // :579-591

@@ -35,6 +35,9 @@ def lib():
         L.ipcs_cpu_set_vec.argtypes = [vp, i32, i32, vp]
         L.ipcs_cpu_get_vec.argtypes = [vp, i32, i32, vp]
         L.ipcs_cpu_get_matrix.argtypes = [vp, i32, i32, vp]
+        L.ipcs_cpu_mg_add_level.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.ipcs_cpu_mg_set_dense.argtypes = [vp, i32, vp]
+        L.ipcs_cpu_set_pressure_mg.argtypes = [vp, i32, dbl]
         L.ipcs_cpu_step.restype = i32
         L.ipcs_cpu_step.argtypes = [vp, dbl, dbl, vp]
         _lib = L
@@ -104,6 +107,52 @@ class CpuIPCS:
         out = np.empty(nnz)
         self.L.ipcs_cpu_get_matrix(self.h, which, comp, _p(out))
         return out
+
+    def attach_pressure_multigrid(self, msh, dense_max: int = 5000, omega: float = 0.85) -> int:
+        """The GPU arm's pressure preconditioner on the CPU (pc_type=mg): nested box/rectangle hierarchy from the mesh
+        provider, Galerkin coarse operators (= the stiffness matrices of the coarse meshes: the P1 spaces are nested),
+        V(1,1) damped-Jacobi cycle, exact dense solve on the first level with at most `dense_max` dofs.  Returns the
+        number of coarse levels (0: the mesh carries no hierarchy, Jacobi stays)."""
+        import scipy.sparse as sp
+
+        from oasisx_b200 import multigrid as mg
+
+        levels = mg.box_hierarchy(msh)
+        if not levels:
+            return 0
+        nnz = self.L.ipcs_cpu_nnz(self.h, 3)
+        ip, ix = self.pattern(3, self.nQ)
+        A = sp.csr_matrix((self.matrix(3, 0, nnz), ix, ip), shape=(self.nQ, self.nQ))
+        p0, h = msh._lattice
+        d = len(msh._shape)
+        idx = np.rint((self.xQ[:, :d] - p0[:d]) / h[:d]).astype(np.int64)
+        node_of_dof = mg._node_ids(idx, msh._shape)
+        n_levels = 0
+        for lvl, (cm, P) in enumerate(levels):
+            Pl = sp.csr_matrix(P)[node_of_dof, :].tocsr() if lvl == 0 else sp.csr_matrix(P)
+            Pl.sort_indices()
+            R = sp.csr_matrix(Pl.T)
+            R.sort_indices()
+            A = sp.csr_matrix(R @ A @ Pl)
+            A.sort_indices()
+            n = A.shape[0]
+            i32 = lambda a: np.ascontiguousarray(a, np.int32)
+            f64 = lambda a: np.ascontiguousarray(a, np.float64)
+            arrs = [i32(A.indptr), i32(A.indices), f64(A.data), i32(Pl.indptr), i32(Pl.indices), f64(Pl.data),
+                    i32(R.indptr), i32(R.indices), f64(R.data)]
+            self.L.ipcs_cpu_mg_add_level(self.h, n, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), Pl.shape[0], _p(arrs[3]), _p(arrs[4]),
+                                         _p(arrs[5]), _p(arrs[6]), _p(arrs[7]), _p(arrs[8]))
+            n_levels += 1
+            if n <= dense_max:
+                alpha = A[0, 0] / n
+                inv = f64(np.linalg.inv(A.toarray() + alpha))
+                self.L.ipcs_cpu_mg_set_dense(self.h, n, _p(inv))
+                break
+        else:  # no level small enough for the exact coarse solve: keep Jacobi
+            self.L.ipcs_cpu_set_pressure_mg(self.h, 0, float(omega))
+            return 0
+        self.L.ipcs_cpu_set_pressure_mg(self.h, 1, float(omega))
+        return n_levels
 
     def solve(self, dt, nu):
         self.update_bcs()
