@@ -510,6 +510,9 @@ def run_ours(args):
                              f"multigrid, and initial guesses as the GPU arm), {2 if n_cpu < 96 else 1} full IPCS step(s) after 1 warm-up on "
                              f"a {n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {cits})"
                              + ("" if n_cpu == N else f", scaled by cell count to {N}^3"),
+                   "note": "bounded sample: the CPU steps are steps 2.. of a run (start-up transient, more Krylov iterations per "
+                           "step: see its u/p/m) while `value` averages all timed steps of the GPU run (`iterations`); at equal "
+                           "iteration counts the CPU step would be shorter by about the ratio of the velocity iteration counts",
                    "host_cpus": os.cpu_count()}
         except Exception as exc:  # the GPU measurements above must not be lost to a failure of the CPU leg
             cpu = {"value": None, "unit": "steps/s", "kind": "port", "error": repr(exc)}
