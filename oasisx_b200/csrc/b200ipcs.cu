@@ -155,6 +155,7 @@ struct b2_ctx {
   int mg_small_from = 1 << 30; // first level (>= 1) handled by the single-block kernel
   int mg_dense_max = 5000;     // the first coarse level with at most this many dofs is solved exactly (dense inverse); 0 = off
   int mg_dense_level = -1;     // index into mg (level - 1) of that level, -1: none
+  int mg_fused = 0;            // tuning "mg_fused": fused first+residual / prolongation+sweep kernels (mg.cuh; not yet measured)
   int mg_dense_on = 1;         // tuning "mg_dense": 0 falls back to smoothing all the way down (A/B comparisons)
   DBuf<double> mg_dense;       // (A_l + alpha e e^T)^-1, row-major
   double** d_mg_result = nullptr; double** h_mg_result = nullptr;
@@ -778,15 +779,30 @@ double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
     mg_sweeps(c, L, fine, b, x, tmp, c->mg_coarse, true);
     return x;
   }
-  mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
-  // residual and restriction
   MgLevel& C = c->mg[l];
-  if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
-  B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
+  // fused variants need D^-1, b and P at every COLUMN: replicated levels, or the fine level of a single rank
+  const bool can_fuse = c->mg_fused && (!fine || c->nranks == 1);
+  if (can_fuse && c->mg_pre == 1) {
+    B2_LAUNCH(c, k_mg_first_resid, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, c->mg_omega, x, tmp);
+  } else {
+    mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
+    // residual
+    if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
+    B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
+  }
+  // restriction
   B2_LAUNCH(c, (k_rect_vq<1, 8>), blocks_for((int64_t)C.n * 8, 256), 256, C.n, C.R.rowptr.p, C.R.cols.p, C.Rv.p, tmp,
             (const double*)nullptr, C.n, 1.0, C.b.p);
   if (fine && c->nranks > 1) allreduce_sum(c, C.b.p, C.n);  // coarse levels are replicated: sum the partial restrictions
   double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p);
+  if (can_fuse && c->mg_post >= 1) {
+    // x <- (x + P xc) + omega D^-1 (b - A (x + P xc)) in one kernel, then the remaining post-sweeps
+    B2_LAUNCH(c, k_mg_prolong_sweep, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x,
+              C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, c->mg_omega, tmp);
+    std::swap(x, tmp);
+    mg_sweeps(c, L, fine, b, x, tmp, c->mg_post - 1, false);
+    return x;
+  }
   // x += P xc   (rows: owned dofs of this level)
   B2_LAUNCH(c, (k_rect_vq<1, 4>), blocks_for((int64_t)L.n * 4, 256), 256, L.n, C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, x, L.ld, 1.0, x);
   mg_sweeps(c, L, fine, b, x, tmp, c->mg_post, false);
@@ -1559,6 +1575,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     if (const char* e = std::getenv("B200_MG_SWEEPS")) c->mg_pre = c->mg_post = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("B200_MG_OMEGA")) c->mg_omega = std::atof(e);
     if (const char* e = std::getenv("B200_MG_DENSE")) c->mg_dense_max = std::atoi(e);
+    if (const char* e = std::getenv("B200_MG_FUSED")) c->mg_fused = std::atoi(e);
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -2163,6 +2180,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "assemble_rows") c->assemble_rows = value;
     else if (k == "graphs") c->use_graphs = value;
+    else if (k == "mg_fused") c->mg_fused = value;
     else if (k == "combine") c->combine_variant = value;
     else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
