@@ -155,7 +155,7 @@ struct b2_ctx {
   int mg_small_from = 1 << 30; // first level (>= 1) handled by the single-block kernel
   int mg_dense_max = 5000;     // the first coarse level with at most this many dofs is solved exactly (dense inverse); 0 = off
   int mg_dense_level = -1;     // index into mg (level - 1) of that level, -1: none
-  int mg_fused = 0;            // tuning "mg_fused": fused first+residual / prolongation+sweep kernels (mg.cuh; not yet measured)
+  int mg_fused = 0;            // tuning "mg_fused": fused first+residual / prolongation+sweep kernels (mg.cuh; measured slower)
   int mg_dense_on = 1;         // tuning "mg_dense": 0 falls back to smoothing all the way down (A/B comparisons)
   DBuf<double> mg_dense;       // (A_l + alpha e e^T)^-1, row-major
   double** d_mg_result = nullptr; double** h_mg_result = nullptr;

@@ -40,7 +40,10 @@ __global__ void k_mg_first(int64_t n, const double* __restrict__ dinv, const dou
     x[i] = omega * dinv[i] * b[i];
 }
 
-// ---- fused cycle kernels (tuning "mg_fused", OFF by default: written for the next round, not yet measured) ------
+// ---- fused cycle kernels (tuning "mg_fused", OFF by default: a measured negative result) -------------------------
+// Measured at 48^3 (tools/exp_mg_fused.py): same fields to 1e-13, same 9 iterations, but the pressure stage takes
+// 1.27 ms instead of 1.01 ms -- re-evaluating the prolongation at each of the ~15 gathered columns costs more inside
+// the kernel than the two saved launches (already cheap inside the CUDA graph) return.
 // A V(1,1) cycle spends 5 launches per level (first sweep, residual, restriction, prolongation, post-sweep); on levels
 // of 10^4..10^6 unknowns each is a few microseconds of work behind a launch.  Two pairs fuse without changing a bit of
 // the result, because the first sweep from zero is local (x = omega D^-1 b) and a nested P1 prolongation has at most
