@@ -124,3 +124,38 @@ def test_no_gpu_fails_loudly(lib):
         pytest.skip("GPU present")
     with pytest.raises(_lib.B200Error):
         _lib.Context()
+
+
+def test_taylor_green_spatial_cache_is_bitwise_and_keyed_by_array():
+    """tests/problems.py caches the spatial factor of the separable exact solution per coordinate ARRAY (the boundary
+    conditions pass the same array every step): same bits as the direct formula, and a different array is recomputed."""
+    from problems import TaylorGreen
+
+    nu = 0.01
+    tg = TaylorGreen(nu, 3)
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(-1, 1, (3, 257)), rng.uniform(-1, 1, (3, 257))
+    for t in (0.0, 0.3, 0.7):
+        tg.t_u, tg.t_p = t, t - 0.0025
+        for arr in (x, y, x):
+            ex = -np.cos(np.pi * arr[0]) * np.sin(np.pi * arr[1]) * np.exp(-2.0 * nu * np.pi**2 * tg.t_u)
+            ey = np.cos(np.pi * arr[1]) * np.sin(np.pi * arr[0]) * np.exp(-2.0 * nu * np.pi**2 * tg.t_u)
+            ep = -0.25 * (np.cos(2 * np.pi * arr[0]) + np.cos(2 * np.pi * arr[1])) * np.exp(-4 * nu * np.pi**2 * tg.t_p)
+            assert (tg.eval_x(arr) == ex).all() and (tg.eval_y(arr) == ey).all() and (tg.eval_p(arr) == ep).all()
+            assert (tg.eval_z(arr) == 0).all()
+
+
+def test_step_byte_accounting_is_consistent():
+    """bench.step_algorithmic_bytes: stage sums add up and every extra Krylov iteration costs what SURVEY.md 8(d) says."""
+    import bench
+
+    n2, n1, nnz22, nnz21, nnz11 = 7189057, 912673, 204763393, 58034593, 13465441
+    spmm = 12.0 * nnz22 + 4.0 * (n2 + 1) + 8.0 * 3 * 2 * n2
+    spmv_q = 12.0 * nnz11 + 4.0 * (n1 + 1) + 16.0 * n1
+    a = bench.step_algorithmic_bytes(n2, n1, nnz22, nnz21, nnz11, 3, (3, 9, 4), 13.5e9, spmm, spmv_q)
+    b = bench.step_algorithmic_bytes(n2, n1, nnz22, nnz21, nnz11, 3, (4, 9, 4), 13.5e9, spmm, spmv_q)
+    c = bench.step_algorithmic_bytes(n2, n1, nnz22, nnz21, nnz11, 3, (3, 9, 5), 13.5e9, spmm, spmv_q)
+    assert abs(a["total"] - (a["assemble_first"] + a["tentative"] + a["pressure"] + a["update"]) - (2 * 24.0 * n2 + 16.0 * n1)) < 1.0
+    assert abs((b["tentative"] - a["tentative"]) - (2 * spmm + 14 * 24.0 * n2)) < 1.0  # one BiCGStab iteration: 2 SpMM + 14 vector passes
+    assert abs((c["update"] - a["update"]) - (spmm + 10 * 24.0 * n2)) < 1.0            # one CG iteration: 1 SpMM + 10 vector passes
+    assert 70e9 < a["total"] < 100e9
