@@ -38,6 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "IPCS steps/s, 3D Taylor-Green P2-P1 box"
 DT, NU = 0.005, 0.01
+PARITY_TOL = 1e-8  # GPU fields against the CPU port after the same steps (north_star: 1e-8 relative at rtol 1e-10)
 KRYLOV = {
     "tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True,
                   "b200_guess": "extrapolate2", "b200_block_rtol": True},
@@ -180,6 +181,7 @@ def cpu_sample_cavity(n_cpu: int, n_steps: int, n_warm: int = 1):
     from oasisx_b200 import fem, mesh as bmesh
     from oracle import ipcs_cpu as cpu
 
+    cpu.use_all_cores()
     msh = bmesh.create_unit_cube(None, n_cpu, n_cpu, n_cpu)
     V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
     lid, walls = _cavity_markers()
@@ -280,24 +282,83 @@ def run_cavity(args):
     comm.Barrier()
 
 
-def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1):
+def run_assembly_strategies(args):
+    raise SystemExit("assembly-strategies workload: not built yet")
+
+
+def make_field(workload: str):
+    """The exact solution a Taylor-Green workload runs on: `taylor-green-rot` = the 2D vortex rotated out of the x-y
+    plane (three live velocity components, PETSc-standard per-component rtol), `taylor-green-z` = the z-extruded field
+    (w = 0) with the block-relative tolerance of round 1."""
+    from problems import TaylorGreen, TaylorGreenRot
+
+    return TaylorGreenRot(NU) if workload == "taylor-green-rot" else TaylorGreen(NU, 3)
+
+
+def krylov_for(workload: str) -> dict:
+    import copy
+
+    k = copy.deepcopy(KRYLOV)
+    if workload == "taylor-green-rot":  # PETSc's convergence test: every component against its own right-hand side
+        for o in k.values():
+            o.pop("b200_block_rtol", None)
+    return k
+
+
+def host_info(stream: bool = True) -> dict:
+    """CPU model, affinity, the OpenMP team the CPU port runs with, and a STREAM-triad figure of the host memory."""
+    from oracle import ipcs_cpu as cpu
+
+    info = cpu.use_all_cores()
+    try:
+        with open("/proc/cpuinfo") as f:
+            models = [ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")]
+        info["cpu_model"] = models[0] if models else None
+    except Exception:
+        info["cpu_model"] = None
+    if stream:
+        info["stream_triad_GBs"] = round(cpu.stream_triad_gbs(), 1)
+    return info
+
+
+def cpu_step_bytes(n2, n1, nnz22, nnz21, nnz11, gdim, its, mg: bool) -> float:
+    """Algorithmic bytes of one step of the CPU port's OWN algorithm (oracle/ipcs_cpu.cpp: unfused CSR passes of
+    fracstep.py:435-469, one component at a time): what its achieved bandwidth is computed from."""
+    k_u, k_p, k_m = its
+    v2, v1 = 8.0 * n2, 8.0 * n1
+    spmv22 = 12.0 * nnz22 + 4.0 * n2 + 2 * v2
+    spmv21 = 12.0 * nnz21 + 4.0 * n2 + v2 + v1
+    spmv11 = 12.0 * nnz11 + 4.0 * n1 + 2 * v1
+    assemble = 8.0 * nnz22 * (1 + 2) + 3 * 8.0 * nnz22 + 3 * 8.0 * nnz22 + gdim * (spmv22 + 3 * v2)  # zero+RMW, 2 value passes, d SpMV
+    tent = gdim * (spmv21 + 3 * v2) + gdim * (spmv22 + 5 * v2 + k_u * (2 * spmv22 + 12 * v2))
+    pres = gdim * (spmv21 + 2 * v1) + 6 * v1 + k_p * ((3.3 if mg else 1.0) * spmv11 + 10 * v1)
+    upd = gdim * (spmv22 + spmv21 + 3 * v2) + gdim * (spmv22 + 4 * v2 + k_m * (spmv22 + 10 * v2))
+    return assemble + tent + pres + upd
+
+
+def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1, workload: str = "taylor-green-z", want_fields: bool = False,
+               krylov: dict | None = None):
     """Time the CPU restatement (oracle/ipcs_cpu.cpp: C++/OpenMP, CSR, BiCGStab+Jacobi / CG+multigrid / CG+Jacobi: the
-    same Krylov options, preconditioners and initial guesses as the GPU arm) on an n_cpu^3 box with all host threads.
-    Returns (seconds per step, cells, threads, iterations)."""
+    same Krylov options, preconditioners and initial guesses as the GPU arm) on an n_cpu^3 box with all host threads
+    (set explicitly: host_info()).  Returns a dict: seconds per step, cells, threads, iterations, sizes, and -- when
+    asked -- the fields after the last step (the parity check of bench.py compares the GPU state with them)."""
     from oasisx_b200 import fem
     from oracle import ipcs_cpu as cpu
-    from problems import TaylorGreen, boundary_facets, make_mesh
+    from problems import boundary_facets, make_mesh
 
-    tg = TaylorGreen(NU, 3)
+    cpu.use_all_cores()
+    krylov = krylov or krylov_for(workload)
+    tg = make_field(workload)
     msh = make_mesh(3, n_cpu)
     V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
     bd = fem.locate_dofs_topological(V, 2, boundary_facets(msh))
     c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
                     Q.tabulate_dof_coordinates(), 2, bcs_u=[[(bd, f)] for f in tg.components],
-                    rtol=KRYLOV["tentative"]["ksp_rtol"], nonzero_guess=KRYLOV["tentative"]["ksp_initial_guess_nonzero"],
-                    block_rtol=KRYLOV["tentative"]["b200_block_rtol"],
-                    extrapolate={"extrapolate": 1, "extrapolate2": 2}.get(KRYLOV["tentative"].get("b200_guess"), 0))
-    if KRYLOV["pressure"].get("pc_type") == "mg":  # the GPU arm's pressure preconditioner on the CPU arm too
+                    rtol=krylov["tentative"]["ksp_rtol"], nonzero_guess=krylov["tentative"]["ksp_initial_guess_nonzero"],
+                    block_rtol=bool(krylov["tentative"].get("b200_block_rtol", False)),
+                    extrapolate={"extrapolate": 1, "extrapolate2": 2}.get(krylov["tentative"].get("b200_guess"), 0))
+    mg = krylov["pressure"].get("pc_type") == "mg"
+    if mg:  # the GPU arm's pressure preconditioner on the CPU arm too
         c.attach_pressure_multigrid(msh)
     xV, xQ = V.tabulate_dof_coordinates().T, Q.tabulate_dof_coordinates().T
     tg.t_u = -DT
@@ -312,11 +373,21 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1):
         tg.t_u += DT
         c.solve(DT, NU)
     t0 = time.perf_counter()
+    all_its = []
     for _ in range(n_steps):
         tg.t_u += DT
         c.solve(DT, NU)
-    sec = (time.perf_counter() - t0) / n_steps
-    return sec, msh.num_cells, cpu.lib().ipcs_cpu_threads(), c.its.tolist()
+        all_its.append(c.its.tolist())
+    sec = (time.perf_counter() - t0) / max(n_steps, 1)
+    nnz = [int(cpu.lib().ipcs_cpu_nnz(c.h, k)) for k in range(4)]
+    med = [int(np.median([i[j] for i in all_its])) for j in range(3)] if all_its else [0, 0, 0]
+    out = {"sec_per_step": sec, "cells": msh.num_cells, "threads": int(cpu.lib().ipcs_cpu_threads()), "its": c.its.tolist(),
+           "its_median": med, "bytes_per_step": cpu_step_bytes(c.nV, c.nQ, nnz[0], nnz[1], nnz[3], 3, med, mg),
+           "steps_done": n_warm + n_steps}
+    if want_fields:
+        out["u"] = [c.get(cpu.U, i) for i in range(3)]
+        out["p"] = c.get(cpu.P, 0)
+    return out
 
 
 def cpu_mesh_for(args) -> int:
@@ -327,29 +398,36 @@ def cpu_mesh_for(args) -> int:
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the path (the DOLFINx/PETSc reference cannot be installed here) on ALL
+    host cores of the box -- the OpenMP team is set from the CPU affinity mask, not from OMP_NUM_THREADS, which
+    torch.distributed.run forces to 1 -- on rank 0 only.  The line declares the steps it EXECUTED."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    hi = host_info()
     n_cpu = cpu_mesh_for(args)
     W, K = max(args.warmup, 0), max(args.steps, 1)
-    # keep the whole run within a few minutes (about 7 s per step at 96^3 during the start-up transient, less later): the
-    # same 3 warm-up steps as the GPU arm, then up to 12 timed steps
+    # keep the whole run within a few minutes (3-7 s per step at 96^3 during the start-up transient): the GPU arm's
+    # minimum of 3 warm-up steps, then at most 12 timed steps; the EXECUTED counts are what the line declares
     K_run, W_run = (K, W) if n_cpu < 96 else (min(K, 12), min(W, 3))
-    sec, cells, threads, its = cpu_sample(n_cpu, K_run, W_run)
+    wl = args.workload
+    r = cpu_sample(n_cpu, K_run, W_run, wl)
+    sec = r["sec_per_step"]
     target_cells = 6 * args.mesh**3
-    sps = (1.0 / sec) * cells / target_cells
+    sps = (1.0 / sec) * r["cells"] / target_cells
+    gbs = r["bytes_per_step"] / sec / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": K,
-        "warmup": W, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D Taylor-Green P2-P1 {args.mesh}^3 box (z-extruded exact solution), dt={DT}, nu={NU}, "
-                               "max_iter=1, rtol=1e-10", "mesh": args.mesh, "krylov": KRYLOV},
-        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": K_run,
+        "warmup": W_run, "requested": {"steps": K, "warmup": W}, "ms_per_step": 1000.0 / sps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(wl, args.mesh), "mesh": args.mesh, "krylov": krylov_for(wl)},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": r["threads"], "kind": "port",
                          "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp, same Krylov methods, preconditioners incl. the pressure multigrid, and "
                                    f"initial guesses as the GPU arm), {K_run} full IPCS steps after {W_run} warm-up on a "
-                                   f"{n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {its})"
+                                   f"{n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m median {r['its_median']})"
                                    + ("" if n_cpu == args.mesh else f", scaled by cell count to {args.mesh}^3"),
-                         "host_cpus": os.cpu_count()},
+                         "host": hi, "achieved_GBs": round(gbs, 1),
+                         "frac_of_stream_triad": round(gbs / hi["stream_triad_GBs"], 3) if hi.get("stream_triad_GBs") else None},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference algorithm on the host cores; the DOLFINx/PETSc/MUMPS reference itself "
                 "cannot be installed in this image (DESIGN.md)",
@@ -357,21 +435,76 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def workload_name(wl: str, N: int) -> str:
+    field = {"taylor-green-rot": "exact 2D vortex rotated out of the x-y plane: 3 live components, per-component rtol",
+             "taylor-green-z": "z-extruded exact solution, w = 0, block-relative rtol"}[wl]
+    return f"3D Taylor-Green P2-P1 {N}^3 box ({field}), dt={DT}, nu={NU}, max_iter=1, rtol=1e-10"
+
+
+def reinit_state(solver, tg):
+    """ICs of demo/taylor_green.py:167-182 again (u2 = u(-dt), u1 = u(0), p = p(-dt/2)), solution histories forgotten."""
+    solver._written(solver._u, solver._u1, solver._u2, solver._p, solver._ps, solver._dp)
+    tg.t_u = -DT
+    for i, f in enumerate(tg.components):
+        solver._u2[i].interpolate(f)
+    tg.t_u = 0.0
+    for i, f in enumerate(tg.components):
+        solver._u1[i].interpolate(f)
+        solver._u[i].x.array[:] = 0.0
+    tg.t_p = -DT / 2
+    solver._p.interpolate(tg.eval_p)
+    solver._dp.x.array[:] = 0.0
+    solver._flush()
+    solver._ctx.reset_time_history()
+    solver._ctx.select_bc_step(-1)
+
+
+def parity_vs_cpu_port(solver, tg, cpu_fields: dict) -> dict:
+    """The GPU path against the CPU port at FULL size: same mesh, same ICs, same Krylov options, the same number of
+    steps; max-norm difference of every velocity component (relative to the largest component) and of the pressure."""
+    n = int(cpu_fields["steps_done"])
+    reinit_state(solver, tg)
+    for _ in range(n):
+        tg.t_u += DT
+        tg.t_p += DT
+        solver.solve(DT, NU, max_iter=1)
+    u = [solver._u[i].x.array_ro() for i in range(3)]
+    scale = max(float(np.abs(v).max()) for v in cpu_fields["u"])
+    du = max(float(np.abs(u[i] - cpu_fields["u"][i]).max()) for i in range(3)) / scale
+    pg, pc = solver._p.x.array_ro(), cpu_fields["p"]
+    dpp = float(np.abs(pg - pc).max()) / float(np.abs(pc).max())
+    return {"steps": n, "rel_diff_u_vs_cpu_port": du, "rel_diff_p_vs_cpu_port": dpp}
+
+
+def parity_small(workload: str, N: int, n_steps: int, device: int) -> dict:
+    """The same check on a second, smaller box (48^3) with its own solver and CPU port."""
+    from problems import make_mesh, make_solver
+
+    tg = make_field(workload)
+    solver = make_solver(make_mesh(3, N), 2, tg, DT, solver_options=krylov_for(workload), device=device)
+    r = cpu_sample(N, n_steps, 0, workload, want_fields=True)
+    out = parity_vs_cpu_port(solver, tg, r)
+    out["mesh"] = N
+    return out
+
+
 def run_ours(args):
     from oasisx_b200.comm import HostComm
-    from problems import TaylorGreen, make_mesh, make_solver
+    from problems import make_mesh, make_solver
 
     comm = HostComm.from_env()
     rank, world = comm.rank, comm.size
     if world != args.gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     device = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload
+    krylov = krylov_for(wl)
 
     N, K, W = args.mesh, args.steps, max(args.warmup, 3)
     t_setup = time.perf_counter()
-    tg = TaylorGreen(NU, 3)
+    tg = make_field(wl)
     msh = make_mesh(3, N, comm if world > 1 else None)
-    solver = make_solver(msh, 2, tg, DT, solver_options=KRYLOV, device=device)
+    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
     nbc = comm.allreduce(sum(len(d) for d in solver._bc_dofs))
@@ -416,22 +549,26 @@ def run_ours(args):
     ms_per_step = ms_total / K
     value = 1000.0 / ms_per_step
 
+    # ---- full-size sanity of the state the timed steps produced (not part of any timing) --------
+    # the discrete solution against the analytic Taylor-Green field (nodal interpolant, mass-matrix norm), and the
+    # Euclidean norms of the owned entries to 15 digits: equal across 1/2/4/8 ranks up to the summation order
+    tg.t_u = (W + K) * DT
+    xV = solver._Vi[0][0].tabulate_dof_coordinates().T
+    exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][3] at the time of the last step
+    err2 = ctx.l2_diff_sq(L.VEC_U, exact)
+    nrm2 = ctx.l2_diff_sq(L.VEC_U, exact * 0.0)
+    nVo, nQo = solver._nV_owned, solver._nQ_owned
+    su = comm.allreduce(float(sum(np.dot(solver._u[i].x.array_ro()[:nVo], solver._u[i].x.array_ro()[:nVo]) for i in range(3))))
+    sp = comm.allreduce(float(np.dot(solver._p.x.array_ro()[:nQo], solver._p.x.array_ro()[:nQo])))
+    checks = {"t_end": tg.t_u, "rel_l2_error_u_vs_exact": float(np.sqrt(err2 / nrm2)),
+              "norm_u": float(f"{np.sqrt(su):.15e}"), "norm_p": float(f"{np.sqrt(sp):.15e}")}
+    if wl == "taylor-green-z":
+        checks["max_abs_w"] = comm.allreduce(float(np.abs(solver._u[2].x.array_ro()).max()), "max")
+
     # ---- end to end through the public API: callable BCs on the host, H2D, D2H ------------------
     # the SAME K steps again (state re-initialised, solution histories forgotten, W untimed steps first), so that
     # `e2e` and `value` see the same Krylov iteration counts
-    solver._written(solver._u, solver._u1, solver._u2, solver._p, solver._ps, solver._dp)
-    tg.t_u = -DT
-    for i, f in enumerate(tg.components):
-        solver._u2[i].interpolate(f)
-    tg.t_u = 0.0
-    for i, f in enumerate(tg.components):
-        solver._u1[i].interpolate(f)
-        solver._u[i].x.array[:] = 0.0
-    tg.t_p = -DT / 2
-    solver._p.interpolate(tg.eval_p)
-    solver._flush()
-    ctx.reset_time_history()
-    ctx.select_bc_step(-1)
+    reinit_state(solver, tg)
     for s in range(W):
         tg.t_u += DT
         tg.t_p += DT
@@ -455,16 +592,6 @@ def run_ours(args):
            "d2h_bytes_per_step": comm.allreduce(int(stB.bytes_d2h - stA.bytes_d2h)) // K,
            "iterations": [int(np.median([i[j] for i in e2e_its])) for j in range(3)]}
 
-    # ---- full-size sanity of the state the timed steps produced (not part of any timing) --------
-    # the discrete solution against the analytic Taylor-Green field (nodal interpolant, mass-matrix norm) and the
-    # z-component that must stay at round-off (z-extruded field)
-    xV = solver._Vi[0][0].tabulate_dof_coordinates().T
-    exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][3] at the time of the last step
-    err2 = ctx.l2_diff_sq(L.VEC_U, exact)
-    nrm2 = ctx.l2_diff_sq(L.VEC_U, exact * 0.0)
-    wmax = comm.allreduce(float(np.abs(solver._u[2].x.array_ro()).max()), "max")
-    checks = {"t_end": tg.t_u, "rel_l2_error_u_vs_exact": float(np.sqrt(err2 / nrm2)), "max_abs_w": wmax}
-
     # ---- roofline of the dominant kernel, measured live (rank 0's share of the rows) ------------
     peak, peak_kind = measured_peaks()
     comm.Barrier()
@@ -478,6 +605,7 @@ def run_ours(args):
                 "traffic": ncu_traffic(N) if world == 1 else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
                 "other_kernels": {
                     "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
+                    "assemble_first_algorithmic_bytes": bytes_a,
                     "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
     step_roofline = None
     try:
@@ -500,23 +628,37 @@ def run_ours(args):
         comm.Barrier()
         return
 
-    # ---- CPU restatement on the host cores, bounded sample (rank 0, N = 1 only) -----------------
+    # ---- CPU restatement on the host cores, bounded sample (rank 0, N = 1 only), and the parity of the two --------
     cpu = None
+    parity_failed = False
     if not args.no_cpu and world == 1:
         try:
+            hi = host_info()
             n_cpu = cpu_mesh_for(args)
             n_cpu_steps, n_cpu_warm = (2, 1) if n_cpu < 96 else (3, 3)  # 96^3: steps 4-6 after the GPU arm's 3 warm-up steps
-            sec, cells, threads, cits = cpu_sample(n_cpu, n_cpu_steps, n_cpu_warm)
-            sps = (1.0 / sec) * cells / msh.num_cells
-            cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+            r = cpu_sample(n_cpu, n_cpu_steps, n_cpu_warm, wl, want_fields=(n_cpu == N))
+            sec = r["sec_per_step"]
+            sps = (1.0 / sec) * r["cells"] / msh.num_cells
+            gbs = r["bytes_per_step"] / sec / 1e9
+            cpu = {"value": sps, "unit": "steps/s", "cores": r["threads"], "kind": "port",
                    "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp, same Krylov methods, preconditioners incl. the pressure "
                              f"multigrid, and initial guesses as the GPU arm), {n_cpu_steps} full IPCS step(s) after {n_cpu_warm} warm-up on "
-                             f"a {n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {cits})"
+                             f"a {n_cpu}^3 box ({sec:.2f} s/step, Krylov its u/p/m {r['its']})"
                              + ("" if n_cpu == N else f", scaled by cell count to {N}^3"),
                    "note": "bounded sample: the CPU steps are the first steps after the warm-up (start-up transient, more Krylov iterations per "
                            "step: see its u/p/m) while `value` averages all timed steps of the GPU run (`iterations`); at equal "
                            "iteration counts the CPU step would be shorter by about the ratio of the velocity iteration counts",
-                   "host_cpus": os.cpu_count()}
+                   "host": hi, "achieved_GBs": round(gbs, 1),
+                   "frac_of_stream_triad": round(gbs / hi["stream_triad_GBs"], 3) if hi.get("stream_triad_GBs") else None}
+            if n_cpu == N:  # GPU fields against the CPU port's after the same steps, at the benchmark size itself
+                checks["parity"] = [dict(parity_vs_cpu_port(solver, tg, r), mesh=N)]
+                if N > 48 and not args.no_parity48:
+                    checks["parity"].append(parity_small(wl, 48, 6, device))
+                worst = max(max(c["rel_diff_u_vs_cpu_port"], c["rel_diff_p_vs_cpu_port"]) for c in checks["parity"])
+                checks["rel_diff_u_vs_cpu_port"] = max(c["rel_diff_u_vs_cpu_port"] for c in checks["parity"])
+                checks["rel_diff_p_vs_cpu_port"] = max(c["rel_diff_p_vs_cpu_port"] for c in checks["parity"])
+                checks["parity_tolerance"] = PARITY_TOL
+                parity_failed = not (worst <= PARITY_TOL)
         except Exception as exc:  # the GPU measurements above must not be lost to a failure of the CPU leg
             cpu = {"value": None, "unit": "steps/s", "kind": "port", "error": repr(exc)}
 
@@ -526,12 +668,12 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D Taylor-Green P2-P1 {N}^3 box (z-extruded exact solution), dt={DT}, nu={NU}, "
-                               "max_iter=1, rtol=1e-10", "mesh": N, "cells": msh.num_cells,
+        "config": {"workload": workload_name(wl, N), "mesh": N, "cells": msh.num_cells,
                    "dofs": 3 * nV + nQ, "partition": f"{world} z-slab(s), NCCL halo + all-reduce" if world > 1 else "single GPU",
                    "l2": "working set per step >> 126 MB L2 (P2xP2 operators alone "
                          f"{3 * 12 * (230 * N**3) / 1e9:.2f} GB over all ranks); no flush needed",
-                   "krylov": KRYLOV, "multigrid": "V(1,1) damped Jacobi 0.85, exact dense solve on the first level <= 5000 dofs",
+                   "krylov": krylov, "low_memory_version": bool(args.low_memory),
+                   "multigrid": "V(1,1) damped Jacobi 0.85, exact dense solve on the first level <= 5000 dofs",
                    "sell_P2xP2": {"slots": sell[0], "run_slice_columns": sell[1], "slice_columns": sell[0] // 32},
                    "setup_s": t_setup},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
@@ -544,6 +686,11 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     comm.Barrier()
+    if parity_failed:
+        raise SystemExit(f"PARITY FAILURE: GPU fields differ from the CPU port by more than {PARITY_TOL} ({checks['parity']})")
+
+
+HEADLINE = "taylor-green-rot"  # what `--workload taylor-green` (the default) runs: see DESIGN.md section 6
 
 
 def main():
@@ -553,24 +700,34 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", type=int, default=0, help="cubes per direction (default 96 = BASELINE's metric, 48 = configs[2]; cavity: 128)")
-    ap.add_argument("--workload", default="taylor-green", choices=["taylor-green", "cavity"],
-                    help="taylor-green = BASELINE.json's metric (the line the driver reads); cavity = configs[4], an extra line")
+    ap.add_argument("--workload", default="taylor-green",
+                    choices=["taylor-green", "taylor-green-rot", "taylor-green-z", "cavity", "assembly-strategies"],
+                    help="taylor-green = BASELINE.json's metric (the line the driver reads) = taylor-green-rot: the exact vortex "
+                         "rotated out of the x-y plane, three live components, per-component rtol; taylor-green-z = round 1's "
+                         "z-extruded field (w = 0) with the block-relative tolerance; cavity = configs[4]; assembly-strategies = "
+                         "configs[1] (demo/assembly_strategies.py)")
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
+    ap.add_argument("--low-memory", action="store_true", help="options={'low_memory_version': True}: matrix-free element vectors "
+                                                               "instead of the 9 rectangular operators (fracstep.py:259)")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
     ap.add_argument("--scalar-ksp", default="auto", choices=["auto", "cg", "chebyshev"],
                     help="mass-solve method (auto = cg; chebyshev is reduction-free but needs ~3x the iterations once the "
                          "initial guesses are good)")
     args = ap.parse_args()
     KRYLOV["pressure"]["pc_type"] = args.pressure_pc
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     KRYLOV["scalar"]["ksp_type"] = args.scalar_ksp if args.scalar_ksp != "auto" else "cg"
+    if args.workload == "taylor-green":
+        args.workload = HEADLINE
     if args.mesh <= 0:
         args.mesh = 128 if args.workload == "cavity" else 96
     if args.workload == "cavity":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the Taylor-Green metric; the cavity line carries its own cpu_baseline")
         run_cavity(args)
+    elif args.workload == "assembly-strategies":
+        run_assembly_strategies(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -153,10 +153,13 @@ class PressureBC:
         if self._is_callable:
             self._h[:] = np.asarray(self._value(self._Q.tabulate_dof_coordinates().T), dtype=np.float64)
             self._version += 1
-        elif force:
-            v = self._value.value if isinstance(self._value, _fem.Constant) else self._value
-            self._h[:] = float(v)
-            self._version += 1
+        else:
+            # a float or a Constant: the reference keeps the Constant inside the ds-form (bcs.py:233-242), so a
+            # changed `.value` changes the next assembled surface term -- read it live, as DirichletBC does
+            v = float(self._value.value if isinstance(self._value, _fem.Constant) else self._value)
+            if force or (len(self._h) and self._h[0] != v):
+                self._h[:] = v
+                self._version += 1
 
     @property
     def bc(self) -> _DofBC:

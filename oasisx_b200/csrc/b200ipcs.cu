@@ -1803,11 +1803,15 @@ int b2_get_pattern(b2_ctx* c, int pattern, int32_t* indptr, int32_t* indices) {
 int b2_set_velocity_bc_dofs(b2_ctx* c, int comp, int64_t n, const int32_t* dofs) {
   return guarded(c, [&] {
     B2_REQUIRE(comp >= 0 && comp < c->gdim, "bad component");
-    B2_REQUIRE(!c->preassembled || comp != 0 || true, "");
     c->bc_dofs[comp].alloc(n);
     c->bc_vals[comp].alloc(n);
     c->bc_vals[comp].zero(c->stream);
     if (n) B2_CUDA(cudaMemcpyAsync(c->bc_dofs[comp].p, dofs, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    if (c->preassembled && comp == 0) {
+      // component 0's dof set drives the unit rows of the shared matrix (fracstep.py:470-472): rebuild the row mask
+      c->is_bc_row_v.zero(c->stream);
+      if (n) B2_LAUNCH(c, k_mark, blocks_for(n, 256), 256, n, c->bc_dofs[0].p, c->is_bc_row_v.p);
+    }
     B2_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.bytes_h2d += sizeof(int) * n;
   });
@@ -2009,7 +2013,7 @@ int b2_set_solver_option(b2_ctx* c, int solver, const char* key, const char* val
       else if (v == "none") o.pc = 1;
       else if (v == "mg" || v == "gamg" || v == "hypre") o.pc = (solver == B2_SOLVER_PRESSURE) ? 2 : 0;
       else if (v == "lu" || v == "cholesky") { o.pc = 0; o.rtol = 1e-12; o.atol = 1e-50; }  // "exact" solve (Appendix G)
-      else o.pc = 0;  // unknown preconditioners fall back to Jacobi, silently like PETSc's options DB
+      else throw B2Error(-5, "unsupported pc_type " + v + " (jacobi | none | mg | gamg | hypre | lu | cholesky)");  // PETSc errors on an unknown PC type too
     } else if (k == "ksp_rtol") o.rtol = std::stod(v);
     else if (k == "ksp_atol") o.atol = std::stod(v);
     else if (k == "ksp_max_it") o.maxit = std::stoi(v);

@@ -160,6 +160,8 @@ class FractionalStep_AB_CN:
             ctx.set_space(L.SPACE_V, deg_u, lp.V.n_owned, lp.V.n_ghost, lp.V.cell_dofs)
             ctx.set_space(L.SPACE_Q, deg_p, lp.Q.n_owned, lp.Q.n_ghost, lp.Q.cell_dofs)
             ctx.set_global_sizes(lp.V.n_global, lp.Q.n_global)
+            _part.check_halo_counts(comm, lp.V.halo, "V")
+            _part.check_halo_counts(comm, lp.Q.halo, "Q")
             ctx.set_halo(L.SPACE_V, lp.V.halo)
             ctx.set_halo(L.SPACE_Q, lp.Q.halo)
             self._nV_owned, self._nQ_owned = lp.V.n_owned, lp.Q.n_owned
@@ -179,6 +181,7 @@ class FractionalStep_AB_CN:
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
         self._bc_merge_maps: dict = {}
+        self._bc_sorted: dict = {}
         for i in range(gdim):
             dofs = self._merged_bc_dofs(i)
             self._bc_dofs.append(dofs)
@@ -284,8 +287,8 @@ class FractionalStep_AB_CN:
             version = tuple(bc._version for bc in bcl)
             if version == self._bc_versions[i]:
                 continue
-            if len(bcl) == 1 and len(vals[0]) == len(self._bc_dofs[i]):
-                merged = vals[0]
+            if len(bcl) == 1 and len(vals[0]) == len(self._bc_dofs[i]) and self._bc_is_sorted(i, bcl[0]):
+                merged = vals[0]  # the device list is the sorted unique dof list: identical order only if bc._dofs is
             else:
                 # positions of every BC's owned dofs in the merged list: located once, not every time step
                 maps = self._bc_merge_maps.setdefault(i, {})
@@ -299,6 +302,15 @@ class FractionalStep_AB_CN:
                     merged[m[2]] = v[m[1]]
             self._ctx.set_velocity_bc_values(i, merged)
             self._bc_versions[i] = version
+
+    def _bc_is_sorted(self, i: int, bc) -> bool:
+        """bc._dofs strictly increasing (checked once per dof array: `set_dofs` may inject any order)."""
+        hit = self._bc_sorted.get(i)
+        if hit is None or hit[0] is not bc._dofs:
+            d = bc._dofs
+            hit = (d, bool(len(d) < 2 or np.all(d[1:] > d[:-1])))
+            self._bc_sorted[i] = hit
+        return hit[1]
 
     def _assemble_pressure_surface(self):
         """``fracstep.py:445-446,461-465``: refresh the PressureBC values and assemble their ds-terms."""

@@ -92,7 +92,24 @@ def _owners(cell_dofs: np.ndarray, crank: np.ndarray, n_dofs: int, nranks: int) 
     return owner
 
 
-def _local_space(space, cells_local: np.ndarray, owner: np.ndarray, rank: int, nranks: int) -> LocalSpace:
+def cell_holders(crank: np.ndarray, owners_and_dofmaps, nranks: int) -> np.ndarray:
+    """holders[c, q] = rank q keeps cell c in its local mesh: q is the cell's own rank, or q owns a dof of ANY of the
+    spaces on the cell (the ghost-cell rule of `partition`: every cell touching an owned dof).  The send lists are
+    derived from this -- the rule that builds each rank's ghost block -- and not from a per-space shortcut: a rank may
+    hold a cell only through its cell rank or through the other space's ownership, and its ghosts include all dofs of
+    that cell."""
+    H = np.zeros((len(crank), nranks), dtype=bool)
+    rows = np.arange(len(crank))
+    H[rows, crank] = True
+    for owner, dofmap in owners_and_dofmaps:
+        O = owner[dofmap]
+        for j in range(O.shape[1]):
+            H[rows, O[:, j]] = True
+    return H
+
+
+def _local_space(space, cells_local: np.ndarray, owner: np.ndarray, rank: int, nranks: int,
+                 holders: np.ndarray | None = None) -> LocalSpace:
     gd = space.dofmap.list.astype(np.int64)
     n_global = space.num_dofs
     owned = np.flatnonzero(owner == rank)
@@ -105,7 +122,8 @@ def _local_space(space, cells_local: np.ndarray, owner: np.ndarray, rank: int, n
     # receive side: ghosts grouped by owner
     gown = owner[ghosts]
     neigh_recv = np.unique(gown)
-    # send side: owned dofs that share a cell with a dof owned by q  <=> q holds them as ghosts
+    # send side: my owned dofs on every cell rank q holds  <=> q has them in its ghost block (same rule as q's own
+    # `touched` set above, evaluated here without communication because the mesh is replicated)
     O = owner[gd]  # (n_cells, nd)
     send = {}
     mine_in_cell = (O == rank)
@@ -113,7 +131,7 @@ def _local_space(space, cells_local: np.ndarray, owner: np.ndarray, rank: int, n
     for q in range(nranks):
         if q == rank:
             continue
-        m = has_mine & (O == q).any(axis=1)
+        m = has_mine & (holders[:, q] if holders is not None else (O == q).any(axis=1))
         if not m.any():
             continue
         d = np.unique(gd[m][mine_in_cell[m]])
@@ -152,9 +170,26 @@ def partition(mesh, V, Q, nranks: int, rank: int) -> LocalProblem:
     cells_local = np.concatenate([owned_cells, ghost_cells])
     lp = LocalProblem(rank=rank, nranks=nranks, cells=cells_local, n_cells_owned=len(owned_cells),
                       cell_nodes=np.ascontiguousarray(mesh.geometry.dofmap[cells_local]))
-    lp.V = _local_space(V, cells_local, ownV, rank, nranks)
-    lp.Q = _local_space(Q, cells_local, ownQ, rank, nranks)
+    holders = cell_holders(crank, [(ownV, V.dofmap.list), (ownQ, Q.dofmap.list)], nranks)
+    lp.V = _local_space(V, cells_local, ownV, rank, nranks, holders)
+    lp.Q = _local_space(Q, cells_local, ownQ, rank, nranks, holders)
     return lp
+
+
+def check_halo_counts(comm, halo: HaloPlan, name: str = ""):
+    """Cross-check over the ranks, before the first exchange: what rank r sends to q is what q expects from r
+    (a mismatch would hang or corrupt the grouped ncclSend/ncclRecv)."""
+    me = {"n": halo.neighbors.tolist(), "s": np.diff(halo.send_off).tolist(), "r": np.diff(halo.recv_off).tolist()}
+    plans = comm.allgather(me)
+    r = comm.rank
+    for k, q in enumerate(me["n"]):
+        other = plans[int(q)]
+        if r not in other["n"]:
+            raise RuntimeError(f"halo plan {name}: rank {r} lists {q} as neighbour but not vice versa")
+        kq = other["n"].index(r)
+        if other["r"][kq] != me["s"][k] or other["s"][kq] != me["r"][k]:
+            raise RuntimeError(f"halo plan {name}: rank {r} <-> {q} counts disagree: send {me['s'][k]} vs recv "
+                               f"{other['r'][kq]}, recv {me['r'][k]} vs send {other['s'][kq]}")
 
 
 def halo_forward_numpy(plans: list[HaloPlan], n_owned: list[int], vectors: list[np.ndarray]):

@@ -14,6 +14,10 @@
 // oracle in tests/test_cpu_port.py.  Only tests/ and bench.py's cpu_baseline / --impl reference legs
 // load this library.  Build: oracle/build_cpu.py  (g++ -O3 -march=native -fopenmp).
 #include <omp.h>
+#if defined(__linux__)
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -484,6 +488,60 @@ void inv_diag(const Csr& m, const std::vector<double>& v, std::vector<double>& d
 extern "C" {
 
 int ipcs_cpu_threads(void) { return omp_get_max_threads(); }
+
+// The OpenMP team size is set EXPLICITLY by the caller (bench.py passes the size of the process' CPU affinity mask):
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which must not decide how many cores the CPU
+// baseline runs on.
+void ipcs_cpu_set_threads(int n) {
+  if (n > 0) {
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+  }
+}
+
+// Interleave this process' future page allocations over all NUMA nodes (set_mempolicy(MPOL_INTERLEAVE), raw syscall:
+// no libnuma in the image).  The std::vector storage of this port is first touched by the constructing thread, so
+// without this every array of a multi-socket box lives on one node and the other socket's threads pull it over the
+// interconnect.  Returns the number of nodes interleaved over (<= 1: nothing was changed).
+int ipcs_cpu_numa_interleave(void) {
+#if defined(__linux__)
+  int n_nodes = 0;
+  for (int i = 0; i < 64; ++i) {
+    char path[96];
+    std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d", i);
+    if (access(path, F_OK) == 0) n_nodes = i + 1;
+  }
+  if (n_nodes <= 1) return n_nodes;
+  unsigned long mask = n_nodes >= 64 ? ~0ul : ((1ul << n_nodes) - 1);
+  const long rc = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, &mask, (unsigned long)(8 * sizeof(mask)));
+  return rc == 0 ? n_nodes : 0;
+#else
+  return 0;
+#endif
+}
+
+// STREAM triad a = b + s c on `n` doubles per array, arrays first-touched by the threads that stream them:
+// best of `reps`, GB/s counting 24 bytes per element (the host-memory roofline the CPU baseline is held against)
+double ipcs_cpu_stream_triad(int64_t n, int reps) {
+  double* a = (double*)std::malloc(sizeof(double) * (size_t)n);
+  double* b = (double*)std::malloc(sizeof(double) * (size_t)n);
+  double* cc = (double*)std::malloc(sizeof(double) * (size_t)n);
+  if (!a || !b || !cc) { std::free(a); std::free(b); std::free(cc); return 0.0; }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) { a[i] = 0.0; b[i] = 1.0; cc[i] = 2.0; }
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    const double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) a[i] = b[i] + 3.0 * cc[i];
+    const double dt = omp_get_wtime() - t0;
+    if (dt > 0) best = std::max(best, 24.0 * (double)n / dt / 1e9);
+  }
+  volatile double sink = a[n / 2];
+  (void)sink;
+  std::free(a); std::free(b); std::free(cc);
+  return best;
+}
 
 void* ipcs_cpu_create(int gdim, int deg_v, int64_t n_nodes, const double* x, int64_t n_cells, const int* cell_nodes,
                       int64_t nV, const int* vdofs, int64_t nQ, const int* qdofs) {

@@ -20,6 +20,10 @@ def lib():
         L = C.CDLL(LIB)
         vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
         L.ipcs_cpu_threads.restype = i32
+        L.ipcs_cpu_set_threads.argtypes = [i32]
+        L.ipcs_cpu_numa_interleave.restype = i32
+        L.ipcs_cpu_stream_triad.restype = dbl
+        L.ipcs_cpu_stream_triad.argtypes = [i64, i32]
         L.ipcs_cpu_create.restype = vp
         L.ipcs_cpu_create.argtypes = [i32, i32, i64, vp, i64, vp, i64, vp, i64, vp]
         L.ipcs_cpu_destroy.argtypes = [vp]
@@ -46,6 +50,26 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def use_all_cores() -> dict:
+    """Pin the OpenMP team of the CPU port to every core this process may run on (the CPU affinity mask), whatever
+    OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1), and interleave its pages over the NUMA
+    nodes.  Call before the first CpuIPCS is built.  Returns what was set, for the bench line."""
+    L = lib()
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    L.ipcs_cpu_set_threads(int(n))
+    nodes = L.ipcs_cpu_numa_interleave()
+    return {"threads": int(L.ipcs_cpu_threads()), "affinity_cpus": int(n), "host_cpus": os.cpu_count(),
+            "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "numa_nodes_interleaved": int(nodes)}
+
+
+def stream_triad_gbs(n: int = 1 << 26, reps: int = 5) -> float:
+    """STREAM triad on the host with the port's thread team (GB/s, 24 B per element, best of reps)."""
+    return float(lib().ipcs_cpu_stream_triad(int(n), int(reps)))
 
 
 U, U1, U2, P, PS, DP, RHS1, BFIRST, B2 = range(9)

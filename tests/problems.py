@@ -44,6 +44,56 @@ class TaylorGreen:
         return [self.eval_x, self.eval_y, self.eval_z][: self.gdim]
 
 
+class TaylorGreenRot(TaylorGreen):
+    """The 2D Taylor-Green vortex of ``demo/taylor_green.py:36-53`` ROTATED out of the x-y plane: with an orthogonal
+    R and in-plane coordinates (xi, eta) = (R^T x)[:2],
+
+        u(x, t) = R[:, 0] u_xi(xi, eta, t) + R[:, 1] u_eta(xi, eta, t),   p(x, t) = p_2d(xi, eta, t).
+
+    The Navier-Stokes equations are invariant under rotations, so this is still an exact solution on the box with
+    Dirichlet data from the formula -- but all three velocity components are live and of the same size, unlike the
+    z-extruded field (w = 0) whose z-systems are solved for free by a block-relative tolerance.  Same caching of the
+    spatial factors as the parent class (one time factor per evaluation, bitwise reproducible)."""
+
+    def __init__(self, nu: float, gdim: int = 3, axis=(1.0, 2.0, 3.0), angle_deg: float = 50.0):
+        super().__init__(nu, 3)
+        a = np.asarray(axis, dtype=np.float64)
+        a /= np.linalg.norm(a)
+        th = np.deg2rad(angle_deg)
+        Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        self.R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)  # Rodrigues
+
+    def _plane(self, x):
+        R = self.R
+        xi = R[0, 0] * x[0] + R[1, 0] * x[1] + R[2, 0] * x[2]
+        eta = R[0, 1] * x[0] + R[1, 1] * x[1] + R[2, 1] * x[2]
+        return xi, eta
+
+    def _comp(self, k):
+        def spatial(x):
+            xi, eta = self._plane(x)
+            return (self.R[k, 0] * (-np.cos(np.pi * xi) * np.sin(np.pi * eta))
+                    + self.R[k, 1] * (np.cos(np.pi * eta) * np.sin(np.pi * xi)))
+
+        def f(x):
+            return self._spatial(("u", k), x, spatial) * np.exp(-2.0 * self.nu * np.pi**2 * self.t_u)
+
+        return f
+
+    def eval_p(self, x):
+        def spatial(x):
+            xi, eta = self._plane(x)
+            return -0.25 * (np.cos(2 * np.pi * xi) + np.cos(2 * np.pi * eta))
+
+        return self._spatial("p", x, spatial) * np.exp(-4 * self.nu * np.pi**2 * self.t_p)
+
+    @property
+    def components(self):
+        if not hasattr(self, "_comps"):
+            self._comps = [self._comp(k) for k in range(3)]
+        return self._comps
+
+
 def make_mesh(gdim: int, N: int, comm=None):
     if gdim == 2:
         return bmesh.create_rectangle(comm, [[-1.0, -1.0], [1.0, 1.0]], [N, N])
