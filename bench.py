@@ -553,6 +553,7 @@ def run_ours(args):
     # the discrete solution against the analytic Taylor-Green field (nodal interpolant, mass-matrix norm), and the
     # Euclidean norms of the owned entries to 15 digits: equal across 1/2/4/8 ranks up to the summation order
     tg.t_u = (W + K) * DT
+    solver._written(solver._u, solver._u1, solver._u2, solver._p, solver._ps, solver._dp)  # ctx.step bypassed the host mirrors
     xV = solver._Vi[0][0].tabulate_dof_coordinates().T
     exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][3] at the time of the last step
     err2 = ctx.l2_diff_sq(L.VEC_U, exact)
