@@ -675,7 +675,7 @@ def run_ours(args):
                          f"{3 * 12 * (230 * N**3) / 1e9:.2f} GB over all ranks); no flush needed",
                    "krylov": krylov, "low_memory_version": bool(args.low_memory),
                    "multigrid": "V(1,1) damped Jacobi 0.85, exact dense solve on the first level <= 5000 dofs",
-                   "sell_P2xP2": {"slots": sell[0], "run_slice_columns": sell[1], "slice_columns": sell[0] // 32},
+                   "sell_P2xP2": {"slots": sell, "slice_columns": sell // 32},
                    "setup_s": t_setup},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
                        "update": int(np.median([i[2] for i in its]))},

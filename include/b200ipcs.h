@@ -85,8 +85,9 @@ typedef struct b2_stats {
   double ms_assemble_first, ms_tentative, ms_pressure, ms_update; /* CUDA-event times, last step */
   double ms_step;
   int64_t bytes_h2d, bytes_d2h; /* cumulative host<->device traffic through this ABI */
-  int64_t halo_exchanges, allreduces; /* NCCL operations enqueued since creation (multi rank) */
+  int64_t halo_exchanges, allreduces; /* halo exchanges (either path) / ncclAllReduce calls enqueued since creation */
   double res0_tentative, res0_pressure, res0_update; /* |r0|/|b| of the last solves (max over components) */
+  int64_t peer_kernels; /* kernels that carried a peer-memory collective (halo, scalar or vector all-reduce) */
 } b2_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -118,6 +119,21 @@ int b2_set_space(b2_ctx* ctx, int space, int degree, int64_t n_owned, int64_t n_
  * implicit MatMult gather. */
 int b2_set_halo(b2_ctx* ctx, int space, int n_neighbors, const int32_t* neighbor_ranks,
                 const int64_t* send_off, const int32_t* send_idx, const int64_t* recv_off);
+/* Peer-memory collectives between the ranks of one NVSwitch box (replaces the MPI_Neighbor_alltoallv /
+ * MPI_Allreduce traffic of DOLFINx Scatterer and PETSc KSP, SURVEY.md 5.8, WITHOUT a library call per
+ * exchange): every rank exports an arena through CUDA IPC, the host layer all-gathers the
+ * B2_PEER_BLOB_BYTES blobs over its own channel (mpi4py / oasisx_b200.comm) and hands them back.  After
+ * segment 0 is imported, halo exchanges are one kernel (remote stores into the neighbours' staging +
+ * release flag + wait + unpack) and the Krylov dot products are all-reduced inside the reducing kernel;
+ * segment 1 (after the pressure multigrid is attached) carries the replicated coarse right-hand side.
+ * Call order: b2_set_halo (both spaces) -> export(0) -> import(0) [-> mg levels -> export(1) -> import(1)].
+ * If a rank cannot map a peer the call fails and the context keeps the NCCL path; the host layer must
+ * then call b2_peer_disable on EVERY rank (the choice has to be the same everywhere). */
+#define B2_PEER_BLOB_BYTES 256
+int b2_peer_export(b2_ctx* ctx, int segment, void* blob);
+int b2_peer_import(b2_ctx* ctx, int segment, const void* blobs /* [nranks][B2_PEER_BLOB_BYTES] */);
+int b2_peer_disable(b2_ctx* ctx);
+int b2_peer_enabled(b2_ctx* ctx); /* 1: peer-memory path active, 0: NCCL path */
 /* Global (all-rank) sizes for the two means of fracstep.py:573-591. */
 int b2_set_global_sizes(b2_ctx* ctx, int64_t n_global_v, int64_t n_global_q);
 
@@ -127,7 +143,6 @@ int64_t b2_pattern_nnz(b2_ctx* ctx, int pattern);
 /* Layout statistics of a square pattern's sliced-ELL form: slots (padded entries) and the number of 32-entry slice
  * columns whose column indices form a run c0..c0+31 (their index loads are skipped by the SpMM).  -1 if unavailable. */
 int64_t b2_pattern_sell_slots(b2_ctx* ctx, int pattern);
-int64_t b2_pattern_sell_runs(b2_ctx* ctx, int pattern);
 /* Optional schedule for the sliced-ELL kernels on a square pattern: a permutation of the 32-row slices
  * that lists them spatial tile by spatial tile, so that one thread block gathers from one
  * neighbourhood of the vector (host-side analogue of DOLFINx's graph reordering [ext]).  Results do

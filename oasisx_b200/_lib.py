@@ -26,7 +26,8 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_pattern_sell_runs", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
@@ -54,6 +55,7 @@ class Stats(C.Structure):
         ("res0_tentative", C.c_double),
         ("res0_pressure", C.c_double),
         ("res0_update", C.c_double),
+        ("peer_kernels", C.c_int64),
     ]
 
 
@@ -88,11 +90,14 @@ def load_library() -> C.CDLL:
         "b2_set_mesh": (i32, [vp, i32, i64, vp, i64, vp]),
         "b2_set_space": (i32, [vp, i32, i32, i64, i64, vp]),
         "b2_set_halo": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "b2_peer_export": (i32, [vp, i32, vp]),
+        "b2_peer_import": (i32, [vp, i32, vp]),
+        "b2_peer_disable": (i32, [vp]),
+        "b2_peer_enabled": (i32, [vp]),
         "b2_set_global_sizes": (i32, [vp, i64, i64]),
         "b2_build_patterns": (i32, [vp]),
         "b2_pattern_nnz": (i64, [vp, i32]),
         "b2_pattern_sell_slots": (i64, [vp, i32]),
-        "b2_pattern_sell_runs": (i64, [vp, i32]),
         "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
         "b2_pressure_mg_add_level": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
         "b2_pressure_mg_configure": (i32, [vp, i32, i32, i32, dbl]),
@@ -238,12 +243,32 @@ class Context:
         self._check(self.lib.b2_get_pattern(self._h, which, _ptr(indptr), _ptr(indices)), "b2_get_pattern")
         return indptr, indices
 
+    PEER_BLOB_BYTES = 256
+
+    def peer_setup(self, comm, segment: int) -> bool:
+        """Export this rank's arena, all-gather the blobs over `comm`, import the peers' arenas.  Every rank must
+        call it; if ANY rank fails to map a peer, all ranks fall back to the NCCL path.  Returns the agreed state."""
+        blob = C.create_string_buffer(self.PEER_BLOB_BYTES)
+        ok = self.lib.b2_peer_export(self._h, segment, blob) == 0
+        blobs = comm.allgather(bytes(blob.raw) if ok else b"")
+        ok = ok and all(len(b) == self.PEER_BLOB_BYTES for b in blobs)
+        if ok:
+            ok = self.lib.b2_peer_import(self._h, segment, C.create_string_buffer(b"".join(blobs), len(blobs) * self.PEER_BLOB_BYTES)) == 0
+        agreed = bool(comm.allreduce(int(ok), "min"))
+        if not agreed:
+            self.lib.b2_peer_disable(self._h)
+        comm.Barrier()
+        return agreed
+
+    def peer_enabled(self) -> bool:
+        return bool(self.lib.b2_peer_enabled(self._h))
+
     def pattern_nnz(self, which: int) -> int:
         return int(self.lib.b2_pattern_nnz(self._h, which))
 
-    def pattern_sell(self, which: int) -> tuple[int, int]:
+    def pattern_sell(self, which: int) -> int:
         """(slots, run slice columns) of the sliced-ELL form of a square pattern."""
-        return int(self.lib.b2_pattern_sell_slots(self._h, which)), int(self.lib.b2_pattern_sell_runs(self._h, which))
+        return int(self.lib.b2_pattern_sell_slots(self._h, which))
 
     def set_velocity_bc_dofs(self, comp: int, dofs):
         d = _i32(dofs)

@@ -31,9 +31,6 @@ struct CSR {
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
-  DBuf<int> cbase;                             // run-compressed columns, one entry per slice column (k_sell_cbase)
-  int64_t runs = 0;                            // number of slice columns that are runs (their column loads are skipped)
-  DBuf<int> sm_range;                          // k_spmm_sm: schedule ranges per SM, balanced by slots
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
 };
@@ -122,6 +119,33 @@ struct MgLevel {
   DBuf<double> Pv, Rv;
 };
 
+// one IPC-exported allocation of this rank and the peers' mappings of theirs
+struct PeerSeg {
+  void* base = nullptr;
+  size_t bytes = 0;
+  void* peer[B2_MAXR] = {};
+  bool imported = false;
+};
+
+// byte offsets inside segment 0 (identical on every rank up to the staging block)
+enum : size_t {
+  PEER_OFF_SEQ = 128,        // u64 seq_red, seq_halo[2], seq_mg, err
+  PEER_OFF_FLAG_RED = 256,   // u64 [B2_MAXR]
+  PEER_OFF_FLAG_HALO = 320,  // u64 [2][B2_MAXR]
+  PEER_OFF_FLAG_MG = 448,    // u64 [B2_MAXR]
+  PEER_OFF_SLOT_RED = 512,   // double [2][B2_MAXR][B2_RED_MAX]
+  PEER_OFF_STAGE = 512 + 2 * B2_MAXR * B2_RED_MAX * 8
+};
+
+// what travels with an IPC handle through the host channel (b2_peer_export / b2_peer_import)
+struct PeerBlob {
+  cudaIpcMemHandle_t handle;        // 64 bytes
+  int64_t cap[2];                   // segment 0: staging capacity (doubles) per space; segment 1: [n, 0]
+  int64_t recv_cnt[2][B2_MAXR];     // segment 0: ghosts received from each rank, per space; segment 1: [0][0..1] = lo, hi
+  int64_t pad[6];
+};
+static_assert(sizeof(PeerBlob) == B2_PEER_BLOB_BYTES, "PeerBlob size");
+
 struct DVec {
   DBuf<double> buf;
   int K = 1;
@@ -132,9 +156,7 @@ struct DVec {
 
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
-  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_block = 256, spmm_stream = 1, spmm_tma = 0, spmm_sm = 0, spmm_comp = 0;  // spmm_tma: CH*10 + STAGES, 0 = LSU kernel; spmm_sm: SM-local queues; spmm_comp: run-compressed columns (measured no faster: the kernel is bound by the L2->L1 gather path, not by DRAM bytes)
-  DBuf<int> sm_dense, sm_next;  // %smid -> dense SM index; per-range work counters
-  int n_sm_dense = 0;  // sweep: tools/sweep_spmm.py
+  int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -155,12 +177,23 @@ struct b2_ctx {
   int mg_small_from = 1 << 30; // first level (>= 1) handled by the single-block kernel
   int mg_dense_max = 5000;     // the first coarse level with at most this many dofs is solved exactly (dense inverse); 0 = off
   int mg_dense_level = -1;     // index into mg (level - 1) of that level, -1: none
-  int mg_fused = 0;            // tuning "mg_fused": fused first+residual / prolongation+sweep kernels (mg.cuh; measured slower)
   int mg_dense_on = 1;         // tuning "mg_dense": 0 falls back to smoothing all the way down (A/B comparisons)
   DBuf<double> mg_dense;       // (A_l + alpha e e^T)^-1, row-major
   double** d_mg_result = nullptr; double** h_mg_result = nullptr;
   ncclComm_t comm = nullptr;
-  double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank)
+  double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank, NCCL path)
+  // peer-memory collectives (common.cuh): arenas mapped through CUDA IPC, no NCCL call on the data path
+  int use_peer = 1;         // B200_PEER=0 keeps the NCCL path (A/B measurements, boxes without P2P)
+  bool peer_on = false;     // segment 0 imported: halo + scalar all-reduce run through peer memory
+  PeerSeg seg[2];           // 0: flags, scalar slots, halo staging; 1: staging of the replicated multigrid level
+  PeerDev h_peer{};
+  PeerDev* d_peer = nullptr;
+  PeerHalo ph[2];
+  PeerVecSum pvs{};
+  bool pvs_ready = false;
+  int mg_lo = 0, mg_hi = 0;  // range of level-1 dofs this rank's restriction touches
+  unsigned* d_counter_peer = nullptr;
+  unsigned long long* h_peer_err = nullptr;  // pinned copy of the arena's error word
   bool patterns_built = false, preassembled = false;
   bool low_memory = false, rotational = false;
   // matrices (values in pattern order)
@@ -174,12 +207,7 @@ struct b2_ctx {
   int bc_step = -1;                 // >= 0: apply bc_series[.][bc_step] instead of bc_vals
   DBuf<uint8_t> is_bc_row_v, is_bc_q;
   DBuf<uint8_t> pos8;  // per-cell scatter table of the convection assembly (elem.cuh)
-  // row-wise fused assemble_first (k_assemble_first_rows): dof -> (local index, cell) adjacency of the owned rows
-  DBuf<int> adj_ptr, adj;
-  int maxlen_vv = 0;        // longest row of the P2xP2 pattern (slots per lane in shared memory)
-  int assemble_rows = 0;    // tuning "assemble_rows": 1 = row-wise fused kernel (deterministic, no atomics, but 10x redundant
-                            // gathers of the cell data: measured 9.3 ms against 5.7 ms for scatter + combine at 96^3)
-  int rows_blocks_per_sm = 0;
+  int maxlen_vv = 0;        // longest row of the P2xP2 pattern
   // CUDA graph of one multigrid-preconditioned CG iteration of the pressure solve (single rank): ~21 dependent
   // launches of a few microseconds each become one graph launch
   cudaGraphExec_t pcg_graph = nullptr;
@@ -325,13 +353,6 @@ void build_pattern_raw(b2_ctx* c, int64_t n_cells, const int* rdofs, int nr, con
   out.lpr = avg >= 48 ? 16 : (avg >= 20 ? 8 : 4);
 }
 
-__global__ void k_count_nonneg(int64_t n, const int* __restrict__ v, int64_t* __restrict__ out) {
-  int64_t cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) cnt += v[i] >= 0;
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)out, (unsigned long long)cnt);
-}
-
 // SELL-32 companion of a square CSR pattern: slice offsets (in slots), padded column indices,
 // position of the diagonal in each row.
 void build_sell(b2_ctx* c, CSR& pat) {
@@ -355,17 +376,6 @@ void build_sell(b2_ctx* c, CSR& pat) {
   pat.scols.zero(c->stream);
   pat.diag_t.alloc(n_rows);
   B2_LAUNCH(c, k_sell_fill_cols, blocks_for(n_rows, 256), 256, n_rows, pat.rowptr.p, pat.cols.p, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p);
-  const int64_t n_sc = slots / 32;
-  pat.cbase.alloc(std::max<int64_t>(n_sc, 1));
-  pat.runs = 0;
-  if (n_sc > 0) {
-    B2_LAUNCH(c, k_sell_cbase, blocks_for(n_sc * 32, 256), 256, n_rows, n_sc, pat.slice_ptr.p, pat.scols.p, pat.cbase.p);
-    DBuf<int64_t> cnt;
-    cnt.alloc(1);
-    cnt.zero(c->stream);
-    B2_LAUNCH(c, k_count_nonneg, pgrid(c, n_sc), 256, n_sc, pat.cbase.p, cnt.p);
-    B2_CUDA(cudaMemcpyAsync(&pat.runs, cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-  }
   B2_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -390,6 +400,13 @@ void halo_forward(b2_ctx* c, int space, double* v, int K) {
   const Space& S = c->sp[space];
   const int ld = (int)S.n_local();
   const int64_t ns = h.send_off.back(), nr = h.recv_off.back();
+  if (c->peer_on) {  // one kernel: remote stores into the neighbours' staging, signal, wait, unpack
+    const int grid = std::max(1, std::min(c->sm, blocks_for(std::max(ns, nr) * K, 256)));
+    B2_LAUNCH(c, k_halo_peer, grid, 256, c->ph[space], K, ld, v);
+    c->stats.halo_exchanges++;
+    c->stats.peer_kernels++;
+    return;
+  }
   if (ns > 0)
     B2_LAUNCH(c, k_halo_pack, pgrid(c, ns * K), 256, h.n_neighbors, h.d_send_off.p, h.send_idx.p, K, ld, v, h.sendbuf.p);
   B2_NCCL(g_nccl.GroupStart());
@@ -407,17 +424,27 @@ void halo_forward(b2_ctx* c, int space, double* v, int K) {
 // sum over ranks of n doubles on the device (KSP reductions / comm.allreduce)
 void allreduce_sum(b2_ctx* c, double* d, int n) {
   if (c->nranks == 1) return;
+  if (c->peer_on) {
+    for (int off = 0; off < n; off += B2_RED_MAX) {
+      B2_LAUNCH(c, k_peer_allreduce, 1, 32, c->d_peer, d + off, std::min(B2_RED_MAX, n - off));
+      c->stats.peer_kernels++;
+    }
+    return;
+  }
   B2_NCCL(g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
   c->stats.allreduces++;
 }
 
 // after a reducing Krylov kernel: (multi rank) all-reduce the raw totals and run the scalar update
 void reduce_finish_host(b2_ctx* c, int fin, int n, bool is_init = false) {
-  if (c->nranks == 1) return;
+  if (c->nranks == 1 || c->peer_on) return;  // peer path: all-reduced and finalized inside the reducing kernel
   allreduce_sum(c, c->d_red, n);
   B2_LAUNCH(c, k_kry_finalize, 1, 1, fin, c->d_st, c->d_red, (int)is_init);
 }
-inline double* red_ptr(b2_ctx* c) { return c->nranks > 1 ? c->d_red : nullptr; }
+inline RedCtl red_ptr(b2_ctx* c) {
+  if (c->nranks == 1) return RedCtl{nullptr, nullptr};
+  return c->peer_on ? RedCtl{nullptr, c->d_peer} : RedCtl{c->d_red, nullptr};
+}
 
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
@@ -425,21 +452,7 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
-  if (UNROLL == 8 && c->spmm_comp && c->spmm_stream && pat.cbase.p != nullptr && (int64_t)K * ld < (1ll << 31)) {
-    // run-compressed columns; spmm_comp selects (unroll, blocks/SM the registers are bounded for): 1 = (8, 8), 2 = (4, 8),
-    // 3 = (8, 6), 4 = (4, 6)
-#define B2_SPMM_COMP(U, MB)                                                                                              \
-    B2_LAUNCH(c, (k_spmm<K, DOT, U, BLOCK, true, true, MB>), std::max(1, std::min(need, c->sm * std::min(c->spmm_blocks_per_sm, MB))), \
-              BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x, ld, y, w, st, fin, c->partials.p,  \
-              c->d_counter, red_ptr(c), pat.cbase.p)
-    switch (c->spmm_comp) {
-      case 2: B2_SPMM_COMP(4, 8); break;
-      case 3: B2_SPMM_COMP(8, 6); break;
-      case 4: B2_SPMM_COMP(4, 6); break;
-      default: B2_SPMM_COMP(8, 8); break;
-    }
-#undef B2_SPMM_COMP
-  } else if (c->spmm_stream)
+  if (c->spmm_stream)
     B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
               x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
   else
@@ -448,98 +461,10 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
-template <int K, int DOT, int CH, int STAGES>
-void launch_spmm_tma(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                     KryState* st, int fin) {
-  constexpr int BLOCK = 256, WPB = BLOCK / 32;
-  constexpr int ND = DOT == 0 ? 0 : DOT * K;
-  const size_t smem = (size_t)WPB * STAGES * CH * 32 * 12 + WPB * STAGES * 8 + (size_t)ND * BLOCK * 8;
-  auto kern = k_spmm_tma<K, DOT, CH, STAGES, BLOCK>;
-  static bool configured = false;
-  if (!configured) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  int per_sm = std::max(1, std::min(8, (int)(220 * 1024 / (smem + 1024))));
-  const int n_slices = (pat.n_rows + 31) / 32;
-  const int need = (n_slices + WPB - 1) / WPB;
-  const int grid = std::max(1, std::min(need, c->sm * per_sm));
-  kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p, x, ld, y, w, st, fin,
-                                         c->partials.p, c->d_counter, red_ptr(c));
-  c->stats.kernel_launches++;
-  B2_CUDA(cudaGetLastError());
-  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
-}
-
-void build_sm_ranges(b2_ctx* c, CSR& pat) {
-  const int n_slices = (pat.n_rows + 31) / 32;
-  std::vector<int> sp(n_slices + 1), ord(n_slices);
-  B2_CUDA(cudaMemcpyAsync(sp.data(), pat.slice_ptr.p, sizeof(int) * (n_slices + 1), cudaMemcpyDeviceToHost, c->stream));
-  if (pat.order.p) B2_CUDA(cudaMemcpyAsync(ord.data(), pat.order.p, sizeof(int) * n_slices, cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
-  if (!pat.order.p) for (int i = 0; i < n_slices; ++i) ord[i] = i;
-  const int nr = c->n_sm_dense;
-  std::vector<int> range(nr + 1, n_slices);
-  range[0] = 0;
-  const double total = (double)sp[n_slices] + 64.0 * n_slices;  // slots + a per-slice overhead
-  double acc = 0;
-  int r = 1;
-  for (int i = 0; i < n_slices && r < nr; ++i) {
-    acc += (sp[ord[i] + 1] - sp[ord[i]]) + 64.0;
-    if (acc >= total * r / nr) range[r++] = i + 1;
-  }
-  pat.sm_range.alloc(nr + 1);
-  B2_CUDA(cudaMemcpyAsync(pat.sm_range.p, range.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
-}
-
-template <int K, int DOT>
-void launch_spmm_sm(b2_ctx* c, CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                    KryState* st, int fin) {
-  if (c->n_sm_dense == 0) {  // one-off: which %smid values exist on this part
-    DBuf<int> seen;
-    seen.alloc(4096);
-    seen.zero(c->stream);
-    k_probe_smid<<<c->sm * 64, 32, 0, c->stream>>>(seen.p);
-    std::vector<int> h(4096);
-    B2_CUDA(cudaMemcpyAsync(h.data(), seen.p, sizeof(int) * 4096, cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    std::vector<int> dense(4096, 0);
-    int n = 0;
-    for (int i = 0; i < 4096; ++i) dense[i] = h[i] ? n++ : 0;
-    c->n_sm_dense = std::max(n, 1);
-    c->sm_dense.alloc(4096);
-    B2_CUDA(cudaMemcpyAsync(c->sm_dense.p, dense.data(), sizeof(int) * 4096, cudaMemcpyHostToDevice, c->stream));
-    c->sm_next.alloc(c->n_sm_dense);
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  if (pat.sm_range.p == nullptr) build_sm_ranges(c, pat);
-  B2_CUDA(cudaMemsetAsync(c->sm_next.p, 0, sizeof(int) * c->n_sm_dense, c->stream));
-  const int grid = c->sm * 8;
-  B2_LAUNCH(c, (k_spmm_sm<K, DOT, 8, 256>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
-            c->sm_dense.p, c->n_sm_dense, pat.sm_range.p, c->sm_next.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter,
-            red_ptr(c));
-  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
-}
-
 template <int K, int DOT>
 void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin) {
-  if (c->spmm_sm && pat.n_rows >= 32 * 8 * c->sm) {
-    launch_spmm_sm<K, DOT>(c, const_cast<CSR&>(pat), vals, x, ld, y, w, st, fin);
-    return;
-  }
-  switch (c->spmm_tma) {
-    case 82: launch_spmm_tma<K, DOT, 8, 2>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 83: launch_spmm_tma<K, DOT, 8, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 43: launch_spmm_tma<K, DOT, 4, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 44: launch_spmm_tma<K, DOT, 4, 4>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 42: launch_spmm_tma<K, DOT, 4, 2>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 24: launch_spmm_tma<K, DOT, 2, 4>(c, pat, vals, x, ld, y, w, st, fin); return;
-    case 33: launch_spmm_tma<K, DOT, 3, 3>(c, pat, vals, x, ld, y, w, st, fin); return;
-    default: break;
-  }
-  if (c->spmm_mode != 0) {
+  if (c->spmm_mode != 0) {  // diagnostic halves of the kernel (tools/sweep_spmm.py)
     int grid = pgrid(c, (int64_t)pat.n_rows, 256, 8);
     if (c->spmm_mode == 1) B2_LAUNCH(c, (k_spmm_diag<K, 1>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
@@ -780,29 +705,24 @@ double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
     return x;
   }
   MgLevel& C = c->mg[l];
-  // fused variants need D^-1, b and P at every COLUMN: replicated levels, or the fine level of a single rank
-  const bool can_fuse = c->mg_fused && (!fine || c->nranks == 1);
-  if (can_fuse && c->mg_pre == 1) {
-    B2_LAUNCH(c, k_mg_first_resid, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, c->mg_omega, x, tmp);
-  } else {
-    mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
-    // residual
-    if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
-    B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
-  }
+  mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
+  // residual
+  if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
+  B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
   // restriction
   B2_LAUNCH(c, (k_rect_vq<1, 8>), blocks_for((int64_t)C.n * 8, 256), 256, C.n, C.R.rowptr.p, C.R.cols.p, C.Rv.p, tmp,
             (const double*)nullptr, C.n, 1.0, C.b.p);
-  if (fine && c->nranks > 1) allreduce_sum(c, C.b.p, C.n);  // coarse levels are replicated: sum the partial restrictions
-  double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p);
-  if (can_fuse && c->mg_post >= 1) {
-    // x <- (x + P xc) + omega D^-1 (b - A (x + P xc)) in one kernel, then the remaining post-sweeps
-    B2_LAUNCH(c, k_mg_prolong_sweep, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x,
-              C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, c->mg_omega, tmp);
-    std::swap(x, tmp);
-    mg_sweeps(c, L, fine, b, x, tmp, c->mg_post - 1, false);
-    return x;
+  if (fine && c->nranks > 1) {  // coarse levels are replicated: sum the partial restrictions of the slabs
+    if (c->peer_on && c->pvs_ready) {
+      B2_LAUNCH(c, k_peer_vecsum, std::max(1, std::min(c->sm, blocks_for(C.n, 256))), 256, c->pvs, C.b.p);
+      c->stats.peer_kernels++;
+    } else {
+      B2_REQUIRE(!c->peer_on, "peer path: import segment 1 (multigrid staging) before the first pressure solve");
+      B2_NCCL(g_nccl.AllReduce(C.b.p, C.b.p, (size_t)C.n, ncclDouble, ncclSum, c->comm, c->stream));
+      c->stats.allreduces++;
+    }
   }
+  double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p);
   // x += P xc   (rows: owned dofs of this level)
   B2_LAUNCH(c, (k_rect_vq<1, 4>), blocks_for((int64_t)L.n * 4, 256), 256, L.n, C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, x, L.ld, 1.0, x);
   mg_sweeps(c, L, fine, b, x, tmp, c->mg_post, false);
@@ -810,7 +730,7 @@ double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
 }
 
 void cgz_finish(b2_ctx* c, int fin, int n) {
-  if (c->nranks == 1) return;
+  if (c->nranks == 1 || c->peer_on) return;
   allreduce_sum(c, c->d_red, n);
   B2_LAUNCH(c, k_cgz_finalize, 1, 1, fin, c->d_st, c->d_red);
 }
@@ -850,7 +770,7 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
   };
   // Iterations 1, 2, ... are identical streams of small dependent kernels (all scalars live in device memory):
   // captured once into a CUDA graph and replayed.  Multi-rank contexts keep plain launches (NCCL calls in between).
-  const bool graphs = c->use_graphs && c->nranks == 1;
+  const bool graphs = c->use_graphs && (c->nranks == 1 || (c->peer_on && c->pvs_ready));  // no NCCL call inside the body
   for (int it = 0; it <= o.maxit; ++it) {
     if (it >= first_poll) {
       B2_CUDA(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(KryState), cudaMemcpyDeviceToHost, c->stream));
@@ -990,34 +910,6 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   halo_forward(c, B2_SPACE_V, u2, K);
   const int64_t nl = V.n_local() * K;
   B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.5, u1, -0.5, u2, uab);  // :432-434
-  const double* psurf_r = c->vecs.count(B2_VEC_PSURF) ? c->vec(B2_VEC_PSURF) : nullptr;
-  const int scale_r = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
-  constexpr int RB = 128;  // threads per block of the row-wise kernel: 4 slices in flight per block
-  const size_t rows_smem = (size_t)(RB / 32) * c->maxlen_vv * 32 * sizeof(double);
-  if (c->assemble_rows && c->adj.p != nullptr && rows_smem <= 200 * 1024) {
-    // one fused pass, a warp per 32-row slice: C(uab) rows in shared memory, then A, b_first, dinv (:435-472)
-    dispatch_elem(c, [&](auto e) {
-      using E = decltype(e);
-      auto kern = k_assemble_first_rows<E::D, E::DEG>;
-      if (c->rows_blocks_per_sm == 0) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
-        int nb = 0;
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, RB, rows_smem));
-        c->rows_blocks_per_sm = std::max(1, nb);
-      }
-      const int n_slices = (vv.n_rows + 31) / 32;
-      const int grid = std::max(1, std::min((n_slices + RB / 32 - 1) / (RB / 32), c->sm * c->rows_blocks_per_sm));
-      kern<<<grid, RB, rows_smem, c->stream>>>(vv.n_rows, vv.slice_ptr.p, vv.scols.p, vv.diag_t.p, vv.order.p, c->adj_ptr.p,
-                                               c->adj.p, c->x.p, c->cell_nodes.p, V.cell_dofs.p, uab, ld, c->pos8.p, c->M.p,
-                                               c->Kst.p, c->A.p, 1.0 / dt, 0.5 * nu, u1, c->vec(B2_VEC_B0), psurf_r,
-                                               c->is_bc_row_v.p, scale_r, c->vec(B2_VEC_BFIRST), c->dinvA.p, c->maxlen_vv);
-      c->stats.kernel_launches++;
-      B2_CUDA(cudaGetLastError());
-    });
-    c->last_dt = dt;
-    c->fresh_step = true;
-    return;
-  }
   c->A.zero(c->stream);                                                   // :435
   dispatch_elem(c, [&](auto e) {
     using E = decltype(e);
@@ -1345,8 +1237,12 @@ void stage_step(b2_ctx* c, double dt, double nu, double max_error, int max_iter,
   std::swap(c->vecs[B2_VEC_U1].buf, c->vecs[B2_VEC_U2].buf);
   B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_U1), c->vec(B2_VEC_U), sizeof(double) * V.n_local() * K, cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_P), c->vec(B2_VEC_PS), sizeof(double) * Q.n_local(), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->peer_on)
+    B2_CUDA(cudaMemcpyAsync(c->h_peer_err, c->h_peer.err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaEventRecord(c->ev[5], c->stream));
   B2_CUDA(cudaEventSynchronize(c->ev[5]));
+  if (c->peer_on && *c->h_peer_err != 0)
+    throw B2Error(-32, "peer-memory collective timed out: a rank of the job stopped taking part");
   if (pending) {
     ms_t += ev_ms(c->ev[2], c->ev[3]);
     ms_p += ev_ms(c->ev[3], c->ev[4]);
@@ -1436,26 +1332,6 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
                   vv.rowptr.p, vv.cols.p, c->pos8.p);
       });
     }
-  }
-  // adjacency for the row-wise assembly: keys (row, local index, cell) sorted, offsets per owned row
-  if (c->pos8.p != nullptr && c->n_cells < (1ll << 28)) {
-    const int nv = V.nd;
-    const int64_t n_keys = c->n_cells * nv;
-    DBuf<unsigned long long> k0, k1;
-    k0.alloc(n_keys);
-    k1.alloc(n_keys);
-    B2_LAUNCH(c, k_gen_adj_keys, blocks_for(n_keys, 256), 256, c->n_cells, nv, V.cell_dofs.p, (int)V.n_owned, k0.p);
-    int row_bits = 1;
-    while ((1ll << row_bits) <= (int64_t)V.n_owned + 1) ++row_bits;
-    size_t tmp_bytes = 0;
-    B2_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0.p, k1.p, n_keys, 0, 32 + row_bits, c->stream));
-    DBuf<char> tmp;
-    tmp.alloc((int64_t)tmp_bytes);
-    B2_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, k0.p, k1.p, n_keys, 0, 32 + row_bits, c->stream));
-    c->adj_ptr.alloc(V.n_owned + 1);
-    c->adj.alloc(n_keys);
-    B2_LAUNCH(c, k_keys_to_csr, blocks_for(n_keys + 1, 256), 256, n_keys, k1.p, (int)V.n_owned, c->adj_ptr.p, c->adj.p);
-    B2_CUDA(cudaStreamSynchronize(c->stream));
   }
   // Dirichlet masks
   c->is_bc_row_v.alloc(V.n_local()); c->is_bc_row_v.zero(c->stream);
@@ -1568,14 +1444,7 @@ int b2_create(b2_ctx** out, int device, int nranks, int rank, const void* nccl_u
     for (auto& e : c->ev) B2_CUDA(cudaEventCreate(&e));
     for (auto& e : c->user_ev) B2_CUDA(cudaEventCreate(&e));
     c->ksp[B2_SOLVER_TENTATIVE].type = 1;
-    if (const char* e = std::getenv("B200_SPMM_TMA")) c->spmm_tma = std::atoi(e);  // kernel-variant override for experiments
-    if (const char* e = std::getenv("B200_SPMM_SM")) c->spmm_sm = std::atoi(e);
-    if (const char* e = std::getenv("B200_SPMM_COMP")) c->spmm_comp = std::atoi(e);
-    if (const char* e = std::getenv("B200_MG_COARSE")) c->mg_coarse = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("B200_MG_SWEEPS")) c->mg_pre = c->mg_post = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("B200_MG_OMEGA")) c->mg_omega = std::atof(e);
-    if (const char* e = std::getenv("B200_MG_DENSE")) c->mg_dense_max = std::atoi(e);
-    if (const char* e = std::getenv("B200_MG_FUSED")) c->mg_fused = std::atoi(e);
+    if (const char* e = std::getenv("B200_PEER")) c->use_peer = std::atoi(e);  // 0: keep every collective on NCCL
     B2_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 16));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     if (nranks > 1) {
@@ -1601,6 +1470,14 @@ void b2_destroy(b2_ctx* c) {
   cudaFree(c->d_counter);
   cudaFree(c->d_red);
   if (c->pcg_graph) cudaGraphExecDestroy(c->pcg_graph);
+  for (auto& sg : c->seg) {
+    for (int q = 0; q < B2_MAXR; ++q)
+      if (sg.peer[q] && sg.peer[q] != sg.base) cudaIpcCloseMemHandle(sg.peer[q]);
+    if (sg.base) cudaFree(sg.base);
+  }
+  cudaFree(c->d_peer);
+  cudaFree(c->d_counter_peer);
+  if (c->h_peer_err) cudaFreeHost(c->h_peer_err);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->user_ev) cudaEventDestroy(e);
@@ -1675,6 +1552,147 @@ int b2_set_halo(b2_ctx* c, int space, int n_neighbors, const int32_t* neighbor_r
   });
 }
 
+// ---- peer-memory collectives: arena export / import (include/b200ipcs.h) ---------------------------------
+int b2_peer_export(b2_ctx* c, int segment, void* blob_out) {
+  return guarded(c, [&] {
+    B2_REQUIRE(c->nranks > 1 && c->nranks <= B2_MAXR, "peer path: 2..8 ranks of one box");
+    B2_REQUIRE(c->use_peer, "peer path disabled (B200_PEER=0)");
+    B2_REQUIRE(segment == 0 || segment == 1, "bad segment");
+    PeerSeg& sg = c->seg[segment];
+    B2_REQUIRE(sg.base == nullptr, "segment already exported");
+    PeerBlob blob;
+    std::memset(&blob, 0, sizeof(blob));
+    if (segment == 0) {
+      const int K = std::max(c->gdim, 1);
+      blob.cap[0] = std::max<int64_t>(1, c->sp[B2_SPACE_V].n_ghost * K);
+      blob.cap[1] = std::max<int64_t>(1, c->sp[B2_SPACE_Q].n_ghost);
+      for (int sp = 0; sp < 2; ++sp) {
+        const Halo& h = c->halo[sp];
+        for (int j = 0; j < h.n_neighbors; ++j) {
+          B2_REQUIRE(j == 0 || h.ranks[j] > h.ranks[j - 1], "peer path: neighbour ranks must be strictly increasing");
+          blob.recv_cnt[sp][h.ranks[j]] = h.recv_off[j + 1] - h.recv_off[j];
+        }
+      }
+      sg.bytes = PEER_OFF_STAGE + sizeof(double) * 2 * (size_t)(blob.cap[0] + blob.cap[1]);
+    } else {
+      B2_REQUIRE(c->peer_on, "segment 0 must be imported first");
+      B2_REQUIRE(!c->mg.empty(), "segment 1 carries the first replicated multigrid level: add the levels first");
+      blob.cap[0] = c->mg[0].n;
+      blob.recv_cnt[0][0] = c->mg_lo;
+      blob.recv_cnt[0][1] = c->mg_hi;
+      sg.bytes = sizeof(double) * 2 * (size_t)c->nranks * (size_t)c->mg[0].n;
+    }
+    B2_CUDA(cudaMalloc(&sg.base, sg.bytes));
+    B2_CUDA(cudaMemsetAsync(sg.base, 0, sg.bytes, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CUDA(cudaIpcGetMemHandle(&blob.handle, sg.base));
+    std::memcpy(blob_out, &blob, sizeof(blob));
+  });
+}
+
+int b2_peer_import(b2_ctx* c, int segment, const void* blobs_in) {
+  return guarded(c, [&] {
+    B2_REQUIRE(segment == 0 || segment == 1, "bad segment");
+    PeerSeg& sg = c->seg[segment];
+    B2_REQUIRE(sg.base != nullptr && !sg.imported, "export the segment first (once)");
+    const int R = c->nranks, me = c->rank;
+    std::vector<PeerBlob> blobs(R);
+    std::memcpy(blobs.data(), blobs_in, sizeof(PeerBlob) * R);
+    for (int q = 0; q < R; ++q) {
+      if (q == me) { sg.peer[q] = sg.base; continue; }
+      B2_CUDA(cudaIpcOpenMemHandle(&sg.peer[q], blobs[q].handle, cudaIpcMemLazyEnablePeerAccess));
+    }
+    sg.imported = true;
+    auto at = [](void* base, size_t off) { return (void*)((char*)base + off); };
+    if (!c->d_counter_peer) {
+      B2_CUDA(cudaMalloc(&c->d_counter_peer, sizeof(unsigned)));
+      B2_CUDA(cudaMemsetAsync(c->d_counter_peer, 0, sizeof(unsigned), c->stream));
+      B2_CUDA(cudaMallocHost(&c->h_peer_err, sizeof(unsigned long long)));
+      *c->h_peer_err = 0;
+    }
+    unsigned long long* seqs = (unsigned long long*)at(sg.base, PEER_OFF_SEQ);
+    if (segment == 0) {
+      PeerDev& P = c->h_peer;
+      P.nranks = R;
+      P.rank = me;
+      P.seq_red = seqs + 0;
+      P.err = seqs + 4;
+      P.flag_red = (unsigned long long*)at(sg.base, PEER_OFF_FLAG_RED);
+      P.slot_red = (double*)at(sg.base, PEER_OFF_SLOT_RED);
+      for (int q = 0; q < R; ++q) {
+        P.peer_flag_red[q] = (unsigned long long*)at(sg.peer[q], PEER_OFF_FLAG_RED);
+        P.peer_slot_red[q] = (double*)at(sg.peer[q], PEER_OFF_SLOT_RED);
+      }
+      B2_CUDA(cudaMalloc(&c->d_peer, sizeof(PeerDev)));
+      B2_CUDA(cudaMemcpyAsync(c->d_peer, &P, sizeof(PeerDev), cudaMemcpyHostToDevice, c->stream));
+      for (int sp = 0; sp < 2; ++sp) {
+        const Halo& h = c->halo[sp];
+        PeerHalo& H = c->ph[sp];
+        std::memset(&H, 0, sizeof(H));
+        B2_REQUIRE(h.n_neighbors <= B2_MAXR, "too many neighbours");
+        H.n_neighbors = h.n_neighbors;
+        H.rank = me;
+        H.n_owned = (int)c->sp[sp].n_owned;
+        H.send_idx = h.send_idx.p;
+        H.seq = seqs + 1 + sp;
+        H.flag = (unsigned long long*)at(sg.base, PEER_OFF_FLAG_HALO) + sp * B2_MAXR;
+        H.cap = blobs[me].cap[sp];
+        H.recv = (double*)at(sg.base, PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[me].cap[0]);
+        H.counter = c->d_counter_peer;
+        H.err = P.err;
+        for (int j = 0; j <= h.n_neighbors; ++j) { H.send_off[j] = h.send_off[j]; H.recv_off[j] = h.recv_off[j]; }
+        for (int j = 0; j < h.n_neighbors; ++j) {
+          const int q = h.ranks[j];
+          H.nbr[j] = q;
+          H.peer_flag[j] = (unsigned long long*)at(sg.peer[q], PEER_OFF_FLAG_HALO) + sp * B2_MAXR;
+          H.peer_cap[j] = blobs[q].cap[sp];
+          H.peer_recv[j] = (double*)at(sg.peer[q], PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[q].cap[0]);
+          int64_t off = 0;  // my block in q's staging: after what q receives from lower ranks (its neighbours are sorted)
+          for (int r = 0; r < me; ++r) off += blobs[q].recv_cnt[sp][r];
+          H.dst_off[j] = off;
+          const int64_t mine = h.send_off[j + 1] - h.send_off[j];
+          B2_REQUIRE(blobs[q].recv_cnt[sp][me] == mine, "peer path: send count does not match the neighbour's receive count");
+        }
+      }
+      B2_CUDA(cudaStreamSynchronize(c->stream));
+      c->peer_on = true;
+      c->cfg_version++;
+    } else {
+      PeerVecSum& V = c->pvs;
+      std::memset(&V, 0, sizeof(V));
+      V.nranks = R;
+      V.rank = me;
+      V.n = c->mg[0].n;
+      for (int q = 0; q < R; ++q) {
+        B2_REQUIRE(blobs[q].cap[0] == V.n, "peer path: ranks disagree on the size of the replicated level");
+        V.lo[q] = (int)blobs[q].recv_cnt[0][0];
+        V.hi[q] = (int)blobs[q].recv_cnt[0][1];
+        V.peer_stage[q] = (double*)sg.peer[q];
+      }
+      PeerSeg& s0 = c->seg[0];
+      V.seq = (unsigned long long*)at(s0.base, PEER_OFF_SEQ) + 3;
+      V.flag = (unsigned long long*)at(s0.base, PEER_OFF_FLAG_MG);
+      for (int q = 0; q < R; ++q) V.peer_flag[q] = (unsigned long long*)at(s0.peer[q], PEER_OFF_FLAG_MG);
+      V.stage = (double*)sg.base;
+      V.counter = c->d_counter_peer;
+      V.err = c->h_peer.err;
+      c->pvs_ready = true;
+      c->cfg_version++;
+    }
+  });
+}
+
+int b2_peer_disable(b2_ctx* c) {
+  return guarded(c, [&] {
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->peer_on = false;
+    c->pvs_ready = false;
+    c->cfg_version++;
+  });
+}
+
+int b2_peer_enabled(b2_ctx* c) { return c && c->peer_on ? 1 : 0; }
+
 int b2_set_global_sizes(b2_ctx* c, int64_t nv, int64_t nq) {
   return guarded(c, [&] {
     c->sp[B2_SPACE_V].n_global = nv;
@@ -1727,6 +1745,13 @@ int b2_pressure_mg_add_level(b2_ctx* c, int64_t n_nodes, const double* x, int64_
     };
     upload_csr(L.P, L.Pv, (int)fine_n, L.n, P_indptr, P_indices, P_vals);
     upload_csr(L.R, L.Rv, L.n, (int)fine_cols, R_indptr, R_indices, R_vals);
+    if (c->mg.size() == 1) {  // index range of this level that the local restriction writes nonzeros into
+      c->mg_lo = L.n;
+      c->mg_hi = 0;
+      for (int r = 0; r < L.n; ++r)
+        if (R_indptr[r + 1] > R_indptr[r]) { c->mg_lo = std::min(c->mg_lo, r); c->mg_hi = std::max(c->mg_hi, r + 1); }
+      if (c->mg_hi <= c->mg_lo) c->mg_lo = c->mg_hi = 0;
+    }
     if (c->mg_dense_level < 0 && L.n <= c->mg_dense_max) mg_build_dense(c, (int)c->mg.size() - 1);
     if (c->mg.size() == 1) {
       c->mg_x0.alloc(c->sp[B2_SPACE_Q].n_local()); c->mg_x0.zero(c->stream);
@@ -1754,7 +1779,6 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
     B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
     c->cfg_version++;
     pat.order.alloc(n_slices);
-    pat.sm_range.release();
     B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -1782,11 +1806,6 @@ int64_t b2_pattern_nnz(b2_ctx* c, int pattern) {
 int64_t b2_pattern_sell_slots(b2_ctx* c, int pattern) {
   if (!c || pattern < 0 || pattern > 3 || !c->patterns_built || !c->pat[pattern].has_sell()) return -1;
   return c->pat[pattern].slots;
-}
-
-int64_t b2_pattern_sell_runs(b2_ctx* c, int pattern) {
-  if (!c || pattern < 0 || pattern > 3 || !c->patterns_built || !c->pat[pattern].has_sell()) return -1;
-  return c->pat[pattern].runs;
 }
 
 int b2_get_pattern(b2_ctx* c, int pattern, int32_t* indptr, int32_t* indices) {
@@ -2178,15 +2197,9 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_unroll") c->spmm_unroll = value;
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
-    else if (k == "spmm_tma") c->spmm_tma = value;
-    else if (k == "spmm_sm") c->spmm_sm = value;
-    else if (k == "spmm_comp") c->spmm_comp = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
-    else if (k == "assemble_rows") c->assemble_rows = value;
     else if (k == "graphs") c->use_graphs = value;
-    else if (k == "mg_fused") c->mg_fused = value;
     else if (k == "combine") c->combine_variant = value;
-    else if (k == "spmm_block") c->spmm_block = 256;  // only the 256-thread shape is built
     else throw B2Error(-2, "unknown tuning key " + k);
   });
 }

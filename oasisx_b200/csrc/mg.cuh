@@ -40,77 +40,6 @@ __global__ void k_mg_first(int64_t n, const double* __restrict__ dinv, const dou
     x[i] = omega * dinv[i] * b[i];
 }
 
-// ---- fused cycle kernels (tuning "mg_fused", OFF by default: a measured negative result) -------------------------
-// Measured at 48^3 (tools/exp_mg_fused.py): same fields to 1e-13, same 9 iterations, but the pressure stage takes
-// 1.27 ms instead of 1.01 ms -- re-evaluating the prolongation at each of the ~15 gathered columns costs more inside
-// the kernel than the two saved launches (already cheap inside the CUDA graph) return.
-// A V(1,1) cycle spends 5 launches per level (first sweep, residual, restriction, prolongation, post-sweep); on levels
-// of 10^4..10^6 unknowns each is a few microseconds of work behind a launch.  Two pairs fuse without changing a bit of
-// the result, because the first sweep from zero is local (x = omega D^-1 b) and a nested P1 prolongation has at most
-// d+1 entries per row, so both can be RE-EVALUATED at the gathered columns instead of read from a finished vector:
-//   k_mg_first_resid:    x = omega D^-1 b  and  r = b - A x          (replaces k_mg_first + k_mg_sweep<true>)
-//   k_mg_prolong_sweep:  out = xp + omega D^-1 (b - A xp),  xp = x + P xc   (replaces the prolongation + k_mg_sweep<false>)
-// Both need D^-1, b resp. P for every COLUMN of the operator, i.e. replicated levels or a single-rank fine level.
-__global__ void __launch_bounds__(256)
-k_mg_first_resid(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
-                 const double* __restrict__ vals, const double* __restrict__ dinv, const double* __restrict__ b,
-                 double omega, double* __restrict__ x, double* __restrict__ r) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_slices = (n_rows + 31) >> 5;
-  for (int s = warp; s < n_slices; s += nwarps) {
-    const int base = __ldg(slice_ptr + s);
-    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
-    const int row = (s << 5) + lane;
-    double acc = 0.0;
-#pragma unroll 4
-    for (int t = 0; t < len; ++t) {
-      const int c = ld_stream(cols + base + lane + (t << 5));
-      acc = fma(ld_stream(vals + base + lane + (t << 5)), omega * __ldg(dinv + c) * __ldg(b + c), acc);
-    }
-    if (row < n_rows) {
-      x[row] = omega * dinv[row] * b[row];
-      r[row] = b[row] - acc;
-    }
-  }
-}
-
-__device__ __forceinline__ double mg_prolonged(const double* __restrict__ x, const int* __restrict__ Pptr,
-                                               const int* __restrict__ Pcol, const double* __restrict__ Pval,
-                                               const double* __restrict__ xc, int i) {
-  double v = __ldg(x + i);
-  for (int p = __ldg(Pptr + i); p < __ldg(Pptr + i + 1); ++p) v = fma(__ldg(Pval + p), __ldg(xc + __ldg(Pcol + p)), v);
-  return v;
-}
-
-__global__ void __launch_bounds__(256)
-k_mg_prolong_sweep(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
-                   const double* __restrict__ vals, const double* __restrict__ dinv, const double* __restrict__ b,
-                   const double* __restrict__ x, const int* __restrict__ Pptr, const int* __restrict__ Pcol,
-                   const double* __restrict__ Pval, const double* __restrict__ xc, double omega,
-                   double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_slices = (n_rows + 31) >> 5;
-  for (int s = warp; s < n_slices; s += nwarps) {
-    const int base = __ldg(slice_ptr + s);
-    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
-    const int row = (s << 5) + lane;
-    double acc = 0.0;
-    for (int t = 0; t < len; ++t) {
-      const int c = ld_stream(cols + base + lane + (t << 5));
-      const double a = ld_stream(vals + base + lane + (t << 5));
-      if (a != 0.0) acc = fma(a, mg_prolonged(x, Pptr, Pcol, Pval, xc, c), acc);  // pads: (col = row, val = 0)
-    }
-    if (row < n_rows) {
-      const double xp = mg_prolonged(x, Pptr, Pcol, Pval, xc, row);
-      out[row] = fma(omega * dinv[row], b[row] - acc, xp);
-    }
-  }
-}
-
 // ---- the small end of the hierarchy in one kernel ------------------------------------------------
 // Levels with a few thousand unknowns are pure launch latency when every sweep is its own kernel
 // (~60 launches per cycle).  One 1024-thread block runs the whole sub-cycle from level l0 down to the
@@ -296,12 +225,22 @@ __device__ inline void cgz_finalize(int fin, KryState* st, const double* t) {
 
 template <int N>
 __device__ __forceinline__ void cgz_reduce_finish(double (&v)[N], double* partials, unsigned* counter, int fin,
-                                                  KryState* st, double* red_out) {
+                                                  KryState* st, RedCtl red_out) {
   double total[N];
-  if (grid_reduce<N>(v, partials, counter, total) && threadIdx.x == 0) {
-    if (red_out != nullptr) {
+  if (!grid_reduce<N>(v, partials, counter, total)) return;
+  if (red_out.peer != nullptr) {
+    __shared__ double sh[N];
+    if (threadIdx.x == 0) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) red_out[i] = total[i];
+      for (int i = 0; i < N; ++i) sh[i] = total[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) peer_allreduce_warp(red_out.peer, sh, N);
+    if (threadIdx.x == 0) cgz_finalize(fin, st, sh);
+  } else if (threadIdx.x == 0) {
+    if (red_out.out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) red_out.out[i] = total[i];
     } else {
       cgz_finalize(fin, st, total);
     }
@@ -313,7 +252,7 @@ __global__ void k_cgz_finalize(int fin, KryState* st, const double* __restrict__
 // r = b - q (or r = b, x = 0); sums bb, rr
 __global__ void __launch_bounds__(256)
 k_cgz_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ x,
-           double* __restrict__ r, KryState* st, double* partials, unsigned* counter, double* red_out) {
+           double* __restrict__ r, KryState* st, double* partials, unsigned* counter, RedCtl red_out) {
   double s[2] = {0.0, 0.0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double bv = b[i];
@@ -330,7 +269,7 @@ k_cgz_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q
 // sum r.z -> rz (first: beta = 0) / beta = rz'/rz
 __global__ void __launch_bounds__(256)
 k_cgz_rz(int64_t n, const double* __restrict__ r, const double* __restrict__ z, int fin, KryState* st,
-         double* partials, unsigned* counter, double* red_out) {
+         double* partials, unsigned* counter, RedCtl red_out) {
   double s[1] = {0.0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     s[0] = fma(r[i], z[i], s[0]);
@@ -347,7 +286,7 @@ __global__ void k_cgz_p(int64_t n, const double* __restrict__ z, double* __restr
 // x += alpha p ; r -= alpha q ; sum rr
 __global__ void __launch_bounds__(256)
 k_cgz_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
-             double* __restrict__ r, KryState* st, double* partials, unsigned* counter, double* red_out) {
+             double* __restrict__ r, KryState* st, double* partials, unsigned* counter, RedCtl red_out) {
   if (st->done) return;
   const double alpha = st->alpha[0];
   double s[1] = {0.0};

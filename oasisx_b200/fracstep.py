@@ -164,6 +164,9 @@ class FractionalStep_AB_CN:
             _part.check_halo_counts(comm, lp.Q.halo, "Q")
             ctx.set_halo(L.SPACE_V, lp.V.halo)
             ctx.set_halo(L.SPACE_Q, lp.Q.halo)
+            # halo + dot-product all-reduce through peer-mapped memory (NVLink) instead of NCCL calls, if every rank
+            # can map every other rank's arena; otherwise all of them keep the NCCL path
+            self._peer = ctx.peer_setup(comm, 0)
             self._nV_owned, self._nQ_owned = lp.V.n_owned, lp.Q.n_owned
         else:
             self._ctx = ctx = L.Context(device=device)
@@ -224,6 +227,8 @@ class FractionalStep_AB_CN:
             )
             if self._mg_levels == 0:
                 logger.warning("pc_type=mg requested but the mesh carries no nested hierarchy: using Jacobi")
+            elif self._nranks > 1 and ctx.peer_enabled():
+                ctx.peer_setup(comm, 1)  # staging of the replicated level-1 right-hand side
 
         # matrices visible to callers (test/test_tentative_velocity.py:175)
         # (owned rows, local columns = owned + ghosts), like the local part of a PETSc MPIAIJ matrix

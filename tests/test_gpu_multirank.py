@@ -17,14 +17,25 @@ def _ngpu():
     return _lib.load_library().b2_device_count()
 
 
-@pytest.mark.parametrize("nranks,mode", [(2, "lu"), (2, "krylov"), (2, "mg"), (2, "bench"), (2, "pbc"), (4, "krylov")])
-def test_multirank_matches_oracle(nranks, mode):
+CASES = [
+    # ranks, mode, mesh, steps, B200_PEER
+    (2, "lu", 8, 3, "1"), (2, "krylov", 8, 3, "1"), (2, "mg", 8, 3, "1"), (2, "bench", 8, 7, "1"), (2, "pbc", 8, 3, "1"),
+    (2, "bench", 8, 7, "0"),   # the NCCL path (peer memory switched off) must stay correct: it is the fallback
+    (2, "bench", 16, 5, "1"),  # >= 16^3 against the CPU port, rotated field (three live components)
+    (4, "krylov", 8, 3, "1"), (4, "bench", 16, 5, "1"), (4, "bench", 16, 5, "0"),
+    (8, "bench", 16, 5, "1"),
+]
+
+
+@pytest.mark.parametrize("nranks,mode,mesh,steps,peer", CASES)
+def test_multirank_matches_oracle(nranks, mode, mesh, steps, peer):
     if _ngpu() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    port = 29700 + nranks * 10 + {"lu": 0, "krylov": 1, "mg": 2, "bench": 3, "pbc": 4}[mode]
-    steps = "7" if mode == "bench" else "3"  # long enough for the three-deep solution histories to be in use
+    port = 29700 + nranks * 20 + CASES.index((nranks, mode, mesh, steps, peer))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mr_worker.py"), "8", steps, mode]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mr_worker.py"), str(mesh), str(steps), mode]
+    env = dict(os.environ, B200_PEER=peer)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("MR_OK") == nranks
+    print(res.stdout[-1500:])

@@ -116,7 +116,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.b2_abi_version() == 1
-    assert ctypes.sizeof(_lib.Stats) == 8 * 4 + 8 + 5 * 8 + 16 + 16 + 24
+    assert ctypes.sizeof(_lib.Stats) == 8 * 4 + 8 + 5 * 8 + 16 + 16 + 24 + 8
 
 
 def test_no_gpu_fails_loudly(lib):
