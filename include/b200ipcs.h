@@ -242,6 +242,10 @@ int b2_l2_error_quadrature(b2_ctx* ctx, int vec, int64_t n_cells, int n_q, const
                            const double* weights, const double* exact, double* out);
 
 /* ---- measurement ---------------------------------------------------------------------- */
+/* Brick plan of assemble_first (k_first_cells): out[8] = bricks, interior rows, interface rows, shared-memory
+ * accumulator doubles, most interior rows of a brick, nonzeros of the interface rows, shared-memory bytes per block,
+ * cubes per brick edge (b2_set_tuning "first_bricks"; 0 = no bricks). */
+int b2_first_plan_info(b2_ctx* ctx, int64_t* out);
 int b2_get_stats(b2_ctx* ctx, b2_stats* out);
 /* Times `reps` launches of one hot kernel on the context's stream with CUDA events (device
  * resident operands).  kernel: 0 = SpMM A*u (gdim RHS), 1 = convection assembly + fused combine,

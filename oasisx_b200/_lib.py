@@ -26,7 +26,7 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
+    "b2_first_plan_info", "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
     "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
         "b2_set_mesh": (i32, [vp, i32, i64, vp, i64, vp]),
         "b2_set_space": (i32, [vp, i32, i32, i64, i64, vp]),
         "b2_set_halo": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "b2_first_plan_info": (i32, [vp, vp]),
         "b2_peer_export": (i32, [vp, i32, vp]),
         "b2_peer_import": (i32, [vp, i32, vp]),
         "b2_peer_disable": (i32, [vp]),
@@ -259,6 +260,13 @@ class Context:
             self.lib.b2_peer_disable(self._h)
         comm.Barrier()
         return agreed
+
+    def first_plan_info(self) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.b2_first_plan_info(self._h, _ptr(out)), "b2_first_plan_info")
+        keys = ("bricks", "interior_rows", "interface_rows", "acc_doubles", "max_rows_per_brick", "nnz_interface", "smem_bytes",
+                "cubes_per_brick_edge")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def peer_enabled(self) -> bool:
         return bool(self.lib.b2_peer_enabled(self._h))

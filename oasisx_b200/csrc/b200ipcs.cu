@@ -146,6 +146,14 @@ struct PeerBlob {
 };
 static_assert(sizeof(PeerBlob) == B2_PEER_BLOB_BYTES, "PeerBlob size");
 
+struct FirstPlanHost {
+  DBuf<int> brick_cell_ptr, cell_order, brick_row_ptr, brick_rows, brow_off, row_lidx, iface_rows;
+  int n_bricks = 0, n_iface = 0, n_interior = 0, acc_cap = 0, max_rows = 0;
+  int64_t nnz_iface = 0;
+  size_t smem_bytes = 0;
+  bool ready = false;
+};
+
 struct DVec {
   DBuf<double> buf;
   int K = 1;
@@ -208,6 +216,8 @@ struct b2_ctx {
   DBuf<uint8_t> is_bc_row_v, is_bc_q;
   DBuf<uint8_t> pos8;  // per-cell scatter table of the convection assembly (elem.cuh)
   int maxlen_vv = 0;        // longest row of the P2xP2 pattern
+  FirstPlanHost first;      // brick plan of assemble_first (build_first_plan)
+  int first_bricks = 4;     // tuning "first_bricks": cubes per brick edge (0: no bricks, every row through global reductions)
   // CUDA graph of one multigrid-preconditioned CG iteration of the pressure solve (single rank): ~21 dependent
   // launches of a few microseconds each become one graph launch
   cudaGraphExec_t pcg_graph = nullptr;
@@ -216,7 +226,6 @@ struct b2_ctx {
   const double* pcg_graph_b = nullptr;
   int pcg_graph_launches = 0;
   int use_graphs = 1;  // tuning "graphs"
-  int combine_variant = 2;  // tuning "combine": launch shape of k_combine_first (2: unroll 8, 64 registers, 4 blocks per SM)
   DBuf<int> pbc_dofs;
   bool has_pbc = false;
   double vol = 0.0;  // sum of mQ over all ranks
@@ -448,49 +457,50 @@ inline RedCtl red_ptr(b2_ctx* c) {
 
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                   KryState* st, int fin) {
+                   KryState* st, int fin, const double* rscale) {
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
   if (c->spmm_stream)
     B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
-              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
+              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
   else
     B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, false>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
-              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c));
+              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
 template <int K, int DOT>
 void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                   KryState* st, int fin) {
+                   KryState* st, int fin, const double* rscale) {
   if (c->spmm_mode != 0) {  // diagnostic halves of the kernel (tools/sweep_spmm.py)
     int grid = pgrid(c, (int64_t)pat.n_rows, 256, 8);
     if (c->spmm_mode == 1) B2_LAUNCH(c, (k_spmm_diag<K, 1>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     return;
   }
-  if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin);
-  else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin);
+  if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
 }
 
 template <int K>
 void launch_spmm_k(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                   KryState* st, int fin, int dot) {
-  if (dot == 0) launch_spmm_t<K, 0>(c, pat, vals, x, ld, y, w, st, fin);
-  else if (dot == 1) launch_spmm_t<K, 1>(c, pat, vals, x, ld, y, w, st, fin);
-  else launch_spmm_t<K, 2>(c, pat, vals, x, ld, y, w, st, fin);
+                   KryState* st, int fin, int dot, const double* rscale) {
+  if (dot == 0) launch_spmm_t<K, 0>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  else if (dot == 1) launch_spmm_t<K, 1>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  else launch_spmm_t<K, 2>(c, pat, vals, x, ld, y, w, st, fin, rscale);
 }
 
+// rscale: optional row scaling of the result, y = diag(rscale) (A x)
 void spmm(b2_ctx* c, const CSR& pat, const double* vals, int K, double* x, double* y, const double* w = nullptr,
-          KryState* st = nullptr, int fin = FIN_NONE, int dot = 0, int xspace = -1) {
+          KryState* st = nullptr, int fin = FIN_NONE, int dot = 0, int xspace = -1, const double* rscale = nullptr) {
   B2_REQUIRE(pat.has_sell(), "SpMM needs the SELL layout of the pattern");
   if (xspace >= 0) halo_forward(c, xspace, x, K);
   const int ld = pat.n_cols;  // square operators: vectors of the space, owned + ghosts
   switch (K) {
-    case 1: launch_spmm_k<1>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
-    case 2: launch_spmm_k<2>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
-    case 3: launch_spmm_k<3>(c, pat, vals, x, ld, y, w, st, fin, dot); break;
+    case 1: launch_spmm_k<1>(c, pat, vals, x, ld, y, w, st, fin, dot, rscale); break;
+    case 2: launch_spmm_k<2>(c, pat, vals, x, ld, y, w, st, fin, dot, rscale); break;
+    case 3: launch_spmm_k<3>(c, pat, vals, x, ld, y, w, st, fin, dot, rscale); break;
     default: throw B2Error(-3, "K must be 1..3");
   }
 }
@@ -510,9 +520,9 @@ void krylov_iterations(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double
       reduce_finish_host(c, FIN_CG_UPDATE, 2 * K);
       B2_LAUNCH(c, k_cg_p<K>, g, 256, n, ld, r, dinv, p, st);
     } else {
-      spmm(c, pat, vals, K, p, q, rhat, st, FIN_BCGS_V, 1, space);                // v = A p
+      spmm(c, pat, vals, K, p, q, rhat, st, FIN_BCGS_V, 1, space, dinv);          // v = D^-1 A p
       B2_LAUNCH(c, k_bcgs_s<K>, g, 256, n, ld, q, r, st);                            // s = r - alpha v
-      spmm(c, pat, vals, K, r, t, r, st, FIN_BCGS_T, 2, space);                   // t = A s
+      spmm(c, pat, vals, K, r, t, r, st, FIN_BCGS_T, 2, space, dinv);             // t = D^-1 A s
       B2_LAUNCH(c, k_bcgs_update<K>, g, 256, n, ld, p, t, rhat, x, r, st, c->partials.p, c->d_counter, red_ptr(c));
       reduce_finish_host(c, FIN_BCGS_UPDATE, 2 * K);
       B2_LAUNCH(c, k_bcgs_p<K>, g, 256, n, ld, r, q, p, rhat, st);
@@ -528,7 +538,7 @@ void krylov_init(b2_ctx* c, const KSPOpts& o, const CSR& pat, const double* vals
   const int g = pgrid(c, n, 256, 8);
   const double* q0 = nullptr;
   if (o.nonzero_guess) {
-    spmm(c, pat, vals, K, x, q, nullptr, nullptr, FIN_NONE, 0, space);
+    spmm(c, pat, vals, K, x, q, nullptr, nullptr, FIN_NONE, 0, space, o.type == 1 ? dinv : nullptr);
     q0 = q;
   }
   if (o.type == 0) {
@@ -552,9 +562,10 @@ void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, cons
     return;
   }
   DBuf<double>* w = space == B2_SPACE_V ? c->wv : c->wq;
-  // CG: Jacobi through dinv in the vector kernels.  BiCGStab: the operator is already row-scaled
-  // (k_combine_first), dinv only scales the right-hand side in k_bcgs_init.
-  const double* dinv = (o.pc != 1 || o.type == 1) ? dinv_jacobi : (space == B2_SPACE_V ? c->onesV.p : c->onesQ.p);
+  // CG: Jacobi through dinv in the vector kernels.  BiCGStab: left preconditioning D^-1 A x = D^-1 b -- dinv scales
+  // the right-hand side in k_bcgs_init and every operator application in the SpMM epilogue (the matrix is stored as
+  // assembled).  pc_type none: dinv = 1.
+  const double* dinv = (o.pc != 1) ? dinv_jacobi : (space == B2_SPACE_V ? c->onesV.p : c->onesQ.p);
   double *r = w[0].p, *p = w[1].p, *q = w[2].p, *t = nullptr, *rhat = nullptr;
   if (o.type == 1) {
     B2_REQUIRE(space == B2_SPACE_V, "BiCGStab work vectors exist for the velocity space only");
@@ -898,6 +909,187 @@ void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, c
 
 void require_ready(b2_ctx* c) { B2_REQUIRE(c->preassembled, "b2_preassemble has not been called"); }
 
+// ---- brick plan of the cell-parallel assemble_first (elem.cuh: k_first_cells) ---------------------------------
+// Cells are binned into spatial bricks by their centroids (no lattice assumed: the brick edge comes from the mean
+// cell volume), rows whose cells all lie in one brick become that brick's interior rows as long as their
+// accumulators fit the shared memory of a block; everything else is an interface row.
+void build_first_plan(b2_ctx* c) {
+  const Space& V = c->sp[B2_SPACE_V];
+  const CSR& vv = c->pat[B2_PAT_VV];
+  const int d = c->gdim, nv = V.nd;
+  const int64_t nc = c->n_cells;
+  const int n_rows = vv.n_rows;
+  FirstPlanHost& P = c->first;
+  P = FirstPlanHost();
+  if (nc == 0 || n_rows == 0 || c->first_bricks == 0) return;
+  std::vector<double> x((size_t)c->n_nodes * 3);
+  std::vector<int> cn((size_t)nc * (d + 1)), cd((size_t)nc * nv), rowptr((size_t)n_rows + 1);
+  B2_CUDA(cudaMemcpyAsync(x.data(), c->x.p, sizeof(double) * x.size(), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(cn.data(), c->cell_nodes.p, sizeof(int) * cn.size(), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(cd.data(), V.cell_dofs.p, sizeof(int) * cd.size(), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaMemcpyAsync(rowptr.data(), vv.rowptr.p, sizeof(int) * rowptr.size(), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  // centroids, bounding box, mean cell measure
+  std::vector<double> cen((size_t)nc * 3, 0.0);
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, meas = 0.0;
+  for (int64_t e = 0; e < nc; ++e) {
+    double X[4][3];
+    for (int v = 0; v <= d; ++v)
+      for (int k = 0; k < 3; ++k) X[v][k] = x[3 * (size_t)cn[e * (d + 1) + v] + k];
+    for (int k = 0; k < d; ++k) {
+      double s = 0;
+      for (int v = 0; v <= d; ++v) s += X[v][k];
+      cen[3 * e + k] = s / (d + 1);
+      lo[k] = std::min(lo[k], cen[3 * e + k]);
+      hi[k] = std::max(hi[k], cen[3 * e + k]);
+    }
+    double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int k = 0; k < d; ++k)
+      for (int dl = 0; dl < d; ++dl) J[k][dl] = X[dl + 1][k] - X[0][k];
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    meas += std::fabs(det) / (d == 3 ? 6.0 : 2.0);
+  }
+  meas /= (double)nc;
+  // brick edge: `first_bricks` cubes of (d! cells) per direction; box meshes get bricks aligned with their cubes
+  const double cube = d == 3 ? std::cbrt(6.0 * meas) : std::sqrt(2.0 * meas);
+  const double L = cube * c->first_bricks;
+  double org[3];
+  int nb[3] = {1, 1, 1};
+  for (int k = 0; k < d; ++k) {
+    org[k] = lo[k] - (d == 3 ? 0.25 : 1.0 / 3.0) * cube - 1e-9 * cube;  // centroids sit >= cube/4 inside their cube
+    nb[k] = std::max(1, (int)std::ceil((hi[k] - org[k]) / L + 1e-9));
+  }
+  std::vector<int> brick((size_t)nc);
+  for (int64_t e = 0; e < nc; ++e) {
+    int id = 0;
+    for (int k = d - 1; k >= 0; --k) {
+      int q = std::min(nb[k] - 1, std::max(0, (int)std::floor((cen[3 * e + k] - org[k]) / L)));
+      id = id * nb[k] + q;
+    }
+    brick[e] = id;
+  }
+  const int n_bricks_all = nb[0] * nb[1] * nb[2];
+  // cells sorted by brick (counting sort, stable)
+  std::vector<int> cptr((size_t)n_bricks_all + 1, 0);
+  for (int64_t e = 0; e < nc; ++e) cptr[brick[e] + 1]++;
+  for (int b = 0; b < n_bricks_all; ++b) cptr[b + 1] += cptr[b];
+  std::vector<int> order((size_t)nc), fill(cptr.begin(), cptr.end() - 1);
+  for (int64_t e = 0; e < nc; ++e) order[fill[brick[e]]++] = (int)e;
+  // rows: interior iff all adjacent cells share one brick
+  std::vector<int> rmin((size_t)n_rows, INT32_MAX), rmax((size_t)n_rows, -1);
+  for (int64_t e = 0; e < nc; ++e)
+    for (int i = 0; i < nv; ++i) {
+      const int r = cd[e * nv + i];
+      if (r < n_rows) { rmin[r] = std::min(rmin[r], brick[e]); rmax[r] = std::max(rmax[r], brick[e]); }
+    }
+  // interior rows per brick (increasing row id), capped by the shared-memory budget
+  int dev_smem = 0;
+  B2_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  const int K = d;
+  const int budget = std::min(dev_smem - 2048, 110 * 1024);  // two blocks per SM
+  std::vector<int> rcnt((size_t)n_bricks_all + 1, 0);
+  for (int r = 0; r < n_rows; ++r)
+    if (rmax[r] >= 0 && rmin[r] == rmax[r]) rcnt[rmin[r] + 1]++;
+  for (int b = 0; b < n_bricks_all; ++b) rcnt[b + 1] += rcnt[b];
+  std::vector<int> brows((size_t)rcnt[n_bricks_all]), rfill(rcnt.begin(), rcnt.end() - 1);
+  for (int r = 0; r < n_rows; ++r)
+    if (rmax[r] >= 0 && rmin[r] == rmax[r]) brows[rfill[rmin[r]]++] = r;
+  std::vector<int> h_cptr, h_rptr, h_rows, h_off, lidx((size_t)n_rows, -1), iface;
+  h_cptr.push_back(0);
+  h_rptr.push_back(0);
+  std::vector<int> h_order;
+  h_order.reserve((size_t)nc);
+  int acc_cap = 0, max_rows = 0;
+  for (int b = 0; b < n_bricks_all; ++b) {
+    if (cptr[b + 1] == cptr[b]) continue;
+    int off = 0, cnt = 0;
+    for (int q = rcnt[b]; q < rcnt[b + 1]; ++q) {
+      const int r = brows[q], len = rowptr[r + 1] - rowptr[r];
+      if ((size_t)(off + len) * 8 + (size_t)(cnt + 1) * K * 8 > (size_t)budget) break;  // the rest stays interface
+      lidx[r] = (int)h_rows.size();
+      h_rows.push_back(r);
+      h_off.push_back(off);
+      off += len;
+      ++cnt;
+    }
+    acc_cap = std::max(acc_cap, off);
+    max_rows = std::max(max_rows, cnt);
+    for (int q = cptr[b]; q < cptr[b + 1]; ++q) h_order.push_back(order[q]);
+    h_cptr.push_back((int)h_order.size());
+    h_rptr.push_back((int)h_rows.size());
+  }
+  for (int r = 0; r < n_rows; ++r)
+    if (lidx[r] < 0) iface.push_back(r);
+  auto up = [&](DBuf<int>& dst, const std::vector<int>& v) {
+    dst.alloc((int64_t)std::max<size_t>(v.size(), 1));
+    if (!v.empty()) B2_CUDA(cudaMemcpyAsync(dst.p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, c->stream));
+  };
+  up(P.brick_cell_ptr, h_cptr);
+  up(P.cell_order, h_order);
+  up(P.brick_row_ptr, h_rptr);
+  up(P.brick_rows, h_rows);
+  up(P.brow_off, h_off);
+  up(P.row_lidx, lidx);
+  up(P.iface_rows, iface);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  P.n_bricks = (int)h_cptr.size() - 1;
+  P.n_iface = (int)iface.size();
+  P.n_interior = (int)h_rows.size();
+  P.acc_cap = acc_cap;
+  P.max_rows = max_rows;
+  int64_t nnz_if = 0;
+  for (int r : iface) nnz_if += rowptr[r + 1] - rowptr[r];
+  P.nnz_iface = nnz_if;
+  P.smem_bytes = (size_t)(acc_cap + max_rows * K) * sizeof(double);
+  P.ready = true;
+}
+
+// mode & 1: matrix A (as assembled, Dirichlet rows -> identity) + dinv;  mode & 2: b_first = R u1 + b0 (+ p_surf)
+void first_cells(b2_ctx* c, int mode, double dt, double nu, const double* u1, const double* uab, const double* b0,
+                 const double* psurf, double* A, double* bfirst, double* dinv) {
+  const int K = c->gdim;
+  const Space& V = c->sp[B2_SPACE_V];
+  const CSR& vv = c->pat[B2_PAT_VV];
+  const int ld = (int)V.n_local();
+  B2_REQUIRE(c->pos8.p != nullptr, "assemble_first needs the scatter table (rows shorter than 256 entries)");
+  FirstPlanHost& P = c->first;
+  const bool bricks = P.ready && P.n_bricks > 0;
+  const int scale = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
+  const int n_if = bricks ? P.n_iface : vv.n_rows;
+  const int* if_rows = bricks ? P.iface_rows.p : nullptr;
+  const int do_mat = mode & 1, do_vec = (mode & 2) ? 1 : 0;
+  if (n_if > 0) {
+    if (K == 2) B2_LAUNCH(c, k_first_init<2>, blocks_for(n_if, 256), 256, n_if, if_rows, vv.rowptr.p, vv.slice_ptr.p, ld, b0, psurf, do_mat, do_vec, A, bfirst);
+    else B2_LAUNCH(c, k_first_init<3>, blocks_for(n_if, 256), 256, n_if, if_rows, vv.rowptr.p, vv.slice_ptr.p, ld, b0, psurf, do_mat, do_vec, A, bfirst);
+  }
+  FirstPlan plan{};
+  size_t smem = 0;
+  int grid = blocks_for(c->n_cells, 192);
+  if (bricks) {
+    plan = FirstPlan{P.n_bricks, P.brick_cell_ptr.p, P.cell_order.p, P.brick_row_ptr.p, P.brick_rows.p, P.brow_off.p,
+                     P.row_lidx.p, P.acc_cap, P.max_rows};
+    smem = P.smem_bytes;
+    grid = P.n_bricks;
+  }
+  dispatch_elem(c, [&](auto e) {
+    using E = decltype(e);
+    auto launch = [&](auto kern) {
+      if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 192, smem, c->stream>>>(plan, c->n_cells, c->x.p, c->cell_nodes.p, V.cell_dofs.p, (int)V.n_owned, uab, u1, ld,
+                                          vv.rowptr.p, vv.slice_ptr.p, vv.diag_t.p, c->pos8.p, c->is_bc_row_v.p, 1.0 / dt,
+                                          0.5 * nu, scale, b0, psurf, A, bfirst, dinv);
+      c->stats.kernel_launches++;
+      B2_CUDA(cudaGetLastError());
+    };
+    if (mode == 3) launch(k_first_cells<E::D, E::DEG, 3>);
+    else if (mode == 1) launch(k_first_cells<E::D, E::DEG, 1>);
+    else launch(k_first_cells<E::D, E::DEG, 2>);
+  });
+  if (do_mat && n_if > 0)
+    B2_LAUNCH(c, k_first_finalize, blocks_for(n_if, 256), 256, n_if, if_rows, vv.slice_ptr.p, vv.diag_t.p, c->is_bc_row_v.p, scale, A, dinv);
+}
+
 // ---- stages ---------------------------------------------------------------------------------
 void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   require_ready(c);
@@ -910,32 +1102,8 @@ void stage_assemble_first(b2_ctx* c, double dt, double nu) {
   halo_forward(c, B2_SPACE_V, u2, K);
   const int64_t nl = V.n_local() * K;
   B2_LAUNCH(c, k_lincomb2, pgrid(c, nl), 256, nl, 1.5, u1, -0.5, u2, uab);  // :432-434
-  c->A.zero(c->stream);                                                   // :435
-  dispatch_elem(c, [&](auto e) {
-    using E = decltype(e);
-    B2_LAUNCH(c, (k_convection<E::D, E::DEG>), blocks_for(c->n_cells, 128), 128, c->n_cells, c->x.p, c->cell_nodes.p,
-              V.cell_dofs.p, (int)V.n_owned, uab, ld, vv.rowptr.p, vv.cols.p, vv.slice_ptr.p, c->pos8.p, c->A.p);
-  });
   const double* psurf = c->vecs.count(B2_VEC_PSURF) ? c->vec(B2_VEC_PSURF) : nullptr;
-  const int scale = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
-  auto comb = [&](auto kc) {
-    constexpr int KK = decltype(kc)::value;
-    // tuning "combine": (unroll, resident blocks the registers are bounded for, blocks per SM launched)
-#define B2_COMBINE(U, MB, PER_SM)                                                                                          \
-    B2_LAUNCH(c, (k_combine_first<KK, U, MB>), pgrid(c, vv.n_rows, 256, PER_SM), 256, vv.n_rows, vv.slice_ptr.p, vv.scols.p, \
-              vv.diag_t.p, c->A.p, c->M.p, c->Kst.p, vv.order.p, 1.0 / dt, 0.5 * nu, u1, ld, c->vec(B2_VEC_B0), psurf,     \
-              c->is_bc_row_v.p, scale, c->vec(B2_VEC_BFIRST), c->dinvA.p)
-    switch (c->combine_variant) {
-      case 1: B2_COMBINE(4, 5, 5); break;
-      case 2: B2_COMBINE(8, 4, 4); break;
-      case 3: B2_COMBINE(8, 3, 3); break;
-      case 4: B2_COMBINE(8, 4, 8); break;
-      default: B2_COMBINE(4, 5, 8); break;  // the shape measured so far (48 registers: 5 blocks resident of 8 launched)
-    }
-#undef B2_COMBINE
-  };
-  if (K == 2) comb(std::integral_constant<int, 2>{});
-  else comb(std::integral_constant<int, 3>{});
+  first_cells(c, 3, dt, nu, u1, uab, c->vec(B2_VEC_B0), psurf, c->A.p, c->vec(B2_VEC_BFIRST), c->dinvA.p);
   c->last_dt = dt;
   c->fresh_step = true;
 }
@@ -1333,6 +1501,7 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
       });
     }
   }
+  build_first_plan(c);
   // Dirichlet masks
   c->is_bc_row_v.alloc(V.n_local()); c->is_bc_row_v.zero(c->stream);
   c->is_bc_q.alloc(Q.n_local()); c->is_bc_q.zero(c->stream);
@@ -1961,7 +2130,7 @@ void csr_values(b2_ctx* c, int mat, int comp, DBuf<double>& out, const CSR** pat
   if (stride == 1) {
     B2_REQUIRE(pat->has_sell(), "square operator without SELL layout");
     B2_LAUNCH(c, k_sell_convert, blocks_for(pat->n_rows, 256), 256, pat->n_rows, pat->rowptr.p, pat->slice_ptr.p, 0, v->p,
-              out.p, mat == B2_MAT_A ? c->dinvA.p : (const double*)nullptr);
+              out.p, (const double*)nullptr);
   } else {
     B2_REQUIRE(comp >= 0 && comp < stride, "bad component");
     B2_LAUNCH(c, k_extract, pgrid(c, pat->nnz), 256, pat->nnz, stride, comp, v->p, out.p);
@@ -2181,6 +2350,20 @@ int b2_l2_error_quadrature(b2_ctx* c, int vec, int64_t n_cells, int n_q, const d
   });
 }
 
+int b2_first_plan_info(b2_ctx* c, int64_t* out) {
+  return guarded(c, [&] {
+    const FirstPlanHost& P = c->first;
+    out[0] = P.ready ? P.n_bricks : 0;
+    out[1] = P.n_interior;
+    out[2] = P.ready ? P.n_iface : c->pat[B2_PAT_VV].n_rows;
+    out[3] = P.acc_cap;
+    out[4] = P.max_rows;
+    out[5] = P.ready ? P.nnz_iface : c->pat[B2_PAT_VV].nnz;
+    out[6] = (int64_t)P.smem_bytes;
+    out[7] = c->first_bricks;
+  });
+}
+
 int b2_get_stats(b2_ctx* c, b2_stats* out) {
   return guarded(c, [&] { *out = c->stats; });
 }
@@ -2199,7 +2382,10 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
-    else if (k == "combine") c->combine_variant = value;
+    else if (k == "first_bricks") {
+      c->first_bricks = std::max(0, value);
+      if (c->preassembled) build_first_plan(c);
+    }
     else throw B2Error(-2, "unknown tuning key " + k);
   });
 }
@@ -2253,10 +2439,14 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       case 0:
       case 3: *bytes_per_launch = 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc); break;  // algorithmic: K (not KP) components
       case 2: *bytes_per_launch = 12.0 * qq.nnz + 4.0 * (qq.n_rows + 1) + 8.0 * (qq.n_rows + qq.n_cols); break;
-      case 1:  // zero-fill + RMW scatter + fused combine (read C,M,K,cols; write A) + cell data + vectors
-        *bytes_per_launch = 8.0 * vv.nnz * (1 + 2 + 4) + 4.0 * vv.nnz + (double)c->n_cells * 4.0 * (V.nd + c->gdim + 1) +
-                            8.0 * 3 * c->n_nodes + 8.0 * K * nVc * 5;
+      case 1: {  // k_first_cells: A written once (interface rows: zero-fill + read-modify-write on top), cell data
+                 // (dofs, nodes, scatter table), coordinates, uab/u1 read, b0 read, b_first + dinv written, uab = 1.5 u1 - .5 u2
+        const double nvp = (V.nd + 3) / 4 * 4;
+        const double nnz_if = c->first.ready ? (double)c->first.nnz_iface : (double)vv.nnz;
+        *bytes_per_launch = 8.0 * vv.nnz + 16.0 * nnz_if + (double)c->n_cells * (4.0 * (V.nd + c->gdim + 1) + V.nd * nvp) +
+                            8.0 * 3 * c->n_nodes + 8.0 * K * nVc * (2 + 3) + 8.0 * K * nV * 2 + 8.0 * nV;
         break;
+      }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

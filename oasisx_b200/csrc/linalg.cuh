@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
        double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
-       unsigned* counter, RedCtl red_out) {
+       unsigned* counter, RedCtl red_out, const double* __restrict__ rscale) {
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -368,6 +368,11 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
     }
     if (row < n_rows) {
+      if (rscale != nullptr) {  // y = D^-1 (A x): left Jacobi preconditioning of BiCGStab with A stored as assembled
+        const double rs = __ldg(rscale + row);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] *= rs;
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
       if constexpr (DOT >= 1) {
@@ -420,91 +425,6 @@ k_spmm_diag(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict
     if (row < n_rows) {
 #pragma unroll
       for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
-    }
-  }
-}
-
-// ---- fused "matrix-vector strategy" of assemble_first (fracstep.py:438-472) ------------------
-// In:  A = C(uab) (just assembled), M, Kst, all in SELL slots.   Out, in ONE pass over the slots:
-//   b_first[row] = (M/dt - nu/2 K - 1/2 C) u1 + b0 (+ p_surf)        (:438-465)
-//   A            =  D^-1 (M/dt + nu/2 K + 1/2 C), unit rows on Dirichlet dofs (:468-472), stored
-//                   ROW-SCALED by its own diagonal D when `scale` (left Jacobi preconditioning, the
-//                   PETSc default side for BiCGStab [ext]): the Krylov kernels then need no
-//                   preconditioner at all.  b2_get_matrix_values undoes the scaling.
-//   dinv[row]    = 1 / D[row]  (1 when !scale)
-template <int K, int U = 4, int MINB = 4>
-__global__ void __launch_bounds__(256, MINB)
-k_combine_first(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
-                const int* __restrict__ diag_t, double* __restrict__ A, const double* __restrict__ M,
-                const double* __restrict__ Kst, const int* __restrict__ order, double inv_dt,
-                double half_nu, const double* __restrict__ u1, int ld, const double* __restrict__ b0,
-                const double* __restrict__ psurf, const uint8_t* __restrict__ is_bc_row, int scale,
-                double* __restrict__ bfirst, double* __restrict__ dinv) {
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int n_slices = (n_rows + 31) >> 5;
-  for (int i = blockIdx.x * wpb + wib; i < n_slices; i += gridDim.x * wpb) {
-    const int s = order != nullptr ? __ldg(order + i) : i;
-    const int base = __ldg(slice_ptr + s);
-    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
-    const int row = (s << 5) + lane;
-    const bool live = row < n_rows;
-    const bool bc = live && is_bc_row[row];
-    double invd = 1.0;
-    if (live && scale && !bc) {
-      const size_t pd = (size_t)base + ((size_t)__ldg(diag_t + row) << 5) + lane;
-      invd = 1.0 / ((inv_dt * __ldg(M + pd) + 0.5 * A[pd]) + half_nu * __ldg(Kst + pd));
-    }
-    double acc[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.0;
-    const int dt_row = live ? __ldg(diag_t + row) : -1;
-    auto body = [&](int t, int c, double mv, double kv, double av, const double (&xu)[K]) {
-      const double m = inv_dt * mv;
-      const double kk = half_nu * kv;
-      const double cv = 0.5 * av;
-      const double r = (m - cv) - kk;
-      double a = ((m + cv) + kk) * invd;
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] = fma(r, xu[k], acc[k]);
-      if (bc) a = (t == dt_row) ? 1.0 : 0.0;
-      A[(size_t)base + ((size_t)t << 5) + lane] = a;
-    };
-    int t = 0;
-    for (; t + U <= len; t += U) {  // U independent (stream -> gather) chains in flight
-      int cc[U];
-      double mv[U], kv[U], av[U], xu[U][K];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t p = (size_t)base + ((size_t)(t + u) << 5) + lane;
-        cc[u] = ld_stream(cols + p);
-        mv[u] = ld_stream(M + p);
-        kv[u] = ld_stream(Kst + p);
-        av[u] = A[p];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < K; ++k) xu[u][k] = __ldg(u1 + (size_t)k * ld + cc[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) body(t + u, cc[u], mv[u], kv[u], av[u], xu[u]);
-    }
-    for (; t < len; ++t) {
-      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
-      const int c = ld_stream(cols + p);
-      double xu[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) xu[k] = __ldg(u1 + (size_t)k * ld + c);
-      body(t, c, ld_stream(M + p), ld_stream(Kst + p), A[p], xu);
-    }
-    if (live) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        double v = acc[k] + b0[(size_t)k * ld + row];
-        if (psurf != nullptr) v += psurf[(size_t)k * ld + row];
-        bfirst[(size_t)k * ld + row] = v;
-      }
-      dinv[row] = invd;
     }
   }
 }
