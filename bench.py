@@ -283,7 +283,83 @@ def run_cavity(args):
 
 
 def run_assembly_strategies(args):
-    raise SystemExit("assembly-strategies workload: not built yet")
+    """BASELINE.json configs[1] = demo/assembly_strategies.py:56-152,221,230 on the device: P2 on the unit cube
+    30 x 25 x 23 and 50 x 40 x 45, u_1 = sin(x) cos(y), u_ab,i = x, dt = 0.5, nu = 0.3; the tentative-velocity
+    right-hand side b = (M/dt - nu/2 K - 1/2 C(u_ab)) u_1 by the matvec strategy (fused pass over the assembled value
+    arrays) and by the action strategy (matrix-free element kernel), `assert np.allclose(b, b_d)` as the reference
+    (:142), and the CPU port's timings of the reference's two blocks beside them.  One JSON line per mesh."""
+    import oasisx_b200 as oasisx
+    from oasisx_b200 import _lib as L, fem, mesh as bmesh
+
+    dt, nu, reps = 0.5, 0.3, max(args.steps, 10)
+    peak, peak_kind = measured_peaks()
+    sizes = [(30, 25, 23), (50, 40, 45)] if args.mesh <= 0 or args.mesh == 96 else [(args.mesh,) * 3]
+    u1f = lambda x: np.sin(x[0]) * np.cos(x[1])
+    uabf = lambda x: x[0].copy()
+    for shape in sizes:
+        msh = bmesh.create_unit_cube(None, *shape)
+        s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=[[], [], []], bcs_p=[],
+                                        options={"low_memory_version": True}, device=int(os.environ.get("LOCAL_RANK", "0")))
+        ctx = s._ctx
+        for i in range(3):
+            s._u1[i].interpolate(u1f)
+            s._uab[i].interpolate(uabf)
+        s._flush()
+        sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+        sampler.start()
+        r = ctx.bench_assembly_strategies(dt, nu, reps)
+        clocks = sampler.stop()
+        s._written(s._rhs1, s._b_first)
+        b = s._rhs1[0].x.array_ro().copy()
+        b_d = s._b_first[0].x.array_ro().copy()
+        ok = bool(np.allclose(b, b_d))  # the reference's own assertion (rtol 1e-5, atol 1e-8)
+        rel = float(np.abs(b - b_d).max() / np.abs(b).max())
+        cpu = None
+        if not args.no_cpu:
+            from oracle import ipcs_cpu as cpum
+
+            hi = host_info(stream=True)
+            V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+            c = cpum.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+                             Q.tabulate_dof_coordinates(), 2, bcs_u=[[(np.zeros(0, np.int32), u1f)]] * 3)
+            xV = V.tabulate_dof_coordinates().T
+            for i in range(3):
+                c.set(cpum.U1, i, u1f(xV))
+                c.set(cpum.UAB, i, uabf(xV))
+            sec, bm, ba = c.bench_strategies(0, dt, nu, 3)
+            cpu = {"kind": "port", "cores": hi["threads"], "host": hi, "unit": "ms",
+                   "ms_convection_assembly": sec[0] * 1e3, "ms_matvec": sec[1] * 1e3, "ms_action": sec[2] * 1e3,
+                   "value": sec[1] * 1e3,
+                   "sample": "oracle/ipcs_cpu.cpp: the reference's timed blocks (4 CSR passes / one cell loop), ONE scalar field, best of 3",
+                   "allclose": bool(np.allclose(bm, ba)),
+                   "gpu_vs_cpu_rel_diff": float(np.abs(b - bm).max() / np.abs(bm).max())}
+        nnz = ctx.pattern_nnz(L.PAT_VV)
+        line = {
+            "metric": "tentative-velocity RHS assembly time, P2 unit cube (demo/assembly_strategies.py)", "unit": "ms",
+            "value": r["ms_action"], "higher_is_better": False, "n_gpus": 1, "steps": reps, "warmup": 1, "ms_per_step": r["ms_action"],
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"assembly-strategies: unit cube {shape[0]}x{shape[1]}x{shape[2]}, P2, dt={dt}, nu={nu}, "
+                                   "u_1 = sin(x)cos(y), u_ab,i = x; 3 right-hand sides (the reference times one scalar field)",
+                       "cells": msh.num_cells, "dofs_P2": s._nV_owned, "nnz": nnz, "first_plan": ctx.first_plan_info(),
+                       "l2": "flush not needed at 50x40x45 (value arrays 3 x 0.3 GB); 30x25x23 (3 x 57 MB) partly fits the 126 MB L2: "
+                             "back-to-back launches see warm lines there"},
+            "strategies": {
+                "matvec": {"ms": r["ms_matvec"], "algorithmic_bytes": r["bytes_matvec"], "GBs": r["bytes_matvec"] / r["ms_matvec"] / 1e6,
+                           "frac_of_peak": r["bytes_matvec"] / r["ms_matvec"] / 1e6 / peak},
+                "action": {"ms": r["ms_action"], "algorithmic_bytes": r["bytes_action"], "GBs": r["bytes_action"] / r["ms_action"] / 1e6,
+                           "frac_of_peak": r["bytes_action"] / r["ms_action"] / 1e6 / peak,
+                           "note": "FP64-compute-bound (about 2.6 kflop per cell against 56 B): the HBM fraction is not its roofline"},
+                "convection_assembly": {"ms": r["ms_convection_assembly"], "algorithmic_bytes": r["bytes_convection_assembly"],
+                                        "GBs": r["bytes_convection_assembly"] / r["ms_convection_assembly"] / 1e6},
+                "allclose_b_matvec_b_action": ok, "max_rel_diff": rel},
+            "roofline": {"bound": "hbm", "kernel": "k_matvec_rhs<3> (fused matvec strategy)", "achieved": r["bytes_matvec"] / r["ms_matvec"] / 1e6,
+                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": r["bytes_matvec"] / r["ms_matvec"] / 1e6 / peak, "traffic": None},
+            "cpu_baseline": cpu, "gpu_launches": 3 * (reps + 1), "clocks": clocks,
+            "e2e": None,
+        }
+        print(json.dumps(line), flush=True)
+        if not ok:
+            raise SystemExit("assembly-strategies: matvec and action right-hand sides differ")
 
 
 def make_field(workload: str):

@@ -228,8 +228,23 @@ int b2_step(b2_ctx* ctx, double dt, double nu, double max_error, int max_iter, d
 int b2_assemble_pressure_surface(b2_ctx* ctx, int64_t n_facets, const int32_t* facet_cells, const int32_t* facet_local,
                                  const double* h_nodal, int accumulate);
 
-/* ---- Projector (function.py:108-133) on Q: solve MQ x = rhs ---------------------------- */
-int b2_project_q(b2_ctx* ctx, const double* rhs, double* x, int32_t* reason);
+/* ---- Projector (function.py:48-133) ------------------------------------------------------
+ * assemble_rhs (:108-119): b_k[i] = int f_k phi_i dx on the target space (B2_SPACE_V: the velocity component space,
+ * B2_SPACE_Q), n_comp <= 3 components.  The source f is either nodal values of a Lagrange function of `src_space`
+ * on the same mesh ([n_comp][n_local], component-major) -- its value (deriv < 0), its derivative along x_deriv, or,
+ * with grad = 1, the gdim derivatives of ONE scalar function as the components (grad(u), test/test_projector.py:33)
+ * -- or values sampled by the caller at the quadrature points (f_quad [cells][n_q][n_comp]; a Python callable).
+ * solve (:121-133): M x_k = b_k with the options of B2_SOLVER_PROJECTOR; x is [n_comp][n_local], ghosts refreshed. */
+int b2_project_assemble(b2_ctx* ctx, int target_space, int n_comp, int src_space, const double* src_nodal, int deriv,
+                        int grad, int n_q, const double* ref_points, const double* weights, const double* f_quad);
+int b2_project_get_rhs(b2_ctx* ctx, double* rhs);
+/* solve(assemble_rhs=False) with a right-hand side the caller kept: [n_comp][n_local] */
+int b2_project_set_rhs(b2_ctx* ctx, int target_space, int n_comp, const double* rhs);
+int b2_project_solve(b2_ctx* ctx, double* x, int32_t* reasons);
+/* KSPSolver.solve (ksp.py:71-78): Mat x = b with the options of solver slot `solver`, then scatter_forward;
+ * b and x are host vectors of the operator's space (owned + ghosts), x is the initial guess when
+ * ksp_initial_guess_nonzero is set.  Square operators only (B2_MAT_M, _K, _A, _AP, _MQ). */
+int b2_ksp_solve(b2_ctx* ctx, int solver, int mat, const double* b, double* x, int32_t* reason);
 
 /* ---- functionals (assemble_scalar, demo/taylor_green.py:204-207) ----------------------- */
 /* sum_k int (u_h,k - e_k)^2 dx where e is given nodally in a P2 (or P1 for Q) space of the same
@@ -242,6 +257,11 @@ int b2_l2_error_quadrature(b2_ctx* ctx, int vec, int64_t n_cells, int n_q, const
                            const double* weights, const double* exact, double* out);
 
 /* ---- measurement ---------------------------------------------------------------------- */
+/* demo/assembly_strategies.py:56-152 on the device: right-hand side (M/dt - nu/2 K - 1/2 C(UAB)) U1 by the
+ * "matvec strategy" (one fused pass over the three assembled value arrays, result in RHS1; reference timed block
+ * :128-133) and by the "action strategy" (matrix-free element kernel, result in BFIRST; :137-140), each averaged over
+ * `reps` launches (CUDA events).  out[6] = ms of {convection assembly, matvec, action}, then their algorithmic bytes. */
+int b2_bench_assembly_strategies(b2_ctx* ctx, double dt, double nu, int reps, double* out);
 /* Brick plan of assemble_first (k_first_cells): out[8] = bricks, interior rows, interface rows, shared-memory
  * accumulator doubles, most interior rows of a brick, nonzeros of the interface rows, shared-memory bytes per block,
  * cubes per brick edge (b2_set_tuning "first_bricks"; 0 = no bricks). */

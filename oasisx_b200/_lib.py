@@ -26,12 +26,12 @@ SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
-    "b2_first_plan_info", "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
+    "b2_first_plan_info", "b2_bench_assembly_strategies", "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
     "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
-    "b2_assemble_pressure_surface", "b2_project_q", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_assemble_pressure_surface", "b2_project_assemble", "b2_project_get_rhs", "b2_project_set_rhs", "b2_project_solve", "b2_ksp_solve", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
         "b2_set_space": (i32, [vp, i32, i32, i64, i64, vp]),
         "b2_set_halo": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "b2_first_plan_info": (i32, [vp, vp]),
+        "b2_bench_assembly_strategies": (i32, [vp, C.c_double, C.c_double, i32, vp]),
         "b2_peer_export": (i32, [vp, i32, vp]),
         "b2_peer_import": (i32, [vp, i32, vp]),
         "b2_peer_disable": (i32, [vp]),
@@ -126,7 +127,11 @@ def load_library() -> C.CDLL:
         "b2_step_begin": (i32, [vp, dbl, dbl]),
         "b2_step": (i32, [vp, dbl, dbl, dbl, i32, vp]),
         "b2_assemble_pressure_surface": (i32, [vp, i64, vp, vp, vp, i32]),
-        "b2_project_q": (i32, [vp, vp, vp, vp]),
+        "b2_project_assemble": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]),
+        "b2_project_get_rhs": (i32, [vp, vp]),
+        "b2_project_set_rhs": (i32, [vp, i32, i32, vp]),
+        "b2_project_solve": (i32, [vp, vp, vp]),
+        "b2_ksp_solve": (i32, [vp, i32, i32, vp, vp, vp]),
         "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
         "b2_l2_error_quadrature": (i32, [vp, i32, i64, i32, vp, vp, vp, vp]),
         "b2_get_stats": (i32, [vp, vp]),
@@ -204,6 +209,9 @@ class Context:
     def set_space(self, space: int, degree: int, n_owned: int, n_ghost: int, cell_dofs: np.ndarray):
         cd = _i32(cell_dofs)
         self.n[space] = n_owned + n_ghost
+        if not hasattr(self, "_space_info"):
+            self._space_info = {}
+        self._space_info[space] = (n_owned + n_ghost, int(degree))
         self._check(self.lib.b2_set_space(self._h, space, degree, n_owned, n_ghost, _ptr(cd)), "b2_set_space")
 
     def set_halo(self, space: int, plan):
@@ -260,6 +268,12 @@ class Context:
             self.lib.b2_peer_disable(self._h)
         comm.Barrier()
         return agreed
+
+    def bench_assembly_strategies(self, dt: float, nu: float, reps: int = 10) -> dict:
+        out = np.zeros(6, dtype=np.float64)
+        self._check(self.lib.b2_bench_assembly_strategies(self._h, float(dt), float(nu), int(reps), _ptr(out)), "b2_bench_assembly_strategies")
+        return {"ms_convection_assembly": out[0], "ms_matvec": out[1], "ms_action": out[2],
+                "bytes_convection_assembly": out[3], "bytes_matvec": out[4], "bytes_action": out[5]}
 
     def first_plan_info(self) -> dict:
         out = np.zeros(8, dtype=np.int64)
@@ -378,12 +392,42 @@ class Context:
         self._check(self.lib.b2_assemble_pressure_surface(self._h, fc.size, _ptr(fc), _ptr(fl), _ptr(h), int(accumulate)),
                     "b2_assemble_pressure_surface")
 
-    def project_q(self, rhs: np.ndarray):
-        rhs = _f64(rhs)
-        x = np.empty_like(rhs)
+    def project_assemble(self, target_space: int, n_comp: int, pts, w, src_space: int = 0, src_nodal=None, deriv: int = -1,
+                         grad: bool = False, f_quad=None):
+        pts, w = _f64(pts), _f64(w)
+        sn = _f64(src_nodal) if src_nodal is not None else None
+        fq = _f64(f_quad) if f_quad is not None else None
+        self._check(self.lib.b2_project_assemble(self._h, target_space, n_comp, src_space, _ptr(sn) if sn is not None else None,
+                                                 deriv, int(grad), len(w), _ptr(pts), _ptr(w), _ptr(fq) if fq is not None else None),
+                    "b2_project_assemble")
+
+    def project_rhs(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float64)
+        self._check(self.lib.b2_project_get_rhs(self._h, _ptr(out)), "b2_project_get_rhs")
+        return out
+
+    def project_load_rhs(self, target_space: int, rhs: np.ndarray):
+        rhs = _f64(np.atleast_2d(rhs))
+        self._check(self.lib.b2_project_set_rhs(self._h, target_space, rhs.shape[0], _ptr(rhs)), "b2_project_set_rhs")
+
+    def space_size(self, space: int) -> int:
+        return self._space_info[space][0]
+
+    def space_degree(self, space: int) -> int:
+        return self._space_info[space][1]
+
+    def project_solve(self, n_local: int, n_comp: int):
+        x = np.empty(n_local * n_comp, dtype=np.float64)
+        reasons = np.zeros(3, dtype=np.int32)
+        self._check(self.lib.b2_project_solve(self._h, _ptr(x), _ptr(reasons)), "b2_project_solve")
+        return x.reshape(n_comp, n_local), reasons[:n_comp]
+
+    def ksp_solve(self, solver: int, mat: int, b: np.ndarray, x: np.ndarray) -> int:
+        b = _f64(b)
+        assert x.dtype == np.float64 and x.flags.c_contiguous and x.shape == b.shape
         reason = C.c_int32(0)
-        self._check(self.lib.b2_project_q(self._h, _ptr(rhs), _ptr(x), C.byref(reason)), "b2_project_q")
-        return x, reason.value
+        self._check(self.lib.b2_ksp_solve(self._h, solver, mat, _ptr(b), _ptr(x), C.byref(reason)), "b2_ksp_solve")
+        return int(reason.value)
 
     def l2_diff_sq(self, vec: int, exact: np.ndarray) -> float:
         e = _f64(exact)

@@ -232,6 +232,9 @@ struct b2_ctx {
   std::map<int, DVec> vecs;
   // Krylov work space
   DBuf<double> wv[5], wq[4];
+  DBuf<double> wproj[5];    // Projector / KSPSolver.solve work vectors (any space, up to 3 components)
+  DBuf<double> proj_rhs;    // right-hand side of the last b2_project_assemble
+  int proj_space = 0, proj_comp = 1;
   DBuf<double> stage;  // staging for strided host copies
   DBuf<double> dp_old;      // pressure correction of the step before the previous one (extrapolated guess)
   int dp_hist = 0;
@@ -555,20 +558,20 @@ void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, c
                      const double* b, double* x, int32_t* reasons, int32_t* its);
 
 void krylov_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, const double* dinv_jacobi, int space,
-                  int K, const double* b, double* x, int32_t* reasons, int32_t* its) {
+                  int K, const double* b, double* x, int32_t* reasons, int32_t* its, DBuf<double>* work = nullptr) {
   KSPOpts& o = c->ksp[which];
-  if (o.type == 2) {
+  if (o.type == 2 && work == nullptr) {
     chebyshev_solve(c, which, pat, vals, dinv_jacobi, space, K, b, x, reasons, its);
     return;
   }
-  DBuf<double>* w = space == B2_SPACE_V ? c->wv : c->wq;
+  DBuf<double>* w = work != nullptr ? work : (space == B2_SPACE_V ? c->wv : c->wq);
   // CG: Jacobi through dinv in the vector kernels.  BiCGStab: left preconditioning D^-1 A x = D^-1 b -- dinv scales
   // the right-hand side in k_bcgs_init and every operator application in the SpMM epilogue (the matrix is stored as
   // assembled).  pc_type none: dinv = 1.
   const double* dinv = (o.pc != 1) ? dinv_jacobi : (space == B2_SPACE_V ? c->onesV.p : c->onesQ.p);
   double *r = w[0].p, *p = w[1].p, *q = w[2].p, *t = nullptr, *rhat = nullptr;
   if (o.type == 1) {
-    B2_REQUIRE(space == B2_SPACE_V, "BiCGStab work vectors exist for the velocity space only");
+    B2_REQUIRE(space == B2_SPACE_V || work != nullptr, "BiCGStab work vectors exist for the velocity space only");
     t = w[3].p;
     rhat = w[4].p;
   }
@@ -2275,19 +2278,177 @@ int b2_assemble_pressure_surface(b2_ctx* c, int64_t n_facets, const int32_t* fac
   });
 }
 
-int b2_project_q(b2_ctx* c, const double* rhs, double* x, int32_t* reason) {
+}  // extern "C"
+
+namespace {
+
+// the Q mass matrix is assembled with rotational=1; a Projector or KSPSolver may ask for it later
+void ensure_mq(b2_ctx* c) {
+  if (c->MQ.p != nullptr) return;
+  const Space& Q = c->sp[B2_SPACE_Q];
+  const CSR& qq = c->pat[B2_PAT_QQ];
+  c->MQ.alloc(qq.slots);
+  c->MQ.zero(c->stream);
+  dispatch_elem(c, [&](auto e) {
+    using E = decltype(e);
+    B2_LAUNCH(c, (k_assemble_square<E::D, E::DEG, B2_FORM_MASS_Q>), blocks_for(c->n_cells * E::NQ, 128), 128, c->n_cells, c->x.p,
+              c->cell_nodes.p, Q.cell_dofs.p, qq.n_rows, qq.rowptr.p, qq.cols.p, qq.slice_ptr.p, c->MQ.p);
+  });
+  c->dinvMQ.alloc(Q.n_local());
+  B2_LAUNCH(c, k_inv_diag, blocks_for(qq.n_rows, 256), 256, qq.n_rows, qq.slice_ptr.p, qq.diag_t.p, c->MQ.p, c->dinvMQ.p);
+}
+
+// work vectors of a K-component Krylov solve outside the step (Projector, KSPSolver.solve): five of K * n_local
+void ensure_proj_work(b2_ctx* c, int64_t n) {
+  for (auto& w : c->wproj)
+    if (w.n < n) { w.alloc(n); w.zero(c->stream); }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_project_assemble(b2_ctx* c, int target_space, int n_comp, int src_space, const double* src_nodal, int deriv, int grad,
+                        int n_q, const double* ref_points, const double* weights, const double* f_quad) {
   return guarded(c, [&] {
     require_ready(c);
-    B2_REQUIRE(c->MQ.p != nullptr, "Q mass matrix exists only with rotational=1");
-    const Space& Q = c->sp[B2_SPACE_Q];
-    B2_CUDA(cudaMemcpyAsync(c->wq[3].p, rhs, sizeof(double) * Q.n_local(), cudaMemcpyHostToDevice, c->stream));
-    DBuf<double> sol;
-    sol.alloc(Q.n_local());
-    int32_t its = 0;
-    krylov_solve(c, B2_SOLVER_PROJECTOR, c->pat[B2_PAT_QQ], c->MQ.p, c->dinvMQ.p, B2_SPACE_Q, 1, c->wq[3].p, sol.p, reason, &its);
-    c->stats.its_projector = its;
-    B2_CUDA(cudaMemcpyAsync(x, sol.p, sizeof(double) * Q.n_local(), cudaMemcpyDeviceToHost, c->stream));
+    B2_REQUIRE(target_space == B2_SPACE_V || target_space == B2_SPACE_Q, "bad target space");
+    B2_REQUIRE(n_comp >= 1 && n_comp <= 3 && n_q > 0, "1..3 components, at least one quadrature point");
+    B2_REQUIRE((src_nodal != nullptr) != (f_quad != nullptr), "give either nodal source values or values at the quadrature points");
+    B2_REQUIRE(!grad || (n_comp == c->gdim && src_nodal != nullptr), "grad: gdim components from one scalar nodal source");
+    B2_REQUIRE(deriv < c->gdim, "bad derivative direction");
+    const int d = c->gdim;
+    const Space& T = c->sp[target_space];
+    const int64_t ldt = T.n_local();
+    c->proj_rhs.alloc(ldt * n_comp);
+    c->proj_rhs.zero(c->stream);
+    c->proj_space = target_space;
+    c->proj_comp = n_comp;
+    DBuf<double> dsrc, dfq, dp, dw;
+    dp.alloc((int64_t)n_q * d);
+    dw.alloc(n_q);
+    B2_CUDA(cudaMemcpyAsync(dp.p, ref_points, sizeof(double) * n_q * d, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(dw.p, weights, sizeof(double) * n_q, cudaMemcpyHostToDevice, c->stream));
+    int64_t lds = 0;
+    const Space* S = &T;
+    if (src_nodal != nullptr) {
+      B2_REQUIRE(src_space == B2_SPACE_V || src_space == B2_SPACE_Q, "bad source space");
+      S = &c->sp[src_space];
+      lds = S->n_local();
+      const int ncs = grad ? 1 : n_comp;
+      dsrc.alloc(lds * ncs);
+      B2_CUDA(cudaMemcpyAsync(dsrc.p, src_nodal, sizeof(double) * lds * ncs, cudaMemcpyHostToDevice, c->stream));
+      c->stats.bytes_h2d += sizeof(double) * lds * ncs;
+    } else {
+      dfq.alloc(c->n_cells * n_q * n_comp);
+      B2_CUDA(cudaMemcpyAsync(dfq.p, f_quad, sizeof(double) * c->n_cells * n_q * n_comp, cudaMemcpyHostToDevice, c->stream));
+      c->stats.bytes_h2d += sizeof(double) * c->n_cells * n_q * n_comp;
+    }
+    const int grid = blocks_for(c->n_cells, 128);
+    auto launch = [&](auto kern) {
+      B2_LAUNCH(c, kern, grid, 128, c->n_cells, c->x.p, c->cell_nodes.p, T.cell_dofs.p, (int)T.n_owned, (int)ldt, S->cell_dofs.p,
+                (int)lds, (const double*)dsrc.p, (const double*)dfq.p, n_comp, deriv, grad, n_q, (const double*)dp.p,
+                (const double*)dw.p, c->proj_rhs.p);
+    };
+    const int td = T.degree, sd = S->degree;
+    if (d == 2 && td == 1 && sd == 1) launch(k_project_rhs<2, 1, 1>);
+    else if (d == 2 && td == 1 && sd == 2) launch(k_project_rhs<2, 1, 2>);
+    else if (d == 2 && td == 2 && sd == 1) launch(k_project_rhs<2, 2, 1>);
+    else if (d == 2 && td == 2 && sd == 2) launch(k_project_rhs<2, 2, 2>);
+    else if (d == 3 && td == 1 && sd == 1) launch(k_project_rhs<3, 1, 1>);
+    else if (d == 3 && td == 1 && sd == 2) launch(k_project_rhs<3, 1, 2>);
+    else if (d == 3 && td == 2 && sd == 1) launch(k_project_rhs<3, 2, 1>);
+    else launch(k_project_rhs<3, 2, 2>);
     B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int b2_project_set_rhs(b2_ctx* c, int target_space, int n_comp, const double* rhs) {
+  return guarded(c, [&] {
+    require_ready(c);
+    B2_REQUIRE((target_space == B2_SPACE_V || target_space == B2_SPACE_Q) && n_comp >= 1 && n_comp <= 3, "bad space / components");
+    const int64_t n = c->sp[target_space].n_local() * n_comp;
+    c->proj_rhs.alloc(n);
+    c->proj_space = target_space;
+    c->proj_comp = n_comp;
+    B2_CUDA(cudaMemcpyAsync(c->proj_rhs.p, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_h2d += sizeof(double) * n;
+  });
+}
+
+int b2_project_get_rhs(b2_ctx* c, double* rhs) {
+  return guarded(c, [&] {
+    B2_REQUIRE(c->proj_rhs.p != nullptr, "b2_project_assemble first");
+    B2_CUDA(cudaMemcpyAsync(rhs, c->proj_rhs.p, sizeof(double) * c->proj_rhs.n, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int b2_project_solve(b2_ctx* c, double* x, int32_t* reasons) {
+  return guarded(c, [&] {
+    require_ready(c);
+    B2_REQUIRE(c->proj_rhs.p != nullptr, "b2_project_assemble first");
+    const int sp = c->proj_space, K = c->proj_comp;
+    const Space& T = c->sp[sp];
+    const int64_t n = T.n_local() * K;
+    const bool onV = sp == B2_SPACE_V;
+    if (!onV) ensure_mq(c);
+    ensure_proj_work(c, n);
+    DBuf<double> sol;
+    sol.alloc(n);
+    sol.zero(c->stream);
+    int32_t its[B2_MAXK] = {0, 0, 0};
+    KSPOpts& o = c->ksp[B2_SOLVER_PROJECTOR];
+    const bool guess = o.nonzero_guess;
+    o.nonzero_guess = false;
+    krylov_solve(c, B2_SOLVER_PROJECTOR, c->pat[onV ? B2_PAT_VV : B2_PAT_QQ], onV ? c->M.p : c->MQ.p,
+                 onV ? c->dinvM.p : c->dinvMQ.p, sp, K, c->proj_rhs.p, sol.p, reasons, its, c->wproj);
+    o.nonzero_guess = guess;
+    c->stats.its_projector = *std::max_element(its, its + K);
+    halo_forward(c, sp, sol.p, K);  // x.scatter_forward(), function.py:132
+    B2_CUDA(cudaMemcpyAsync(x, sol.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_d2h += sizeof(double) * n;
+  });
+}
+
+/* KSPSolver.solve (ksp.py:71-78): solve  Mat x = b  with the options of solver slot `solver`; x holds the initial
+ * guess on entry when ksp_initial_guess_nonzero is set. */
+int b2_ksp_solve(b2_ctx* c, int solver, int mat, const double* b, double* x, int32_t* reason) {
+  return guarded(c, [&] {
+    require_ready(c);
+    B2_REQUIRE(solver >= 0 && solver < 4, "bad solver id");
+    B2_REQUIRE(mat == B2_MAT_M || mat == B2_MAT_K || mat == B2_MAT_A || mat == B2_MAT_AP || mat == B2_MAT_MQ, "square operators only");
+    if (mat == B2_MAT_MQ) ensure_mq(c);
+    const CSR* pat = nullptr;
+    int stride = 1;
+    const DBuf<double>* v = matrix_values(c, mat, &pat, &stride);
+    const int sp = (mat == B2_MAT_AP || mat == B2_MAT_MQ) ? B2_SPACE_Q : B2_SPACE_V;
+    const int64_t n = c->sp[sp].n_local();
+    ensure_proj_work(c, n);
+    DBuf<double> db, dx, dinv;
+    db.alloc(n);
+    dx.alloc(n);
+    dinv.alloc(n);
+    B2_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    B2_LAUNCH(c, k_fill, pgrid(c, n), 256, n, 1.0, dinv.p);
+    B2_LAUNCH(c, k_inv_diag, blocks_for(pat->n_rows, 256), 256, pat->n_rows, pat->slice_ptr.p, pat->diag_t.p, v->p, dinv.p);
+    int32_t its = 0;
+    if (mat == B2_MAT_AP && c->ksp[solver].pc == 2 && !c->mg.empty() && !c->has_pbc && solver == B2_SOLVER_PRESSURE) {
+      B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_B2), db.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+      B2_CUDA(cudaMemcpyAsync(c->vec(B2_VEC_DP), dx.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+      pcg_mg_solve(c, c->vec(B2_VEC_B2), c->vec(B2_VEC_DP), reason, &its);
+      B2_CUDA(cudaMemcpyAsync(dx.p, c->vec(B2_VEC_DP), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      krylov_solve(c, solver, *pat, v->p, dinv.p, sp, 1, db.p, dx.p, reason, &its, c->wproj);
+    }
+    halo_forward(c, sp, dx.p, 1);  // x.x.scatter_forward(), ksp.py:77
+    B2_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.bytes_h2d += sizeof(double) * 2 * n;
+    c->stats.bytes_d2h += sizeof(double) * n;
   });
 }
 
@@ -2347,6 +2508,57 @@ int b2_l2_error_quadrature(b2_ctx* c, int vec, int64_t n_cells, int n_q, const d
     allreduce_sum(c, c->d_sums, 1);
     read_sums(c, 1);
     *out = c->h_sums[0];
+  });
+}
+
+// demo/assembly_strategies.py:56-152 on the device: the tentative-velocity right-hand side of the current U1 / UAB
+// vectors by the matrix-vector strategy (into RHS1) and by the action strategy (into BFIRST), each timed over `reps`
+// launches with CUDA events.  out[0..6] = ms convection assembly (untimed in the reference), ms matvec, ms action,
+// algorithmic bytes of the three, in the same order.
+int b2_bench_assembly_strategies(b2_ctx* c, double dt, double nu, int reps, double* out) {
+  return guarded(c, [&] {
+    require_ready(c);
+    B2_REQUIRE(reps > 0, "reps must be positive");
+    const int K = c->gdim;
+    const Space& V = c->sp[B2_SPACE_V];
+    const CSR& vv = c->pat[B2_PAT_VV];
+    const int ld = (int)V.n_local();
+    double *u1 = c->vec(B2_VEC_U1), *uab = c->vec(B2_VEC_UAB);
+    halo_forward(c, B2_SPACE_V, u1, K);
+    halo_forward(c, B2_SPACE_V, uab, K);
+    DBuf<double> zero;
+    zero.alloc((int64_t)ld * K);
+    zero.zero(c->stream);
+    cudaEvent_t e[2];
+    for (auto& ev : e) B2_CUDA(cudaEventCreate(&ev));
+    auto timed = [&](auto&& body) {
+      body();  // warm-up
+      B2_CUDA(cudaEventRecord(e[0], c->stream));
+      for (int i = 0; i < reps; ++i) body();
+      B2_CUDA(cudaEventRecord(e[1], c->stream));
+      B2_CUDA(cudaEventSynchronize(e[1]));
+      float ms = 0;
+      B2_CUDA(cudaEventElapsedTime(&ms, e[0], e[1]));
+      return (double)ms / reps;
+    };
+    const double inf = 1.0 / 0.0;
+    // 1/2 C(uab) into A (1/dt = nu = 0): the matrix the reference assembles outside its timed block
+    out[0] = timed([&] { first_cells(c, 1, inf, 0.0, u1, uab, zero.p, nullptr, c->A.p, c->vec(B2_VEC_BFIRST), c->dinvA.p); });
+    const int grid = pgrid(c, vv.n_rows, 256, 4);
+    out[1] = timed([&] {
+      if (K == 2) B2_LAUNCH(c, (k_matvec_rhs<2, 8>), grid, 256, vv.n_rows, vv.slice_ptr.p, vv.scols.p, c->A.p, c->M.p, c->Kst.p, vv.order.p, 1.0 / dt, 0.5 * nu, u1, ld, (const double*)nullptr, c->vec(B2_VEC_RHS1));
+      else B2_LAUNCH(c, (k_matvec_rhs<3, 8>), grid, 256, vv.n_rows, vv.slice_ptr.p, vv.scols.p, c->A.p, c->M.p, c->Kst.p, vv.order.p, 1.0 / dt, 0.5 * nu, u1, ld, (const double*)nullptr, c->vec(B2_VEC_RHS1));
+    });
+    out[2] = timed([&] { first_cells(c, 2, dt, nu, u1, uab, zero.p, nullptr, c->A.p, c->vec(B2_VEC_BFIRST), c->dinvA.p); });
+    const double nV = (double)V.n_owned, nVc = (double)vv.n_cols, cells = (double)c->n_cells;
+    const double nvp = (V.nd + 3) / 4 * 4;
+    const double nnz_if = c->first.ready ? (double)c->first.nnz_iface : (double)vv.nnz;
+    const double cell_bytes = 4.0 * (V.nd + c->gdim + 1);  // dofs + vertices: SURVEY.md 8(d) "cells * 56" for P2 tetrahedra
+    out[3] = 8.0 * vv.nnz + 16.0 * nnz_if + cells * (cell_bytes + V.nd * nvp) + 8.0 * 3 * c->n_nodes + 8.0 * K * nVc;
+    out[4] = 28.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc);
+    out[5] = cells * cell_bytes + 8.0 * 3 * c->n_nodes + 8.0 * K * (2 * nVc + nV);
+    for (auto& ev : e) cudaEventDestroy(ev);
+    c->cfg_version++;
   });
 }
 

@@ -660,6 +660,104 @@ k_l2_error(int64_t n_cells, const double* __restrict__ x, const int* __restrict_
   if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
 }
 
+// ---- right-hand side of an L2 projection (Projector, function.py:108-119): out_k[i] += int f_k phi_i dx -----------
+// The source f is sampled at the quadrature points of each cell either by the host (a Python callable: `fq`,
+// [cell][q][n_comp]) or on the device from the nodal values of a Lagrange function on the same mesh (`src`,
+// n_src_comp components, component-major with leading dimension ld_src): its value (DERIV < 0) or its derivative
+// along x_DERIV, or -- GRAD -- all gdim derivatives of ONE scalar function as the gdim components of f (grad(u) into
+// a vector space, test/test_projector.py:33).  TDEG / SDEG: degree of the target / source space.
+template <int D, int TDEG, int SDEG>
+__global__ void __launch_bounds__(128)
+k_project_rhs(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
+              const int* __restrict__ tdofs, int n_t_owned, int ld_t, const int* __restrict__ sdofs, int ld_src,
+              const double* __restrict__ src, const double* __restrict__ fq, int n_comp, int deriv, int grad, int n_q,
+              const double* __restrict__ ref_pts, const double* __restrict__ weights, double* __restrict__ out) {
+  constexpr int NT = TDEG == 1 ? D + 1 : (D == 2 ? 6 : 10);
+  constexpr int NS = SDEG == 1 ? D + 1 : (D == 2 ? 6 : 10);
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  auto basis = [](const double (&lam)[D + 1], int deg, double* phi, double (*dphi)[D]) {
+    // values and REFERENCE gradients (d/dxi_dl) of the Lagrange basis in the basix dof order
+    double dl[D + 1][D];
+    for (int a = 0; a <= D; ++a)
+      for (int k = 0; k < D; ++k) dl[a][k] = a == 0 ? -1.0 : (a - 1 == k ? 1.0 : 0.0);
+    if (deg == 1) {
+      for (int a = 0; a <= D; ++a) {
+        phi[a] = lam[a];
+        for (int k = 0; k < D; ++k) dphi[a][k] = dl[a][k];
+      }
+      return;
+    }
+    for (int a = 0; a <= D; ++a) {
+      phi[a] = lam[a] * (2.0 * lam[a] - 1.0);
+      for (int k = 0; k < D; ++k) dphi[a][k] = (4.0 * lam[a] - 1.0) * dl[a][k];
+    }
+    const int ea3[6] = {2, 1, 1, 0, 0, 0}, eb3[6] = {3, 3, 2, 3, 2, 1}, ea2[3] = {1, 0, 0}, eb2[3] = {2, 2, 1};
+    const int ne = D == 3 ? 6 : 3;
+    for (int e = 0; e < ne; ++e) {
+      const int a = D == 3 ? ea3[e] : ea2[e], b = D == 3 ? eb3[e] : eb2[e];
+      phi[D + 1 + e] = 4.0 * lam[a] * lam[b];
+      for (int k = 0; k < D; ++k) dphi[D + 1 + e][k] = 4.0 * (lam[a] * dl[b][k] + lam[b] * dl[a][k]);
+    }
+  };
+  double acc[NT][3];
+  for (int i = 0; i < NT; ++i)
+    for (int k = 0; k < 3; ++k) acc[i][k] = 0.0;
+  for (int q = 0; q < n_q; ++q) {
+    double lam[D + 1];
+    lam[0] = 1.0;
+    for (int k = 0; k < D; ++k) {
+      lam[k + 1] = ref_pts[q * D + k];
+      lam[0] -= lam[k + 1];
+    }
+    double f[3] = {0.0, 0.0, 0.0};
+    if (fq != nullptr) {
+      for (int k = 0; k < n_comp; ++k) f[k] = fq[((size_t)c * n_q + q) * n_comp + k];
+    } else {
+      double sphi[NS], sdphi[NS][D];
+      basis(lam, SDEG, sphi, sdphi);
+      if (grad) {  // f_k = d u / d x_k of the scalar source
+        double gr[D];
+        for (int dd = 0; dd < D; ++dd) gr[dd] = 0.0;
+        for (int j = 0; j < NS; ++j) {
+          const double uj = src[sdofs[c * NS + j]];
+          for (int dd = 0; dd < D; ++dd) gr[dd] = fma(uj, sdphi[j][dd], gr[dd]);
+        }
+        for (int k = 0; k < D; ++k) {
+          double v = 0.0;
+          for (int dd = 0; dd < D; ++dd) v = fma(g.Kinv[dd][k], gr[dd], v);
+          f[k] = v;
+        }
+      } else {
+        for (int k = 0; k < n_comp; ++k) {
+          double v = 0.0;
+          for (int j = 0; j < NS; ++j) {
+            const double uj = src[(size_t)k * ld_src + sdofs[c * NS + j]];
+            double b = sphi[j];
+            if (deriv >= 0) {
+              b = 0.0;
+              for (int dd = 0; dd < D; ++dd) b = fma(g.Kinv[dd][deriv], sdphi[j][dd], b);
+            }
+            v = fma(uj, b, v);
+          }
+          f[k] = v;
+        }
+      }
+    }
+    double tphi[NT], tdphi[NT][D];
+    basis(lam, TDEG, tphi, tdphi);
+    const double wq = g.detJ * weights[q];
+    for (int i = 0; i < NT; ++i)
+      for (int k = 0; k < n_comp; ++k) acc[i][k] = fma(wq * tphi[i], f[k], acc[i][k]);
+  }
+  for (int i = 0; i < NT; ++i) {
+    const int row = tdofs[c * NT + i];
+    if (row >= n_t_owned) continue;
+    for (int k = 0; k < n_comp; ++k) atomicAdd(out + (size_t)k * ld_t + row, acc[i][k]);
+  }
+}
+
 // ---- low_memory_version=True: matrix-free element vectors (fracstep.py:305-309,327-330,342-346) -----
 // MODE 0: out_k[j] += int s dphi_j/dx_k          (s in Q: p* for :485-497, out = rhs1 preloaded with b_first)
 // MODE 1: out_k[j] += int ds/dx_k phi_j          (s in Q: dp for :612-622)

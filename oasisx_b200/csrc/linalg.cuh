@@ -429,6 +429,62 @@ k_spmm_diag(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict
   }
 }
 
+// ---- the "matrix-vector strategy" right-hand side in ONE pass (fracstep.py:438-452; the timed block of
+// demo/assembly_strategies.py:128-133: A.scale(-0.5); A.axpy(1/dt, M); A.axpy(-nu/2, K); A.mult(u_1, b)) ------------
+//   out_k[row] = sum_t (inv_dt M - half_nu K - Ch)[slot] * u_k[cols[slot]] (+ add_k[row]),   Ch = 1/2 C(uab) as
+// assembled by k_first_cells with 1/dt = nu = 0.  Three value streams + the column stream are read once; nothing is
+// written back to a matrix (the reference rewrites A three times).  The IPCS step itself uses the matrix-free
+// action (k_first_cells, MODE & 2); this kernel is the other arm of the micro-benchmark and of its allclose test.
+template <int K, int U = 4>
+__global__ void __launch_bounds__(256, 4)
+k_matvec_rhs(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols, const double* __restrict__ Ch,
+             const double* __restrict__ M, const double* __restrict__ Kst, const int* __restrict__ order, double inv_dt,
+             double half_nu, const double* __restrict__ u, int ld, const double* __restrict__ add,
+             double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  for (int i = blockIdx.x * wpb + wib; i < n_slices; i += gridDim.x * wpb) {
+    const int s = order != nullptr ? __ldg(order + i) : i;
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    int t = 0;
+    for (; t + U <= len; t += U) {
+      int cc[U];
+      double r[U], xu[U][K];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const size_t p = (size_t)base + ((size_t)(t + q) << 5) + lane;
+        cc[q] = ld_stream(cols + p);
+        r[q] = (inv_dt * ld_stream(M + p) - ld_stream(Ch + p)) - half_nu * ld_stream(Kst + p);
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+#pragma unroll
+        for (int k = 0; k < K; ++k) xu[q][k] = __ldg(u + (size_t)k * ld + cc[q]);
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fma(r[q], xu[q][k], acc[k]);
+    }
+    for (; t < len; ++t) {
+      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
+      const int c = ld_stream(cols + p);
+      const double r = (inv_dt * ld_stream(M + p) - ld_stream(Ch + p)) - half_nu * ld_stream(Kst + p);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fma(r, __ldg(u + (size_t)k * ld + c), acc[k]);
+    }
+    if (row < n_rows) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) out[(size_t)k * ld + row] = acc[k] + (add != nullptr ? add[(size_t)k * ld + row] : 0.0);
+    }
+  }
+}
+
 // ---- rectangular products on the V x Q and Q x V CSR patterns ([nnz][K] values) -----------------
 // out_k[row] = add_k[row] + scale * sum_p vals[p][k] * xq[cols[p]]   (P_i ps, G_i dp)
 template <int K, int LPR>

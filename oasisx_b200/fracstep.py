@@ -175,6 +175,8 @@ class FractionalStep_AB_CN:
             ctx.set_space(L.SPACE_Q, deg_p, self._Q.num_dofs, 0, self._Q.dofmap.list)
             ctx.set_global_sizes(Vs.num_dofs, self._Q.num_dofs)
             self._nV_owned, self._nQ_owned = Vs.num_dofs, self._Q.num_dofs
+        Vs._b2_ctx = ctx  # a Projector on one of the solver's spaces shares its device context
+        self._Q._scalar._b2_ctx = ctx
         ctx.build_patterns()
         if deg_u == 2:  # tile-major schedule of the SELL slices (L1 reuse of the gathered vector)
             ctx.set_slice_order(

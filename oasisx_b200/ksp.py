@@ -48,6 +48,24 @@ class KSPSolver:
     def setOperators(self, A, P=None):
         self._operator = A
 
+    def solve(self, b, x):
+        """``ksp.py:71-78``: solve ``A x = b`` with this solver's options, refresh the ghosts of ``x`` and return the
+        KSP converged reason.  ``b``: a vector (``Function.x``, its ``petsc_vec`` stand-in or a numpy array) of the
+        operator's row space; ``x``: a Function (initial guess if ``ksp_initial_guess_nonzero``)."""
+        import numpy as np
+
+        if self._ctx is None or self._operator is None:
+            raise RuntimeError("KSPSolver.solve needs bind(ctx, slot) and setOperators(A) first")
+        bv = b
+        for attr in ("x", "petsc_vec"):
+            bv = getattr(bv, attr, bv)
+        barr = np.ascontiguousarray(bv.array_ro() if hasattr(bv, "array_ro") else getattr(bv, "array", bv), dtype=np.float64)
+        xv = x.x
+        xarr = np.ascontiguousarray(xv.array_ro(), dtype=np.float64).copy()
+        reason = self._ctx.ksp_solve(self._slot, self._operator._mat, barr, xarr)
+        xv.array[:] = xarr
+        return reason
+
     @property
     def options(self) -> dict:
         return dict(self._options)

@@ -705,6 +705,7 @@ static std::vector<double>* vec_of(Ctx* c, int which, int comp) {
     case 6: return &c->rhs1[comp];
     case 7: return &c->bfirst[comp];
     case 8: return &c->b2;
+    case 9: return &c->uab[comp];
     default: return nullptr;
   }
 }
@@ -720,6 +721,77 @@ void ipcs_cpu_get_matrix(void* h, int which, int comp, double* v) {
   Ctx* c = (Ctx*)h;
   const std::vector<double>* m[7] = {&c->M, &c->K, &c->A, &c->Ap, &c->P[comp], &c->G[comp], &c->D[comp]};
   std::copy(m[which]->begin(), m[which]->end(), v);
+}
+
+// demo/assembly_strategies.py:56-152 for ONE scalar field (component `comp` of u1, convecting field uab), as the
+// reference times it: the convection matrix is assembled first (untimed there), then
+//   matvec strategy (:128-133): A.scale(-0.5); A.axpy(1/dt, M); A.axpy(-nu/2, K); A.mult(u_1, b)  -- four CSR passes
+//   action strategy (:137-140): assemble_vector(action(lhs, u_1))                                  -- one cell loop
+// out[0..2] = seconds {convection assembly, matvec, action} (best of reps); b_matvec / b_action receive the vectors.
+void ipcs_cpu_bench_strategies(void* h, int comp, double dt, double nu, int reps, double* out, double* b_matvec,
+                               double* b_action) {
+  Ctx* c = (Ctx*)h;
+  const Tables& t = c->t;
+  const int d = c->d, nd = t.nv;
+  const int64_t nV = c->nV, nnz = (int64_t)c->vv.col.size();
+  out[0] = out[1] = out[2] = 1e300;
+  std::vector<double> A, bm(nV), ba(nV);
+  for (int rep = 0; rep < reps; ++rep) {
+    double t0 = omp_get_wtime();
+    assemble_square(*c, true, 2, A);  // zeroEntries + assemble_matrix(convection)
+    out[0] = std::min(out[0], omp_get_wtime() - t0);
+    t0 = omp_get_wtime();
+#pragma omp parallel for
+    for (int64_t p = 0; p < nnz; ++p) A[p] *= -0.5;
+#pragma omp parallel for
+    for (int64_t p = 0; p < nnz; ++p) A[p] += (1.0 / dt) * c->M[p];
+#pragma omp parallel for
+    for (int64_t p = 0; p < nnz; ++p) A[p] += (-0.5 * nu) * c->K[p];
+    spmv(c->vv, A, c->u1[comp].data(), bm.data());
+    out[1] = std::min(out[1], omp_get_wtime() - t0);
+    t0 = omp_get_wtime();
+#pragma omp parallel for
+    for (int64_t i = 0; i < nV; ++i) ba[i] = 0.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t cell = 0; cell < c->n_cells; ++cell) {
+      const Geo g = geometry(*c, cell);
+      const int* dofs = &c->vd[cell * nd];
+      double G[3][3], w[10][3], ue[10], be[10];
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+          double sacc = 0;
+          for (int k = 0; k < d; ++k) sacc += g.Kinv[a][k] * g.Kinv[b][k];
+          G[a][b] = sacc * g.detJ;
+        }
+      for (int a = 0; a < nd; ++a) {
+        ue[a] = c->u1[comp][dofs[a]];
+        for (int dl = 0; dl < d; ++dl) {
+          double sacc = 0;
+          for (int k = 0; k < d; ++k) sacc += g.Kinv[dl][k] * c->uab[k][dofs[a]];
+          w[a][dl] = sacc * g.detJ;
+        }
+      }
+      for (int i = 0; i < nd; ++i) {
+        double acc = 0;
+        for (int j = 0; j < nd; ++j) {
+          double cv = 0, kv = 0;
+          for (int a = 0; a < nd; ++a)
+            for (int dl = 0; dl < d; ++dl) cv += w[a][dl] * t.T[(((size_t)a * d + dl) * nd + i) * nd + j];
+          for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) kv += G[a][b] * t.SV[((a * d + b) * nd + i) * nd + j];
+          acc += ((1.0 / dt) * g.detJ * t.MV[i * nd + j] - 0.5 * nu * kv - 0.5 * cv) * ue[j];
+        }
+        be[i] = acc;
+      }
+      for (int i = 0; i < nd; ++i) {
+#pragma omp atomic
+        ba[dofs[i]] += be[i];
+      }
+    }
+    out[2] = std::min(out[2], omp_get_wtime() - t0);
+  }
+  std::copy(bm.begin(), bm.end(), b_matvec);
+  std::copy(ba.begin(), ba.end(), b_action);
 }
 
 // one time step, fracstep.py:660-696 with max_iter = 1; returns 0 or a negative stage id on divergence

@@ -42,6 +42,7 @@ def lib():
         L.ipcs_cpu_mg_add_level.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         L.ipcs_cpu_mg_set_dense.argtypes = [vp, i32, vp]
         L.ipcs_cpu_set_pressure_mg.argtypes = [vp, i32, dbl]
+        L.ipcs_cpu_bench_strategies.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, vp]
         L.ipcs_cpu_step.restype = i32
         L.ipcs_cpu_step.argtypes = [vp, dbl, dbl, vp]
         _lib = L
@@ -72,7 +73,7 @@ def stream_triad_gbs(n: int = 1 << 26, reps: int = 5) -> float:
     return float(lib().ipcs_cpu_stream_triad(int(n), int(reps)))
 
 
-U, U1, U2, P, PS, DP, RHS1, BFIRST, B2 = range(9)
+U, U1, U2, P, PS, DP, RHS1, BFIRST, B2, UAB = range(10)
 
 
 class CpuIPCS:
@@ -177,6 +178,12 @@ class CpuIPCS:
             return 0
         self.L.ipcs_cpu_set_pressure_mg(self.h, 1, float(omega))
         return n_levels
+
+    def bench_strategies(self, comp: int, dt: float, nu: float, reps: int = 3):
+        """demo/assembly_strategies.py:121-142 on the host: (seconds {assembly, matvec, action}, b_matvec, b_action)."""
+        out, bm, ba = np.zeros(3), np.empty(self.nV), np.empty(self.nV)
+        self.L.ipcs_cpu_bench_strategies(self.h, comp, dt, nu, reps, _p(out), _p(bm), _p(ba))
+        return out, bm, ba
 
     def solve(self, dt, nu):
         self.update_bcs()

@@ -1,0 +1,84 @@
+"""Projector and KSPSolver.solve on the device, mirroring ``/root/reference/test/test_projector.py:16-50`` (projection of
+the gradient of a quadratic P2 function, known answer to 1e-12, then a changed source with ``assemble_rhs()`` +
+``solve(assemble_rhs=False)``) -- with the continuous P1 vector space in place of the reference's DG1: the projected
+gradient is globally linear, so the known answer is the same -- plus the scalar source kinds and ``ksp.py:71-78``."""
+import numpy as np
+import pytest
+
+import oasisx_b200 as oasisx
+from oasisx_b200 import fem, mesh as bmesh
+from oasisx_b200.function import grad
+
+pytestmark = pytest.mark.gpu
+LU = {"ksp_type": "preonly", "pc_type": "lu", "pc_factor_mat_solver_type": "mumps"}
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_projector_gradient_known_answer(gdim):
+    msh = bmesh.create_unit_square(None, 10, 10) if gdim == 2 else bmesh.create_unit_cube(None, 4, 4, 4)
+    V = fem.functionspace(msh, ("Lagrange", 2))
+    u = fem.Function(V)
+    u.interpolate(lambda x: x[0] * x[0] + 3 * x[1] + 2 * x[1] * x[1])
+    W = fem.functionspace(msh, ("Lagrange", 1, (gdim,)))
+    proj = oasisx.Projector(grad(u), W, [], petsc_options=LU)
+    assert proj.solve() > 0
+    xW = W.tabulate_dof_coordinates()
+    exact = np.stack([2 * xW[:, 0], 3 + 4 * xW[:, 1]] + ([0 * xW[:, 0]] if gdim == 3 else []), axis=1)
+    ph = proj.x.x.array.reshape(-1, gdim)
+    assert np.abs(ph - exact).max() < 1e-10  # nodal values of a P1 function: the L2 error of the reference test is below this
+    # new source, right-hand side re-assembled explicitly (test_projector.py:41-50)
+    u.interpolate(lambda x: x[0] + 2 * x[1] * x[1])
+    proj.assemble_rhs()
+    assert proj.solve(assemble_rhs=False) > 0
+    exact = np.stack([1 + 0 * xW[:, 0], 4 * xW[:, 1]] + ([0 * xW[:, 0]] if gdim == 3 else []), axis=1)
+    assert np.abs(proj.x.x.array.reshape(-1, gdim) - exact).max() < 1e-10
+
+
+def test_projector_scalar_sources_and_spaces():
+    msh = bmesh.create_unit_cube(None, 3, 4, 3)
+    V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    lin = lambda x: 1 + 2 * x[0] - x[1] + 0.5 * x[2]
+    quad = lambda x: x[0] * x[1] - 2 * x[2] * x[2] + x[0]
+    f2 = fem.Function(V)
+    f2.interpolate(lin)
+    # P2 function (linear) into P1, callable (quadratic) into P2, d/dy of a P2 function into P1, P1 function into P2
+    p = oasisx.Projector(f2, Q, petsc_options=LU)
+    assert p.solve() > 0
+    assert np.abs(p.x.x.array - lin(Q.tabulate_dof_coordinates().T)).max() < 1e-10
+    p = oasisx.Projector(quad, V, petsc_options=LU, metadata={"quadrature_degree": 4})
+    assert p.solve() > 0
+    assert np.abs(p.x.x.array - quad(V.tabulate_dof_coordinates().T)).max() < 1e-10
+    g2 = fem.Function(V)
+    g2.interpolate(quad)
+    p = oasisx.Projector(grad(g2)[0], Q, petsc_options=LU)
+    assert p.solve() > 0
+    xq = Q.tabulate_dof_coordinates().T
+    assert np.abs(p.x.x.array - (xq[1] + 1)).max() < 1e-10
+    f1 = fem.Function(Q)
+    f1.interpolate(lin)
+    p = oasisx.Projector(f1, V, petsc_options=LU)
+    assert p.solve() > 0
+    assert np.abs(p.x.x.array - lin(V.tabulate_dof_coordinates().T)).max() < 1e-10
+    with pytest.raises(NotImplementedError):
+        oasisx.Projector(f1, V, bcs=[object()])
+
+
+def test_kspsolver_solve_matches_the_operator():
+    """``KSPSolver.solve(b, x)`` (ksp.py:71-78) on the solver's own operators: x recovers g from b = Mat g."""
+    from problems import TaylorGreen, make_mesh, make_solver
+
+    msh = make_mesh(3, 4)
+    s = make_solver(msh, 2, TaylorGreen(0.01, 3), 0.005)
+    rng = np.random.default_rng(3)
+    for ksp, mat, space in ((s._solver_c, s._M, s._Vi[0][0]), (s._solver_p, s._Ap, s._Q)):
+        g = rng.uniform(-1, 1, space.num_dofs)
+        if mat is s._Ap:
+            g -= g.mean()  # the Neumann operator is singular: compare in the complement of the constants
+        b = fem.Function(space)
+        mat.mult(g, b.x)
+        x = fem.Function(space)
+        assert ksp.solve(b.x, x) > 0
+        sol = x.x.array.copy()
+        if mat is s._Ap:
+            sol -= sol.mean()
+        assert np.abs(sol - g).max() < 1e-7 * np.abs(g).max()
