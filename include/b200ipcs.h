@@ -262,9 +262,8 @@ int b2_l2_error_quadrature(b2_ctx* ctx, int vec, int64_t n_cells, int n_q, const
  * :128-133) and by the "action strategy" (matrix-free element kernel, result in BFIRST; :137-140), each averaged over
  * `reps` launches (CUDA events).  out[6] = ms of {convection assembly, matvec, action}, then their algorithmic bytes. */
 int b2_bench_assembly_strategies(b2_ctx* ctx, double dt, double nu, int reps, double* out);
-/* Brick plan of assemble_first (k_first_cells): out[8] = bricks, interior rows, interface rows, shared-memory
- * accumulator doubles, most interior rows of a brick, nonzeros of the interface rows, shared-memory bytes per block,
- * cubes per brick edge (b2_set_tuning "first_bricks"; 0 = no bricks). */
+/* Cell schedule of assemble_first (k_first_cells): out[4] = schedule built (0/1), congruence classes found, slab
+ * thickness (b2_set_tuning "first_slab"), cells.  b2_set_tuning "first_order" 0 keeps the mesh order. */
 int b2_first_plan_info(b2_ctx* ctx, int64_t* out);
 int b2_get_stats(b2_ctx* ctx, b2_stats* out);
 /* Times `reps` launches of one hot kernel on the context's stream with CUDA events (device

@@ -276,11 +276,9 @@ class Context:
                 "bytes_convection_assembly": out[3], "bytes_matvec": out[4], "bytes_action": out[5]}
 
     def first_plan_info(self) -> dict:
-        out = np.zeros(8, dtype=np.int64)
+        out = np.zeros(4, dtype=np.int64)
         self._check(self.lib.b2_first_plan_info(self._h, _ptr(out)), "b2_first_plan_info")
-        keys = ("bricks", "interior_rows", "interface_rows", "acc_doubles", "max_rows_per_brick", "nnz_interface", "smem_bytes",
-                "cubes_per_brick_edge")
-        return dict(zip(keys, (int(v) for v in out)))
+        return dict(zip(("cell_schedule", "congruence_classes", "slab", "cells"), (int(v) for v in out)))
 
     def peer_enabled(self) -> bool:
         return bool(self.lib.b2_peer_enabled(self._h))

@@ -147,10 +147,8 @@ struct PeerBlob {
 static_assert(sizeof(PeerBlob) == B2_PEER_BLOB_BYTES, "PeerBlob size");
 
 struct FirstPlanHost {
-  DBuf<int> brick_cell_ptr, cell_order, brick_row_ptr, brick_rows, brow_off, row_lidx, iface_rows;
-  int n_bricks = 0, n_iface = 0, n_interior = 0, acc_cap = 0, max_rows = 0;
-  int64_t nnz_iface = 0;
-  size_t smem_bytes = 0;
+  DBuf<int> cell_order;   // cells by congruence class, slab by slab (build_first_plan)
+  int64_t n_classes = 0;
   bool ready = false;
 };
 
@@ -216,8 +214,9 @@ struct b2_ctx {
   DBuf<uint8_t> is_bc_row_v, is_bc_q;
   DBuf<uint8_t> pos8;  // per-cell scatter table of the convection assembly (elem.cuh)
   int maxlen_vv = 0;        // longest row of the P2xP2 pattern
-  FirstPlanHost first;      // brick plan of assemble_first (build_first_plan)
-  int first_bricks = 4;     // tuning "first_bricks": cubes per brick edge (0: no bricks, every row through global reductions)
+  FirstPlanHost first;      // cell schedule of assemble_first (build_first_plan)
+  int first_order = 1;      // tuning "first_order": 1 = congruence-class cell order (coalesced scatter), 0 = mesh order
+  int first_slab = 1;       // tuning "first_slab": slab thickness of the class interleaving, in reference edge lengths
   // CUDA graph of one multigrid-preconditioned CG iteration of the pressure solve (single rank): ~21 dependent
   // launches of a few microseconds each become one graph launch
   cudaGraphExec_t pcg_graph = nullptr;
@@ -912,139 +911,77 @@ void chebyshev_solve(b2_ctx* c, int which, const CSR& pat, const double* vals, c
 
 void require_ready(b2_ctx* c) { B2_REQUIRE(c->preassembled, "b2_preassemble has not been called"); }
 
-// ---- brick plan of the cell-parallel assemble_first (elem.cuh: k_first_cells) ---------------------------------
-// Cells are binned into spatial bricks by their centroids (no lattice assumed: the brick edge comes from the mean
-// cell volume), rows whose cells all lie in one brick become that brick's interior rows as long as their
-// accumulators fit the shared memory of a block; everything else is an interface row.
+// ---- cell schedule of the cell-parallel assemble_first (elem.cuh: k_first_cells) ------------------------------
+// Cells are grouped by congruence class (equal edge vectors up to rounding: translates of each other) and listed,
+// inside a class, along x then y then z, so that consecutive threads scatter to consecutive dofs; classes are
+// interleaved slab by slab (a few cell layers in z) to keep the accumulated rows resident in L2.  No lattice is
+// assumed: a mesh without congruent cells yields one class per cell and keeps its (z, y, x) order.
 void build_first_plan(b2_ctx* c) {
-  const Space& V = c->sp[B2_SPACE_V];
-  const CSR& vv = c->pat[B2_PAT_VV];
-  const int d = c->gdim, nv = V.nd;
+  const int d = c->gdim;
   const int64_t nc = c->n_cells;
-  const int n_rows = vv.n_rows;
   FirstPlanHost& P = c->first;
   P = FirstPlanHost();
-  if (nc == 0 || n_rows == 0 || c->first_bricks == 0) return;
+  if (nc == 0 || c->first_order == 0) return;
   std::vector<double> x((size_t)c->n_nodes * 3);
-  std::vector<int> cn((size_t)nc * (d + 1)), cd((size_t)nc * nv), rowptr((size_t)n_rows + 1);
+  std::vector<int> cn((size_t)nc * (d + 1));
   B2_CUDA(cudaMemcpyAsync(x.data(), c->x.p, sizeof(double) * x.size(), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaMemcpyAsync(cn.data(), c->cell_nodes.p, sizeof(int) * cn.size(), cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaMemcpyAsync(cd.data(), V.cell_dofs.p, sizeof(int) * cd.size(), cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaMemcpyAsync(rowptr.data(), vv.rowptr.p, sizeof(int) * rowptr.size(), cudaMemcpyDeviceToHost, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
-  // centroids, bounding box, mean cell measure
-  std::vector<double> cen((size_t)nc * 3, 0.0);
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, meas = 0.0;
-  for (int64_t e = 0; e < nc; ++e) {
-    double X[4][3];
-    for (int v = 0; v <= d; ++v)
-      for (int k = 0; k < 3; ++k) X[v][k] = x[3 * (size_t)cn[e * (d + 1) + v] + k];
+  // reference length: mean edge of the first cells' first edges
+  double h = 0.0;
+  const int64_t ns = std::min<int64_t>(nc, 4096);
+  for (int64_t e = 0; e < ns; ++e) {
+    double l2 = 0;
     for (int k = 0; k < d; ++k) {
-      double s = 0;
-      for (int v = 0; v <= d; ++v) s += X[v][k];
-      cen[3 * e + k] = s / (d + 1);
-      lo[k] = std::min(lo[k], cen[3 * e + k]);
-      hi[k] = std::max(hi[k], cen[3 * e + k]);
+      const double v = x[3 * (size_t)cn[e * (d + 1) + 1] + k] - x[3 * (size_t)cn[e * (d + 1)] + k];
+      l2 += v * v;
     }
-    double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int k = 0; k < d; ++k)
-      for (int dl = 0; dl < d; ++dl) J[k][dl] = X[dl + 1][k] - X[0][k];
-    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-    meas += std::fabs(det) / (d == 3 ? 6.0 : 2.0);
+    h += std::sqrt(l2);
   }
-  meas /= (double)nc;
-  // brick edge: `first_bricks` cubes of (d! cells) per direction; box meshes get bricks aligned with their cubes
-  const double cube = d == 3 ? std::cbrt(6.0 * meas) : std::sqrt(2.0 * meas);
-  const double L = cube * c->first_bricks;
-  double org[3];
-  int nb[3] = {1, 1, 1};
-  for (int k = 0; k < d; ++k) {
-    org[k] = lo[k] - (d == 3 ? 0.25 : 1.0 / 3.0) * cube - 1e-9 * cube;  // centroids sit >= cube/4 inside their cube
-    nb[k] = std::max(1, (int)std::ceil((hi[k] - org[k]) / L + 1e-9));
-  }
-  std::vector<int> brick((size_t)nc);
-  for (int64_t e = 0; e < nc; ++e) {
-    int id = 0;
-    for (int k = d - 1; k >= 0; --k) {
-      int q = std::min(nb[k] - 1, std::max(0, (int)std::floor((cen[3 * e + k] - org[k]) / L)));
-      id = id * nb[k] + q;
-    }
-    brick[e] = id;
-  }
-  const int n_bricks_all = nb[0] * nb[1] * nb[2];
-  // cells sorted by brick (counting sort, stable)
-  std::vector<int> cptr((size_t)n_bricks_all + 1, 0);
-  for (int64_t e = 0; e < nc; ++e) cptr[brick[e] + 1]++;
-  for (int b = 0; b < n_bricks_all; ++b) cptr[b + 1] += cptr[b];
-  std::vector<int> order((size_t)nc), fill(cptr.begin(), cptr.end() - 1);
-  for (int64_t e = 0; e < nc; ++e) order[fill[brick[e]]++] = (int)e;
-  // rows: interior iff all adjacent cells share one brick
-  std::vector<int> rmin((size_t)n_rows, INT32_MAX), rmax((size_t)n_rows, -1);
+  h = std::max(h / (double)ns, 1e-300);
+  struct Key { uint64_t cls; int64_t q[3]; int cell; };
+  std::vector<Key> keys((size_t)nc);
+  double lo[3] = {1e300, 1e300, 1e300};
+  std::vector<double> cen((size_t)nc * 3, 0.0);
   for (int64_t e = 0; e < nc; ++e)
-    for (int i = 0; i < nv; ++i) {
-      const int r = cd[e * nv + i];
-      if (r < n_rows) { rmin[r] = std::min(rmin[r], brick[e]); rmax[r] = std::max(rmax[r], brick[e]); }
+    for (int k = 0; k < d; ++k) {
+      double sacc = 0;
+      for (int v = 0; v <= d; ++v) sacc += x[3 * (size_t)cn[e * (d + 1) + v] + k];
+      cen[3 * e + k] = sacc / (d + 1);
+      lo[k] = std::min(lo[k], cen[3 * e + k]);
     }
-  // interior rows per brick (increasing row id), capped by the shared-memory budget
-  int dev_smem = 0;
-  B2_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const int K = d;
-  const int budget = std::min(dev_smem - 2048, 110 * 1024);  // two blocks per SM
-  std::vector<int> rcnt((size_t)n_bricks_all + 1, 0);
-  for (int r = 0; r < n_rows; ++r)
-    if (rmax[r] >= 0 && rmin[r] == rmax[r]) rcnt[rmin[r] + 1]++;
-  for (int b = 0; b < n_bricks_all; ++b) rcnt[b + 1] += rcnt[b];
-  std::vector<int> brows((size_t)rcnt[n_bricks_all]), rfill(rcnt.begin(), rcnt.end() - 1);
-  for (int r = 0; r < n_rows; ++r)
-    if (rmax[r] >= 0 && rmin[r] == rmax[r]) brows[rfill[rmin[r]]++] = r;
-  std::vector<int> h_cptr, h_rptr, h_rows, h_off, lidx((size_t)n_rows, -1), iface;
-  h_cptr.push_back(0);
-  h_rptr.push_back(0);
-  std::vector<int> h_order;
-  h_order.reserve((size_t)nc);
-  int acc_cap = 0, max_rows = 0;
-  for (int b = 0; b < n_bricks_all; ++b) {
-    if (cptr[b + 1] == cptr[b]) continue;
-    int off = 0, cnt = 0;
-    for (int q = rcnt[b]; q < rcnt[b + 1]; ++q) {
-      const int r = brows[q], len = rowptr[r + 1] - rowptr[r];
-      if ((size_t)(off + len) * 8 + (size_t)(cnt + 1) * K * 8 > (size_t)budget) break;  // the rest stays interface
-      lidx[r] = (int)h_rows.size();
-      h_rows.push_back(r);
-      h_off.push_back(off);
-      off += len;
-      ++cnt;
-    }
-    acc_cap = std::max(acc_cap, off);
-    max_rows = std::max(max_rows, cnt);
-    for (int q = cptr[b]; q < cptr[b + 1]; ++q) h_order.push_back(order[q]);
-    h_cptr.push_back((int)h_order.size());
-    h_rptr.push_back((int)h_rows.size());
+  for (int64_t e = 0; e < nc; ++e) {
+    uint64_t hsh = 1469598103934665603ull;  // FNV-1a over the rounded edge vectors (1/64 of the reference length)
+    for (int v = 1; v <= d; ++v)
+      for (int k = 0; k < d; ++k) {
+        const double ev = x[3 * (size_t)cn[e * (d + 1) + v] + k] - x[3 * (size_t)cn[e * (d + 1)] + k];
+        const int64_t r = (int64_t)std::llround(ev / h * 64.0);
+        hsh = (hsh ^ (uint64_t)r) * 1099511628211ull;
+      }
+    Key& kk = keys[e];
+    kk.cls = hsh;
+    kk.cell = (int)e;
+    for (int k = 0; k < 3; ++k) kk.q[k] = k < d ? (int64_t)std::floor((cen[3 * e + k] - lo[k]) / h * 8.0) : 0;  // h/8 bins
   }
-  for (int r = 0; r < n_rows; ++r)
-    if (lidx[r] < 0) iface.push_back(r);
-  auto up = [&](DBuf<int>& dst, const std::vector<int>& v) {
-    dst.alloc((int64_t)std::max<size_t>(v.size(), 1));
-    if (!v.empty()) B2_CUDA(cudaMemcpyAsync(dst.p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, c->stream));
-  };
-  up(P.brick_cell_ptr, h_cptr);
-  up(P.cell_order, h_order);
-  up(P.brick_row_ptr, h_rptr);
-  up(P.brick_rows, h_rows);
-  up(P.brow_off, h_off);
-  up(P.row_lidx, lidx);
-  up(P.iface_rows, iface);
+  const int zk = d - 1;
+  const int64_t slab = 8 * (int64_t)std::max(1, c->first_slab);  // bins per slab: first_slab reference lengths
+  std::sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
+    const int64_t sa = a.q[zk] / slab, sb = b.q[zk] / slab;
+    if (sa != sb) return sa < sb;
+    if (a.cls != b.cls) return a.cls < b.cls;
+    for (int k = d - 1; k >= 0; --k)
+      if (a.q[k] != b.q[k]) return a.q[k] < b.q[k];
+    return a.cell < b.cell;
+  });
+  std::vector<int> order((size_t)nc);
+  for (int64_t e = 0; e < nc; ++e) order[e] = keys[e].cell;
+  P.cell_order.alloc(nc);
+  B2_CUDA(cudaMemcpyAsync(P.cell_order.p, order.data(), sizeof(int) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
-  P.n_bricks = (int)h_cptr.size() - 1;
-  P.n_iface = (int)iface.size();
-  P.n_interior = (int)h_rows.size();
-  P.acc_cap = acc_cap;
-  P.max_rows = max_rows;
-  int64_t nnz_if = 0;
-  for (int r : iface) nnz_if += rowptr[r + 1] - rowptr[r];
-  P.nnz_iface = nnz_if;
-  P.smem_bytes = (size_t)(acc_cap + max_rows * K) * sizeof(double);
+  std::vector<uint64_t> cls((size_t)nc);
+  for (int64_t e = 0; e < nc; ++e) cls[e] = keys[e].cls;
+  std::sort(cls.begin(), cls.end());
+  P.n_classes = (int64_t)(std::unique(cls.begin(), cls.end()) - cls.begin());
   P.ready = true;
 }
 
@@ -1056,41 +993,23 @@ void first_cells(b2_ctx* c, int mode, double dt, double nu, const double* u1, co
   const CSR& vv = c->pat[B2_PAT_VV];
   const int ld = (int)V.n_local();
   B2_REQUIRE(c->pos8.p != nullptr, "assemble_first needs the scatter table (rows shorter than 256 entries)");
-  FirstPlanHost& P = c->first;
-  const bool bricks = P.ready && P.n_bricks > 0;
   const int scale = (int)(c->ksp[B2_SOLVER_TENTATIVE].pc == 0);
-  const int n_if = bricks ? P.n_iface : vv.n_rows;
-  const int* if_rows = bricks ? P.iface_rows.p : nullptr;
-  const int do_mat = mode & 1, do_vec = (mode & 2) ? 1 : 0;
-  if (n_if > 0) {
-    if (K == 2) B2_LAUNCH(c, k_first_init<2>, blocks_for(n_if, 256), 256, n_if, if_rows, vv.rowptr.p, vv.slice_ptr.p, ld, b0, psurf, do_mat, do_vec, A, bfirst);
-    else B2_LAUNCH(c, k_first_init<3>, blocks_for(n_if, 256), 256, n_if, if_rows, vv.rowptr.p, vv.slice_ptr.p, ld, b0, psurf, do_mat, do_vec, A, bfirst);
-  }
-  FirstPlan plan{};
-  size_t smem = 0;
-  int grid = blocks_for(c->n_cells, 192);
-  if (bricks) {
-    plan = FirstPlan{P.n_bricks, P.brick_cell_ptr.p, P.cell_order.p, P.brick_row_ptr.p, P.brick_rows.p, P.brow_off.p,
-                     P.row_lidx.p, P.acc_cap, P.max_rows};
-    smem = P.smem_bytes;
-    grid = P.n_bricks;
-  }
+  if (mode & 1) B2_CUDA(cudaMemsetAsync(A, 0, sizeof(double) * (size_t)vv.slots, c->stream));  // :435
+  if (mode & 2) B2_LAUNCH(c, k_first_init, pgrid(c, (int64_t)ld * K), 256, (int64_t)ld * K, b0, psurf, bfirst);
+  const int* order = c->first.ready ? c->first.cell_order.p : nullptr;
+  const int grid = blocks_for(c->n_cells, 128);
   dispatch_elem(c, [&](auto e) {
     using E = decltype(e);
     auto launch = [&](auto kern) {
-      if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, 192, smem, c->stream>>>(plan, c->n_cells, c->x.p, c->cell_nodes.p, V.cell_dofs.p, (int)V.n_owned, uab, u1, ld,
-                                          vv.rowptr.p, vv.slice_ptr.p, vv.diag_t.p, c->pos8.p, c->is_bc_row_v.p, 1.0 / dt,
-                                          0.5 * nu, scale, b0, psurf, A, bfirst, dinv);
-      c->stats.kernel_launches++;
-      B2_CUDA(cudaGetLastError());
+      B2_LAUNCH(c, kern, grid, 128, c->n_cells, order, c->x.p, c->cell_nodes.p, V.cell_dofs.p, (int)V.n_owned, uab, u1, ld,
+                vv.slice_ptr.p, c->pos8.p, c->is_bc_row_v.p, 1.0 / dt, 0.5 * nu, A, bfirst);
     };
     if (mode == 3) launch(k_first_cells<E::D, E::DEG, 3>);
     else if (mode == 1) launch(k_first_cells<E::D, E::DEG, 1>);
     else launch(k_first_cells<E::D, E::DEG, 2>);
   });
-  if (do_mat && n_if > 0)
-    B2_LAUNCH(c, k_first_finalize, blocks_for(n_if, 256), 256, n_if, if_rows, vv.slice_ptr.p, vv.diag_t.p, c->is_bc_row_v.p, scale, A, dinv);
+  if (mode & 1)
+    B2_LAUNCH(c, k_first_finalize, blocks_for(vv.n_rows, 256), 256, vv.n_rows, vv.slice_ptr.p, vv.diag_t.p, c->is_bc_row_v.p, scale, A, dinv);
 }
 
 // ---- stages ---------------------------------------------------------------------------------
@@ -2552,9 +2471,8 @@ int b2_bench_assembly_strategies(b2_ctx* c, double dt, double nu, int reps, doub
     out[2] = timed([&] { first_cells(c, 2, dt, nu, u1, uab, zero.p, nullptr, c->A.p, c->vec(B2_VEC_BFIRST), c->dinvA.p); });
     const double nV = (double)V.n_owned, nVc = (double)vv.n_cols, cells = (double)c->n_cells;
     const double nvp = (V.nd + 3) / 4 * 4;
-    const double nnz_if = c->first.ready ? (double)c->first.nnz_iface : (double)vv.nnz;
     const double cell_bytes = 4.0 * (V.nd + c->gdim + 1);  // dofs + vertices: SURVEY.md 8(d) "cells * 56" for P2 tetrahedra
-    out[3] = 8.0 * vv.nnz + 16.0 * nnz_if + cells * (cell_bytes + V.nd * nvp) + 8.0 * 3 * c->n_nodes + 8.0 * K * nVc;
+    out[3] = 24.0 * vv.nnz + cells * (cell_bytes + V.nd * nvp) + 8.0 * 3 * c->n_nodes + 8.0 * K * nVc;
     out[4] = 28.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc);
     out[5] = cells * cell_bytes + 8.0 * 3 * c->n_nodes + 8.0 * K * (2 * nVc + nV);
     for (auto& ev : e) cudaEventDestroy(ev);
@@ -2564,15 +2482,10 @@ int b2_bench_assembly_strategies(b2_ctx* c, double dt, double nu, int reps, doub
 
 int b2_first_plan_info(b2_ctx* c, int64_t* out) {
   return guarded(c, [&] {
-    const FirstPlanHost& P = c->first;
-    out[0] = P.ready ? P.n_bricks : 0;
-    out[1] = P.n_interior;
-    out[2] = P.ready ? P.n_iface : c->pat[B2_PAT_VV].n_rows;
-    out[3] = P.acc_cap;
-    out[4] = P.max_rows;
-    out[5] = P.ready ? P.nnz_iface : c->pat[B2_PAT_VV].nnz;
-    out[6] = (int64_t)P.smem_bytes;
-    out[7] = c->first_bricks;
+    out[0] = c->first.ready ? 1 : 0;
+    out[1] = c->first.n_classes;
+    out[2] = c->first_slab;
+    out[3] = c->n_cells;
   });
 }
 
@@ -2594,8 +2507,8 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
-    else if (k == "first_bricks") {
-      c->first_bricks = std::max(0, value);
+    else if (k == "first_order" || k == "first_slab") {
+      (k == "first_order" ? c->first_order : c->first_slab) = std::max(0, value);
       if (c->preassembled) build_first_plan(c);
     }
     else throw B2Error(-2, "unknown tuning key " + k);
@@ -2653,10 +2566,9 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       case 2: *bytes_per_launch = 12.0 * qq.nnz + 4.0 * (qq.n_rows + 1) + 8.0 * (qq.n_rows + qq.n_cols); break;
       case 1: {  // k_first_cells: A written once (interface rows: zero-fill + read-modify-write on top), cell data
                  // (dofs, nodes, scatter table), coordinates, uab/u1 read, b0 read, b_first + dinv written, uab = 1.5 u1 - .5 u2
-        const double nvp = (V.nd + 3) / 4 * 4;
-        const double nnz_if = c->first.ready ? (double)c->first.nnz_iface : (double)vv.nnz;
-        *bytes_per_launch = 8.0 * vv.nnz + 16.0 * nnz_if + (double)c->n_cells * (4.0 * (V.nd + c->gdim + 1) + V.nd * nvp) +
-                            8.0 * 3 * c->n_nodes + 8.0 * K * nVc * (2 + 3) + 8.0 * K * nV * 2 + 8.0 * nV;
+        const double nvp = (V.nd + 3) / 4 * 4;  // zero-fill (8 nnz) + read-modify-write of the reductions (16 nnz)
+        *bytes_per_launch = 24.0 * vv.nnz + (double)c->n_cells * (4.0 * (V.nd + c->gdim + 1 + 1) + V.nd * nvp) +
+                            8.0 * 3 * c->n_nodes + 8.0 * K * nVc * (2 + 3) + 8.0 * K * nV * 4 + 8.0 * nV;
         break;
       }
     }

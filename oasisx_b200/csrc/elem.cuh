@@ -268,243 +268,149 @@ __global__ void k_build_pos8(int64_t n_cells, const int* __restrict__ vdofs, int
   for (int j = 0; j < NVP; ++j) out[j] = j < NV ? (uint8_t)(csr_find(cols, lo, hi, dofs[j]) - lo) : 0;
 }
 
-// ---- assemble_first, cell-parallel and brick-local (fracstep.py:432-472 in one pass) ---------------------------
+// ---- assemble_first, cell-parallel (fracstep.py:432-472 in one pass over the cells) -----------------------------
 // One thread per cell forms, row by row, the COMPLETE element operators of the step
 //     A_e = M_e/dt + nu/2 K_e + 1/2 C_e(uab)      (left-hand side, :468-469)
 //     R_e = M_e/dt - nu/2 K_e - 1/2 C_e(uab)      (right-hand side operator, :438-442)
 // from the exact reference tensors (every tensor entry a compile-time operand of its DFMA; M and K are never read
 // from memory) and, matrix-free, the action  b_first += R_e u1_e  (the "action strategy" of
-// demo/assembly_strategies.py:83-88,137-140) -- no separate CSR-value passes, no SpMV.
+// demo/assembly_strategies.py:83-88,137-140): no separate CSR-value passes, no SpMV, A written by FP64 reductions
+// into zero-filled slots and finished (Dirichlet rows -> identity, dinv = 1/diagonal) by k_first_finalize.
 //
-// Where the contributions go depends on the row: a block owns a spatial BRICK of cells (host-built from the cell
-// centroids, any mesh); rows all of whose cells lie in the brick ("interior", ~2/3 of the rows for 4^3-cube bricks)
-// are accumulated in SHARED memory and written ONCE, finished (Dirichlet rows -> identity, dinv = 1/diagonal), with
-// no zero-fill and no global atomics; the remaining "interface" rows are accumulated with global FP64 reductions
-// into slots a small kernel zeroed before (k_first_init) and finished by k_first_finalize.  Summation order inside a
-// row is not fixed (shared-memory CAS adds / L2 reductions): results are reproducible to rounding, like PETSc's
-// ADD_VALUES assembly over ranks.
-//   MODE & 1: matrix,  MODE & 2: vector (b_first).  Plan without bricks (all rows interface): row_lidx == nullptr.
-struct FirstPlan {
-  int n_bricks;
-  const int* brick_cell_ptr;   // [n_bricks + 1] into cell_order
-  const int* cell_order;       // cells sorted by brick
-  const int* brick_row_ptr;    // [n_bricks + 1] into brick_rows / brow_off
-  const int* brick_rows;       // interior rows, grouped by brick, increasing inside a brick
-  const int* brow_off;         // offset (doubles) of the row's accumulators in the brick's shared memory
-  const int* row_lidx;         // [n_rows_owned] index into brick_rows, or -1 for interface rows
-  int acc_cap;                 // doubles of shared memory for matrix accumulators per block
-  int max_rows;                // most interior rows of any brick
-};
-
-__device__ __forceinline__ void smem_add(double* p, double v) { atomicAdd(p, v); }
-
+// COALESCED SCATTER.  The kernel is bound by the number of 32-byte sectors its reductions touch (one LSU wavefront
+// each), not by bytes or flops: with cells in mesh order the 32 lanes of a RED hit 32 sectors.  `cell_order` (host:
+// build_first_plan) lists the cells by congruence class -- cells that are translates of each other -- and, inside a
+// class, along x: consecutive lanes then hold the same local dof of consecutive dofs of one stencil class, the
+// scatter position t is the same for all of them, and a RED instruction covers 32 CONSECUTIVE doubles of one
+// sliced-ELL column (8 sectors instead of 32); the gathers of uab / u1 coalesce the same way.  Classes are
+// interleaved slab by slab so that the rows being accumulated stay resident in L2.  Meshes without congruent cells
+// simply keep their order (nothing assumes a lattice).  Summation order inside an entry is not fixed (L2
+// reductions): reproducible to rounding, like PETSc's ADD_VALUES over ranks.
+//   MODE & 1: matrix,  MODE & 2: vector (b_first, preloaded with b0 + p_surf by k_first_init).
 template <int D, int DEG, int MODE>
-__global__ void __launch_bounds__(192, 2)
-k_first_cells(FirstPlan plan, int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
-              const int* __restrict__ vdofs, int n_rows_owned, const double* __restrict__ uab,
-              const double* __restrict__ u1, int ld, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr,
-              const int* __restrict__ diag_t, const uint8_t* __restrict__ pos8, const uint8_t* __restrict__ is_bc_row,
-              double inv_dt, double half_nu, int scale, const double* __restrict__ b0, const double* __restrict__ psurf,
-              double* __restrict__ Avals, double* __restrict__ bfirst, double* __restrict__ dinv) {
+__global__ void __launch_bounds__(128, 3)
+k_first_cells(int64_t n_cells, const int* __restrict__ cell_order, const double* __restrict__ x,
+              const int* __restrict__ cell_nodes, const int* __restrict__ vdofs, int n_rows_owned,
+              const double* __restrict__ uab, const double* __restrict__ u1, int ld, const int* __restrict__ slice_ptr,
+              const uint8_t* __restrict__ pos8, const uint8_t* __restrict__ is_bc_row, double inv_dt, double half_nu,
+              double* __restrict__ Avals, double* __restrict__ bfirst) {
   using E = El<D, DEG>;
   constexpr int NV = E::NV, K = D;
   constexpr int NVP = (NV + 3) / 4 * 4;
   constexpr bool MAT = (MODE & 1) != 0, VEC = (MODE & 2) != 0;
-  extern __shared__ double s_first[];
-  const bool bricks = plan.row_lidx != nullptr;
-  double* acc = s_first;                    // [acc_cap]
-  double* bfs = s_first + plan.acc_cap;     // [max_rows][K]
-  int64_t c0, c1;
-  int r0 = 0, r1 = 0;
-  if (bricks) {
-    c0 = plan.brick_cell_ptr[blockIdx.x];
-    c1 = plan.brick_cell_ptr[blockIdx.x + 1];
-    r0 = plan.brick_row_ptr[blockIdx.x];
-    r1 = plan.brick_row_ptr[blockIdx.x + 1];
-    const int n_acc = r1 > r0 ? plan.brow_off[r1 - 1] + (rowptr[plan.brick_rows[r1 - 1] + 1] - rowptr[plan.brick_rows[r1 - 1]]) : 0;
-    if (MAT)
-      for (int t = threadIdx.x; t < n_acc; t += blockDim.x) acc[t] = 0.0;
-    if (VEC)
-      for (int t = threadIdx.x; t < (r1 - r0) * K; t += blockDim.x) bfs[t] = 0.0;
-    __syncthreads();
-  } else {
-    c0 = (int64_t)blockIdx.x * blockDim.x;
-    c1 = min(c0 + (int64_t)blockDim.x, n_cells);
+  const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= n_cells) return;
+  const int64_t c = cell_order != nullptr ? (int64_t)__ldg(cell_order + ci) : ci;
+  const Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+  int dofs[NV];
+#pragma unroll
+  for (int a = 0; a < NV; ++a) dofs[a] = vdofs[c * NV + a];
+  double w[NV][D], u1e[NV][K];
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double u[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      u[k] = __ldg(uab + (size_t)k * ld + dofs[a]);
+      if (VEC) u1e[a][k] = __ldg(u1 + (size_t)k * ld + dofs[a]);
+    }
+#pragma unroll
+    for (int dl = 0; dl < D; ++dl) {
+      double sacc = 0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) sacc += g.Kinv[dl][k] * u[k];
+      w[a][dl] = sacc * (0.5 * g.detJ);  // 1/2 C_e
+    }
   }
-  for (int64_t ci = c0 + threadIdx.x; ci < c1; ci += blockDim.x) {
-    const int64_t c = bricks ? (int64_t)plan.cell_order[ci] : ci;
-    const Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
-    int dofs[NV];
+  // Gh = nu/2 |detJ| Kinv Kinv^T (symmetric): nu/2 K_e[i][j] = sum_ab Gh[a][b] SV[a][b][i][j]
+  double Gh[D][D];
 #pragma unroll
-    for (int a = 0; a < NV; ++a) dofs[a] = vdofs[c * NV + a];
-    double w[NV][D], u1e[NV][K];
+  for (int a = 0; a < D; ++a)
 #pragma unroll
-    for (int a = 0; a < NV; ++a) {
-      double u[D];
+    for (int b = a; b < D; ++b) {
+      double sacc = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        u[k] = __ldg(uab + (size_t)k * ld + dofs[a]);
-        if (VEC) u1e[a][k] = __ldg(u1 + (size_t)k * ld + dofs[a]);
-      }
+      for (int k = 0; k < D; ++k) sacc += g.Kinv[a][k] * g.Kinv[b][k];
+      Gh[a][b] = Gh[b][a] = sacc * (half_nu * g.detJ);
+    }
+  const double mdt = inv_dt * g.detJ;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int row = dofs[i];
+    if (row >= n_rows_owned) continue;
+    double cv[NV], kv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { cv[j] = 0.0; kv[j] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
 #pragma unroll
       for (int dl = 0; dl < D; ++dl) {
-        double sacc = 0;
+        const double wv = w[a][dl];
 #pragma unroll
-        for (int k = 0; k < D; ++k) sacc += g.Kinv[dl][k] * u[k];
-        w[a][dl] = sacc * (0.5 * g.detJ);  // 1/2 C_e
+        for (int j = 0; j < NV; ++j)
+          if (E::T(a, dl, i, j) != 0.0) cv[j] = fma(wv, E::T(a, dl, i, j), cv[j]);
       }
-    }
-    // Gh = nu/2 |detJ| Kinv Kinv^T (symmetric): nu/2 K_e[i][j] = sum_ab Gh[a][b] SV[a][b][i][j]
-    double Gh[D][D];
 #pragma unroll
     for (int a = 0; a < D; ++a)
 #pragma unroll
       for (int b = a; b < D; ++b) {
-        double sacc = 0;
+        const double gv = Gh[a][b];
 #pragma unroll
-        for (int k = 0; k < D; ++k) sacc += g.Kinv[a][k] * g.Kinv[b][k];
-        Gh[a][b] = Gh[b][a] = sacc * (half_nu * g.detJ);
-      }
-    const double mdt = inv_dt * g.detJ;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int row = dofs[i];
-      if (row >= n_rows_owned) continue;
-      double cv[NV], kv[NV];
-#pragma unroll
-      for (int j = 0; j < NV; ++j) { cv[j] = 0.0; kv[j] = 0.0; }
-#pragma unroll
-      for (int a = 0; a < NV; ++a)
-#pragma unroll
-        for (int dl = 0; dl < D; ++dl) {
-          const double wv = w[a][dl];
-#pragma unroll
-          for (int j = 0; j < NV; ++j)
-            if (E::T(a, dl, i, j) != 0.0) cv[j] = fma(wv, E::T(a, dl, i, j), cv[j]);
-        }
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int b = a; b < D; ++b) {
-          const double gv = Gh[a][b];
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const double sv = (a == b) ? E::SV(a, b, i, j) : (E::SV(a, b, i, j) + E::SV(b, a, i, j));
-            if (sv != 0.0) kv[j] = fma(gv, sv, kv[j]);
-          }
-        }
-      double dot[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) dot[k] = 0.0;
-      double av[NV];
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const double m = mdt * E::MV(i, j);
-        av[j] = (m + cv[j]) + kv[j];
-        if (VEC) {
-          const double rr = (m - cv[j]) - kv[j];
-#pragma unroll
-          for (int k = 0; k < K; ++k) dot[k] = fma(rr, u1e[j][k], dot[k]);
+        for (int j = 0; j < NV; ++j) {
+          const double sv = (a == b) ? E::SV(a, b, i, j) : (E::SV(a, b, i, j) + E::SV(b, a, i, j));
+          if (sv != 0.0) kv[j] = fma(gv, sv, kv[j]);
         }
       }
-      const int l = bricks ? __ldg(plan.row_lidx + row) : -1;
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(pos8 + ((size_t)c * NV + i) * NVP);
-      if (l >= 0) {  // interior row of this brick: shared memory
-        if (MAT) {
-          double* rowbase = acc + __ldg(plan.brow_off + l);
-          uint32_t word = 0;
+    double dot[K];
 #pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            if ((j & 3) == 0) word = __ldg(pw + (j >> 2));
-            smem_add(rowbase + ((word >> (8 * (j & 3))) & 0xff), av[j]);
-          }
-        }
-        if (VEC) {
+    for (int k = 0; k < K; ++k) dot[k] = 0.0;
+    double av[NV];
 #pragma unroll
-          for (int k = 0; k < K; ++k) smem_add(bfs + (l - r0) * K + k, dot[k]);
-        }
-      } else {  // interface row: global reductions into the slots k_first_init zeroed
-        if (MAT && !is_bc_row[row]) {
-          double* rowbase = Avals + (size_t)__ldg(slice_ptr + (row >> 5)) + (row & 31);
-          uint32_t word = 0;
+    for (int j = 0; j < NV; ++j) {
+      const double m = mdt * E::MV(i, j);
+      av[j] = (m + cv[j]) + kv[j];
+      if (VEC) {
+        const double rr = (m - cv[j]) - kv[j];
 #pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            if ((j & 3) == 0) word = __ldg(pw + (j >> 2));
-            atomicAdd(rowbase + ((size_t)((word >> (8 * (j & 3))) & 0xff) << 5), av[j]);
-          }
-        }
-        if (VEC) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) atomicAdd(bfirst + (size_t)k * ld + row, dot[k]);
-        }
+        for (int k = 0; k < K; ++k) dot[k] = fma(rr, u1e[j][k], dot[k]);
       }
     }
-  }
-  if (!bricks) return;
-  __syncthreads();
-  // finish the interior rows of the brick: one thread per row
-  for (int l = r0 + threadIdx.x; l < r1; l += blockDim.x) {
-    const int row = plan.brick_rows[l];
-    if (MAT) {
-      const double* rowacc = acc + plan.brow_off[l];
-      const int len = rowptr[row + 1] - rowptr[row];
-      const int td = diag_t[row];
-      const bool bc = is_bc_row[row];
-      const double d = rowacc[td];
-      const double invd = (scale && !bc) ? 1.0 / d : 1.0;
+    if (MAT && !is_bc_row[row]) {
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(pos8 + ((size_t)c * NV + i) * NVP);
       double* rowbase = Avals + (size_t)__ldg(slice_ptr + (row >> 5)) + (row & 31);
-      for (int t = 0; t < len; ++t) rowbase[(size_t)t << 5] = bc ? (t == td ? 1.0 : 0.0) : rowacc[t];
-      dinv[row] = invd;
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if ((j & 3) == 0) word = __ldg(pw + (j >> 2));
+        atomicAdd(rowbase + ((size_t)((word >> (8 * (j & 3))) & 0xff) << 5), av[j]);
+      }
     }
     if (VEC) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        double v = bfs[(l - r0) * K + k] + b0[(size_t)k * ld + row];
-        if (psurf != nullptr) v += psurf[(size_t)k * ld + row];
-        bfirst[(size_t)k * ld + row] = v;
-      }
+      for (int k = 0; k < K; ++k) atomicAdd(bfirst + (size_t)k * ld + row, dot[k]);
     }
   }
 }
 
-// interface rows before k_first_cells: zero the row's slots, b_first <- b0 (+ p_surf)
-template <int K>
-__global__ void k_first_init(int n, const int* __restrict__ rows, const int* __restrict__ rowptr,
-                             const int* __restrict__ slice_ptr, int ld, const double* __restrict__ b0,
-                             const double* __restrict__ psurf, int do_mat, int do_vec, double* __restrict__ Avals,
+// b_first <- b0 (+ p_surf) before the cell kernel adds R u1 (:449-465)
+__global__ void k_first_init(int64_t n, const double* __restrict__ b0, const double* __restrict__ psurf,
                              double* __restrict__ bfirst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int row = rows != nullptr ? rows[i] : i;
-  if (do_mat) {
-    const int len = rowptr[row + 1] - rowptr[row];
-    double* rowbase = Avals + (size_t)slice_ptr[row >> 5] + (row & 31);
-    for (int t = 0; t < len; ++t) rowbase[(size_t)t << 5] = 0.0;
-  }
-  if (do_vec) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double v = b0[(size_t)k * ld + row];
-      if (psurf != nullptr) v += psurf[(size_t)k * ld + row];
-      bfirst[(size_t)k * ld + row] = v;
-    }
-  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bfirst[i] = psurf != nullptr ? b0[i] + psurf[i] : b0[i];
 }
 
-// interface rows after k_first_cells: Dirichlet rows -> identity, dinv = 1 / diagonal
-__global__ void k_first_finalize(int n, const int* __restrict__ rows, const int* __restrict__ slice_ptr,
-                                 const int* __restrict__ diag_t, const uint8_t* __restrict__ is_bc_row, int scale,
-                                 double* __restrict__ Avals, double* __restrict__ dinv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int row = rows != nullptr ? rows[i] : i;
-  double* rowbase = Avals + (size_t)slice_ptr[row >> 5] + (row & 31);
-  const int td = diag_t[row];
+// after the cell kernel: Dirichlet rows -> identity (:470-472; their slots still hold the zero-fill), dinv = 1 / diagonal
+__global__ void k_first_finalize(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ diag_t,
+                                 const uint8_t* __restrict__ is_bc_row, int scale, double* __restrict__ Avals,
+                                 double* __restrict__ dinv) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  double* d = Avals + (size_t)slice_ptr[row >> 5] + (row & 31) + ((size_t)diag_t[row] << 5);
   if (is_bc_row[row]) {
-    rowbase[(size_t)td << 5] = 1.0;  // the other slots of a Dirichlet row stay at the zeros of k_first_init
+    *d = 1.0;
     dinv[row] = 1.0;
   } else {
-    dinv[row] = scale ? 1.0 / rowbase[(size_t)td << 5] : 1.0;
+    dinv[row] = scale ? 1.0 / *d : 1.0;
   }
 }
 

@@ -55,14 +55,14 @@ def test_preassembled_matrices(gdim, N, deg):
 @pytest.mark.parametrize("rows", [1, 0])
 def test_assemble_first_and_tentative_rhs(gdim, N, deg, body_force, rows):
     """A, b_first and rhs1 after assemble_first + velocity_tentative_assemble
-    (test/test_tentative_velocity.py:172-173,235), with the row-wise fused kernel (rows=1, the default) and with
-    the scatter + combine pair it replaces."""
+    (test/test_tentative_velocity.py:172-173,235), with the congruence-class cell schedule (rows=1, the default:
+    coalesced scatter) and in mesh order (rows=0)."""
     dt, nu = 0.1, 0.5
     f = [0.3, -0.1, 0.2][:gdim] if body_force else None
     msh = make_mesh(gdim, N)
     tg = TaylorGreen(nu, gdim)
     s = make_solver(msh, deg, tg, dt, body_force=f)
-    s._ctx.set_tuning("assemble_rows", rows)
+    s._ctx.set_tuning("first_order", rows)
     o = make_oracle(msh, deg, tg, dt, body_force=f)
     ps = lambda x: x[1] + 0.5 * x[0] ** 2
     s._ps.interpolate(ps)
@@ -102,7 +102,7 @@ def test_rowwise_and_scatter_assembly_agree_on_larger_meshes(gdim, N):
     tg.t_u = dt
     out = []
     for rows in (1, 0):
-        s._ctx.set_tuning("assemble_rows", rows)
+        s._ctx.set_tuning("first_order", rows)
         s.assemble_first(dt, nu)
         out.append((_csr(s._A), [s._b_first[i].x.array_ro().copy() for i in range(gdim)]))
     (A1, b1), (A0, b0) = out
