@@ -1,4 +1,7 @@
 #!/usr/bin/env python3
+# This driver follows demo/taylor_green.py of Oasisx (argument list, exact-solution classes, loop and rate tail):
+#   Copyright (C) 2022 Jørgen Schartum Dokken -- This file is part of Oasisx -- SPDX-License-Identifier: MIT
+# with every DOLFINx / UFL / PETSc call replaced by oasisx_b200.
 """Taylor-Green convergence demo on B200 -- the driver of /root/reference/demo/taylor_green.py with
 `oasisx` replaced by `oasisx_b200` and the DOLFINx mesh/tag calls by the built-in provider.  Same
 command line (-N, -T0, -T1, -dt, -nu, -u, -p, -lm, -r), same initial/boundary data, same error
@@ -31,6 +34,11 @@ class U:
     def eval_z(self, x):
         return np.zeros_like(x[0])
 
+    def trig_terms(self, which):
+        """The same field as trigonometric product terms: evaluated on the device by assemble_l2_error_sq."""
+        g, pi = np.exp(-2.0 * self.nu * np.pi**2 * float(self.t)), np.pi
+        return [[-g, pi, 0, 0, 0, 0, pi, 0, 0, 2, 1, 0], [g, pi, 0, 0, 0, 0, pi, 0, 0, 1, 2, 1]]
+
 
 class Pexact:
     def __init__(self, t, nu):
@@ -38,6 +46,10 @@ class Pexact:
 
     def __call__(self, x):
         return -0.25 * (np.cos(2 * np.pi * x[0]) + np.cos(2 * np.pi * x[1])) * np.exp(-4 * np.pi**2 * self.nu * float(self.t))
+
+    def trig_terms(self, which):
+        g, pi = -0.25 * np.exp(-4 * np.pi**2 * self.nu * float(self.t)), np.pi
+        return [[g, 2 * pi, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0], [g, 0, 2 * pi, 0, 0, 0, 0, 0, 0, 2, 0, 0]]
 
 
 parser = argparse.ArgumentParser(description="Taylor-Green convergence demo", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
@@ -52,6 +64,12 @@ parser.add_argument("-p", dest="p_deg", type=int, default=1, help="Degree of pre
 parser.add_argument("-lm", "--low-memory", dest="lm", action="store_true", default=False)
 parser.add_argument("-r", "--rotational", dest="rot", action="store_true", default=False)
 parser.add_argument("-d", "--dim", dest="dim", type=int, default=2, choices=[2, 3], help="2: the reference demo; 3: z-extruded field")
+parser.add_argument("--krylov", action="store_true", help="Krylov solvers (BiCGStab / CG + multigrid / CG, rtol 1e-10) instead of the "
+                                                          "'preonly + lu' of the reference: what large 3D meshes need")
+parser.add_argument("--host-errors", action="store_true", help="sample the exact fields on the host for the error functionals "
+                                                               "(the reference's way; moves cells x points x components doubles per step)")
+parser.add_argument("--export", default=None, help="write <prefix>_N<N>.vtu with u and p after the last step (VTXWriter stand-in)")
+parser.add_argument("--checkpoint", default=None, help="write <prefix>_N<N>.npz with u1, u2, p and t after the last step")
 inputs = parser.parse_args()
 logger = logging.getLogger("Oasisx")
 
@@ -67,6 +85,11 @@ solver_options = {
     "pressure": {"ksp_type": "preonly", "pc_type": "lu"},
     "scalar": {"ksp_type": "preonly", "pc_type": "lu"},
 }
+if inputs.krylov:
+    kry = {"ksp_rtol": 1e-10, "ksp_initial_guess_nonzero": True}
+    solver_options = {"tentative": {"ksp_type": "bcgs", "pc_type": "jacobi", "b200_guess": "extrapolate2", **kry},
+                      "pressure": {"ksp_type": "cg", "pc_type": "mg", "b200_guess": "extrapolate", **kry},
+                      "scalar": {"ksp_type": "cg", "pc_type": "jacobi", "b200_guess": "extrapolate2", **kry}}
 gdim = inputs.dim
 space_errors = np.zeros((2, len(inputs.Ns)))
 hs = np.zeros(len(inputs.Ns))
@@ -111,9 +134,20 @@ for n, N in enumerate(inputs.Ns):
         u_time.value += dt
         p_time.value += dt
         solver.solve(dt, nu, max_iter=1)
-        error_u = mesh.comm.allreduce(solver.assemble_l2_error_sq("u", comps, degree=10))
-        error_p = mesh.comm.allreduce(solver.assemble_l2_error_sq("p", p_ex, degree=10))
+        # demo/taylor_green.py:204-207; the analytic fields are evaluated on the device unless --host-errors
+        error_u = mesh.comm.allreduce(solver.assemble_l2_error_sq("u", comps if inputs.host_errors else u_ex, degree=10))
+        error_p = mesh.comm.allreduce(solver.assemble_l2_error_sq("p", p_ex.__call__ if inputs.host_errors else p_ex, degree=10))
         error_space_time[:, i] = [error_u, error_p]
+    if inputs.export:
+        from oasisx_b200.io import write_vtu
+
+        Vs = solver._Vi[0][0]
+        write_vtu(f"{inputs.export}_N{N}.vtu", Vs, {"u": solver.u.x.array.reshape(-1, gdim)})
+        write_vtu(f"{inputs.export}_N{N}_p.vtu", solver._Q, {"p": solver._p.x.array})
+    if inputs.checkpoint:
+        from oasisx_b200.io import save_checkpoint
+
+        save_checkpoint(f"{inputs.checkpoint}_N{N}", solver, float(u_time.value))
     hmax = mesh.comm.allreduce(np.max(mesh.h(mesh.topology.dim, np.arange(mesh.num_cells, dtype=np.int32))), op="max")
     space_time_u_L2 = np.sqrt(dt * np.sum(error_space_time[0, :]))
     space_time_p_L2 = np.sqrt(dt * np.sum(error_space_time[1, :]))

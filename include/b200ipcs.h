@@ -257,6 +257,12 @@ int b2_l2_error_quadrature(b2_ctx* ctx, int vec, int64_t n_cells, int n_q, const
                            const double* weights, const double* exact, double* out);
 
 /* ---- measurement ---------------------------------------------------------------------- */
+/* The same functional with the exact field evaluated on the device from `n_terms` trigonometric product terms
+ * (12 doubles each: c, a[3], a0, b[3], b0, f1, f2, component; value c F(f1, a.x + a0) F(f2, b.x + b0) with
+ * F(0,.) = 1, F(1,.) = sin, F(2,.) = cos): the Taylor-Green fields of demo/taylor_green.py:41-53,176-191.  Moves a
+ * few hundred bytes instead of cells x points x components doubles. */
+int b2_l2_error_trig(b2_ctx* ctx, int vec, int64_t n_cells_owned, int n_q, const double* ref_points, const double* weights,
+                     int n_terms, const double* terms, double* out);
 /* demo/assembly_strategies.py:56-152 on the device: right-hand side (M/dt - nu/2 K - 1/2 C(UAB)) U1 by the
  * "matvec strategy" (one fused pass over the three assembled value arrays, result in RHS1; reference timed block
  * :128-133) and by the "action strategy" (matrix-free element kernel, result in BFIRST; :137-140), each averaged over

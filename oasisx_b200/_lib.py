@@ -31,7 +31,7 @@ SYMBOLS = [
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
-    "b2_assemble_pressure_surface", "b2_project_assemble", "b2_project_get_rhs", "b2_project_set_rhs", "b2_project_solve", "b2_ksp_solve", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_assemble_pressure_surface", "b2_project_assemble", "b2_project_get_rhs", "b2_project_set_rhs", "b2_project_solve", "b2_ksp_solve", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_l2_error_trig", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
@@ -134,6 +134,7 @@ def load_library() -> C.CDLL:
         "b2_ksp_solve": (i32, [vp, i32, i32, vp, vp, vp]),
         "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
         "b2_l2_error_quadrature": (i32, [vp, i32, i64, i32, vp, vp, vp, vp]),
+        "b2_l2_error_trig": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp]),
         "b2_get_stats": (i32, [vp, vp]),
         "b2_bench_kernel": (i32, [vp, i32, i32, vp, vp]),
         "b2_synchronize": (i32, [vp]),
@@ -389,6 +390,14 @@ class Context:
         fc, fl, h = _i32(facet_cells), _i32(facet_local), _f64(h_nodal)
         self._check(self.lib.b2_assemble_pressure_surface(self._h, fc.size, _ptr(fc), _ptr(fl), _ptr(h), int(accumulate)),
                     "b2_assemble_pressure_surface")
+
+    def l2_error_trig(self, vec: int, n_cells: int, pts, w, terms) -> float:
+        pts, w = _f64(pts), _f64(w)
+        terms = _f64(np.asarray(terms, dtype=np.float64).reshape(-1, 12))
+        out = C.c_double(0.0)
+        self._check(self.lib.b2_l2_error_trig(self._h, vec, n_cells, len(w), _ptr(pts), _ptr(w), terms.shape[0], _ptr(terms), C.byref(out)),
+                    "b2_l2_error_trig")
+        return out.value
 
     def project_assemble(self, target_space: int, n_comp: int, pts, w, src_space: int = 0, src_nodal=None, deriv: int = -1,
                          grad: bool = False, f_quad=None):

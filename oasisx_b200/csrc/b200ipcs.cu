@@ -2489,6 +2489,41 @@ int b2_first_plan_info(b2_ctx* c, int64_t* out) {
   });
 }
 
+int b2_l2_error_trig(b2_ctx* c, int vec, int64_t n_cells, int n_q, const double* ref_points, const double* weights,
+                     int n_terms, const double* terms, double* out) {
+  return guarded(c, [&] {
+    require_ready(c);
+    auto it = c->vecs.find(vec);
+    B2_REQUIRE(it != c->vecs.end(), "unknown vector id");
+    DVec& v = it->second;
+    const Space& S = c->sp[v.space];
+    B2_REQUIRE(n_cells >= 0 && n_cells <= c->n_cells && n_q > 0 && n_terms >= 0, "bad cell / point / term count");
+    halo_forward(c, v.space, v.buf.p, v.K);
+    const int d = c->gdim;
+    DBuf<double> dp, dw, dt;
+    dp.alloc((int64_t)n_q * d);
+    dw.alloc(n_q);
+    dt.alloc(std::max(1, n_terms) * 12);
+    B2_CUDA(cudaMemcpyAsync(dp.p, ref_points, sizeof(double) * n_q * d, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(dw.p, weights, sizeof(double) * n_q, cudaMemcpyHostToDevice, c->stream));
+    if (n_terms) B2_CUDA(cudaMemcpyAsync(dt.p, terms, sizeof(double) * 12 * n_terms, cudaMemcpyHostToDevice, c->stream));
+    c->stats.bytes_h2d += sizeof(double) * (12 * n_terms + n_q * (d + 1));
+    const int grid = pgrid(c, n_cells, 128, 8);
+    dispatch_elem(c, [&](auto e) {
+      using E = decltype(e);
+      if (v.space == B2_SPACE_V)
+        B2_LAUNCH(c, (k_l2_error_trig<E::D, E::DEG, true>), grid, 128, n_cells, c->x.p, c->cell_nodes.p, S.cell_dofs.p, v.K,
+                  (int)S.n_local(), v.buf.p, n_q, dp.p, dw.p, n_terms, dt.p, c->d_sums, c->partials.p, c->d_counter);
+      else
+        B2_LAUNCH(c, (k_l2_error_trig<E::D, E::DEG, false>), grid, 128, n_cells, c->x.p, c->cell_nodes.p, S.cell_dofs.p, v.K,
+                  (int)S.n_local(), v.buf.p, n_q, dp.p, dw.p, n_terms, dt.p, c->d_sums, c->partials.p, c->d_counter);
+    });
+    allreduce_sum(c, c->d_sums, 1);
+    read_sums(c, 1);
+    *out = c->h_sums[0];
+  });
+}
+
 int b2_get_stats(b2_ctx* c, b2_stats* out) {
   return guarded(c, [&] { *out = c->stats; });
 }

@@ -566,6 +566,80 @@ k_l2_error(int64_t n_cells, const double* __restrict__ x, const int* __restrict_
   if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
 }
 
+// The same functional with the exact field evaluated ON THE DEVICE from a short list of trigonometric product terms
+//   exact_k(x) = sum_m c_m F(f1_m, a_m . x + a0_m) F(f2_m, b_m . x + b0_m),   F(0, s) = 1, F(1, s) = sin s, F(2, s) = cos s
+// (terms[m] = {c, a[3], a0, b[3], b0, f1, f2, component}: 12 doubles) -- the Taylor-Green fields of
+// demo/taylor_green.py:41-53,176-191, also rotated, are sums of two such terms per component.  A call moves a few
+// hundred bytes to the device instead of cells x points x components doubles (27 GB at 96^3 with a degree-10 rule).
+template <int D, int DEG, bool SPACE_V>
+__global__ void __launch_bounds__(128)
+k_l2_error_trig(int64_t n_cells, const double* __restrict__ x, const int* __restrict__ cell_nodes,
+                const int* __restrict__ cdofs, int K, int ld, const double* __restrict__ vec, int n_q,
+                const double* __restrict__ ref_pts, const double* __restrict__ weights, int n_terms,
+                const double* __restrict__ terms, double* out, double* partials, unsigned* counter) {
+  using E = El<D, DEG>;
+  constexpr int ND = SPACE_V ? E::NV : E::NQ;
+  constexpr bool P2 = SPACE_V && DEG == 2;
+  double s[1] = {0.0};
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    Geo<D> g = cell_geometry<D>(x, cell_nodes + c * (D + 1));
+    double X[D + 1][3];
+    for (int v = 0; v <= D; ++v)
+      for (int k = 0; k < 3; ++k) X[v][k] = x[3 * (size_t)cell_nodes[c * (D + 1) + v] + k];
+    int dofs[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) dofs[j] = cdofs[c * ND + j];
+    for (int q = 0; q < n_q; ++q) {
+      double lam[D + 1];
+      lam[0] = 1.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        lam[k + 1] = ref_pts[q * D + k];
+        lam[0] -= lam[k + 1];
+      }
+      double xq[3] = {0.0, 0.0, 0.0};
+      for (int v = 0; v <= D; ++v)
+        for (int k = 0; k < 3; ++k) xq[k] = fma(lam[v], X[v][k], xq[k]);
+      double phi[ND];
+      if (!P2) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) phi[j] = lam[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j <= D; ++j) phi[j] = lam[j] * (2.0 * lam[j] - 1.0);
+        if (D == 3) {
+          const int ea[6] = {2, 1, 1, 0, 0, 0}, eb[6] = {3, 3, 2, 3, 2, 1};
+#pragma unroll
+          for (int e = 0; e < 6; ++e) phi[(D + 1 + e) < ND ? (D + 1 + e) : 0] = 4.0 * lam[ea[e]] * lam[eb[e]];
+        } else {
+          const int ea[3] = {1, 0, 0}, eb[3] = {2, 2, 1};
+#pragma unroll
+          for (int e = 0; e < 3; ++e) phi[(D + 1 + e) < ND ? (D + 1 + e) : 0] = 4.0 * lam[ea[e]] * lam[eb[e]];
+        }
+      }
+      double ex[3] = {0.0, 0.0, 0.0};
+      for (int m = 0; m < n_terms; ++m) {
+        const double* t = terms + 12 * m;
+        const double sa = t[1] * xq[0] + t[2] * xq[1] + t[3] * xq[2] + t[4];
+        const double sb = t[5] * xq[0] + t[6] * xq[1] + t[7] * xq[2] + t[8];
+        const int f1 = (int)t[9], f2 = (int)t[10], comp = (int)t[11];
+        const double v1 = f1 == 0 ? 1.0 : (f1 == 1 ? sin(sa) : cos(sa));
+        const double v2 = f2 == 0 ? 1.0 : (f2 == 1 ? sin(sb) : cos(sb));
+        if (comp < 3) ex[comp] = fma(t[0], v1 * v2, ex[comp]);
+      }
+      for (int k = 0; k < K; ++k) {
+        double uh = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) uh = fma(phi[j], vec[(size_t)k * ld + dofs[j]], uh);
+        const double e = uh - ex[k];
+        s[0] = fma(g.detJ * weights[q], e * e, s[0]);
+      }
+    }
+  }
+  double total[1];
+  if (grid_reduce<1>(s, partials, counter, total) && threadIdx.x == 0) out[0] = total[0];
+}
+
 // ---- right-hand side of an L2 projection (Projector, function.py:108-119): out_k[i] += int f_k phi_i dx -----------
 // The source f is sampled at the quadrature points of each cell either by the host (a Python callable: `fq`,
 // [cell][q][n_comp]) or on the device from the nodal values of a Lagrange function on the same mesh (`src`,

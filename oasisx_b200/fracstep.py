@@ -398,7 +398,9 @@ class FractionalStep_AB_CN:
         """``assemble_scalar(inner(u_h - u_ex, u_h - u_ex) * dx)`` summed over ranks
         (``demo/taylor_green.py:186-207``).  which: "u" (the velocity, `exact` = one callable per
         component) or "p" (the pressure `_p`, `exact` = one callable).  The exact field is sampled by the
-        host at the quadrature points of a degree-`degree` rule; the integration runs on the device."""
+        host at the quadrature points of a degree-`degree` rule; the integration runs on the device.  An `exact` object
+        with a ``trig_terms(which)`` method (the Taylor-Green fields of tests/problems.py and demo/taylor_green.py) is
+        evaluated on the device instead: usable at 96^3, where the sampled field would be 27 GB per call."""
         from .quadrature import simplex_rule
 
         mesh, d = self._mesh, self._mesh.geometry.dim
@@ -407,6 +409,13 @@ class FractionalStep_AB_CN:
             cells = self._lp.cell_nodes[: self._lp.n_cells_owned]
         else:
             cells = mesh.geometry.dofmap
+        vec = L.VEC_U if which == "u" else L.VEC_P
+        terms = getattr(exact, "trig_terms", None)
+        if terms is not None:
+            # analytic field given as trigonometric product terms (see b2_l2_error_trig): evaluated on the device at
+            # the quadrature points, nothing but the term list crosses the bus
+            self._flush()
+            return self._ctx.l2_error_trig(vec, len(cells), pts, w, terms(which))
         X = mesh.geometry.x[cells]  # (nc, d+1, 3)
         lam = np.hstack([1.0 - pts.sum(axis=1, keepdims=True), pts])  # (nq, d+1)
         xq = np.einsum("qa,cak->kcq", lam, X)  # (3, nc, nq)
@@ -414,7 +423,6 @@ class FractionalStep_AB_CN:
         fs = list(exact) if which == "u" else [exact]
         ex = np.stack([np.asarray(f(flat), dtype=np.float64).reshape(len(cells), len(w)) for f in fs], axis=2)
         self._flush()
-        vec = L.VEC_U if which == "u" else L.VEC_P
         return self._ctx.l2_error_quadrature(vec, len(cells), pts, w, np.ascontiguousarray(ex))
 
     def stats(self):

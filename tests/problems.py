@@ -43,6 +43,16 @@ class TaylorGreen:
     def components(self):
         return [self.eval_x, self.eval_y, self.eval_z][: self.gdim]
 
+    def trig_terms(self, which: str):
+        """The field at the current time as trigonometric product terms (c, a[3], a0, b[3], b0, f1, f2, component) for
+        the device-side evaluator of ``FractionalStep_AB_CN.assemble_l2_error_sq`` (1 = sin, 2 = cos, 0 = one)."""
+        pi = np.pi
+        if which == "p":
+            g = -0.25 * np.exp(-4 * self.nu * pi**2 * self.t_p)
+            return [[g, 2 * pi, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0], [g, 0, 2 * pi, 0, 0, 0, 0, 0, 0, 2, 0, 0]]
+        g = np.exp(-2.0 * self.nu * pi**2 * self.t_u)
+        return [[-g, pi, 0, 0, 0, 0, pi, 0, 0, 2, 1, 0], [g, pi, 0, 0, 0, 0, pi, 0, 0, 1, 2, 1]]
+
 
 class TaylorGreenRot(TaylorGreen):
     """The 2D Taylor-Green vortex of ``demo/taylor_green.py:36-53`` ROTATED out of the x-y plane: with an orthogonal
@@ -86,6 +96,19 @@ class TaylorGreenRot(TaylorGreen):
             return -0.25 * (np.cos(2 * np.pi * xi) + np.cos(2 * np.pi * eta))
 
         return self._spatial("p", x, spatial) * np.exp(-4 * self.nu * np.pi**2 * self.t_p)
+
+    def trig_terms(self, which: str):
+        pi, R = np.pi, self.R
+        a, b = (pi * R[:, 0]).tolist(), (pi * R[:, 1]).tolist()
+        if which == "p":
+            g = -0.25 * np.exp(-4 * self.nu * pi**2 * self.t_p)
+            return [[g, *(2 * pi * R[:, 0]), 0, 0, 0, 0, 0, 2, 0, 0], [g, *(2 * pi * R[:, 1]), 0, 0, 0, 0, 0, 2, 0, 0]]
+        g = np.exp(-2.0 * self.nu * pi**2 * self.t_u)
+        out = []
+        for k in range(3):  # u_k = R[k,0] (-cos(pi xi) sin(pi eta)) g + R[k,1] (sin(pi xi) cos(pi eta)) g
+            out.append([-g * R[k, 0], *a, 0, *b, 0, 2, 1, k])
+            out.append([g * R[k, 1], *a, 0, *b, 0, 1, 2, k])
+        return out
 
     @property
     def components(self):

@@ -350,6 +350,28 @@ def test_l2_error_functional_matches_oracle(gdim, N):
     assert abs(eu - ou) <= 1e-8 * ou and abs(ep - op) <= 1e-8 * op
 
 
+@pytest.mark.parametrize("field", ["z", "rot", "2d"])
+def test_l2_error_functional_device_evaluator(field):
+    """The analytic field evaluated ON THE DEVICE (trigonometric product terms, b2_l2_error_trig) gives the same
+    functional as the host-sampled path: the demo loop's error norms without moving the field over the bus."""
+    from problems import TaylorGreenRot
+
+    dt, nu = 0.005, 0.01
+    gdim = 2 if field == "2d" else 3
+    msh = make_mesh(gdim, 8 if gdim == 2 else 4)
+    tg = TaylorGreenRot(nu) if field == "rot" else TaylorGreen(nu, gdim)
+    s = make_solver(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = dt, dt / 2
+    s.solve(dt, nu, max_iter=1)
+    eu_h = s.assemble_l2_error_sq("u", tg.components, degree=10)
+    ep_h = s.assemble_l2_error_sq("p", tg.eval_p, degree=10)
+    h2d = s.stats().bytes_h2d
+    eu_d = s.assemble_l2_error_sq("u", tg, degree=10)
+    ep_d = s.assemble_l2_error_sq("p", tg, degree=10)
+    assert s.stats().bytes_h2d - h2d < 20000  # a term list and a quadrature rule, not the sampled field
+    assert abs(eu_d - eu_h) <= 1e-10 * eu_h and abs(ep_d - ep_h) <= 1e-10 * ep_h
+
+
 @pytest.mark.parametrize("gdim,N,deg", [(2, 8, 2), (3, 4, 2), (2, 8, 1)])
 @pytest.mark.parametrize("rotational", [False, True])
 def test_low_memory_version_matches_oracle(gdim, N, deg, rotational):
@@ -424,3 +446,42 @@ def test_chebyshev_mass_solve_matches_oracle(gdim, N, deg):
         for i in range(gdim):
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
     assert 0 < max(s.stats().its_update) < 80
+
+
+def test_checkpoint_restart_reproduces_the_run(tmp_path):
+    """u1, u2, p and t (fracstep.py:689-693) are all a restart needs: 3 steps + checkpoint + 2 steps equals
+    5 steps; the VTU export of the final state is written and well-formed."""
+    from oasisx_b200.io import load_checkpoint, save_checkpoint, write_vtu
+
+    dt, nu = 0.005, 0.01
+    msh = make_mesh(3, 4)
+    tg = TaylorGreen(nu, 3)
+    s = make_solver(msh, 2, tg, dt)
+    tg.t_u, tg.t_p = 0.0, -dt / 2
+    for n in range(3):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+    save_checkpoint(str(tmp_path / "chk"), s, tg.t_u)
+    for n in range(2):
+        tg.t_u += dt
+        tg.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+    ref_u = [s._u[i].x.array_ro().copy() for i in range(3)]
+    ref_p = s._p.x.array_ro().copy()
+    tg2 = TaylorGreen(nu, 3)
+    s2 = make_solver(make_mesh(3, 4), 2, tg2, dt)
+    t = load_checkpoint(str(tmp_path / "chk"), s2)
+    assert abs(t - 3 * dt) < 1e-15
+    tg2.t_u, tg2.t_p = t, t - dt / 2
+    for n in range(2):
+        tg2.t_u += dt
+        tg2.t_p += dt
+        s2.solve(dt, nu, max_iter=1)
+    for i in range(3):
+        assert relerr(s2._u[i].x.array_ro(), ref_u[i], vscale(ref_u)) <= 1e-10
+    assert relerr(s2._p.x.array_ro(), ref_p) <= 1e-9
+    out = tmp_path / "state.vtu"
+    write_vtu(str(out), s2._Vi[0][0], {"u": s2.u.x.array.reshape(-1, 3)})
+    txt = out.read_text()
+    assert txt.count("<DataArray") == 5 and 'Name="u"' in txt and txt.rstrip().endswith("</VTKFile>")
