@@ -162,14 +162,17 @@ def _cavity_markers():
     return lid, walls
 
 
-def make_cavity_solver(N: int, comm, device: int):
-    """Unit cube, u = (1, 0, 0) on the lid z = 1, no slip on the other walls, no pressure BC, start from rest
-    (the set-up of tests/test_gpu_parity.py::test_lid_driven_cavity_matches_oracle at Re = 1000)."""
+def make_cavity_solver(N: int, comm, device: int, nz_factor: int = 1):
+    """Unit cube, u = (1, 0, 0) on the lid z = top, no slip on the other walls, no pressure BC, start from rest
+    (the set-up of tests/test_gpu_parity.py::test_lid_driven_cavity_matches_oracle at Re = 1000).  nz_factor > 1
+    (weak scaling): the box [0,1]^2 x [0, nz_factor] with N x N x (N nz_factor) cubes -- one N^3 block per rank."""
     import oasisx_b200 as oasisx
     from oasisx_b200 import mesh as bmesh
 
-    msh = bmesh.create_unit_cube(comm, N, N, N)
-    lid, walls = _cavity_markers()
+    top = float(nz_factor)
+    msh = bmesh.create_box(comm, [[0.0, 0.0, 0.0], [1.0, 1.0, top]], [N, N, N * nz_factor])
+    lid = lambda x: np.isclose(x[2], top)
+    walls = lambda x: (np.isclose(x[0], 0) | np.isclose(x[0], 1) | np.isclose(x[1], 0) | np.isclose(x[1], 1) | np.isclose(x[2], 0)) & ~lid(x)
     G = oasisx.LocatorMethod.GEOMETRICAL
     bcs_u = [[oasisx.DirichletBC(0.0, G, walls), oasisx.DirichletBC(1.0 if k == 0 else 0.0, G, lid)] for k in range(3)]
     s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[], solver_options=KRYLOV,
@@ -213,8 +216,9 @@ def run_cavity(args):
     rank, world = comm.rank, comm.size
     device = int(os.environ.get("LOCAL_RANK", "0"))
     N, K, W = args.mesh, args.steps, max(args.warmup, 3)
+    weak = bool(args.weak)
     t_setup = time.perf_counter()
-    msh, solver = make_cavity_solver(N, comm if world > 1 else None, device)
+    msh, solver = make_cavity_solver(N, comm if world > 1 else None, device, world if weak else 1)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
     dt, nu = CAVITY_DT, CAVITY_NU
@@ -260,9 +264,11 @@ def run_cavity(args):
     nQ = solver._lp.Q.n_global if world > 1 else solver._nQ_owned
     line = {
         "metric": "IPCS steps/s, 3D lid-driven cavity P2-P1 box", "value": 1000.0 * K / ms_total, "unit": "steps/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D lid-driven cavity P2-P1 {N}^3 unit cube, Re=1000 (nu={nu}, lid speed 1), dt={dt}, from rest, max_iter=1, rtol=1e-10",
+        "config": {"workload": (f"3D lid-driven cavity P2-P1, WEAK scaling: one {N}^3 block of cubes per GPU, box [0,1]^2 x [0,{world}] "
+                                f"({N}x{N}x{N * world} cubes)" if weak else f"3D lid-driven cavity P2-P1 {N}^3 unit cube")
+                               + f", Re=1000 (nu={nu}, lid speed 1), dt={dt}, from rest, max_iter=1, rtol=1e-10",
                    "mesh": N, "cells": msh.num_cells, "dofs": 3 * nV + nQ, "krylov": KRYLOV, "setup_s": t_setup,
                    "l2": "working set per step >> 126 MB L2; no flush needed"},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
@@ -786,6 +792,8 @@ def main():
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
+    ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4]; "
+                                                         "default block 64^3: the host provider still builds the global mesh on every rank)")
     ap.add_argument("--low-memory", action="store_true", help="options={'low_memory_version': True}: matrix-free element vectors "
                                                                "instead of the 9 rectangular operators (fracstep.py:259)")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")
@@ -798,7 +806,7 @@ def main():
     if args.workload == "taylor-green":
         args.workload = HEADLINE
     if args.mesh <= 0:
-        args.mesh = 128 if args.workload == "cavity" else 96
+        args.mesh = (64 if args.weak else 128) if args.workload == "cavity" else 96
     if args.workload == "cavity":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the Taylor-Green metric; the cavity line carries its own cpu_baseline")
