@@ -19,15 +19,36 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import fem as _fem
 from .partition import HaloPlan, LocalProblem, LocalSpace
 
 
-def halo_plan_from_index_map(index_map, comm) -> HaloPlan:
-    """Pack/unpack lists of a ``dolfinx.common.IndexMap``: ghosts are received from their owners; what
-    this rank must send is learnt from the other ranks' ghost lists (one all-to-all of global indices)."""
+def is_foreign_mesh(mesh) -> bool:
+    """True for a mesh that is not the built-in provider's (a ``dolfinx.mesh.Mesh``): it is consumed through this
+    module -- geometry, dof maps and index maps are taken as they are (``fracstep.py:187-190,212``)."""
+    from .mesh import Mesh
+
+    return not isinstance(mesh, Mesh)
+
+
+def _ghost_permutation(index_map):
+    """DOLFINx keeps ghosts in discovery order; the library wants them grouped by owner, sorted by global index inside
+    a group (one contiguous receive block per neighbour).  Returns new_of_old for the whole local range."""
     n_owned = index_map.size_local
     ghosts = np.asarray(index_map.ghosts, dtype=np.int64)
     owners = np.asarray(index_map.owners, dtype=np.int32)
+    order = np.lexsort((ghosts, owners))  # old ghost position of the k-th ghost in the new order
+    new_of_old = np.arange(n_owned + len(ghosts), dtype=np.int64)
+    new_of_old[n_owned + order] = n_owned + np.arange(len(order))
+    return new_of_old, ghosts[order], owners[order]
+
+
+def halo_plan_from_index_map(index_map, comm, ghosts=None, owners=None) -> HaloPlan:
+    """Pack/unpack lists of a ``dolfinx.common.IndexMap``: ghosts are received from their owners; what
+    this rank must send is learnt from the other ranks' ghost lists (one all-to-all of global indices)."""
+    n_owned = index_map.size_local
+    ghosts = np.asarray(index_map.ghosts if ghosts is None else ghosts, dtype=np.int64)
+    owners = np.asarray(index_map.owners if owners is None else owners, dtype=np.int32)
     lo, _ = index_map.local_range
     order = np.lexsort((ghosts, owners))
     if not np.array_equal(order, np.arange(len(order))):
@@ -54,13 +75,19 @@ def local_space_from_dolfinx(V, comm) -> LocalSpace:
     im = V.dofmap.index_map
     n_owned, n_ghost = im.size_local, im.num_ghosts
     lo, _ = im.local_range
-    l2g = np.concatenate([np.arange(lo, lo + n_owned, dtype=np.int64), np.asarray(im.ghosts, dtype=np.int64)])
+    new_of_old, ghosts, owners = _ghost_permutation(im)
+    l2g = np.concatenate([np.arange(lo, lo + n_owned, dtype=np.int64), ghosts])
     g2l = np.full(im.size_global, -1, dtype=np.int64)
     g2l[l2g] = np.arange(len(l2g))
     nd = V.dofmap.cell_dofs(0).shape[0]
-    cell_dofs = np.ascontiguousarray(np.asarray(V.dofmap.list).reshape(-1, nd), dtype=np.int32)
-    return LocalSpace(n_owned=n_owned, n_ghost=n_ghost, n_global=im.size_global, l2g=l2g, g2l=g2l, cell_dofs=cell_dofs,
-                      halo=halo_plan_from_index_map(im, comm), x=np.ascontiguousarray(V.tabulate_dof_coordinates()[: n_owned + n_ghost]))
+    cell_dofs = np.ascontiguousarray(new_of_old[np.asarray(V.dofmap.list).reshape(-1, nd)], dtype=np.int32)
+    x = np.empty((n_owned + n_ghost, 3))
+    x[new_of_old] = np.asarray(V.tabulate_dof_coordinates())[: n_owned + n_ghost]
+    sp = LocalSpace(n_owned=n_owned, n_ghost=n_ghost, n_global=im.size_global, l2g=l2g, g2l=g2l, cell_dofs=cell_dofs,
+                    halo=halo_plan_from_index_map(im, comm, ghosts, owners), x=np.ascontiguousarray(x))
+    sp.new_of_old = new_of_old
+    sp.owners = owners
+    return sp
 
 
 def local_problem_from_dolfinx(mesh, Vi, Q) -> LocalProblem:
@@ -74,3 +101,43 @@ def local_problem_from_dolfinx(mesh, Vi, Q) -> LocalProblem:
     lp.V = local_space_from_dolfinx(Vi, comm)
     lp.Q = local_space_from_dolfinx(Q, comm)
     return lp
+
+
+class AdapterSpace(_fem.FunctionSpace):
+    """A DOLFINx scalar Lagrange space seen through the surface the host layer uses (``oasisx_b200.fem.FunctionSpace``):
+    local dofs owned-first with the ghost block regrouped by owner; dof LOCATION (boundary conditions) is delegated to
+    DOLFINx and mapped through that regrouping."""
+
+    def __init__(self, Vd, lsp: LocalSpace, bs: int = 1, _scalar=None):
+        self.mesh = Vd.mesh
+        self.degree = int(getattr(getattr(Vd, "element", None), "degree", None) or getattr(Vd.ufl_element(), "degree"))
+        self.bs = bs
+        self.element = Vd.element
+        self._dolfinx, self._l = Vd, lsp
+        self._x = lsp.x
+        self._scalar = self if bs == 1 else (_scalar or AdapterSpace(Vd, lsp, 1))
+        self.dofmap = _fem.DofMap(lsp.cell_dofs, _fem.IndexMap(lsp.n_owned, ghosts=lsp.l2g[lsp.n_owned:], owners=lsp.owners,
+                                                             size_global=lsp.n_global, offset=int(lsp.l2g[0]) if lsp.n_owned else 0), bs)
+
+    def entity_closure_dofs(self, edim: int, entities: np.ndarray) -> np.ndarray:
+        import dolfinx
+
+        d = np.asarray(dolfinx.fem.locate_dofs_topological(self._dolfinx, edim, np.asarray(entities, dtype=np.int32)), dtype=np.int64)
+        return np.sort(self._l.new_of_old[d]).astype(np.int32)
+
+
+def problem_from_dolfinx(mesh, deg_u: int, deg_p: int):
+    """Spaces, local problem and geometry of a DOLFINx mesh for ``FractionalStep_AB_CN`` (``fracstep.py:187-190,212``):
+    returns (LocalProblem, V blocked adapter space, Q adapter space, local geometry x)."""
+    import dolfinx
+
+    gdim = mesh.geometry.dim
+    Vd = dolfinx.fem.functionspace(mesh, ("Lagrange", int(deg_u)))  # the collapsed component space: all Vi share its dof map
+    Qd = dolfinx.fem.functionspace(mesh, ("Lagrange", int(deg_p)))
+    lp = local_problem_from_dolfinx(mesh, Vd, Qd)
+    Vs = AdapterSpace(Vd, lp.V, 1)
+    V = AdapterSpace(Vd, lp.V, gdim, _scalar=Vs)
+    Q = AdapterSpace(Qd, lp.Q, 1)
+    x = np.zeros((np.asarray(mesh.geometry.x).shape[0], 3))
+    x[:, : np.asarray(mesh.geometry.x).shape[1]] = np.asarray(mesh.geometry.x)
+    return lp, V, Q, x

@@ -107,9 +107,18 @@ class FractionalStep_AB_CN:
         # mesh it owns plus a ghost layer (oasisx_b200.partition)
         comm = mesh.comm
         self._nranks, self._rank = int(getattr(comm, "size", 1)), int(getattr(comm, "rank", 0))
-        gV = _fem.functionspace(mesh, ("Lagrange", deg_u))
-        gQ = _fem.functionspace(mesh, ("Lagrange", deg_p))
-        if self._nranks > 1:
+        from . import adapter as _adapter
+
+        self._foreign = _adapter.is_foreign_mesh(mesh)
+        if self._foreign:
+            # a DOLFINx mesh: its partition, dof maps and index maps are consumed as they are (north_star: "reuses
+            # DOLFINx's mesh partition"); also on one rank, where the ghost blocks are simply empty
+            if bcs_p:
+                raise NotImplementedError("PressureBC on a DOLFINx mesh needs its facet-cell connectivity: not wired yet")
+            self._lp, self._V, self._Q, self._geom_x = _adapter.problem_from_dolfinx(mesh, deg_u, deg_p)
+        elif self._nranks > 1:
+            gV = _fem.functionspace(mesh, ("Lagrange", deg_u))
+            gQ = _fem.functionspace(mesh, ("Lagrange", deg_p))
             from . import partition as _part
 
             self._lp = lp = _part.partition(mesh, gV, gQ, self._nranks, self._rank)
@@ -120,7 +129,7 @@ class FractionalStep_AB_CN:
         else:
             self._lp = None
             self._V = _fem.functionspace(mesh, ("Lagrange", deg_u, (gdim,)))
-            self._Q = gQ
+            self._Q = _fem.functionspace(mesh, ("Lagrange", deg_p))
         self._sol_u = _fem.Function(self._V, name="u")
         self._Vi = [self._V.sub(i).collapse() for i in range(self._V.num_sub_spaces)]
         Vs = self._Vi[0][0]
@@ -152,21 +161,27 @@ class FractionalStep_AB_CN:
         body_force = [float(f.value) if isinstance(f, _fem.Constant) else float(f) for f in body_force]
 
         # ---- device context: upload mesh + dof maps, build patterns, preassemble (:265-268) ----
-        if self._nranks > 1:
-            uid = comm.bcast(L.nccl_unique_id() if self._rank == 0 else None)
-            self._ctx = ctx = L.Context(device=device, nranks=self._nranks, rank=self._rank, nccl_uid=uid)
+        if self._lp is not None:
+            if self._nranks > 1:
+                uid = comm.bcast(L.nccl_unique_id() if self._rank == 0 else None)
+                self._ctx = ctx = L.Context(device=device, nranks=self._nranks, rank=self._rank, nccl_uid=uid)
+            else:
+                self._ctx = ctx = L.Context(device=device)
             lp = self._lp
-            ctx.set_mesh(gdim, mesh.geometry.x, lp.cell_nodes)
+            ctx.set_mesh(gdim, self._geom_x if self._foreign else mesh.geometry.x, lp.cell_nodes)
             ctx.set_space(L.SPACE_V, deg_u, lp.V.n_owned, lp.V.n_ghost, lp.V.cell_dofs)
             ctx.set_space(L.SPACE_Q, deg_p, lp.Q.n_owned, lp.Q.n_ghost, lp.Q.cell_dofs)
             ctx.set_global_sizes(lp.V.n_global, lp.Q.n_global)
-            _part.check_halo_counts(comm, lp.V.halo, "V")
-            _part.check_halo_counts(comm, lp.Q.halo, "Q")
-            ctx.set_halo(L.SPACE_V, lp.V.halo)
-            ctx.set_halo(L.SPACE_Q, lp.Q.halo)
-            # halo + dot-product all-reduce through peer-mapped memory (NVLink) instead of NCCL calls, if every rank
-            # can map every other rank's arena; otherwise all of them keep the NCCL path
-            self._peer = ctx.peer_setup(comm, 0)
+            if self._nranks > 1:
+                from . import partition as _part
+
+                _part.check_halo_counts(comm, lp.V.halo, "V")
+                _part.check_halo_counts(comm, lp.Q.halo, "Q")
+                ctx.set_halo(L.SPACE_V, lp.V.halo)
+                ctx.set_halo(L.SPACE_Q, lp.Q.halo)
+                # halo + dot-product all-reduce through peer-mapped memory (NVLink) instead of NCCL calls, if every
+                # rank can map every other rank's arena; otherwise all of them keep the NCCL path
+                self._peer = ctx.peer_setup(comm, 0)
             self._nV_owned, self._nQ_owned = lp.V.n_owned, lp.Q.n_owned
         else:
             self._ctx = ctx = L.Context(device=device)

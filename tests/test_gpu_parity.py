@@ -9,7 +9,7 @@ import scipy.sparse as sp
 
 from oasisx_b200 import _lib as L
 from oasisx_b200 import fem
-from problems import TaylorGreen, make_mesh, make_oracle, make_solver, relerr, vscale
+from problems import TaylorGreen, boundary_facets, make_mesh, make_oracle, make_solver, relerr, vscale
 
 pytestmark = pytest.mark.gpu
 
@@ -485,3 +485,47 @@ def test_checkpoint_restart_reproduces_the_run(tmp_path):
     write_vtu(str(out), s2._Vi[0][0], {"u": s2.u.x.array.reshape(-1, 3)})
     txt = out.read_text()
     assert txt.count("<DataArray") == 5 and 'Name="u"' in txt and txt.rstrip().endswith("</VTKFile>")
+
+
+def test_foreign_mesh_goes_through_the_dolfinx_adapter(monkeypatch):
+    """``FractionalStep_AB_CN(mesh=<DOLFINx mesh>)`` (fracstep.py:187-190,212): a mesh that is not the provider's is
+    consumed through ``oasisx_b200.adapter`` -- here duck-typed DOLFINx objects (tests/fake_dolfinx.py) -- and the step
+    gives the oracle's fields."""
+    import sys
+
+    import oasisx_b200 as oasisx
+    from fake_dolfinx import make_fake
+    from oasisx_b200 import mesh as bmesh
+
+    dt, nu, gdim = 0.005, 0.01, 3
+    msh = make_mesh(gdim, 4)
+    mod, fmesh, _ = make_fake(msh, 2, 1, 1, 0)
+    monkeypatch.setitem(sys.modules, "dolfinx", mod)
+    tg, tg2 = TaylorGreen(nu, gdim), TaylorGreen(nu, gdim)
+    facets = boundary_facets(msh)
+    tags = bmesh.meshtags(msh, gdim - 1, facets, np.full_like(facets, 3, dtype=np.int32))
+    bcs_u = [[oasisx.DirichletBC(f, oasisx.LocatorMethod.TOPOLOGICAL, (tags, np.int32(3)))] for f in tg.components]
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    s = oasisx.FractionalStep_AB_CN(fmesh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[],
+                                    solver_options={"tentative": lu, "pressure": lu, "scalar": lu}, options={"low_memory_version": False})
+    assert s._foreign and s._lp is not None
+    o = make_oracle(msh, 2, tg2, dt)
+    tg.t_u = -dt
+    for i, f in enumerate(tg.components):
+        s._u2[i].interpolate(f)
+    tg.t_u = 0.0
+    for i, f in enumerate(tg.components):
+        s._u1[i].interpolate(f)
+    tg.t_p = -dt / 2
+    s._p.interpolate(tg.eval_p)
+    for t in (tg, tg2):
+        t.t_u, t.t_p = 0.0, -dt / 2
+    for n in range(2):
+        for t in (tg, tg2):
+            t.t_u += dt
+            t.t_p += dt
+        s.solve(dt, nu, max_iter=1)
+        o.solve(dt, nu, max_iter=1)
+    for i in range(gdim):
+        assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8
+    assert relerr(s._p.x.array_ro(), o.p) <= 1e-8

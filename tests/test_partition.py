@@ -149,3 +149,86 @@ def test_pressure_bc_facets_split_over_ranks(gdim, N):
         expect = np.sort(lp.Q.g2l[gd][lp.Q.g2l[gd] >= 0])
         np.testing.assert_array_equal(np.sort(bc.bc.dofs), expect)
     assert sorted(owned_seen) == sorted(glob)
+
+
+@pytest.mark.parametrize("gdim,N,nranks", [(3, 4, 1), (3, 6, 2), (2, 12, 3)])
+def test_dolfinx_adapter_with_a_duck_typed_index_map(gdim, N, nranks, monkeypatch):
+    """``adapter.problem_from_dolfinx`` on fake DOLFINx objects (contiguous owned global ranges, SHUFFLED ghost blocks):
+    the regrouped local numbering, halo plans and coordinates it produces are a valid plan -- the forward halo carries
+    every owner value to its ghost copies -- and its cell dof maps address the same global dofs as the provider's."""
+    import sys
+
+    from fake_dolfinx import _NeedOthers, make_fake
+    from oasisx_b200 import adapter
+
+    msh = make_mesh(gdim, N)
+    board = {"phase": 0}
+    out = {}
+    for attempt in range(2):  # pass 0 collects every rank's allgather contributions, pass 1 replays them
+        board["n"] = {}
+        for r in range(nranks):
+            mod, fmesh, lp = make_fake(msh, 2, 1, nranks, r, board)
+            monkeypatch.setitem(sys.modules, "dolfinx", mod)
+            try:
+                out[r] = adapter.problem_from_dolfinx(fmesh, 2, 1) + (lp, mod)
+            except _NeedOthers:
+                pass
+        board["known"] = {k: v for k, v in board.get("calls", {}).get(0, {}).items()}
+        # allgather call k of every rank is now known; further calls need another round
+        for k in list(board["known"]):
+            if len(board["known"][k]) < nranks:
+                del board["known"][k]
+        if len(out) == nranks:
+            break
+        for _ in range(4):  # later allgather calls (second space) become known one round at a time
+            board["n"] = {}
+            for r in range(nranks):
+                mod, fmesh, lp = make_fake(msh, 2, 1, nranks, r, board)
+                monkeypatch.setitem(sys.modules, "dolfinx", mod)
+                try:
+                    out[r] = adapter.problem_from_dolfinx(fmesh, 2, 1) + (lp, mod)
+                except _NeedOthers:
+                    pass
+            board["known"] = {k: v for k, v in board["calls"][0].items() if len(v) == nranks}
+            if len(out) == nranks:
+                break
+    assert len(out) == nranks
+    for name in ("V", "Q"):
+        sps = [getattr(out[r][0], name) for r in range(nranks)]
+        for r, s in enumerate(sps):
+            # owned-first, ghosts grouped by owner and sorted
+            assert np.all(np.diff(s.l2g[: s.n_owned]) == 1)
+            g, o = s.l2g[s.n_owned:], s.owners
+            assert np.array_equal(np.lexsort((g, o)), np.arange(len(g)))
+        # forward halo reproduces a global vector on every rank
+        n_global = sps[0].n_global
+        gvec = np.random.default_rng(5).uniform(-1, 1, n_global)
+        vecs = []
+        for s in sps:
+            v = np.full(s.n_local, np.nan)
+            v[: s.n_owned] = gvec[s.l2g[: s.n_owned]]
+            vecs.append(v)
+        if nranks > 1:
+            part.halo_forward_numpy([s.halo for s in sps], [s.n_owned for s in sps], vecs)
+            for s, v in zip(sps, vecs):
+                np.testing.assert_array_equal(v, gvec[s.l2g])
+    # the adapter space: coordinates follow the regrouped numbering; boundary dofs located through "DOLFINx" map into it
+    for r in range(nranks):
+        lp_a, Va, Qa, x, lp_p, mod = out[r]
+        monkeypatch.setitem(sys.modules, "dolfinx", mod)  # this rank's "DOLFINx"
+        Vs = Va._scalar
+        assert Vs.num_dofs == lp_a.V.n_local and Va.bs == gdim and Va.sub(0).collapse()[0] is Vs
+        # same physical dofs per cell as the provider's local problem
+        np.testing.assert_allclose(Vs.tabulate_dof_coordinates()[lp_a.V.cell_dofs], lp_p.V.x[lp_p.V.cell_dofs])
+        tdim = msh.topology.dim
+        msh.topology.create_connectivity(tdim - 1, tdim)
+        from oasisx_b200 import mesh as bmesh
+
+        facets = bmesh.exterior_facet_indices(msh.topology)
+        d = Vs.entity_closure_dofs(tdim - 1, facets)
+        xb = Vs.tabulate_dof_coordinates()[d]
+        lo, hi = msh.geometry.x.min(axis=0), msh.geometry.x.max(axis=0)
+        on_bd = np.zeros(len(xb), bool)
+        for k in range(gdim):
+            on_bd |= np.isclose(xb[:, k], lo[k]) | np.isclose(xb[:, k], hi[k])
+        assert on_bd.all() and len(d) > 0
