@@ -682,6 +682,14 @@ def run_ours(args):
     achieved = bytes_k / (ms_k * 1e-3) / 1e9
     ms_a, bytes_a = ctx.bench_kernel(1, 5)
     ms_q, bytes_q = ctx.bench_kernel(2, 50)
+    collectives = None
+    if world > 1:  # latency of the cross-GPU building blocks, 200 back-to-back launches each (every rank takes part)
+        collectives = {"path": "peer memory (CUDA IPC over NVLink)" if ctx.peer_enabled() else "NCCL"}
+        for name, kid in (("halo_Q_us", 10), ("halo_V3_us", 11), ("allreduce_3_doubles_us", 12), ("mg_level1_vector_sum_us", 13)):
+            try:
+                collectives[name] = round(1e3 * ctx.bench_kernel(kid, 200)[0], 2)
+            except Exception:
+                collectives[name] = None
     comm.Barrier()
     roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 SELL-32 operator, 3 right-hand sides)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
@@ -752,7 +760,8 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(wl, N), "mesh": N, "cells": msh.num_cells,
-                   "dofs": 3 * nV + nQ, "partition": f"{world} z-slab(s), NCCL halo + all-reduce" if world > 1 else "single GPU",
+                   "dofs": 3 * nV + nQ, "partition": (f"{world} z-slab(s), " + ("peer-memory halo + in-kernel all-reduce (no NCCL call on the data path)"
+                                                           if ctx.peer_enabled() else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "working set per step >> 126 MB L2 (P2xP2 operators alone "
                          f"{3 * 12 * (230 * N**3) / 1e9:.2f} GB over all ranks); no flush needed",
                    "krylov": krylov, "low_memory_version": bool(args.low_memory),
@@ -763,7 +772,7 @@ def run_ours(args):
                        "update": int(np.median([i[2] for i in its]))},
         "initial_rel_residual": dict(zip(["tentative", "pressure", "update"], [float(f"{r:.3e}") for r in res0])),
         "stage_ms": dict(zip(["assemble_first", "tentative", "pressure", "update"], (stage_ms / K).round(3).tolist())),
-        "nccl_per_step": {"halo_exchanges": halos, "allreduces": allred},
+        "nccl_per_step": {"halo_exchanges": halos, "allreduces": allred}, "collectives": collectives,
         "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "bc_dofs": nbc, "checks": checks,
     }

@@ -190,6 +190,7 @@ struct b2_ctx {
   double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank, NCCL path)
   // peer-memory collectives (common.cuh): arenas mapped through CUDA IPC, no NCCL call on the data path
   int use_peer = 1;         // B200_PEER=0 keeps the NCCL path (A/B measurements, boxes without P2P)
+  int peer_grid = 32;       // tuning "peer_grid": most blocks of a halo / vector-sum kernel
   bool peer_on = false;     // segment 0 imported: halo + scalar all-reduce run through peer memory
   PeerSeg seg[2];           // 0: flags, scalar slots, halo staging; 1: staging of the replicated multigrid level
   PeerDev h_peer{};
@@ -412,7 +413,8 @@ void halo_forward(b2_ctx* c, int space, double* v, int K) {
   const int ld = (int)S.n_local();
   const int64_t ns = h.send_off.back(), nr = h.recv_off.back();
   if (c->peer_on) {  // one kernel: remote stores into the neighbours' staging, signal, wait, unpack
-    const int grid = std::max(1, std::min(c->sm, blocks_for(std::max(ns, nr) * K, 256)));
+    // few, fat blocks: every block polls the neighbours' flags, and the exchange is latency-, not bandwidth-bound
+    const int grid = std::max(1, std::min(c->peer_grid, blocks_for(std::max(ns, nr) * K, 1024)));
     B2_LAUNCH(c, k_halo_peer, grid, 256, c->ph[space], K, ld, v);
     c->stats.halo_exchanges++;
     c->stats.peer_kernels++;
@@ -627,16 +629,27 @@ struct MgView {
   const double *A, *dinv;
 };
 
-void mg_sweeps(b2_ctx* c, const MgView& L, bool fine, const double* b, double*& x, double*& tmp, int n_sweeps, bool from_zero) {
+void cgz_finish(b2_ctx* c, int fin, int n);
+
+// first_done: x already holds the first sweep from zero (omega D^-1 b, written by the kernel that produced b);
+// rz_fin >= 0: the LAST sweep also accumulates the PCG scalar product b.x_new (fine level, b = r)
+void mg_sweeps(b2_ctx* c, const MgView& L, bool fine, const double* b, double*& x, double*& tmp, int n_sweeps, bool from_zero,
+               bool first_done = false, int rz_fin = -1) {
   const int g = pgrid(c, L.n, 256, 8);
   int s = 0;
   if (from_zero && n_sweeps > 0) {
-    B2_LAUNCH(c, k_mg_first, pgrid(c, L.n), 256, (int64_t)L.n, L.dinv, b, c->mg_omega, x);
+    if (!first_done) B2_LAUNCH(c, k_mg_first, pgrid(c, L.n), 256, (int64_t)L.n, L.dinv, b, c->mg_omega, x);
     s = 1;
   }
   for (; s < n_sweeps; ++s) {
     if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
-    B2_LAUNCH(c, k_mg_sweep<false>, g, 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, c->mg_omega, tmp);
+    if (rz_fin >= 0 && s == n_sweeps - 1) {
+      B2_LAUNCH(c, k_mg_sweep_rz, g, 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, c->mg_omega, tmp, rz_fin, c->d_st,
+                c->partials.p, c->d_counter, red_ptr(c));
+      cgz_finish(c, rz_fin, 1);
+    } else {
+      B2_LAUNCH(c, k_mg_sweep<false>, g, 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, c->mg_omega, tmp);
+    }
     std::swap(x, tmp);
   }
 }
@@ -686,7 +699,10 @@ void mg_build_dense(b2_ctx* c, int i) {
 }
 
 // x_l <- V-cycle(b_l), zero initial guess.  Returns the buffer that holds the result.
-double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
+// first_done: x already holds omega D^-1 b; rz_fin >= 0 (level 0 only): fuse the PCG product r.z into the last post-sweep
+// -- *rz_done tells the caller whether that happened.
+double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp, bool first_done = false, int rz_fin = -1,
+                  bool* rz_done = nullptr) {
   if (c->mg_dev_levels != (int)c->mg.size()) mg_build_descriptors(c);
   if (l >= 1 && l - 1 == c->mg_dense_level && c->mg_dense_on) {
     // exact solve on this level: one dense mat-vec with the precomputed inverse; deeper levels are not visited
@@ -714,20 +730,22 @@ double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
   }
   const bool coarsest = (l == (int)c->mg.size());
   if (coarsest) {
-    mg_sweeps(c, L, fine, b, x, tmp, c->mg_coarse, true);
+    mg_sweeps(c, L, fine, b, x, tmp, c->mg_coarse, true, first_done);
     return x;
   }
   MgLevel& C = c->mg[l];
-  mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true);
+  mg_sweeps(c, L, fine, b, x, tmp, c->mg_pre, true, first_done);
   // residual
   if (fine) halo_forward(c, B2_SPACE_Q, x, 1);
   B2_LAUNCH(c, k_mg_sweep<true>, pgrid(c, L.n, 256, 8), 256, L.n, L.pat->slice_ptr.p, L.pat->scols.p, L.A, L.dinv, b, x, 0.0, tmp);
-  // restriction
-  B2_LAUNCH(c, (k_rect_vq<1, 8>), blocks_for((int64_t)C.n * 8, 256), 256, C.n, C.R.rowptr.p, C.R.cols.p, C.Rv.p, tmp,
-            (const double*)nullptr, C.n, 1.0, C.b.p);
-  if (fine && c->nranks > 1) {  // coarse levels are replicated: sum the partial restrictions of the slabs
+  // restriction, with the coarse level's first sweep x_c = omega D_c^-1 b_c fused in when b_c is complete (one rank, or
+  // a replicated level); partial sums of several slabs are added up first
+  const bool partial = fine && c->nranks > 1;
+  B2_LAUNCH(c, k_mg_restrict, blocks_for((int64_t)C.n * 8, 256), 256, C.n, C.R.rowptr.p, C.R.cols.p, C.Rv.p, tmp, C.dinv.p,
+            c->mg_omega, C.b.p, partial ? (double*)nullptr : C.x.p);
+  if (partial) {  // coarse levels are replicated: sum the partial restrictions of the slabs
     if (c->peer_on && c->pvs_ready) {
-      B2_LAUNCH(c, k_peer_vecsum, std::max(1, std::min(c->sm, blocks_for(C.n, 256))), 256, c->pvs, C.b.p);
+      B2_LAUNCH(c, k_peer_vecsum, std::max(1, std::min(c->peer_grid, blocks_for(C.n, 1024))), 256, c->pvs, C.b.p);
       c->stats.peer_kernels++;
     } else {
       B2_REQUIRE(!c->peer_on, "peer path: import segment 1 (multigrid staging) before the first pressure solve");
@@ -735,10 +753,12 @@ double* mg_vcycle(b2_ctx* c, int l, const double* b, double* x, double* tmp) {
       c->stats.allreduces++;
     }
   }
-  double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p);
+  double* xc = mg_vcycle(c, l + 1, C.b.p, C.x.p, C.tmp.p, !partial);
   // x += P xc   (rows: owned dofs of this level)
-  B2_LAUNCH(c, (k_rect_vq<1, 4>), blocks_for((int64_t)L.n * 4, 256), 256, L.n, C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, x, L.ld, 1.0, x);
-  mg_sweeps(c, L, fine, b, x, tmp, c->mg_post, false);
+  B2_LAUNCH(c, k_mg_prolong, blocks_for(L.n, 256), 256, L.n, C.P.rowptr.p, C.P.cols.p, C.Pv.p, xc, x);
+  const bool fuse_rz = rz_fin >= 0 && c->mg_post >= 1;
+  mg_sweeps(c, L, fine, b, x, tmp, c->mg_post, false, false, fuse_rz ? rz_fin : -1);
+  if (rz_done != nullptr) *rz_done = fuse_rz;
   return x;
 }
 
@@ -766,19 +786,24 @@ void pcg_mg_solve(b2_ctx* c, const double* b, double* x, int32_t* reason, int32_
     spmm(c, qq, c->Ap.p, 1, x, q, nullptr, nullptr, FIN_NONE, 0, B2_SPACE_Q);
     q0 = q;
   }
-  B2_LAUNCH(c, k_cgz_init, g, 256, n, b, q0, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+  // the first smoothing sweep of every V-cycle (x0 = omega D^-1 r) is written by the kernel that updates r
+  B2_LAUNCH(c, k_cgz_init_x0, g, 256, n, b, q0, x, r, c->dinvAp.p, c->mg_omega, c->mg_x0.p, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
   cgz_finish(c, FIN_CGZ_INIT, 2);
   // The device decides convergence; the host only has to stop enqueueing.  Iteration counts barely change
   // from one time step to the next, so nothing is polled (no pipeline drain) until one iteration short of
   // what the previous solve needed; kernels of a surplus iteration leave x untouched (st->done).
   const int first_poll = o.expected_its > 0 ? o.expected_its - 1 : 0;
   auto body = [&](int it) {
-    double* z = mg_vcycle(c, 0, r, c->mg_x0.p, c->mg_t0.p);
-    B2_LAUNCH(c, k_cgz_rz, g, 256, n, r, z, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
-    cgz_finish(c, it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ, 1);
+    const int rz_fin = it == 0 ? FIN_CGZ_RZ0 : FIN_CGZ_RZ;
+    bool rz_done = false;
+    double* z = mg_vcycle(c, 0, r, c->mg_x0.p, c->mg_t0.p, true, rz_fin, &rz_done);  // r.z fused into the last post-sweep
+    if (!rz_done) {
+      B2_LAUNCH(c, k_cgz_rz, g, 256, n, r, z, rz_fin, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+      cgz_finish(c, rz_fin, 1);
+    }
     B2_LAUNCH(c, k_cgz_p, g, 256, n, z, p, c->d_st);
     spmm(c, qq, c->Ap.p, 1, p, q, p, c->d_st, FIN_CG_PQ, 1, B2_SPACE_Q);
-    B2_LAUNCH(c, k_cgz_update, g, 256, n, p, q, x, r, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
+    B2_LAUNCH(c, k_cgz_update_x0, g, 256, n, p, q, x, r, c->dinvAp.p, c->mg_omega, c->mg_x0.p, c->d_st, c->partials.p, c->d_counter, red_ptr(c));
     cgz_finish(c, FIN_CGZ_UPDATE, 1);
   };
   // Iterations 1, 2, ... are identical streams of small dependent kernels (all scalars live in device memory):
@@ -2542,6 +2567,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
+    else if (k == "peer_grid") c->peer_grid = std::max(1, std::min(value, 148));
     else if (k == "first_order" || k == "first_slab") {
       (k == "first_order" ? c->first_order : c->first_slab) = std::max(0, value);
       if (c->preassembled) build_first_plan(c);
@@ -2583,6 +2609,13 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
         case 3: spmm(c, vv, c->M.p, K, c->vec(B2_VEC_U), c->wv[2].p); break;
         case 2: spmm(c, qq, c->Ap.p, 1, c->vec(B2_VEC_DP), c->wq[2].p); break;
         case 1: stage_assemble_first(c, c->last_dt > 0 ? c->last_dt : 0.005, 0.01); break;
+        case 10: halo_forward(c, B2_SPACE_Q, c->vec(B2_VEC_DP), 1); break;          // latency of the collectives
+        case 11: halo_forward(c, B2_SPACE_V, c->vec(B2_VEC_U), K); break;
+        case 12: allreduce_sum(c, c->d_sums, 3); break;
+        case 13:
+          B2_REQUIRE(c->peer_on && c->pvs_ready, "vector-sum benchmark needs the peer path with a multigrid attached");
+          B2_LAUNCH(c, k_peer_vecsum, std::max(1, std::min(c->peer_grid, blocks_for(c->mg[0].n, 1024))), 256, c->pvs, c->mg[0].b.p);
+          break;
         default: throw B2Error(-2, "unknown bench kernel");
       }
     };
@@ -2596,6 +2629,10 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
     *ms_per_launch = ms / reps;
     double nV = (double)V.n_owned, nVc = (double)vv.n_cols;
     switch (kernel) {
+      case 10: *bytes_per_launch = 8.0 * (c->halo[B2_SPACE_Q].send_off.empty() ? 0 : c->halo[B2_SPACE_Q].send_off.back()); break;
+      case 11: *bytes_per_launch = 8.0 * K * (c->halo[B2_SPACE_V].send_off.empty() ? 0 : c->halo[B2_SPACE_V].send_off.back()); break;
+      case 12: *bytes_per_launch = 24.0; break;
+      case 13: *bytes_per_launch = 8.0 * (c->mg_hi - c->mg_lo) * (c->nranks - 1); break;
       case 0:
       case 3: *bytes_per_launch = 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc); break;  // algorithmic: K (not KP) components
       case 2: *bytes_per_launch = 12.0 * qq.nnz + 4.0 * (qq.n_rows + 1) + 8.0 * (qq.n_rows + qq.n_cols); break;

@@ -179,19 +179,29 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin on a flag a peer writes with st.release.sys: relaxed polls (one thread per flag, never a whole grid hammering
+// the line the incoming NVLink write has to land in), then one acquire fence.
 __device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long want,
                                           unsigned long long* err) {
-  if (ld_acquire_sys(flag) >= want) return true;
-  const unsigned long long t0 = global_timer_ns();
-  for (unsigned spin = 1;; ++spin) {
-    if (ld_acquire_sys(flag) >= want) return true;
-    if ((spin & 255u) == 0u) {
-      if (global_timer_ns() - t0 > B2_PEER_TIMEOUT_NS) break;
-      __nanosleep(100);
+  bool ok = ld_relaxed_sys_u64(flag) >= want;
+  if (!ok) {
+    const unsigned long long t0 = global_timer_ns();
+    for (unsigned spin = 1;; ++spin) {
+      if (ld_relaxed_sys_u64(flag) >= want) { ok = true; break; }
+      if ((spin & 63u) == 0u) {
+        if (global_timer_ns() - t0 > B2_PEER_TIMEOUT_NS) break;
+        __nanosleep(40);
+      }
     }
   }
-  if (err != nullptr) atomicExch(err, 1ull);
-  return false;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  if (!ok && err != nullptr) atomicExch(err, 1ull);
+  return ok;
 }
 
 // Sum of `n` doubles over the ranks, called by ONE warp (all 32 lanes) of ONE block per rank; `v` is the

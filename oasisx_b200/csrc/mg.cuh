@@ -33,11 +33,52 @@ k_mg_sweep(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict_
   }
 }
 
+// the LAST post-smoothing sweep of the fine level with the PCG scalar product fused in: z = x_in + omega D^-1 (r - A x_in)
+// and sum r.z (fin = FIN_CGZ_RZ0 / FIN_CGZ_RZ) -- one launch and one pass over r and z less per iteration
+__global__ void __launch_bounds__(256)
+k_mg_sweep_rz(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols, const double* __restrict__ vals,
+              const double* __restrict__ dinv, const double* __restrict__ b, const double* __restrict__ x_in, double omega,
+              double* __restrict__ out, int fin, KryState* st, double* partials, unsigned* counter, RedCtl red_out);
+
 // x = omega * dinv * b  (first sweep from a zero initial guess)
 __global__ void k_mg_first(int64_t n, const double* __restrict__ dinv, const double* __restrict__ b, double omega,
                            double* __restrict__ x) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     x[i] = omega * dinv[i] * b[i];
+}
+
+// restriction with the first smoothing sweep of the coarse level fused in: b_c = R r_f, x_c = omega D_c^-1 b_c
+// (PARTIAL: on several ranks b_c is a partial sum -- the caller then all-reduces b_c and launches k_mg_first)
+__global__ void __launch_bounds__(256)
+k_mg_restrict(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols, const double* __restrict__ vals,
+              const double* __restrict__ rf, const double* __restrict__ dinv, double omega, double* __restrict__ bc,
+              double* __restrict__ xc) {
+  constexpr int LPR = 8;
+  const int lane = threadIdx.x % LPR;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  double acc = 0.0;
+  if (row < n_rows) {
+    const int end = __ldg(rowptr + row + 1);
+    for (int p = __ldg(rowptr + row) + lane; p < end; p += LPR) acc = fma(__ldg(vals + p), __ldg(rf + __ldg(cols + p)), acc);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < n_rows && lane == 0) {
+    bc[row] = acc;
+    if (xc != nullptr) xc[row] = omega * dinv[row] * acc;
+  }
+}
+
+// x_f += P x_c: nested P1 prolongations have at most d + 1 entries per row -- one thread per row
+__global__ void __launch_bounds__(256)
+k_mg_prolong(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols, const double* __restrict__ vals,
+             const double* __restrict__ xc, double* __restrict__ xf) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  double acc = xf[row];
+  const int end = __ldg(rowptr + row + 1);
+  for (int p = __ldg(rowptr + row); p < end; ++p) acc = fma(__ldg(vals + p), __ldg(xc + __ldg(cols + p)), acc);
+  xf[row] = acc;
 }
 
 // ---- the small end of the hierarchy in one kernel ------------------------------------------------
@@ -294,6 +335,71 @@ k_cgz_update(int64_t n, const double* __restrict__ p, const double* __restrict__
     x[i] = fma(alpha, p[i], x[i]);
     const double rv = fma(-alpha, q[i], r[i]);
     r[i] = rv;
+    s[0] = fma(rv, rv, s[0]);
+  }
+  cgz_reduce_finish<1>(s, partials, counter, FIN_CGZ_UPDATE, st, red_out);
+}
+
+__global__ void __launch_bounds__(256)
+k_mg_sweep_rz(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols, const double* __restrict__ vals,
+              const double* __restrict__ dinv, const double* __restrict__ b, const double* __restrict__ x_in, double omega,
+              double* __restrict__ out, int fin, KryState* st, double* partials, unsigned* counter, RedCtl red_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  double s[1] = {0.0};
+  for (int sl = warp; sl < n_slices; sl += nwarps) {
+    const int base = __ldg(slice_ptr + sl);
+    const int len = (__ldg(slice_ptr + sl + 1) - base) >> 5;
+    const int row = (sl << 5) + lane;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) {
+      const int c = ld_stream(cols + base + lane + (t << 5));
+      acc = fma(ld_stream(vals + base + lane + (t << 5)), __ldg(x_in + c), acc);
+    }
+    if (row < n_rows) {
+      const double r = b[row];
+      const double z = fma(omega * dinv[row], r - acc, x_in[row]);
+      out[row] = z;
+      s[0] = fma(r, z, s[0]);
+    }
+  }
+  cgz_reduce_finish<1>(s, partials, counter, fin, st, red_out);
+}
+
+// k_cgz_init / k_cgz_update with the first smoothing sweep of the next V-cycle fused in: x0 = omega D^-1 r
+__global__ void __launch_bounds__(256)
+k_cgz_init_x0(int64_t n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ x,
+              double* __restrict__ r, const double* __restrict__ dinv, double omega, double* __restrict__ x0, KryState* st,
+              double* partials, unsigned* counter, RedCtl red_out) {
+  double s[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bv = b[i];
+    double rv = bv;
+    if (q != nullptr) rv -= q[i];
+    else x[i] = 0.0;
+    r[i] = rv;
+    x0[i] = omega * dinv[i] * rv;
+    s[0] = fma(bv, bv, s[0]);
+    s[1] = fma(rv, rv, s[1]);
+  }
+  cgz_reduce_finish<2>(s, partials, counter, FIN_CGZ_INIT, st, red_out);
+}
+
+__global__ void __launch_bounds__(256)
+k_cgz_update_x0(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+                double* __restrict__ r, const double* __restrict__ dinv, double omega, double* __restrict__ x0, KryState* st,
+                double* partials, unsigned* counter, RedCtl red_out) {
+  if (st->done) return;
+  const double alpha = st->alpha[0];
+  double s[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double rv = fma(-alpha, q[i], r[i]);
+    r[i] = rv;
+    x0[i] = omega * dinv[i] * rv;
     s[0] = fma(rv, rv, s[0]);
   }
   cgz_reduce_finish<1>(s, partials, counter, FIN_CGZ_UPDATE, st, red_out);
