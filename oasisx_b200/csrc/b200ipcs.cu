@@ -129,12 +129,9 @@ struct PeerSeg {
 
 // byte offsets inside segment 0 (identical on every rank up to the staging block)
 enum : size_t {
-  PEER_OFF_SEQ = 128,        // u64 seq_red, seq_halo[2], seq_mg, err
-  PEER_OFF_FLAG_RED = 256,   // u64 [B2_MAXR]
-  PEER_OFF_FLAG_HALO = 320,  // u64 [2][B2_MAXR]
-  PEER_OFF_FLAG_MG = 448,    // u64 [B2_MAXR]
-  PEER_OFF_SLOT_RED = 512,   // double [2][B2_MAXR][B2_RED_MAX]
-  PEER_OFF_STAGE = 512 + 2 * B2_MAXR * B2_RED_MAX * 8
+  PEER_OFF_SEQ = 128,        // u64 seq_red, seq_halo[2], seq_mg, err (local use only)
+  PEER_OFF_SLOT_RED = 512,   // LLSlot [2][B2_MAXR][B2_RED_MAX]
+  PEER_OFF_STAGE = 512 + 2 * B2_MAXR * B2_RED_MAX * sizeof(LLSlot)
 };
 
 // what travels with an IPC handle through the host channel (b2_peer_export / b2_peer_import)
@@ -190,7 +187,7 @@ struct b2_ctx {
   double* d_red = nullptr;  // raw reduction totals awaiting the all-reduce (multi rank, NCCL path)
   // peer-memory collectives (common.cuh): arenas mapped through CUDA IPC, no NCCL call on the data path
   int use_peer = 1;         // B200_PEER=0 keeps the NCCL path (A/B measurements, boxes without P2P)
-  int peer_grid = 32;       // tuning "peer_grid": most blocks of a halo / vector-sum kernel
+  int peer_grid = 128;      // tuning "peer_grid": most blocks of a halo / vector-sum kernel (two values per thread)
   bool peer_on = false;     // segment 0 imported: halo + scalar all-reduce run through peer memory
   PeerSeg seg[2];           // 0: flags, scalar slots, halo staging; 1: staging of the replicated multigrid level
   PeerDev h_peer{};
@@ -414,7 +411,7 @@ void halo_forward(b2_ctx* c, int space, double* v, int K) {
   const int64_t ns = h.send_off.back(), nr = h.recv_off.back();
   if (c->peer_on) {  // one kernel: remote stores into the neighbours' staging, signal, wait, unpack
     // few, fat blocks: every block polls the neighbours' flags, and the exchange is latency-, not bandwidth-bound
-    const int grid = std::max(1, std::min(c->peer_grid, blocks_for(std::max(ns, nr) * K, 1024)));
+    const int grid = std::max(1, std::min(c->peer_grid, blocks_for(std::max(ns, nr) * K, 512)));
     B2_LAUNCH(c, k_halo_peer, grid, 256, c->ph[space], K, ld, v);
     c->stats.halo_exchanges++;
     c->stats.peer_kernels++;
@@ -465,12 +462,17 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
-  if (c->spmm_stream)
-    B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
-              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
-  else
-    B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, false>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, pat.order.p,
-              x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
+#define B2_SPMM(STREAM_, RS_)                                                                                            \
+  B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
+            pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
+  if (c->spmm_stream) {
+    if (rscale != nullptr) B2_SPMM(true, true);
+    else B2_SPMM(true, false);
+  } else {
+    if (rscale != nullptr) B2_SPMM(false, true);
+    else B2_SPMM(false, false);
+  }
+#undef B2_SPMM
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
@@ -1689,14 +1691,14 @@ int b2_peer_export(b2_ctx* c, int segment, void* blob_out) {
           blob.recv_cnt[sp][h.ranks[j]] = h.recv_off[j + 1] - h.recv_off[j];
         }
       }
-      sg.bytes = PEER_OFF_STAGE + sizeof(double) * 2 * (size_t)(blob.cap[0] + blob.cap[1]);
+      sg.bytes = PEER_OFF_STAGE + sizeof(LLSlot) * 2 * (size_t)(blob.cap[0] + blob.cap[1]);
     } else {
       B2_REQUIRE(c->peer_on, "segment 0 must be imported first");
       B2_REQUIRE(!c->mg.empty(), "segment 1 carries the first replicated multigrid level: add the levels first");
       blob.cap[0] = c->mg[0].n;
       blob.recv_cnt[0][0] = c->mg_lo;
       blob.recv_cnt[0][1] = c->mg_hi;
-      sg.bytes = sizeof(double) * 2 * (size_t)c->nranks * (size_t)c->mg[0].n;
+      sg.bytes = sizeof(LLSlot) * 2 * (size_t)c->nranks * (size_t)c->mg[0].n;
     }
     B2_CUDA(cudaMalloc(&sg.base, sg.bytes));
     B2_CUDA(cudaMemsetAsync(sg.base, 0, sg.bytes, c->stream));
@@ -1733,12 +1735,8 @@ int b2_peer_import(b2_ctx* c, int segment, const void* blobs_in) {
       P.rank = me;
       P.seq_red = seqs + 0;
       P.err = seqs + 4;
-      P.flag_red = (unsigned long long*)at(sg.base, PEER_OFF_FLAG_RED);
-      P.slot_red = (double*)at(sg.base, PEER_OFF_SLOT_RED);
-      for (int q = 0; q < R; ++q) {
-        P.peer_flag_red[q] = (unsigned long long*)at(sg.peer[q], PEER_OFF_FLAG_RED);
-        P.peer_slot_red[q] = (double*)at(sg.peer[q], PEER_OFF_SLOT_RED);
-      }
+      P.slot_red = (LLSlot*)at(sg.base, PEER_OFF_SLOT_RED);
+      for (int q = 0; q < R; ++q) P.peer_slot_red[q] = (LLSlot*)at(sg.peer[q], PEER_OFF_SLOT_RED);
       B2_CUDA(cudaMalloc(&c->d_peer, sizeof(PeerDev)));
       B2_CUDA(cudaMemcpyAsync(c->d_peer, &P, sizeof(PeerDev), cudaMemcpyHostToDevice, c->stream));
       for (int sp = 0; sp < 2; ++sp) {
@@ -1751,18 +1749,16 @@ int b2_peer_import(b2_ctx* c, int segment, const void* blobs_in) {
         H.n_owned = (int)c->sp[sp].n_owned;
         H.send_idx = h.send_idx.p;
         H.seq = seqs + 1 + sp;
-        H.flag = (unsigned long long*)at(sg.base, PEER_OFF_FLAG_HALO) + sp * B2_MAXR;
         H.cap = blobs[me].cap[sp];
-        H.recv = (double*)at(sg.base, PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[me].cap[0]);
+        H.recv = (LLSlot*)at(sg.base, PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[me].cap[0]);
         H.counter = c->d_counter_peer;
         H.err = P.err;
         for (int j = 0; j <= h.n_neighbors; ++j) { H.send_off[j] = h.send_off[j]; H.recv_off[j] = h.recv_off[j]; }
         for (int j = 0; j < h.n_neighbors; ++j) {
           const int q = h.ranks[j];
           H.nbr[j] = q;
-          H.peer_flag[j] = (unsigned long long*)at(sg.peer[q], PEER_OFF_FLAG_HALO) + sp * B2_MAXR;
           H.peer_cap[j] = blobs[q].cap[sp];
-          H.peer_recv[j] = (double*)at(sg.peer[q], PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[q].cap[0]);
+          H.peer_recv[j] = (LLSlot*)at(sg.peer[q], PEER_OFF_STAGE) + (sp == 0 ? 0 : 2 * blobs[q].cap[0]);
           int64_t off = 0;  // my block in q's staging: after what q receives from lower ranks (its neighbours are sorted)
           for (int r = 0; r < me; ++r) off += blobs[q].recv_cnt[sp][r];
           H.dst_off[j] = off;
@@ -1783,13 +1779,11 @@ int b2_peer_import(b2_ctx* c, int segment, const void* blobs_in) {
         B2_REQUIRE(blobs[q].cap[0] == V.n, "peer path: ranks disagree on the size of the replicated level");
         V.lo[q] = (int)blobs[q].recv_cnt[0][0];
         V.hi[q] = (int)blobs[q].recv_cnt[0][1];
-        V.peer_stage[q] = (double*)sg.peer[q];
+        V.peer_stage[q] = (LLSlot*)sg.peer[q];
       }
       PeerSeg& s0 = c->seg[0];
       V.seq = (unsigned long long*)at(s0.base, PEER_OFF_SEQ) + 3;
-      V.flag = (unsigned long long*)at(s0.base, PEER_OFF_FLAG_MG);
-      for (int q = 0; q < R; ++q) V.peer_flag[q] = (unsigned long long*)at(s0.peer[q], PEER_OFF_FLAG_MG);
-      V.stage = (double*)sg.base;
+      V.stage = (LLSlot*)sg.base;
       V.counter = c->d_counter_peer;
       V.err = c->h_peer.err;
       c->pvs_ready = true;

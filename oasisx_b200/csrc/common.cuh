@@ -135,99 +135,84 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[N], double* __restrict__
 
 // ---- peer-memory communication between the ranks of one NVSwitch box -------------------------------
 // Every rank owns one "arena" (cudaMalloc) that the other ranks map through CUDA IPC.  Collectives are done
-// INSIDE the compute kernels by plain remote stores over NVLink followed by a release-flag; nothing waits
-// across launches (a kernel only ever waits, inside its own launch, for the matching kernel of a peer, which
-// does not depend on it), so the sequence is safe to capture into a CUDA graph and needs no NCCL call.
-// It replaces, per Krylov iteration, 2-3 ncclAllReduce of <= 9 doubles + 1-thread scalar kernels and 2-3
-// pack -> ncclSend/Recv -> unpack halo exchanges ("latency is everything").
+// INSIDE the compute kernels by plain remote stores over NVLink; nothing waits across launches (a kernel only ever
+// waits, inside its own launch, for the matching kernel of a peer, which does not depend on it), so the sequence is
+// safe to capture into a CUDA graph and needs no NCCL call.  It replaces, per Krylov iteration, 2-3 ncclAllReduce of
+// <= 9 doubles + 1-thread scalar kernels and 2-3 pack -> ncclSend/Recv -> unpack halo exchanges (SURVEY.md 5.8:
+// "latency is everything").
+//
+// Wire format ("LL", as NCCL's low-latency protocol): a double travels as two 8-byte stores {low word, seq} and
+// {high word, seq}; 8-byte stores are single-copy atomic, so a receiver that reads seq in both halves has the
+// value -- no fence, no separate flag, one NVLink crossing per collective.  Buffers are double-buffered by the
+// parity of the sequence number: a peer can be at most one collective ahead (its next one needs my next
+// contribution, which I send only after consuming this one).
 #define B2_MAXR 8        // ranks of one box
 #define B2_RED_MAX 16    // doubles per fused scalar all-reduce
-
-struct PeerDev {
-  int nranks, rank;
-  unsigned long long* seq_red;        // local: number of scalar all-reduces done
-  unsigned long long* err;            // local: set when a wait timed out (host checks after the step)
-  // local views (this rank's arena)
-  unsigned long long* flag_red;       // [B2_MAXR]   written by peer q at [q]
-  double* slot_red;                   // [2][B2_MAXR][B2_RED_MAX]
-  // remote views (peer arenas), index = peer rank
-  unsigned long long* peer_flag_red[B2_MAXR];
-  double* peer_slot_red[B2_MAXR];
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// bounded spin (B2_PEER_TIMEOUT_NS of wall clock): a peer that died must not hang this GPU for ever
 #define B2_PEER_TIMEOUT_NS 30000000000ull
+
+struct __align__(16) LLSlot { unsigned lo, f0, hi, f1; };
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void ll_store(LLSlot* dst, double v, unsigned seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"((unsigned)b), "r"(seq) : "memory");
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"((char*)dst + 8), "r"((unsigned)(b >> 32)), "r"(seq) : "memory");
 }
-// Spin on a flag a peer writes with st.release.sys: relaxed polls (one thread per flag, never a whole grid hammering
-// the line the incoming NVLink write has to land in), then one acquire fence.
-__device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long want,
-                                          unsigned long long* err) {
-  bool ok = ld_relaxed_sys_u64(flag) >= want;
-  if (!ok) {
-    const unsigned long long t0 = global_timer_ns();
-    for (unsigned spin = 1;; ++spin) {
-      if (ld_relaxed_sys_u64(flag) >= want) { ok = true; break; }
-      if ((spin & 63u) == 0u) {
-        if (global_timer_ns() - t0 > B2_PEER_TIMEOUT_NS) break;
-        __nanosleep(40);
+// spin until both halves carry `seq` (bounded by B2_PEER_TIMEOUT_NS of wall clock: a dead peer must not hang the GPU)
+__device__ __forceinline__ double ll_load(const LLSlot* src, unsigned seq, unsigned long long* err) {
+  unsigned lo, f0, hi, f1;
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(f0) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(f1) : "l"((const char*)src + 8) : "memory");
+    if (f0 == seq && f1 == seq) break;
+    if ((spin & 255u) == 255u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > B2_PEER_TIMEOUT_NS) {
+        if (err != nullptr) atomicExch(err, 1ull);
+        break;
       }
     }
   }
-  asm volatile("fence.acq_rel.sys;" ::: "memory");
-  if (!ok && err != nullptr) atomicExch(err, 1ull);
-  return ok;
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
-// Sum of `n` doubles over the ranks, called by ONE warp (all 32 lanes) of ONE block per rank; `v` is the
-// local contribution in shared or global memory (read by every lane), the result overwrites it (every rank gets
-// the same bits: summation in rank order).  Lane q talks to peer q.
+struct PeerDev {
+  int nranks, rank;
+  unsigned long long* seq_red;        // local: number of scalar all-reduces done
+  unsigned long long* err;            // local: set when a wait timed out (host checks after the step)
+  LLSlot* slot_red;                   // local [2][B2_MAXR][B2_RED_MAX]
+  LLSlot* peer_slot_red[B2_MAXR];     // the same array in each peer's arena
+};
+
+// Sum of `n` doubles over the ranks, called by ONE warp (all 32 lanes) of ONE block per rank; `v` is the local
+// contribution in shared or global memory, the result overwrites it (every rank gets the same bits: summation in
+// rank order).  Lane q sends to peer q; lane i then gathers entry i of every rank.
 __device__ __forceinline__ void peer_allreduce_warp(const PeerDev* pr, double* v, int n) {
   const int lane = threadIdx.x & 31;
   const int R = pr->nranks, me = pr->rank;
   unsigned long long s = 0;
   if (lane == 0) s = *pr->seq_red + 1;
   s = __shfl_sync(0xffffffffu, s, 0);
-  const int par = (int)(s & 1ull);
-  if (lane < R) {
-    double* dst = (lane == me ? pr->slot_red : pr->peer_slot_red[lane]) + ((size_t)par * B2_MAXR + me) * B2_RED_MAX;
-    for (int i = 0; i < n; ++i) st_relaxed_sys(dst + i, v[i]);
-    __threadfence_system();
-    if (lane != me) st_release_sys(pr->peer_flag_red[lane] + me, s);
+  const unsigned seq = (unsigned)s;
+  const size_t base = ((size_t)(s & 1ull) * B2_MAXR) * B2_RED_MAX;
+  if (lane < R && lane != me) {
+    LLSlot* dst = pr->peer_slot_red[lane] + base + (size_t)me * B2_RED_MAX;
+    for (int i = 0; i < n; ++i) ll_store(dst + i, v[i], seq);
   }
   __syncwarp();
-  if (lane < R && lane != me) peer_wait(pr->flag_red + lane, s, pr->err);
-  __syncwarp();
+  double acc = 0.0;
   if (lane < n) {
-    double acc = 0.0;
-    for (int q = 0; q < R; ++q) acc += ld_relaxed_sys(pr->slot_red + ((size_t)par * B2_MAXR + q) * B2_RED_MAX + lane);
-    v[lane] = acc;
+    for (int q = 0; q < R; ++q)
+      acc += (q == me) ? v[lane] : ll_load(pr->slot_red + base + (size_t)q * B2_RED_MAX + lane, seq, pr->err);
   }
+  __syncwarp();
+  if (lane < n) v[lane] = acc;
   __syncwarp();
   if (lane == 0) *pr->seq_red = s;
 }
@@ -240,24 +225,21 @@ struct PeerHalo {
   long long dst_off[B2_MAXR];                 // where my block starts in neighbour j's staging (in dofs)
   const int* send_idx;                        // local
   unsigned long long* seq;                    // local exchange counter of this space
-  unsigned long long* flag;                   // local [B2_MAXR], written by source rank
-  unsigned long long* peer_flag[B2_MAXR];     // by neighbour list index j: the flag array of rank nbr[j]
-  double* recv;                               // local staging [2][cap]
+  LLSlot* recv;                               // local staging [2][cap]
   long long cap;
-  double* peer_recv[B2_MAXR];                 // by j: staging base of rank nbr[j]
+  LLSlot* peer_recv[B2_MAXR];                 // by j: staging base of rank nbr[j]
   long long peer_cap[B2_MAXR];
   unsigned* counter;                          // local ticket counter (zero between launches)
   unsigned long long* err;
 };
 
-// Forward halo of K components in ONE kernel: pack my owned interface values straight into the neighbours'
-// staging buffers (remote stores over NVLink), release-signal them, wait for their signals, unpack into my
-// ghost slots.  Staging is double-buffered by the parity of the exchange number: a neighbour can be at most one
-// exchange ahead (its next one needs my next signal, which I send after this unpack).
+// Forward halo of K components in ONE kernel: my owned interface values go straight into the neighbours' staging
+// buffers (remote LL stores over NVLink); their values are picked out of my staging as they arrive and written to my
+// ghost slots.
 __global__ void __launch_bounds__(256)
 k_halo_peer(PeerHalo h, int K, int ld, double* __restrict__ v) {
-  __shared__ bool is_last;
   const unsigned long long s = *((volatile unsigned long long*)h.seq) + 1;
+  const unsigned seq = (unsigned)s;
   const int par = (int)(s & 1ull);
   const long long ns = h.send_off[h.n_neighbors], nr = h.recv_off[h.n_neighbors];
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ns * K; t += (long long)gridDim.x * blockDim.x) {
@@ -266,31 +248,26 @@ k_halo_peer(PeerHalo h, int K, int ld, double* __restrict__ v) {
     int j = 0;
     while (j + 1 < h.n_neighbors && i >= h.send_off[j + 1]) ++j;
     const long long cnt = h.send_off[j + 1] - h.send_off[j];
-    double* dst = h.peer_recv[j] + (size_t)par * h.peer_cap[j] + K * h.dst_off[j] + k * cnt + (i - h.send_off[j]);
-    *dst = v[(size_t)k * ld + h.send_idx[i]];
+    LLSlot* dst = h.peer_recv[j] + (size_t)par * h.peer_cap[j] + K * h.dst_off[j] + k * cnt + (i - h.send_off[j]);
+    ll_store(dst, v[(size_t)k * ld + h.send_idx[i]], seq);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(h.counter, 1u);
-    is_last = (t == gridDim.x - 1);
-    if (is_last) {
-      *h.counter = 0u;
-      *h.seq = s;
-      __threadfence_system();
-      for (int j = 0; j < h.n_neighbors; ++j) st_release_sys(h.peer_flag[j] + h.rank, s);
-    }
-  }
-  if (threadIdx.x < h.n_neighbors) peer_wait(h.flag + h.nbr[threadIdx.x], s, h.err);
-  __syncthreads();
-  const double* src = h.recv + (size_t)par * h.cap;
+  const LLSlot* src = h.recv + (size_t)par * h.cap;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nr * K; t += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(t / nr);
     const long long i = t - (long long)k * nr;
     int j = 0;
     while (j + 1 < h.n_neighbors && i >= h.recv_off[j + 1]) ++j;
     const long long cnt = h.recv_off[j + 1] - h.recv_off[j];
-    v[(size_t)k * ld + h.n_owned + i] = __ldcg(src + K * h.recv_off[j] + k * cnt + (i - h.recv_off[j]));
+    v[(size_t)k * ld + h.n_owned + i] = ll_load(src + K * h.recv_off[j] + k * cnt + (i - h.recv_off[j]), seq, h.err);
+  }
+  // the exchange counter moves on once every block has read it (each block reads it before taking its ticket)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(h.counter, 1u);
+    if (t == gridDim.x - 1) {
+      *h.counter = 0u;
+      *h.seq = s;
+    }
   }
 }
 
@@ -304,52 +281,43 @@ __global__ void k_peer_allreduce(const PeerDev* pr, double* v, int n) {
 }
 
 // Sum over ranks of a replicated-level vector (the restricted multigrid right-hand side): every rank pushes the
-// index range [lo, hi) its slab contributes to into every peer's staging, signals, waits, and adds up the ranges
-// that cover each entry in rank order.
+// index range [lo, hi) its slab contributes to into every peer's staging and adds up, in rank order, the ranges
+// that cover each entry as they arrive.
 struct PeerVecSum {
   int nranks, rank, n;
   int lo[B2_MAXR], hi[B2_MAXR];
   unsigned long long* seq;
-  unsigned long long* flag;                  // local [B2_MAXR]
-  unsigned long long* peer_flag[B2_MAXR];
-  double* stage;                             // local [2][nranks][n]
-  double* peer_stage[B2_MAXR];
+  LLSlot* stage;                             // local [2][nranks][n]
+  LLSlot* peer_stage[B2_MAXR];
   unsigned* counter;
   unsigned long long* err;
 };
 
 __global__ void __launch_bounds__(256)
 k_peer_vecsum(PeerVecSum h, double* __restrict__ v) {
-  __shared__ bool is_last;
   const unsigned long long s = *((volatile unsigned long long*)h.seq) + 1;
+  const unsigned seq = (unsigned)s;
   const int par = (int)(s & 1ull);
   const int me = h.rank, lo = h.lo[me], hi = h.hi[me];
   const size_t mine = ((size_t)par * h.nranks + me) * h.n;
   for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
     const double x = v[i];
     for (int q = 0; q < h.nranks; ++q)
-      if (q != me) h.peer_stage[q][mine + i] = x;
+      if (q != me) ll_store(h.peer_stage[q] + mine + i, x, seq);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(h.counter, 1u);
-    is_last = (t == gridDim.x - 1);
-    if (is_last) {
-      *h.counter = 0u;
-      *h.seq = s;
-      __threadfence_system();
-      for (int q = 0; q < h.nranks; ++q)
-        if (q != me) st_release_sys(h.peer_flag[q] + me, s);
-    }
-  }
-  if (threadIdx.x < h.nranks && threadIdx.x != me) peer_wait(h.flag + threadIdx.x, s, h.err);
-  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h.n; i += gridDim.x * blockDim.x) {
     double acc = 0.0;
     for (int q = 0; q < h.nranks; ++q)
-      if (i >= h.lo[q] && i < h.hi[q])  // my own partial is read in place (no intra-grid dependency); rank order kept
-        acc += (q == me) ? v[i] : __ldcg(h.stage + ((size_t)par * h.nranks + q) * h.n + i);
+      if (i >= h.lo[q] && i < h.hi[q])  // my own partial is read in place; rank order kept
+        acc += (q == me) ? v[i] : ll_load(h.stage + ((size_t)par * h.nranks + q) * h.n + i, seq, h.err);
     v[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(h.counter, 1u);
+    if (t == gridDim.x - 1) {
+      *h.counter = 0u;
+      *h.seq = s;
+    }
   }
 }

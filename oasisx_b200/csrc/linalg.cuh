@@ -312,7 +312,7 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
 // those lines in L1 instead of each pulling them through the L2 fabric.
 // MINB: resident blocks per SM the register allocation is bounded for (8 x 256 threads = 32 registers, 6 = 40).
-template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, int MINB = 2048 / BLOCK>
+template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, bool RS = false, int MINB = 2048 / BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
@@ -368,7 +368,7 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
     }
     if (row < n_rows) {
-      if (rscale != nullptr) {  // y = D^-1 (A x): left Jacobi preconditioning of BiCGStab with A stored as assembled
+      if constexpr (RS) {  // y = D^-1 (A x): left Jacobi preconditioning of BiCGStab with A stored as assembled
         const double rs = __ldg(rscale + row);
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] *= rs;

@@ -61,6 +61,8 @@ class FakeComm:
         self.rank, self.size, self._board = rank, size, board
 
     def allgather(self, value):
+        if self.size == 1:
+            return [value]
         slot = self._board.setdefault("calls", {}).setdefault(self._board["phase"], {})
         key = self._board.setdefault("n", {}).get(self.rank, 0)
         self._board["n"][self.rank] = key + 1
