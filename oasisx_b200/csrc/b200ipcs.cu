@@ -202,6 +202,7 @@ struct b2_ctx {
   bool low_memory = false, rotational = false;
   // matrices (values in pattern order)
   DBuf<double> M, Kst, A, Ap, MQ, P, G, D;
+  DBuf<double> Psell, Gsell;  // P, G once more in sliced-ELL slots, component-major (the form the step multiplies with)
   DBuf<double> dinvA, dinvM, dinvAp, dinvMQ, onesV, onesQ;
   // boundary conditions
   DBuf<int> bc_dofs[B2_MAXK];
@@ -384,7 +385,7 @@ void build_sell(b2_ctx* c, CSR& pat) {
   pat.scols.alloc(slots);
   pat.scols.zero(c->stream);
   pat.diag_t.alloc(n_rows);
-  B2_LAUNCH(c, k_sell_fill_cols, blocks_for(n_rows, 256), 256, n_rows, pat.rowptr.p, pat.cols.p, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p);
+  B2_LAUNCH(c, k_sell_fill_cols, blocks_for(n_rows, 256), 256, n_rows, pat.rowptr.p, pat.cols.p, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p, pat.n_cols);
   B2_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -1061,6 +1062,12 @@ template <int K>
 void rect_vq(b2_ctx* c, const double* vals, const double* xq, const double* add, double scale, double* out) {
   const CSR& vq = c->pat[B2_PAT_VQ];
   const int ld = (int)c->sp[B2_SPACE_V].n_local();
+  const double* sell = vals == c->P.p ? c->Psell.p : (vals == c->G.p ? c->Gsell.p : nullptr);
+  if (sell != nullptr && vq.has_sell()) {
+    B2_LAUNCH(c, k_rect_vq_sell<K>, pgrid(c, vq.n_rows, 256, 4), 256, vq.n_rows, vq.slice_ptr.p, vq.scols.p, sell, (int64_t)vq.slots, xq,
+              add, ld, scale, out);
+    return;
+  }
   if (vq.lpr >= 8)
     B2_LAUNCH(c, (k_rect_vq<K, 8>), blocks_for((int64_t)vq.n_rows * 8, 256), 256, vq.n_rows, vq.rowptr.p, vq.cols.p, vals, xq, add, ld, scale, out);
   else
@@ -1428,6 +1435,12 @@ void do_preassemble(b2_ctx* c, const double* body_force, int low_memory, int rot
                 Q.cell_dofs.p, vq.n_rows, vq.rowptr.p, vq.cols.p, c->P.p, c->G.p);              // :395,399
       B2_LAUNCH(c, (k_assemble_D<D, DEG>), blocks_for(nc * E::NQ, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p,
                 Q.cell_dofs.p, qv.n_rows, qv.rowptr.p, qv.cols.p, c->D.p);                      // :403
+      if (vq.has_sell()) {
+        c->Psell.alloc(vq.slots * D); c->Psell.zero(c->stream);
+        c->Gsell.alloc(vq.slots * D); c->Gsell.zero(c->stream);
+        B2_LAUNCH(c, k_rect_to_sell<D>, blocks_for(vq.n_rows, 256), 256, vq.n_rows, vq.rowptr.p, vq.slice_ptr.p, (int64_t)vq.slots, c->P.p, c->Psell.p);
+        B2_LAUNCH(c, k_rect_to_sell<D>, blocks_for(vq.n_rows, 256), 256, vq.n_rows, vq.rowptr.p, vq.slice_ptr.p, (int64_t)vq.slots, c->G.p, c->Gsell.p);
+      }
     }
     B2_LAUNCH(c, (k_assemble_loads<D, DEG>), blocks_for(nc, 128), 128, nc, c->x.p, c->cell_nodes.p, V.cell_dofs.p, Q.cell_dofs.p,
               (int)V.n_owned, (int)Q.n_owned, (int)V.n_local(), f[0], f[1], f[2], c->vec(B2_VEC_B0), c->vec(B2_VEC_MQ));  // :387-390
@@ -1904,6 +1917,7 @@ int b2_build_patterns(b2_ctx* c) {
     build_pattern(c, Q, Q, c->pat[B2_PAT_QQ]);
     build_sell(c, c->pat[B2_PAT_VV]);
     build_sell(c, c->pat[B2_PAT_QQ]);
+    build_sell(c, c->pat[B2_PAT_VQ]);  // P_i / G_i products run on the sliced-ELL form too (component-major values)
     c->patterns_built = true;
   });
 }

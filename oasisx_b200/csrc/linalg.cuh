@@ -271,7 +271,7 @@ __global__ void k_sell_slice_len(int n_rows, const int* __restrict__ rowptr, int
 
 __global__ void k_sell_fill_cols(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ cols,
                                  const int* __restrict__ slice_ptr, int* __restrict__ scols,
-                                 int* __restrict__ diag_t) {
+                                 int* __restrict__ diag_t, int n_cols) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
   const int s = row >> 5;
@@ -279,7 +279,7 @@ __global__ void k_sell_fill_cols(int n_rows, const int* __restrict__ rowptr, con
   const int start = rowptr[row], n = rowptr[row + 1] - start;
   int dt = -1;
   for (int t = 0; t < len; ++t) {
-    int c = t < n ? cols[start + t] : row;
+    int c = t < n ? cols[start + t] : (row < n_cols ? row : 0);  // pads: (a valid column, value 0)
     if (t < n && c == row) dt = t;
     scols[(size_t)slice_ptr[s] + ((size_t)t << 5) + (row & 31)] = c;
   }
@@ -368,8 +368,15 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
     }
     if (row < n_rows) {
-      if constexpr (RS) {  // y = D^-1 (A x): left Jacobi preconditioning of BiCGStab with A stored as assembled
-        const double rs = __ldg(rscale + row);
+      // epilogue: every load is issued before the first use, so that one memory latency is exposed per slice, not
+      // one per dependent step (the row scale alone cost +45 us of 565 when it was loaded, used, and only then w)
+      double rs = 1.0, wv[DOT >= 1 ? K : 1];
+      if constexpr (RS) rs = __ldg(rscale + row);  // y = D^-1 (A x): left Jacobi preconditioning of BiCGStab, A stored as assembled
+      if constexpr (DOT >= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) wv[k] = __ldg(w + (size_t)k * ld + row);
+      }
+      if constexpr (RS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] *= rs;
       }
@@ -377,7 +384,7 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
       if constexpr (DOT >= 1) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) sdots[k][threadIdx.x] = fma(acc[k], w[(size_t)k * ld + row], sdots[k][threadIdx.x]);
+        for (int k = 0; k < K; ++k) sdots[k][threadIdx.x] = fma(acc[k], wv[k], sdots[k][threadIdx.x]);
       }
       if constexpr (DOT == 2) {
 #pragma unroll
@@ -516,6 +523,54 @@ k_rect_vq(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ co
       out[(size_t)k * ld + row] = fma(scale, acc[k], a);
     }
   }
+}
+
+// The same products on the sliced-ELL form of the V x Q pattern with COMPONENT-MAJOR values (vals + k * slots): the
+// P2 rows have only 4-14 entries, so the CSR kernel above (4-8 lanes per row, [nnz][K] values) runs at 0.56 of the HBM
+// peak; one thread per row over coalesced streams reads (8 K + 4) bytes per slot and nothing else.
+template <int K>
+__global__ void __launch_bounds__(256, 4)
+k_rect_vq_sell(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols, const double* __restrict__ vals,
+               int64_t slots, const double* __restrict__ xq, const double* add, int ld, double scale, double* out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_slices = (n_rows + 31) >> 5;
+  for (int s = warp; s < n_slices; s += nwarps) {
+    const int base = __ldg(slice_ptr + s);
+    const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int row = (s << 5) + lane;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) {
+      const size_t p = (size_t)base + ((size_t)t << 5) + lane;
+      const double xv = __ldg(xq + ld_stream(cols + p));
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fma(ld_stream(vals + (size_t)k * slots + p), xv, acc[k]);
+    }
+    if (row < n_rows) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double a = add != nullptr ? add[(size_t)k * ld + row] : 0.0;
+        out[(size_t)k * ld + row] = fma(scale, acc[k], a);
+      }
+    }
+  }
+}
+
+// [nnz][K] CSR values -> component-major sliced-ELL slots (pads stay 0)
+template <int K>
+__global__ void k_rect_to_sell(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr, int64_t slots,
+                               const double* __restrict__ in, double* __restrict__ out) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int start = rowptr[row], n = rowptr[row + 1] - start;
+  const size_t base = (size_t)slice_ptr[row >> 5] + (row & 31);
+  for (int t = 0; t < n; ++t)
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[(size_t)k * slots + base + ((size_t)t << 5)] = in[(size_t)(start + t) * K + k];
 }
 
 // out[q] = scale * sum_p sum_k vals[p][k] * xv_k[cols[p]]            (sum_i D_i u_i)
