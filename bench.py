@@ -51,14 +51,15 @@ KRYLOV = {
 
 def ncu_traffic(mesh: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_spmm launch from the committed `ncu --set full`
-    capture (profiles/r01_ncu_spmm_final_96cube.txt); only valid for the mesh it was taken on."""
+    capture (profiles/r02_ncu_spmm_96cube.txt, first kernel of the file); only valid for the mesh it was taken on."""
     if mesh != 96:
         return None
     try:
-        tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_spmm_final_96cube.txt")):
+        tot, seen = 0.0, set()
+        for line in open(os.path.join(ROOT, "profiles", "r02_ncu_spmm_96cube.txt")):
             f = line.split()
-            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[0] not in seen:
+                seen.add(f[0])
                 tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
         return tot or None
     except Exception:
@@ -374,14 +375,20 @@ def make_field(workload: str):
     (w = 0) with the block-relative tolerance of round 1."""
     from problems import TaylorGreen, TaylorGreenRot
 
+    if workload == "taylor-green-2d":
+        return TaylorGreen(NU, 2)
     return TaylorGreenRot(NU) if workload == "taylor-green-rot" else TaylorGreen(NU, 3)
+
+
+def gdim_of(workload: str) -> int:
+    return 2 if workload == "taylor-green-2d" else 3
 
 
 def krylov_for(workload: str) -> dict:
     import copy
 
     k = copy.deepcopy(KRYLOV)
-    if workload == "taylor-green-rot":  # PETSc's convergence test: every component against its own right-hand side
+    if workload in ("taylor-green-rot", "taylor-green-2d"):  # PETSc's convergence test: every component against its own right-hand side
         for o in k.values():
             o.pop("b200_block_rtol", None)
     return k
@@ -431,10 +438,11 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1, workload: str = "taylo
     cpu.use_all_cores()
     krylov = krylov or krylov_for(workload)
     tg = make_field(workload)
-    msh = make_mesh(3, n_cpu)
+    gd = gdim_of(workload)
+    msh = make_mesh(gd, n_cpu)
     V, Q = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
-    bd = fem.locate_dofs_topological(V, 2, boundary_facets(msh))
-    c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, 3, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
+    bd = fem.locate_dofs_topological(V, gd - 1, boundary_facets(msh))
+    c = cpu.CpuIPCS(msh.geometry.x, msh.geometry.dofmap, gd, V.dofmap.list, Q.dofmap.list, V.tabulate_dof_coordinates(),
                     Q.tabulate_dof_coordinates(), 2, bcs_u=[[(bd, f)] for f in tg.components],
                     rtol=krylov["tentative"]["ksp_rtol"], nonzero_guess=krylov["tentative"]["ksp_initial_guess_nonzero"],
                     block_rtol=bool(krylov["tentative"].get("b200_block_rtol", False)),
@@ -464,10 +472,10 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1, workload: str = "taylo
     nnz = [int(cpu.lib().ipcs_cpu_nnz(c.h, k)) for k in range(4)]
     med = [int(np.median([i[j] for i in all_its])) for j in range(3)] if all_its else [0, 0, 0]
     out = {"sec_per_step": sec, "cells": msh.num_cells, "threads": int(cpu.lib().ipcs_cpu_threads()), "its": c.its.tolist(),
-           "its_median": med, "bytes_per_step": cpu_step_bytes(c.nV, c.nQ, nnz[0], nnz[1], nnz[3], 3, med, mg),
+           "its_median": med, "bytes_per_step": cpu_step_bytes(c.nV, c.nQ, nnz[0], nnz[1], nnz[3], gd, med, mg),
            "steps_done": n_warm + n_steps}
     if want_fields:
-        out["u"] = [c.get(cpu.U, i) for i in range(3)]
+        out["u"] = [c.get(cpu.U, i) for i in range(gd)]
         out["p"] = c.get(cpu.P, 0)
     return out
 
@@ -495,7 +503,7 @@ def run_reference(args):
     wl = args.workload
     r = cpu_sample(n_cpu, K_run, W_run, wl)
     sec = r["sec_per_step"]
-    target_cells = 6 * args.mesh**3
+    target_cells = 6 * args.mesh**3 if gdim_of(wl) == 3 else 2 * args.mesh**2
     sps = (1.0 / sec) * r["cells"] / target_cells
     gbs = r["bytes_per_step"] / sec / 1e9
     line = {
@@ -518,6 +526,9 @@ def run_reference(args):
 
 
 def workload_name(wl: str, N: int) -> str:
+    if wl == "taylor-green-2d":
+        return (f"2D Taylor-Green P2-P1 {N}x{N} rectangle [-1,1]^2 (demo/taylor_green.py, BASELINE configs[0]), dt={DT}, nu={NU}, "
+                "max_iter=1, rtol=1e-10")
     field = {"taylor-green-rot": "exact 2D vortex rotated out of the x-y plane: 3 live components, per-component rtol",
              "taylor-green-z": "z-extruded exact solution, w = 0, block-relative rtol"}[wl]
     return f"3D Taylor-Green P2-P1 {N}^3 box ({field}), dt={DT}, nu={NU}, max_iter=1, rtol=1e-10"
@@ -550,9 +561,10 @@ def parity_vs_cpu_port(solver, tg, cpu_fields: dict) -> dict:
         tg.t_u += DT
         tg.t_p += DT
         solver.solve(DT, NU, max_iter=1)
-    u = [solver._u[i].x.array_ro() for i in range(3)]
+    gd = len(cpu_fields["u"])
+    u = [solver._u[i].x.array_ro() for i in range(gd)]
     scale = max(float(np.abs(v).max()) for v in cpu_fields["u"])
-    du = max(float(np.abs(u[i] - cpu_fields["u"][i]).max()) for i in range(3)) / scale
+    du = max(float(np.abs(u[i] - cpu_fields["u"][i]).max()) for i in range(gd)) / scale
     pg, pc = solver._p.x.array_ro(), cpu_fields["p"]
     dpp = float(np.abs(pg - pc).max()) / float(np.abs(pc).max())
     return {"steps": n, "rel_diff_u_vs_cpu_port": du, "rel_diff_p_vs_cpu_port": dpp}
@@ -563,7 +575,7 @@ def parity_small(workload: str, N: int, n_steps: int, device: int) -> dict:
     from problems import make_mesh, make_solver
 
     tg = make_field(workload)
-    solver = make_solver(make_mesh(3, N), 2, tg, DT, solver_options=krylov_for(workload), device=device)
+    solver = make_solver(make_mesh(gdim_of(workload), N), 2, tg, DT, solver_options=krylov_for(workload), device=device)
     r = cpu_sample(N, n_steps, 0, workload, want_fields=True)
     out = parity_vs_cpu_port(solver, tg, r)
     out["mesh"] = N
@@ -585,7 +597,8 @@ def run_ours(args):
     N, K, W = args.mesh, args.steps, max(args.warmup, 3)
     t_setup = time.perf_counter()
     tg = make_field(wl)
-    msh = make_mesh(3, N, comm if world > 1 else None)
+    gd = gdim_of(wl)
+    msh = make_mesh(gd, N, comm if world > 1 else None)
     solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
@@ -637,11 +650,11 @@ def run_ours(args):
     tg.t_u = (W + K) * DT
     solver._written(solver._u, solver._u1, solver._u2, solver._p, solver._ps, solver._dp)  # ctx.step bypassed the host mirrors
     xV = solver._Vi[0][0].tabulate_dof_coordinates().T
-    exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][3] at the time of the last step
+    exact = np.stack([f(xV) for f in tg.components], axis=1)  # blocked [n][gdim] at the time of the last step
     err2 = ctx.l2_diff_sq(L.VEC_U, exact)
     nrm2 = ctx.l2_diff_sq(L.VEC_U, exact * 0.0)
     nVo, nQo = solver._nV_owned, solver._nQ_owned
-    su = comm.allreduce(float(sum(np.dot(solver._u[i].x.array_ro()[:nVo], solver._u[i].x.array_ro()[:nVo]) for i in range(3))))
+    su = comm.allreduce(float(sum(np.dot(solver._u[i].x.array_ro()[:nVo], solver._u[i].x.array_ro()[:nVo]) for i in range(gd))))
     sp = comm.allreduce(float(np.dot(solver._p.x.array_ro()[:nQo], solver._p.x.array_ro()[:nQo])))
     checks = {"t_end": tg.t_u, "rel_l2_error_u_vs_exact": float(np.sqrt(err2 / nrm2)),
               "norm_u": float(f"{np.sqrt(su):.15e}"), "norm_p": float(f"{np.sqrt(sp):.15e}")}
@@ -691,7 +704,7 @@ def run_ours(args):
             except Exception:
                 collectives[name] = None
     comm.Barrier()
-    roofline = {"bound": "hbm", "kernel": "k_spmm<K=3> (P2xP2 SELL-32 operator, 3 right-hand sides)",
+    roofline = {"bound": "hbm", "kernel": f"k_spmm<K={gd}> (P2xP2 SELL-32 operator, {gd} right-hand sides)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(N) if world == 1 else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
                 "other_kernels": {
@@ -703,7 +716,7 @@ def run_ours(args):
         if world == 1:
             med = (int(np.median([i[0] for i in its])), int(np.median([i[1] for i in its])), int(np.median([i[2] for i in its])))
             sb = step_algorithmic_bytes(solver._nV_owned, solver._nQ_owned, ctx.pattern_nnz(L.PAT_VV), ctx.pattern_nnz(L.PAT_VQ),
-                                        ctx.pattern_nnz(L.PAT_QQ), 3, med, bytes_a, bytes_k, bytes_q)
+                                        ctx.pattern_nnz(L.PAT_QQ), gd, med, bytes_a, bytes_k, bytes_q)
             gbs = sb["total"] / (ms_per_step * 1e-3) / 1e9
             step_roofline = {"algorithmic_bytes_per_step": sb["total"], "iterations_assumed": list(med), "achieved": gbs, "peak": peak,
                              "unit": "GB/s", "frac": gbs / peak,
@@ -756,8 +769,8 @@ def run_ours(args):
     nV = solver._lp.V.n_global if world > 1 else solver._nV_owned
     nQ = solver._lp.Q.n_global if world > 1 else solver._nQ_owned
     line = {
-        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC if gd == 3 else "IPCS steps/s, 2D Taylor-Green P2-P1 rectangle", "value": value, "unit": "steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(wl, N), "mesh": N, "cells": msh.num_cells,
                    "dofs": 3 * nV + nQ, "partition": (f"{world} z-slab(s), " + ("peer-memory halo + in-kernel all-reduce (no NCCL call on the data path)"
@@ -793,7 +806,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", type=int, default=0, help="cubes per direction (default 96 = BASELINE's metric, 48 = configs[2]; cavity: 128)")
     ap.add_argument("--workload", default="taylor-green",
-                    choices=["taylor-green", "taylor-green-rot", "taylor-green-z", "cavity", "assembly-strategies"],
+                    choices=["taylor-green", "taylor-green-rot", "taylor-green-z", "taylor-green-2d", "cavity", "assembly-strategies"],
                     help="taylor-green = BASELINE.json's metric (the line the driver reads) = taylor-green-rot: the exact vortex "
                          "rotated out of the x-y plane, three live components, per-component rtol; taylor-green-z = round 1's "
                          "z-extruded field (w = 0) with the block-relative tolerance; cavity = configs[4]; assembly-strategies = "
@@ -815,7 +828,7 @@ def main():
     if args.workload == "taylor-green":
         args.workload = HEADLINE
     if args.mesh <= 0:
-        args.mesh = (64 if args.weak else 128) if args.workload == "cavity" else 96
+        args.mesh = (64 if args.weak else 128) if args.workload == "cavity" else (64 if args.workload == "taylor-green-2d" else 96)
     if args.workload == "cavity":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the Taylor-Green metric; the cavity line carries its own cpu_baseline")
