@@ -33,6 +33,8 @@ class KSPSolver:
             return
         for k, v in options.items():
             if k in _UNDERSTOOD:
+                if k == "ksp_type" and str(v) == "gmres":
+                    logger.warning("%sksp_type=gmres: the device Krylov stack solves nonsymmetric systems with BiCGStab", self._prefix)
                 self._ctx.set_solver_option(self._slot, k, v)
             else:
                 logger.debug("option %s%s=%s ignored by the B200 Krylov stack", self._prefix, k, v)
