@@ -160,6 +160,7 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
+  int spmm_min_slices = 16;  // tuning "spmm_min_slices": below this many slices per warp the grid is not persistent
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -462,7 +463,11 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
                    KryState* st, int fin, const double* rscale) {
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
-  const int grid = std::max(1, std::min(need, c->sm * c->spmm_blocks_per_sm));
+  // persistent grid (a warp walks many slices of the tile schedule) for large operators; when a warp would get fewer
+  // than `spmm_min_slices` slices -- the 1/4 or 1/8 slab of a multi-GPU run -- the 3-or-4-slices quantisation costs
+  // up to 17 % (tools/exp_slab.py: 103 -> 86 us on the 96 x 96 x 12 slab), so every warp takes ONE slice instead
+  const int persistent = c->sm * c->spmm_blocks_per_sm;
+  const int grid = std::max(1, need < c->spmm_min_slices * persistent ? need : persistent);
 #define B2_SPMM(STREAM_, RS_)                                                                                            \
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
             pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
@@ -1064,7 +1069,7 @@ void rect_vq(b2_ctx* c, const double* vals, const double* xq, const double* add,
   const int ld = (int)c->sp[B2_SPACE_V].n_local();
   const double* sell = vals == c->P.p ? c->Psell.p : (vals == c->G.p ? c->Gsell.p : nullptr);
   if (sell != nullptr && vq.has_sell()) {
-    B2_LAUNCH(c, k_rect_vq_sell<K>, pgrid(c, vq.n_rows, 256, 4), 256, vq.n_rows, vq.slice_ptr.p, vq.scols.p, sell, (int64_t)vq.slots, xq,
+    B2_LAUNCH(c, k_rect_vq_sell<K>, blocks_for(vq.n_rows, 256), 256, vq.n_rows, vq.slice_ptr.p, vq.scols.p, sell, (int64_t)vq.slots, xq,
               add, ld, scale, out);
     return;
   }
@@ -2571,6 +2576,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     std::string k(key);
     if (k == "spmm_blocks_per_sm") c->spmm_blocks_per_sm = std::max(1, std::min(value, 32));
     else if (k == "spmm_unroll") c->spmm_unroll = value;
+    else if (k == "spmm_min_slices") c->spmm_min_slices = std::max(0, value);
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
