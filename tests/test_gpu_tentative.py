@@ -122,3 +122,65 @@ def test_channel_time_steps_with_pressure_bc():
         for i in range(2):
             assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-8, n
         assert relerr(s._p.x.array_ro(), o.p) <= 1e-8, n
+
+
+def test_pressure_bc_constant_is_read_live():
+    """A `fem.Constant` outlet pressure changed between two `assemble_first` calls changes the assembled surface term
+    (the reference keeps the Constant inside the ds-form, bcs.py:233-242; round-1 advisor finding: it was frozen)."""
+    msh = bmesh.create_unit_square(None, 6, 6)
+    dim = msh.topology.dim - 1
+    right = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 1))
+    left = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 0))
+    facets = np.hstack([left, right])
+    values = np.hstack([np.full_like(left, 1), np.full_like(right, 3)])
+    order = np.argsort(facets)
+    tags = bmesh.meshtags(msh, dim, facets[order], values[order])
+    pc = fem.Constant(msh, 4.0)
+    bcs_u = [[DirichletBC(1.0, LocatorMethod.TOPOLOGICAL, (tags, 1))], [DirichletBC(0.0, LocatorMethod.TOPOLOGICAL, (tags, 1))]]
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    s = FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[PressureBC(pc, (tags, 3))],
+                             solver_options={"tentative": lu, "pressure": lu, "scalar": lu}, options={"low_memory_version": False})
+    s.assemble_first(0.1, 0.5)
+    b4 = [f.x.array_ro().copy() for f in s._b_first]
+    pc.value = np.asarray(8.0)
+    s.assemble_first(0.1, 0.5)
+    b8 = [f.x.array_ro().copy() for f in s._b_first]
+    # u1 = 0 and no body force: b_first is the surface term alone, linear in the boundary pressure
+    assert max(np.abs(b).max() for b in b4) > 1e-3
+    for a, b in zip(b4, b8):
+        assert np.allclose(b, 2.0 * a, rtol=1e-12, atol=1e-14)
+
+
+def test_dirichlet_dofs_injected_in_any_order():
+    """`DirichletBC.set_dofs` with an unsorted dof array (bcs.py:103-104): values land on the right dofs (round-1
+    advisor finding: the single-BC fast path assumed the sorted order of the device list)."""
+    from problems import TaylorGreen, boundary_facets, make_mesh
+
+    gdim, dt, nu = 2, 0.005, 0.01
+    msh = make_mesh(gdim, 6)
+    V = fem.functionspace(msh, ("Lagrange", 2))
+    bd = fem.locate_dofs_topological(V, gdim - 1, boundary_facets(msh))
+    tg = TaylorGreen(nu, gdim)
+    lu = {"ksp_type": "preonly", "pc_type": "lu"}
+    out = []
+    for perm in (np.arange(len(bd)), np.random.default_rng(1).permutation(len(bd))):
+        bcs_u = []
+        for f in tg.components:
+            bc = DirichletBC(f, LocatorMethod.GEOMETRICAL, lambda x: np.zeros(x.shape[1], bool))
+            bc.set_dofs(bd[perm])
+            bcs_u.append([bc])
+        s = FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[],
+                                 solver_options={"tentative": lu, "pressure": lu, "scalar": lu}, options={"low_memory_version": False})
+        tg.t_u = -dt
+        for i, f in enumerate(tg.components):
+            s._u2[i].interpolate(f)
+        tg.t_u = 0.0
+        for i, f in enumerate(tg.components):
+            s._u1[i].interpolate(f)
+        tg.t_p = -dt / 2
+        s._p.interpolate(tg.eval_p)
+        tg.t_u, tg.t_p = dt, dt / 2
+        s.solve(dt, nu, max_iter=1)
+        out.append([f.x.array_ro().copy() for f in s._u])
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-12 * max(np.abs(a).max(), 1e-30)
