@@ -241,6 +241,9 @@ int b2_project_get_rhs(b2_ctx* ctx, double* rhs);
 /* solve(assemble_rhs=False) with a right-hand side the caller kept: [n_comp][n_local] */
 int b2_project_set_rhs(b2_ctx* ctx, int target_space, int n_comp, const double* rhs);
 int b2_project_solve(b2_ctx* ctx, double* x, int32_t* reasons);
+/* Dirichlet conditions of the projection (function.py:70 assemble_matrix(lhs, bcs), :114-118 apply_lifting + set_bc):
+ * x_k[dofs[i]] = values[k][i] (values: [n_comp][n]); applied by b2_project_solve; n = 0 removes them. */
+int b2_project_set_bcs(b2_ctx* ctx, int target_space, int n_comp, int64_t n, const int32_t* dofs, const double* values);
 /* KSPSolver.solve (ksp.py:71-78): Mat x = b with the options of solver slot `solver`, then scatter_forward;
  * b and x are host vectors of the operator's space (owned + ghosts), x is the initial guess when
  * ksp_initial_guess_nonzero is set.  Square operators only (B2_MAT_M, _K, _A, _AP, _MQ). */

@@ -31,7 +31,7 @@ SYMBOLS = [
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
-    "b2_assemble_pressure_surface", "b2_project_assemble", "b2_project_get_rhs", "b2_project_set_rhs", "b2_project_solve", "b2_ksp_solve", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_l2_error_trig", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
+    "b2_assemble_pressure_surface", "b2_project_assemble", "b2_project_get_rhs", "b2_project_set_rhs", "b2_project_set_bcs", "b2_project_solve", "b2_ksp_solve", "b2_l2_diff_sq", "b2_l2_error_quadrature", "b2_l2_error_trig", "b2_get_stats", "b2_bench_kernel", "b2_synchronize",
     "b2_event_record", "b2_event_elapsed_ms", "b2_set_tuning",
 ]
 
@@ -130,6 +130,7 @@ def load_library() -> C.CDLL:
         "b2_project_assemble": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]),
         "b2_project_get_rhs": (i32, [vp, vp]),
         "b2_project_set_rhs": (i32, [vp, i32, i32, vp]),
+        "b2_project_set_bcs": (i32, [vp, i32, i32, i64, vp, vp]),
         "b2_project_solve": (i32, [vp, vp, vp]),
         "b2_ksp_solve": (i32, [vp, i32, i32, vp, vp, vp]),
         "b2_l2_diff_sq": (i32, [vp, i32, vp, i64, vp]),
@@ -412,6 +413,12 @@ class Context:
         out = np.empty(n, dtype=np.float64)
         self._check(self.lib.b2_project_get_rhs(self._h, _ptr(out)), "b2_project_get_rhs")
         return out
+
+    def project_set_bcs(self, target_space: int, dofs, values):
+        d = _i32(dofs)
+        v = _f64(np.atleast_2d(values))
+        assert v.shape[1] == d.size
+        self._check(self.lib.b2_project_set_bcs(self._h, target_space, v.shape[0], d.size, _ptr(d), _ptr(v)), "b2_project_set_bcs")
 
     def project_load_rhs(self, target_space: int, rhs: np.ndarray):
         rhs = _f64(np.atleast_2d(rhs))

@@ -234,6 +234,15 @@ struct b2_ctx {
   DBuf<double> wproj[5];    // Projector / KSPSolver.solve work vectors (any space, up to 3 components)
   DBuf<double> proj_rhs;    // right-hand side of the last b2_project_assemble
   int proj_space = 0, proj_comp = 1;
+  // Dirichlet conditions of a Projector (function.py:70,114-118), per target space: dofs, values per component, the mass
+  // matrix with their rows and columns replaced by the identity, its inverse diagonal
+  struct ProjBC {
+    DBuf<int> dofs;
+    DBuf<double> vals;  // [n_comp][n]
+    DBuf<uint8_t> mask;
+    DBuf<double> Mbc, dinv;
+    int n_comp = 0;
+  } proj_bc[2];
   DBuf<double> stage;  // staging for strided host copies
   DBuf<double> dp_old;      // pressure correction of the step before the previous one (extrapolated guess)
   int dp_hist = 0;
@@ -2334,6 +2343,36 @@ int b2_project_set_rhs(b2_ctx* c, int target_space, int n_comp, const double* rh
   });
 }
 
+/* Dirichlet conditions of the projection (function.py:70 assemble_matrix(bcs=), :114-118 apply_lifting + set_bc):
+ * x_k[dofs[i]] = values[k][i]; n = 0 removes them.  Applied by b2_project_solve to whatever right-hand side is loaded. */
+int b2_project_set_bcs(b2_ctx* c, int target_space, int n_comp, int64_t n, const int32_t* dofs, const double* values) {
+  return guarded(c, [&] {
+    require_ready(c);
+    B2_REQUIRE((target_space == B2_SPACE_V || target_space == B2_SPACE_Q) && n_comp >= 1 && n_comp <= 3 && n >= 0, "bad space / components");
+    auto& B = c->proj_bc[target_space];
+    B.n_comp = n > 0 ? n_comp : 0;
+    B.dofs.alloc(n);
+    B.vals.alloc(n * n_comp);
+    if (n == 0) return;
+    const bool onV = target_space == B2_SPACE_V;
+    if (!onV) ensure_mq(c);
+    const CSR& pat = c->pat[onV ? B2_PAT_VV : B2_PAT_QQ];
+    const int64_t nl = c->sp[target_space].n_local();
+    B2_CUDA(cudaMemcpyAsync(B.dofs.p, dofs, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(B.vals.p, values, sizeof(double) * n * n_comp, cudaMemcpyHostToDevice, c->stream));
+    B.mask.alloc(nl);
+    B.mask.zero(c->stream);
+    B2_LAUNCH(c, k_mark, blocks_for(n, 256), 256, n, B.dofs.p, B.mask.p);
+    B.Mbc.alloc(pat.slots);
+    B2_CUDA(cudaMemcpyAsync(B.Mbc.p, onV ? c->M.p : c->MQ.p, sizeof(double) * (size_t)pat.slots, cudaMemcpyDeviceToDevice, c->stream));
+    B2_LAUNCH(c, k_apply_bc_rows_cols, blocks_for(pat.n_rows, 256), 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, pat.diag_t.p, B.mask.p, B.Mbc.p);
+    B.dinv.alloc(nl);
+    B2_LAUNCH(c, k_fill, pgrid(c, nl), 256, nl, 1.0, B.dinv.p);
+    B2_LAUNCH(c, k_inv_diag, blocks_for(pat.n_rows, 256), 256, pat.n_rows, pat.slice_ptr.p, pat.diag_t.p, B.Mbc.p, B.dinv.p);
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 int b2_project_get_rhs(b2_ctx* c, double* rhs) {
   return guarded(c, [&] {
     B2_REQUIRE(c->proj_rhs.p != nullptr, "b2_project_assemble first");
@@ -2359,8 +2398,30 @@ int b2_project_solve(b2_ctx* c, double* x, int32_t* reasons) {
     KSPOpts& o = c->ksp[B2_SOLVER_PROJECTOR];
     const bool guess = o.nonzero_guess;
     o.nonzero_guess = false;
-    krylov_solve(c, B2_SOLVER_PROJECTOR, c->pat[onV ? B2_PAT_VV : B2_PAT_QQ], onV ? c->M.p : c->MQ.p,
-                 onV ? c->dinvM.p : c->dinvMQ.p, sp, K, c->proj_rhs.p, sol.p, reasons, its, c->wproj);
+    const CSR& ppat = c->pat[onV ? B2_PAT_VV : B2_PAT_QQ];
+    const double* Mv = onV ? c->M.p : c->MQ.p;
+    const double* dinv = onV ? c->dinvM.p : c->dinvMQ.p;
+    auto& B = c->proj_bc[sp];
+    DBuf<double> rhs_bc, gext;
+    const double* rhs = c->proj_rhs.p;
+    if (B.n_comp > 0) {
+      // lifting: b -= M g (g extended by zero), then b[dofs] = g; solve with the identity on the Dirichlet rows/columns
+      B2_REQUIRE(B.n_comp == K, "Projector BCs were set for a different number of components");
+      const int64_t nl = T.n_local(), nb = B.dofs.n;
+      gext.alloc(n);
+      gext.zero(c->stream);
+      rhs_bc.alloc(n);
+      for (int k = 0; k < K; ++k)
+        B2_LAUNCH(c, k_set_bc, blocks_for(nb, 256), 256, nb, B.dofs.p, B.vals.p + (size_t)k * nb, gext.p + (size_t)k * nl);
+      spmm(c, ppat, Mv, K, gext.p, rhs_bc.p, nullptr, nullptr, FIN_NONE, 0, sp);
+      B2_LAUNCH(c, k_lincomb2, pgrid(c, n), 256, n, 1.0, c->proj_rhs.p, -1.0, rhs_bc.p, rhs_bc.p);
+      for (int k = 0; k < K; ++k)
+        B2_LAUNCH(c, k_set_bc, blocks_for(nb, 256), 256, nb, B.dofs.p, B.vals.p + (size_t)k * nb, rhs_bc.p + (size_t)k * nl);
+      rhs = rhs_bc.p;
+      Mv = B.Mbc.p;
+      dinv = B.dinv.p;
+    }
+    krylov_solve(c, B2_SOLVER_PROJECTOR, ppat, Mv, dinv, sp, K, rhs, sol.p, reasons, its, c->wproj);
     o.nonzero_guess = guess;
     c->stats.its_projector = *std::max_element(its, its + K);
     halo_forward(c, sp, sol.p, K);  // x.scatter_forward(), function.py:132

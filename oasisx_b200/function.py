@@ -76,8 +76,6 @@ class Projector:
     def __init__(self, function, space: _fem.FunctionSpace, bcs=None, petsc_options: dict | None = None,
                  jit_options: dict | None = None, form_compiler_options: dict | None = None,
                  metadata: dict | None = None, device: int = 0):
-        if bcs:
-            raise NotImplementedError("Projector with Dirichlet BCs is not built (function.py:70,114-118)")
         if space.degree not in (1, 2):
             raise NotImplementedError("Lagrange P1 / P2 targets")
         self._function, self._space = function, space
@@ -92,6 +90,10 @@ class Projector:
         self._x = _fem.Function(space)
         self._b = _fem.Function(space)
         self._sources = self._parse(function)
+        self._bcs = list(bcs) if bcs else []
+        for bc in self._bcs:  # our DirichletBC objects, one list entry per condition; blocked targets: one per component
+            if not hasattr(bc, "_values"):
+                bc.create_bc(space._scalar)
         self.assemble_rhs()
 
     # ---- helpers ---------------------------------------------------------------------------
@@ -172,10 +174,29 @@ class Projector:
         if assemble_rhs:
             self.assemble_rhs()
         ctx, bs, n = self._ctx, self._space.bs, self._space._scalar.num_dofs
+        self._push_bcs()
         ctx.project_load_rhs(self._slot, self._rhs)  # the right-hand side this object assembled last, all components
         out, reasons = ctx.project_solve(n, bs)      # one Krylov run on bs systems sharing the mass matrix
         self._x.x.array[:] = np.ascontiguousarray(out.T).reshape(-1) if bs > 1 else out[0]
         return int(min(reasons))
+
+    def _push_bcs(self):
+        """``function.py:70,114-118``: Dirichlet rows/columns of the mass matrix -> identity, lifting, set_bc.  The
+        conditions (``oasisx_b200.DirichletBC``; for a blocked space a condition may carry ``component = k``, default
+        all components) are merged into one dof list per projector, later conditions winning on shared dofs."""
+        ctx, bs = self._ctx, self._space.bs
+        if not self._bcs:
+            ctx.project_set_bcs(self._slot, np.zeros(0, np.int32), np.zeros((bs, 0)))
+            return
+        dofs = np.unique(np.concatenate([bc._dofs for bc in self._bcs])).astype(np.int32)
+        vals = np.zeros((bs, len(dofs)))
+        for bc in self._bcs:
+            bc.update_bc()
+            pos = np.searchsorted(dofs, bc._dofs)
+            comp = getattr(bc, "component", None)
+            for k in (range(bs) if comp is None else [int(comp)]):
+                vals[k, pos] = bc.current_values()
+        ctx.project_set_bcs(self._slot, dofs, vals)
 
     @property
     def x(self):

@@ -59,8 +59,42 @@ def test_projector_scalar_sources_and_spaces():
     p = oasisx.Projector(f1, V, petsc_options=LU)
     assert p.solve() > 0
     assert np.abs(p.x.x.array - lin(V.tabulate_dof_coordinates().T)).max() < 1e-10
-    with pytest.raises(NotImplementedError):
-        oasisx.Projector(f1, V, bcs=[object()])
+
+
+def test_projector_with_dirichlet_bcs():
+    """``Projector(..., bcs)`` (function.py:70,114-118): rows/columns of the Dirichlet dofs -> identity, lifting, set_bc.
+    Checked against the same constrained system solved with scipy on the host."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    from oasisx_b200 import DirichletBC, LocatorMethod
+
+    msh = bmesh.create_unit_square(None, 6, 5)
+    V = fem.functionspace(msh, ("Lagrange", 2))
+    f = lambda x: np.sin(2 * x[0]) + x[1] ** 2
+    g = lambda x: 3.0 + x[1]
+    bc = DirichletBC(g, LocatorMethod.GEOMETRICAL, lambda x: np.isclose(x[0], 0.0))
+    p = oasisx.Projector(f, V, [bc], petsc_options=LU, metadata={"quadrature_degree": 8})
+    assert p.solve() > 0
+    # host restatement: M from the device (getValuesCSR-like through mat_mult on unit vectors would be slow: use the solver's API)
+    s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", 2), ("Lagrange", 1), bcs_u=[[], []], bcs_p=[], options={"low_memory_version": True})
+    ip, ix, vals = s._M.getValuesCSR()
+    M = sp.csr_matrix((vals, ix, ip), shape=(V.num_dofs, V.num_dofs))
+    q = oasisx.Projector(f, V, petsc_options=LU, metadata={"quadrature_degree": 8})
+    b = q._rhs[0].copy()
+    d = bc._dofs
+    gv = g(V.tabulate_dof_coordinates()[d].T)
+    gext = np.zeros(V.num_dofs)
+    gext[d] = gv
+    b = b - M @ gext
+    b[d] = gv
+    Mbc = M.tolil()
+    Mbc[d, :] = 0.0
+    Mbc[:, d] = 0.0
+    Mbc[d, d] = 1.0
+    ref = spla.spsolve(Mbc.tocsc(), b)
+    assert np.abs(p.x.x.array[d] - gv).max() < 1e-12
+    assert np.abs(p.x.x.array - ref).max() < 1e-9 * np.abs(ref).max()
 
 
 def test_kspsolver_solve_matches_the_operator():
