@@ -160,7 +160,7 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
-  int spmm_min_slices = 16;  // tuning "spmm_min_slices": below this many slices per warp the grid is not persistent
+  int spmm_min_slices = 1;   // tuning "spmm_min_slices": 0 = round 1's fixed persistent grid (sm x spmm_blocks_per_sm), else equal shares
   cudaStream_t stream = nullptr;
   std::string err;
   int gdim = 0;
@@ -472,11 +472,14 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
                    KryState* st, int fin, const double* rscale) {
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
-  // persistent grid (a warp walks many slices of the tile schedule) for large operators; when a warp would get fewer
-  // than `spmm_min_slices` slices -- the 1/4 or 1/8 slab of a multi-GPU run -- the 3-or-4-slices quantisation costs
-  // up to 17 % (tools/exp_slab.py: 103 -> 86 us on the 96 x 96 x 12 slab), so every warp takes ONE slice instead
-  const int persistent = c->sm * c->spmm_blocks_per_sm;
-  const int grid = std::max(1, need < c->spmm_min_slices * persistent ? need : persistent);
+  // Every warp takes the same whole number k of slices (k = 1 when the grid fits): a fixed persistent grid quantises
+  // small operators -- the 1/4 or 1/8 slab of a multi-GPU run got 3.07 slices per warp, i.e. 3 or 4: 103 us against 86
+  // on the 96 x 96 x 12 slab (tools/exp_slab.py) -- and is no faster on large ones.  The cap is what the grid-wide
+  // reduction has room for (one set of partial sums per block).
+  const int cap = (int)std::min<int64_t>(c->partials.n / 16, (int64_t)c->sm * 32);
+  const int k_slices = std::max(1, (need + cap - 1) / cap);
+  const int grid = std::max(1, c->spmm_min_slices > 0 ? (need + k_slices - 1) / k_slices : std::min(need, c->sm * c->spmm_blocks_per_sm));
+  B2_REQUIRE(grid <= cap, "SpMM grid exceeds the reduction scratch");
 #define B2_SPMM(STREAM_, RS_)                                                                                            \
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
             pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
