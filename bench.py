@@ -599,6 +599,8 @@ def run_ours(args):
     tg = make_field(wl)
     gd = gdim_of(wl)
     msh = make_mesh(gd, N, comm if world > 1 else None)
+    if args.dof_order == "generic":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
+        msh._dof_order = "generic"
     solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
@@ -777,7 +779,7 @@ def run_ours(args):
                                                            if ctx.peer_enabled() else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "working set per step >> 126 MB L2 (P2xP2 operators alone "
                          f"{3 * 12 * (230 * N**3) / 1e9:.2f} GB over all ranks); no flush needed",
-                   "krylov": krylov, "low_memory_version": bool(args.low_memory),
+                   "krylov": krylov, "low_memory_version": bool(args.low_memory), "dof_order": args.dof_order,
                    "multigrid": "V(1,1) damped Jacobi 0.85, exact dense solve on the first level <= 5000 dofs",
                    "sell_P2xP2": {"slots": sell, "slice_columns": sell // 32},
                    "setup_s": t_setup},
@@ -816,6 +818,9 @@ def main():
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
     ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4]; "
                                                          "default block 64^3: the host provider still builds the global mesh on every rank)")
+    ap.add_argument("--dof-order", default="class", choices=["class", "generic"],
+                    help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
+                         "coordinate sort every other mesh gets (DOLFINx, unstructured): how much of the SpMM roofline fraction is the lattice")
     ap.add_argument("--low-memory", action="store_true", help="options={'low_memory_version': True}: matrix-free element vectors "
                                                                "instead of the 9 rectangular operators (fracstep.py:259)")
     ap.add_argument("--pressure-pc", default="mg", choices=["mg", "jacobi"], help="pressure preconditioner of the GPU arm")

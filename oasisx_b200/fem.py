@@ -110,6 +110,8 @@ class FunctionSpace:
         # renumber for locality (DOLFINx applies a graph reordering here [ext]); vertex-first
         # numbering would scatter every P2 row's columns over the whole vector
         lattice = getattr(mesh, "_lattice", None)
+        if getattr(mesh, "_dof_order", "class") != "class":
+            lattice = None  # "generic": what a mesh without lattice information (DOLFINx, unstructured) gets
         order = _class_order(x, lattice) if (lattice is not None and degree == 2) else _lex_order(x)
         new_of_old = np.empty(len(order), dtype=np.int64)
         new_of_old[order] = np.arange(len(order))

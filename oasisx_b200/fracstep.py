@@ -196,7 +196,8 @@ class FractionalStep_AB_CN:
         if deg_u == 2:  # tile-major schedule of the SELL slices (L1 reuse of the gathered vector)
             ctx.set_slice_order(
                 L.PAT_VV,
-                _fem.slice_order(Vs.tabulate_dof_coordinates()[: self._nV_owned], self._nV_owned, getattr(mesh, "_lattice", None)),
+                _fem.slice_order(Vs.tabulate_dof_coordinates()[: self._nV_owned], self._nV_owned,
+                                 getattr(mesh, "_lattice", None) if getattr(mesh, "_dof_order", "class") == "class" else None),
             )
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
