@@ -18,8 +18,9 @@
  *     <0 diverged: -3 ITS, -5 BREAKDOWN, -9 NANORINF), as the reference's callers assert on
  *     them (fracstep.py:681,684);
  *   - FP64 values, int32 indices (fracstep.py:63); velocity-space vectors are stored on the
- *     device interleaved by component ([dof][gdim], == the blocked layout of `solver.u`,
- *     fracstep.py:698-705) and addressed per component through `comp`.
+ *     device component-major (component k at offset k * n_local: one contiguous array per
+ *     component, as the reference's per-component Functions) and addressed through `comp`;
+ *     comp = -1 moves the blocked [dof][gdim] view of `solver.u` (fracstep.py:698-705).
  */
 #ifndef B200IPCS_H
 #define B200IPCS_H
@@ -276,12 +277,15 @@ int b2_bench_assembly_strategies(b2_ctx* ctx, double dt, double nu, int reps, do
 int b2_first_plan_info(b2_ctx* ctx, int64_t* out);
 int b2_get_stats(b2_ctx* ctx, b2_stats* out);
 /* Times `reps` launches of one hot kernel on the context's stream with CUDA events (device
- * resident operands).  kernel: 0 = SpMM A*u (gdim RHS), 1 = convection assembly + fused combine,
- * 2 = SpMV Ap*dp, 3 = SpMM M*u.  Returns average ms per launch and the algorithmic bytes moved. */
+ * resident operands).  kernel: 0 = SpMM A*u (gdim RHS), 1 = assemble_first (k_first_cells and its row passes),
+ * 2 = SpMV Ap*dp, 3 = SpMM M*u; multi-rank only (every rank must call): 10 = halo exchange of a Q vector, 11 = of a
+ * V vector (gdim components), 12 = all-reduce of 3 doubles, 13 = sum of the replicated multigrid level.  Returns
+ * average ms per launch and the algorithmic bytes moved. */
 int b2_bench_kernel(b2_ctx* ctx, int kernel, int reps, double* ms_per_launch, double* bytes_per_launch);
 int b2_synchronize(b2_ctx* ctx);
-/* Launch-shape knobs for the hot kernels ("spmm_blocks_per_sm", "spmm_unroll"; "spmm_mode" != 0 selects
- * a diagnostic half-kernel and makes results meaningless). */
+/* Launch-shape knobs for the hot kernels: "spmm_blocks_per_sm", "spmm_unroll", "spmm_stream", "spmm_min_slices"
+ * (0 = fixed persistent SpMM grid), "spmm_mode" (!= 0 selects a diagnostic half-kernel and makes results
+ * meaningless), "first_order" / "first_slab" (cell schedule of assemble_first), "peer_grid", "graphs", "mg_dense". */
 int b2_set_tuning(b2_ctx* ctx, const char* key, int value);
 /* CUDA events on the context's stream (slots 0..7) for callers that time a region of stage calls. */
 int b2_event_record(b2_ctx* ctx, int slot);

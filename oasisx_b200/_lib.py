@@ -22,7 +22,7 @@ VEC_U, VEC_U1, VEC_U2, VEC_UAB, VEC_RHS1, VEC_BFIRST, VEC_B0, VEC_PSURF, VEC_B3,
 VEC_PS, VEC_P, VEC_DP, VEC_B2, VEC_MQ = 16, 17, 18, 19, 20
 SOLVER_TENTATIVE, SOLVER_PRESSURE, SOLVER_SCALAR, SOLVER_PROJECTOR = range(4)
 
-# every symbol include/b200ipcs.h declares (tests/test_abi.py checks the .so exports them all)
+# every symbol include/b200ipcs.h declares (tests/test_host.py::test_abi_exports_every_declared_symbol checks the .so exports them all)
 SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",

@@ -24,8 +24,6 @@ Vs = s._Vi[0][0]
 n_slices = (Vs.num_dofs + 31) // 32
 for tile in ((8, 8), (4, 4), (2, 2), (16, 16)):
     ctx.set_slice_order(L.PAT_VV, fem.slice_order(Vs.tabulate_dof_coordinates(), Vs.num_dofs, msh._lattice, tile=tile))
-    for sm in (0, 1):
-        ctx.set_tuning("spmm_sm", sm)
-        for kern in (3, 0):
-            ms, nbytes = ctx.bench_kernel(kern, 10)
-            print(f"tile {tile} sm-local {sm} kernel {kern}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
+    for kern in (3, 0):
+        ms, nbytes = ctx.bench_kernel(kern, 10)
+        print(f"tile {tile} kernel {kern}: {ms:.4f} ms  {nbytes / ms / 1e6:7.1f} GB/s", flush=True)
