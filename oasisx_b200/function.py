@@ -9,7 +9,9 @@ The reference takes a UFL expression; there is no form compiler here (SURVEY.md 
 * a Python callable ``f(x)`` (``x`` of shape (3, n)), sampled at the quadrature points by the host,
 * a list of the scalar kinds above, one per component of a blocked target space.
 
-``space`` is a scalar or blocked Lagrange P1/P2 space of the mesh (the reference's test uses DG1; the continuous
+``bcs`` is a list of :class:`oasisx_b200.DirichletBC` (``function.py:70,114-118``: identity rows and columns in the
+mass matrix, lifting of the right-hand side, ``set_bc``; on a blocked space a condition applies to every component
+unless it carries ``component = k``).  ``space`` is a scalar or blocked Lagrange P1/P2 space of the mesh (the reference's test uses DG1; the continuous
 space reproduces its known-answer check because the projected gradient is globally linear).  The right-hand side
 ``(f, v)`` is integrated by a device element kernel (``b2_project_assemble``), the mass solve runs with the
 options of the ``oasis_projector`` prefix (``b2_project_solve``).  On the IPCS hot path the projector appears only
