@@ -19,6 +19,7 @@
 #include "elem.cuh"
 #include "linalg.cuh"
 #include "mg.cuh"
+#include "bricks.hpp"
 
 namespace {
 
@@ -33,6 +34,13 @@ struct CSR {
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
+  // brick form of the SELL layout (bricks.hpp): brick schedule of the slices, brick offsets into it, gather lists,
+  // 16-bit positions per slot
+  DBuf<int> border, bptr, gptr, glist;
+  DBuf<unsigned short> lcols;
+  int n_bricks = 0, brick_cap = 0;
+  int64_t n_gather = 0;
+  bool has_bricks() const { return n_bricks > 0; }
 };
 
 struct Space {
@@ -160,6 +168,9 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
+  int spmm_brick_diag = 0;       // timing of the halves of k_spmm_brick (1: no fill, 2: no stream); results meaningless
+  int spmm_brick = 1;            // use the brick form of a pattern when it has one (b2_set_bricks); tuning "spmm_brick"
+  unsigned brick_attr_mask = 0;  // k_spmm_brick instantiations whose shared-memory limit has been raised on this device
   int spmm_min_slices = 1;   // tuning "spmm_min_slices": 0 = round 1's fixed persistent grid (sm x spmm_blocks_per_sm), else equal shares
   cudaStream_t stream = nullptr;
   std::string err;
@@ -467,9 +478,41 @@ inline RedCtl red_ptr(b2_ctx* c) {
   return c->peer_on ? RedCtl{nullptr, c->d_peer} : RedCtl{c->d_red, nullptr};
 }
 
+// brick SpMM (linalg.cuh: k_spmm_brick): persistent grid of 2 blocks per SM, K * cap * 8 bytes of shared memory each
+template <int K, int DOT>
+void launch_spmm_brick(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
+                       KryState* st, int fin, const double* rscale) {
+  constexpr int BLOCK = 512, UNROLL = 8;
+  const size_t smem = sizeof(double) * (size_t)K * pat.brick_cap;
+  const int cap = (int)std::min<int64_t>(c->partials.n / 16, (int64_t)c->sm * 32);
+  const int grid = std::max(1, std::min(std::min(pat.n_bricks, c->sm * 2), cap));
+#define B2_SPMM_BRICK(RS_)                                                                                                \
+  do {                                                                                                                    \
+    auto kern = k_spmm_brick<K, DOT, RS_, BLOCK, UNROLL>;                                                                 \
+    const unsigned bit = 1u << ((K - 1) * 6 + DOT * 2 + (RS_ ? 1 : 0));                                                   \
+    if (!(c->brick_attr_mask & bit)) { /* once per context (= per device) and instantiation */                            \
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * B2_BRICK_CAP))); \
+      c->brick_attr_mask |= bit;                                                                                          \
+    }                                                                                                                     \
+    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, pat.border.p, pat.bptr.p,      \
+                                           pat.gptr.p, pat.glist.p, pat.n_bricks, pat.brick_cap, x, ld, y, w, st, fin,    \
+                                           c->partials.p, c->d_counter, red_ptr(c), rscale, c->spmm_brick_diag);          \
+    B2_CUDA(cudaGetLastError());                                                                                          \
+    c->stats.kernel_launches++;                                                                                           \
+  } while (0)
+  if (rscale != nullptr) B2_SPMM_BRICK(true);
+  else B2_SPMM_BRICK(false);
+#undef B2_SPMM_BRICK
+  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
+}
+
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin, const double* rscale) {
+  if (c->spmm_brick && pat.has_bricks()) {
+    launch_spmm_brick<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+    return;
+  }
   const int n_slices = (pat.n_rows + 31) / 32;
   const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   // Every warp takes the same whole number k of slices (k = 1 when the grid fits): a fixed persistent grid quantises
@@ -1924,6 +1967,65 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
   });
 }
 
+int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order, int64_t n_hints, const int32_t* hint_ptr,
+                  int64_t* info) {
+  return guarded(c, [&] {
+    B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "bricks: square patterns, after b2_build_patterns");
+    CSR& pat = c->pat[pattern];
+    B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "brick schedule length must equal the number of 32-row slices");
+    B2_REQUIRE(n_hints >= 1 && hint_ptr[0] == 0 && hint_ptr[n_hints] == n_slices, "brick hints must cover the schedule");
+    c->cfg_version++;
+    std::vector<int> sp((size_t)n_slices + 1), sc((size_t)pat.slots);
+    B2_CUDA(cudaMemcpyAsync(sp.data(), pat.slice_ptr.p, sizeof(int) * sp.size(), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(sc.data(), pat.scols.p, sizeof(int) * sc.size(), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    b2bricks::Bricks B;
+    const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    b2bricks::build(pat.n_rows, pat.n_cols, sp.data(), sc.data(), order, hint_ptr, (int)n_hints, B2_BRICK_CAP, B2_BRICK_MAX_SLICES, threads, B);
+    B2_REQUIRE(B.error == 0, "bricks: one slice touches more distinct columns than the shared-memory gather list holds");
+    pat.border.alloc(n_slices);
+    pat.bptr.alloc((int64_t)B.brick_ptr.size());
+    pat.gptr.alloc((int64_t)B.gptr.size());
+    pat.glist.alloc((int64_t)B.glist.size());
+    pat.lcols.alloc(pat.slots);
+    B2_CUDA(cudaMemcpyAsync(pat.border.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.bptr.p, B.brick_ptr.data(), sizeof(int) * B.brick_ptr.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.gptr.p, B.gptr.data(), sizeof(int) * B.gptr.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.glist.p, B.glist.data(), sizeof(int) * B.glist.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.lcols.p, B.lcols.data(), sizeof(unsigned short) * B.lcols.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    pat.n_bricks = B.n_bricks();
+    pat.brick_cap = B2_BRICK_CAP;
+    pat.n_gather = (int64_t)B.glist.size();
+    if (info != nullptr) {
+      info[0] = pat.n_bricks;
+      info[1] = pat.n_gather;
+      info[2] = B.max_gather;
+    }
+  });
+}
+
+// the brick builder on host arrays (no device, no context): the CPU test of the format
+int b2_host_build_bricks(int32_t n_rows, int32_t n_cols, const int32_t* slice_ptr, const int32_t* scols, const int32_t* order,
+                         int64_t n_hints, const int32_t* hint_ptr, int32_t cap, int32_t max_slices, int32_t n_threads,
+                         int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols) {
+  try {
+    b2bricks::Bricks B;
+    b2bricks::build(n_rows, n_cols, slice_ptr, scols, order, hint_ptr, (int)n_hints, cap, max_slices, n_threads, B);
+    if (B.error) return -3;
+    *n_bricks = B.n_bricks();
+    *n_gather = (int64_t)B.glist.size();
+    if (brick_ptr) std::copy(B.brick_ptr.begin(), B.brick_ptr.end(), brick_ptr);
+    if (gptr) std::copy(B.gptr.begin(), B.gptr.end(), gptr);
+    if (glist) std::copy(B.glist.begin(), B.glist.end(), glist);
+    if (lcols) std::copy(B.lcols.begin(), B.lcols.end(), lcols);
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return -99;
+  }
+}
+
 int b2_build_patterns(b2_ctx* c) {
   return guarded(c, [&] {
     Space &V = c->sp[B2_SPACE_V], &Q = c->sp[B2_SPACE_Q];
@@ -2126,7 +2228,7 @@ int b2_get_matrix_values(b2_ctx* c, int mat, int comp, double* host) {
   });
 }
 
-// y = Mat * x through a plain CSR row kernel (parity-test hook, not a hot path)
+// y = Mat * x: square operators through the production SpMM, rectangular ones through a CSR row kernel
 int b2_mat_mult(b2_ctx* c, int mat, int comp, const double* x, double* y) {
   return guarded(c, [&] {
     B2_REQUIRE(c->preassembled, "matrices exist after b2_preassemble");
@@ -2138,8 +2240,8 @@ int b2_mat_mult(b2_ctx* c, int mat, int comp, const double* x, double* y) {
     dx.alloc(pat->n_cols);
     dy.alloc(pat->n_rows);
     B2_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * pat->n_cols, cudaMemcpyHostToDevice, c->stream));
-    if (stride == 1 && mat != B2_MAT_A) {
-      spmm(c, *pat, v->p, 1, dx.p, dy.p);  // the production SELL kernel
+    if (stride == 1) {
+      spmm(c, *pat, v->p, 1, dx.p, dy.p);  // the production SpMM (brick form when the pattern has one, else SELL-32)
     } else {
       DBuf<double> vals;
       const CSR* p2 = nullptr;
@@ -2643,6 +2745,8 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_min_slices") c->spmm_min_slices = std::max(0, value);
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
+    else if (k == "spmm_brick") c->spmm_brick = value;
+    else if (k == "spmm_brick_diag") c->spmm_brick_diag = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
     else if (k == "peer_grid") c->peer_grid = std::max(1, std::min(value, 148));
@@ -2712,7 +2816,11 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       case 12: *bytes_per_launch = 24.0; break;
       case 13: *bytes_per_launch = 8.0 * (c->mg_hi - c->mg_lo) * (c->nranks - 1); break;
       case 0:
-      case 3: *bytes_per_launch = 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc); break;  // algorithmic: K (not KP) components
+      case 3:  // algorithmic: K (not KP) components; brick form: 8 B value + 2 B list position per entry, the gather lists, x and y once
+        *bytes_per_launch = (c->spmm_brick && vv.has_bricks())
+                                ? 10.0 * vv.nnz + 4.0 * (double)vv.n_gather + 4.0 * (nV / 32 + 1) + 8.0 * K * (nV + nVc)
+                                : 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc);
+        break;
       case 2: *bytes_per_launch = 12.0 * qq.nnz + 4.0 * (qq.n_rows + 1) + 8.0 * (qq.n_rows + qq.n_cols); break;
       case 1: {  // k_first_cells: A written once (interface rows: zero-fill + read-modify-write on top), cell data
                  // (dofs, nodes, scatter table), coordinates, uab/u1 read, b0 read, b_first + dinv written, uab = 1.5 u1 - .5 u2

@@ -400,6 +400,119 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
 }
 
+// ---- brick SpMM: the same product with the gathered vector staged in shared memory (bricks.hpp) --------------------
+// One block walks bricks b = blockIdx.x, blockIdx.x + gridDim.x, ...  Per brick: (1) the x values of the brick's gather
+// list go to shared memory, component-major (coalesced: the list is sorted, i.e. runs of consecutive dofs); (2) every
+// warp takes slices of the brick and streams values (8 B) and 16-bit list positions (2 B) from HBM, the operands of the
+// FMAs come from shared memory.  Same slots, same order of the FMAs as k_spmm: y is bitwise the same.  Two resident
+// blocks per SM (K * cap * 8 B of shared memory each) overlap one block's fill with the other's stream.
+__device__ __forceinline__ int ld_stream(const unsigned short* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (int)v;
+}
+
+template <int K, int DOT, bool RS, int BLOCK, int UNROLL>
+__global__ void __launch_bounds__(BLOCK, 2)
+k_spmm_brick(int n_rows, const int* __restrict__ slice_ptr, const unsigned short* __restrict__ lcols,
+             const double* __restrict__ vals, const int* __restrict__ order, const int* __restrict__ bptr,
+             const int* __restrict__ gptr, const int* __restrict__ glist, int n_bricks, int cap,
+             const double* __restrict__ x, int ld, double* __restrict__ y, const double* __restrict__ w, KryState* st,
+             int fin, double* partials, unsigned* counter, RedCtl red_out, const double* __restrict__ rscale, int diag) {
+  // diag (b2_set_tuning "spmm_brick_diag", timing only, results meaningless): 1 = no fill phase, 2 = no stream phase
+  if (st != nullptr && st->done) return;
+  extern __shared__ double sx[];  // [K][cap]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  constexpr int WPB = BLOCK / 32;
+  constexpr int ND = DOT == 0 ? 1 : DOT * K;
+  double dots[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) dots[i] = 0.0;
+  for (int b = blockIdx.x; b < n_bricks; b += gridDim.x) {
+    const int g0 = __ldg(gptr + b), ng = __ldg(gptr + b + 1) - g0;
+    __syncthreads();  // the previous brick's operands are no longer read
+    if (diag != 1) {  // fill: every list entry of this thread is requested before the first x value is (two memory
+                      // latencies per group of FG entries, not two per entry)
+      constexpr int F = (B2_BRICK_CAP + BLOCK - 1) / BLOCK, FG = 3;
+      int col[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int i = threadIdx.x + f * BLOCK;
+        col[f] = i < ng ? ld_stream(glist + g0 + i) : -1;
+      }
+#pragma unroll
+      for (int f0 = 0; f0 < F; f0 += FG) {
+        double xv[FG][K];
+#pragma unroll
+        for (int f = f0; f < f0 + FG && f < F; ++f)
+#pragma unroll
+          for (int k = 0; k < K; ++k) xv[f - f0][k] = col[f] >= 0 ? __ldg(x + (size_t)k * ld + col[f]) : 0.0;
+#pragma unroll
+        for (int f = f0; f < f0 + FG && f < F; ++f)
+          if (col[f] >= 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) sx[k * cap + threadIdx.x + f * BLOCK] = xv[f - f0][k];
+          }
+      }
+    }
+    __syncthreads();
+    const int j1 = diag != 2 ? __ldg(bptr + b + 1) : 0;
+    for (int j = __ldg(bptr + b) + wib; j < j1; j += WPB) {
+      const int s = order != nullptr ? __ldg(order + j) : j;
+      const int base = __ldg(slice_ptr + s);
+      const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
+      const int row = (s << 5) + lane;
+      const unsigned short* cp = lcols + base + lane;
+      const double* vp = vals + base + lane;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.0;
+      // UNROLL entries per trip, the last trip predicated: all its loads are in flight together as well (a scalar
+      // remainder loop would expose one memory latency per leftover entry at this kernel's 32 warps per SM)
+      for (int t = 0; t < len; t += UNROLL) {
+        int c[UNROLL];
+        double v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const bool ok = t + u < len;
+          c[u] = ok ? ld_stream(cp + ((t + u) << 5)) : 0;
+          v[u] = ok ? ld_stream(vp + ((t + u) << 5)) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (t + u < len) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fma(v[u], sx[k * cap + c[u]], acc[k]);
+          }
+      }
+      if (row < n_rows) {
+        double rs = 1.0, wv[DOT >= 1 ? K : 1];
+        if constexpr (RS) rs = __ldg(rscale + row);
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) wv[k] = __ldg(w + (size_t)k * ld + row);
+        }
+        if constexpr (RS) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] *= rs;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], wv[k], dots[k]);
+        }
+        if constexpr (DOT == 2) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) dots[K + k] = fma(acc[k], acc[k], dots[K + k]);
+        }
+      }
+    }
+  }
+  if constexpr (DOT > 0) reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+}
+
 // Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
 // gather), 2 = gather only (values taken as 1).  Results are meaningless; they time the two halves.
 template <int K, int MODE>
