@@ -602,10 +602,8 @@ def run_ours(args):
     msh = make_mesh(gd, N, comm if world > 1 else None)
     if args.dof_order == "generic":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
         msh._dof_order = "generic"
-    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory)
+    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory, bricks=args.bricks)
     ctx = solver._ctx
-    if args.no_bricks:
-        ctx.set_tuning("spmm_brick", 0)
     t_setup = time.perf_counter() - t_setup
     nbc = comm.allreduce(sum(len(d) for d in solver._bc_dofs))
     from oasisx_b200 import _lib as L
@@ -700,7 +698,7 @@ def run_ours(args):
     achieved = bytes_k / (ms_k * 1e-3) / 1e9
     bricks = getattr(solver, "_brick_info", None)
     plain = None
-    if bricks and not args.no_bricks:  # the same product by the plain sliced-ELL kernel (32-bit columns, gathers through L1/L2)
+    if bricks:  # the same product by the plain sliced-ELL kernel (32-bit columns, gathers through L1/L2)
         halves = {}
         for name, mode in (("stream_only_ms", 1), ("fill_only_ms", 2)):  # timing of the two phases of the brick kernel
             ctx.set_tuning("spmm_brick_diag", mode)
@@ -723,7 +721,7 @@ def run_ours(args):
             except Exception:
                 collectives[name] = None
     comm.Barrier()
-    brick_on = bool(bricks) and not args.no_bricks
+    brick_on = bool(bricks)
     roofline = {"bound": "hbm", "kernel": (f"k_spmm_brick<K={gd}> (P2xP2 operator in brick form: x staged in shared memory, 16-bit "
                                            f"positions, {gd} right-hand sides)" if brick_on else
                                            f"k_spmm<K={gd}> (P2xP2 SELL-32 operator, {gd} right-hand sides)"),
@@ -839,7 +837,7 @@ def main():
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
     ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4]; "
                                                          "default block 64^3: the host provider still builds the global mesh on every rank)")
-    ap.add_argument("--no-bricks", action="store_true", help="run the plain sliced-ELL SpMM (k_spmm) instead of the brick form (A/B)")
+    ap.add_argument("--bricks", action="store_true", help="run the brick form of the SpMM (k_spmm_brick) instead of the plain sliced-ELL kernel (A/B)")
     ap.add_argument("--dof-order", default="class", choices=["class", "generic"],
                     help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
                          "coordinate sort every other mesh gets (DOLFINx, unstructured): how much of the SpMM roofline fraction is the lattice")

@@ -32,6 +32,8 @@ struct CSR {
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
+  DBuf<int> porder;                           // the same schedule padded with -1 (box-aligned groups), if one was given
+  int porder_len = 0;
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
   // brick form of the SELL layout (bricks.hpp): brick schedule of the slices, brick offsets into it, gather lists,
@@ -168,6 +170,7 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
+  int spmm_block = 256;          // threads per block of k_spmm (256 / 512 / 1024): tuning "spmm_block"
   int spmm_brick_diag = 0;       // timing of the halves of k_spmm_brick (1: no fill, 2: no stream); results meaningless
   int spmm_brick = 1;            // use the brick form of a pattern when it has one (b2_set_bricks); tuning "spmm_brick"
   unsigned brick_attr_mask = 0;  // k_spmm_brick instantiations whose shared-memory limit has been raised on this device
@@ -513,8 +516,9 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
     launch_spmm_brick<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
     return;
   }
-  const int n_slices = (pat.n_rows + 31) / 32;
-  const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
+  const int n_list = pat.porder_len > 0 ? pat.porder_len : (pat.n_rows + 31) / 32;
+  const int* order = pat.porder_len > 0 ? pat.porder.p : pat.order.p;
+  const int need = (n_list + BLOCK / 32 - 1) / (BLOCK / 32);
   // Every warp takes the same whole number k of slices (k = 1 when the grid fits): a fixed persistent grid quantises
   // small operators -- the 1/4 or 1/8 slab of a multi-GPU run got 3.07 slices per warp, i.e. 3 or 4: 103 us against 86
   // on the 96 x 96 x 12 slab (tools/exp_slab.py) -- and is no faster on large ones.  The cap is what the grid-wide
@@ -525,7 +529,7 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   B2_REQUIRE(grid <= cap, "SpMM grid exceeds the reduction scratch");
 #define B2_SPMM(STREAM_, RS_)                                                                                            \
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
-            pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
+            order, n_list, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
   if (c->spmm_stream) {
     if (rscale != nullptr) B2_SPMM(true, true);
     else B2_SPMM(true, false);
@@ -546,7 +550,15 @@ void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* 
     else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     return;
   }
-  if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  // (DOT == 2 at 1024 threads would need more than the 48 KB of static shared memory for its running sums)
+  if constexpr (DOT < 2) {
+    if (c->spmm_block >= 1024) {
+      launch_spmm_u<K, DOT, 8, 1024>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+      return;
+    }
+  }
+  if (c->spmm_block >= 512) launch_spmm_u<K, DOT, 8, 512>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  else if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
   else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
 }
 
@@ -1959,10 +1971,28 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
   return guarded(c, [&] {
     B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "slice order: square patterns, after b2_build_patterns");
     CSR& pat = c->pat[pattern];
-    B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
+    // a permutation of the slices, optionally padded with -1 entries (box-aligned groups: see k_spmm)
+    const int64_t ns = (pat.n_rows + 31) / 32;
+    std::vector<int> compact;
+    std::vector<char> seen((size_t)ns, 0);
+    for (int64_t i = 0; i < n_slices; ++i) {
+      const int s = order[i];
+      if (s < 0) continue;
+      B2_REQUIRE(s < ns && !seen[(size_t)s], "slice order must list every 32-row slice exactly once");
+      seen[(size_t)s] = 1;
+      compact.push_back(s);
+    }
+    B2_REQUIRE((int64_t)compact.size() == ns, "slice order must list every 32-row slice exactly once");
     c->cfg_version++;
-    pat.order.alloc(n_slices);
-    B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
+    pat.order.alloc(ns);
+    B2_CUDA(cudaMemcpyAsync(pat.order.p, compact.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    pat.porder_len = 0;
+    pat.porder.release();
+    if (n_slices > ns) {
+      pat.porder.alloc(n_slices);
+      pat.porder_len = (int)n_slices;
+      B2_CUDA(cudaMemcpyAsync(pat.porder.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
+    }
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
@@ -2747,6 +2777,7 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_stream") c->spmm_stream = value;
     else if (k == "spmm_brick") c->spmm_brick = value;
     else if (k == "spmm_brick_diag") c->spmm_brick_diag = value;
+    else if (k == "spmm_block") c->spmm_block = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
     else if (k == "peer_grid") c->peer_grid = std::max(1, std::min(value, 148));
@@ -2789,6 +2820,10 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       switch (kernel) {
         case 0: spmm(c, vv, c->A.p, K, c->vec(B2_VEC_U), c->wv[2].p); break;
         case 3: spmm(c, vv, c->M.p, K, c->vec(B2_VEC_U), c->wv[2].p); break;
+        case 4:  // with the fused dot products and the row scale of the BiCGStab products (state: a solve in progress that stores nothing)
+        case 5:
+          spmm(c, vv, c->M.p, K, c->vec(B2_VEC_U), c->wv[2].p, c->vec(B2_VEC_U1), c->d_st, FIN_STORE, kernel - 3, -1, c->dinvM.p);
+          break;
         case 2: spmm(c, qq, c->Ap.p, 1, c->vec(B2_VEC_DP), c->wq[2].p); break;
         case 1: stage_assemble_first(c, c->last_dt > 0 ? c->last_dt : 0.005, 0.01); break;
         case 10: halo_forward(c, B2_SPACE_Q, c->vec(B2_VEC_DP), 1); break;          // latency of the collectives
@@ -2801,6 +2836,11 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
         default: throw B2Error(-2, "unknown bench kernel");
       }
     };
+    if (kernel == 4 || kernel == 5) {
+      std::memset(c->h_st, 0, sizeof(KryState));
+      c->h_st->K = K;
+      B2_CUDA(cudaMemcpyAsync(c->d_st, c->h_st, sizeof(KryState), cudaMemcpyHostToDevice, c->stream));
+    }
     body();  // warm-up
     B2_CUDA(cudaEventRecord(e0, c->stream));
     for (int i = 0; i < reps; ++i) body();
@@ -2816,6 +2856,8 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       case 12: *bytes_per_launch = 24.0; break;
       case 13: *bytes_per_launch = 8.0 * (c->mg_hi - c->mg_lo) * (c->nranks - 1); break;
       case 0:
+      case 4:
+      case 5:
       case 3:  // algorithmic: K (not KP) components; brick form: 8 B value + 2 B list position per entry, the gather lists, x and y once
         *bytes_per_launch = (c->spmm_brick && vv.has_bricks())
                                 ? 10.0 * vv.nnz + 4.0 * (double)vv.n_gather + 4.0 * (nV / 32 + 1) + 8.0 * K * (nV + nVc)

@@ -315,14 +315,16 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, bool RS = false, int MINB = 2048 / BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
-       const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
+       const double* __restrict__ vals, const int* __restrict__ order, int n_list, const double* __restrict__ x, int ld,
        double* __restrict__ y, const double* __restrict__ w, KryState* st, int fin, double* partials,
        unsigned* counter, RedCtl red_out, const double* __restrict__ rscale) {
   if (st != nullptr && st->done) return;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   constexpr int WPB = BLOCK / 32;
-  const int n_slices = (n_rows + 31) >> 5;
+  // `order` may be padded with -1 entries (n_list of them in all) so that every group of WPB consecutive entries -- what
+  // one block works on at a time -- is one spatial box of slices
+  const int n_slices = order != nullptr ? n_list : (n_rows + 31) >> 5;
   constexpr int ND = DOT == 0 ? 1 : DOT * K;
   // the running dot products live in shared memory between slices: keeping them in registers across
   // the gather loop costs 8-16 registers, i.e. one to three resident blocks per SM on a kernel whose
@@ -334,6 +336,7 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
   for (int i = blockIdx.x * WPB + wib; i < n_slices; i += gridDim.x * WPB) {
     const int s = order != nullptr ? __ldg(order + i) : i;
+    if (s < 0) continue;
     const int base = __ldg(slice_ptr + s);
     const int len = (__ldg(slice_ptr + s + 1) - base) >> 5;
     const int row = (s << 5) + lane;

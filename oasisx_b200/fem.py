@@ -236,6 +236,18 @@ def brick_schedule(x: np.ndarray, n_rows: int, lattice=None, tile=(2, 2), rows_p
     return order.astype(np.int32), hint_ptr.astype(np.int32)
 
 
+def pad_order(order: np.ndarray, hint_ptr: np.ndarray, group: int = 32) -> np.ndarray:
+    """The schedule `order` with every hint group padded by -1 entries to a multiple of `group`: a thread block of
+    `group` warps then always works on the slices of ONE spatial box (csrc/linalg.cuh: k_spmm)."""
+    sizes = np.diff(hint_ptr)
+    padded = (sizes + group - 1) // group * group
+    out = np.full(int(padded.sum()), -1, dtype=np.int32)
+    start = np.concatenate([[0], np.cumsum(padded)[:-1]])
+    pos = np.repeat(start - hint_ptr[:-1], sizes) + np.arange(len(order))
+    out[pos] = order
+    return out
+
+
 def mass_jacobi_bounds(gdim: int, degree: int) -> tuple[float, float]:
     """[lambda_min, lambda_max] of diag(M_e)^-1 M_e on the reference simplex: bounds of the spectrum of the
     Jacobi-scaled assembled mass matrix on any affine mesh (element-by-element bound)."""

@@ -21,7 +21,7 @@ def test_brick_product_is_bitwise_the_plain_product(gdim, N, order):
     msh = make_mesh(gdim, N)
     msh._dof_order = order
     tg = TaylorGreen(0.01, gdim)
-    s = make_solver(msh, 2, tg, 0.01, solver_options=KRYLOV)
+    s = make_solver(msh, 2, tg, 0.01, solver_options=KRYLOV, bricks=True)
     info = s._brick_info
     assert info and info["bricks"] >= 1 and info["max_gather"] <= 4352
     ctx = s._ctx
@@ -50,7 +50,7 @@ def test_steps_with_bricks_match_plain_kernel_and_oracle(gdim, N):
     for brick in (1, 0):
         msh = make_mesh(gdim, N)
         tg = TaylorGreenRot(nu) if gdim == 3 else TaylorGreen(nu, 2)
-        s = make_solver(msh, 2, tg, dt, solver_options=KRYLOV)
+        s = make_solver(msh, 2, tg, dt, solver_options=KRYLOV, bricks=True)
         s._ctx.set_tuning("spmm_brick", brick)
         tg.t_u, tg.t_p = 0.0, -dt / 2
         its = []
