@@ -203,7 +203,7 @@ def cpu_sample_cavity(n_cpu: int, n_steps: int, n_warm: int = 1):
     t0 = time.perf_counter()
     for _ in range(n_steps):
         c.solve(CAVITY_DT, CAVITY_NU)
-    return (time.perf_counter() - t0) / n_steps, msh.num_cells, cpu.lib().ipcs_cpu_threads(), c.its.tolist()
+    return (time.perf_counter() - t0) / n_steps, getattr(msh, "num_cells_global", msh.num_cells), cpu.lib().ipcs_cpu_threads(), c.its.tolist()
 
 
 def run_cavity(args):
@@ -257,7 +257,7 @@ def run_cavity(args):
     if not args.no_cpu and world == 1:
         n_cpu = args.cpu_mesh if args.cpu_mesh > 0 else min(N, 64)
         sec, cells, threads, cits = cpu_sample_cavity(n_cpu, 2, 1)
-        sps = (1.0 / sec) * cells / msh.num_cells
+        sps = (1.0 / sec) * cells / getattr(msh, "num_cells_global", msh.num_cells)
         cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
                "sample": f"C++/OpenMP restatement, 2 cavity steps after 1 warm-up on a {n_cpu}^3 cube ({sec:.2f} s/step, its u/p/m {cits})"
                          + ("" if n_cpu == N else f", scaled by cell count to {N}^3 (optimistic for the CPU: its Jacobi-PCG pressure iterations grow with N)"),
@@ -271,7 +271,7 @@ def run_cavity(args):
         "config": {"workload": (f"3D lid-driven cavity P2-P1, WEAK scaling: one {N}^3 block of cubes per GPU, box [0,1]^2 x [0,{world}] "
                                 f"({N}x{N}x{N * world} cubes)" if weak else f"3D lid-driven cavity P2-P1 {N}^3 unit cube")
                                + f", Re=1000 (nu={nu}, lid speed 1), dt={dt}, from rest, max_iter=1, rtol=1e-10",
-                   "mesh": N, "cells": msh.num_cells, "dofs": 3 * nV + nQ, "krylov": KRYLOV, "setup_s": t_setup,
+                   "mesh": N, "cells": getattr(msh, "num_cells_global", msh.num_cells), "dofs": 3 * nV + nQ, "krylov": KRYLOV, "setup_s": t_setup,
                    "l2": "working set per step >> 126 MB L2; no flush needed"},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
                        "update": int(np.median([i[2] for i in its]))},
@@ -348,7 +348,7 @@ def run_assembly_strategies(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"assembly-strategies: unit cube {shape[0]}x{shape[1]}x{shape[2]}, P2, dt={dt}, nu={nu}, "
                                    "u_1 = sin(x)cos(y), u_ab,i = x; 3 right-hand sides (the reference times one scalar field)",
-                       "cells": msh.num_cells, "dofs_P2": s._nV_owned, "nnz": nnz, "first_plan": ctx.first_plan_info(),
+                       "cells": getattr(msh, "num_cells_global", msh.num_cells), "dofs_P2": s._nV_owned, "nnz": nnz, "first_plan": ctx.first_plan_info(),
                        "l2": "flush not needed at 50x40x45 (value arrays 3 x 0.3 GB); 30x25x23 (3 x 57 MB) partly fits the 126 MB L2: "
                              "back-to-back launches see warm lines there"},
             "strategies": {
@@ -472,7 +472,7 @@ def cpu_sample(n_cpu: int, n_steps: int, n_warm: int = 1, workload: str = "taylo
     sec = (time.perf_counter() - t0) / max(n_steps, 1)
     nnz = [int(cpu.lib().ipcs_cpu_nnz(c.h, k)) for k in range(4)]
     med = [int(np.median([i[j] for i in all_its])) for j in range(3)] if all_its else [0, 0, 0]
-    out = {"sec_per_step": sec, "cells": msh.num_cells, "threads": int(cpu.lib().ipcs_cpu_threads()), "its": c.its.tolist(),
+    out = {"sec_per_step": sec, "cells": getattr(msh, "num_cells_global", msh.num_cells), "threads": int(cpu.lib().ipcs_cpu_threads()), "its": c.its.tolist(),
            "its_median": med, "bytes_per_step": cpu_step_bytes(c.nV, c.nQ, nnz[0], nnz[1], nnz[3], gd, med, mg),
            "steps_done": n_warm + n_steps}
     if want_fields:
@@ -763,7 +763,7 @@ def run_ours(args):
             n_cpu_steps, n_cpu_warm = (2, 1) if n_cpu < 96 else (3, 3)  # 96^3: steps 4-6 after the GPU arm's 3 warm-up steps
             r = cpu_sample(n_cpu, n_cpu_steps, n_cpu_warm, wl, want_fields=(n_cpu == N))
             sec = r["sec_per_step"]
-            sps = (1.0 / sec) * r["cells"] / msh.num_cells
+            sps = (1.0 / sec) * r["cells"] / getattr(msh, "num_cells_global", msh.num_cells)
             gbs = r["bytes_per_step"] / sec / 1e9
             cpu = {"value": sps, "unit": "steps/s", "cores": r["threads"], "kind": "port",
                    "sample": f"C++/OpenMP restatement (oracle/ipcs_cpu.cpp, same Krylov methods, preconditioners incl. the pressure "
@@ -793,7 +793,7 @@ def run_ours(args):
         "metric": METRIC if gd == 3 else "IPCS steps/s, 2D Taylor-Green P2-P1 rectangle", "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(wl, N), "mesh": N, "cells": msh.num_cells,
+        "config": {"workload": workload_name(wl, N), "mesh": N, "cells": getattr(msh, "num_cells_global", msh.num_cells),
                    "dofs": 3 * nV + nQ, "partition": (f"{world} z-slab(s), " + ("peer-memory halo + in-kernel all-reduce (no NCCL call on the data path)"
                                                            if ctx.peer_enabled() else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "working set per step >> 126 MB L2 (P2xP2 operators alone "

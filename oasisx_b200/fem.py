@@ -266,6 +266,10 @@ def functionspace(mesh: Mesh, element) -> FunctionSpace:
     family, degree = element[0], int(element[1])
     if family not in ("Lagrange", "CG", "P"):
         raise NotImplementedError(family)
+    if hasattr(mesh, "is_global_boundary"):  # slab-local mesh of a multi-rank run: local space, owned dofs first
+        from .slab import slab_functionspace
+
+        return slab_functionspace(mesh, degree, int(element[2][0]) if len(element) > 2 and element[2] else 1)
     cache = mesh.__dict__.setdefault("_spaces", {})
     if degree not in cache:
         cache[degree] = FunctionSpace(mesh, degree)

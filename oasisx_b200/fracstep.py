@@ -116,6 +116,13 @@ class FractionalStep_AB_CN:
             if bcs_p:
                 raise NotImplementedError("PressureBC on a DOLFINx mesh needs its facet-cell connectivity: not wired yet")
             self._lp, self._V, self._Q, self._geom_x = _adapter.problem_from_dolfinx(mesh, deg_u, deg_p)
+        elif hasattr(mesh, "is_global_boundary"):
+            # slab-local box mesh (oasisx_b200.slab): this rank built only its own slab; same LocalProblem as the
+            # partition of a replicated mesh below
+            from . import slab as _slab
+
+            self._lp, _, self._Q = _slab.local_problem(mesh, deg_u, deg_p)
+            self._V = _fem.functionspace(mesh, ("Lagrange", deg_u, (gdim,)))
         elif self._nranks > 1:
             gV = _fem.functionspace(mesh, ("Lagrange", deg_u))
             gQ = _fem.functionspace(mesh, ("Lagrange", deg_p))

@@ -193,9 +193,21 @@ def meshtags(mesh: Mesh, dim: int, entities, values) -> MeshTags:
     return MeshTags(mesh, dim, entities, values)
 
 
+def _distributed(comm) -> bool:
+    """Several ranks: every rank builds only its slab (oasisx_b200.slab), as DOLFINx's create_box(MPI.COMM_WORLD, ...)
+    does [ext]; B200_GLOBAL_MESH=1 keeps the replicated mesh that oasisx_b200.partition cuts afterwards."""
+    import os
+
+    return comm is not None and int(getattr(comm, "size", 1)) > 1 and os.environ.get("B200_GLOBAL_MESH", "0") != "1"
+
+
 def create_rectangle(comm, points, n, cell_type=CellType.triangle) -> Mesh:
     """Rectangle split into nx*ny squares, each into 2 triangles along the "right" diagonal
     (v0,v1,v3),(v0,v2,v3) -- the DOLFINx default [ext]."""
+    if _distributed(comm):
+        from .slab import create_slab_mesh
+
+        return create_slab_mesh(comm, points, n, 2)
     (x0, y0), (x1, y1) = np.asarray(points, dtype=np.float64)[:, :2]
     nx, ny = int(n[0]), int(n[1])
     xs = np.linspace(x0, x1, nx + 1)
@@ -221,6 +233,10 @@ def create_unit_square(comm, nx, ny, cell_type=CellType.triangle) -> Mesh:
 
 def create_box(comm, points, n, cell_type=CellType.tetrahedron) -> Mesh:
     """Box split into nx*ny*nz cubes, each into 6 tetrahedra around the v0-v7 diagonal."""
+    if _distributed(comm):
+        from .slab import create_slab_mesh
+
+        return create_slab_mesh(comm, points, n, 3)
     p0, p1 = np.asarray(points, dtype=np.float64)
     nx, ny, nz = (int(v) for v in n)
     xs = np.linspace(p0[0], p1[0], nx + 1)
@@ -252,7 +268,11 @@ def exterior_facet_indices(topology: Topology) -> np.ndarray:
     fdim = topology.dim - 1
     cf = topology.cell_entities(fdim)
     counts = np.bincount(cf.ravel(), minlength=topology.num_entities(fdim))
-    return np.flatnonzero(counts == 1).astype(np.int32)
+    ext = np.flatnonzero(counts == 1)
+    msh = topology._mesh
+    if hasattr(msh, "is_global_boundary"):  # slab-local mesh: the cut planes between the ranks' slabs are not exterior
+        ext = ext[msh.is_global_boundary(topology.entities(fdim)[ext])]
+    return ext.astype(np.int32)
 
 
 def _entity_marker(mesh: Mesh, edim: int, marker, candidates=None) -> np.ndarray:

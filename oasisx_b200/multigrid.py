@@ -28,11 +28,15 @@ def _node_ids(idx: np.ndarray, shape) -> np.ndarray:
     return out
 
 
-def lattice_prolongation(fine_shape, coarse_shape) -> sp.csr_matrix:
-    """(fine nodes) x (coarse nodes) P1 interpolation, both in lexicographic node numbering."""
+def lattice_prolongation(fine_shape, coarse_shape, rows: np.ndarray | None = None) -> sp.csr_matrix:
+    """(fine nodes) x (coarse nodes) P1 interpolation, both in lexicographic node numbering.  `rows`: lattice indices
+    (n, d) of the fine nodes wanted, in that order (a rank's owned pressure dofs) instead of all fine nodes."""
     d = len(fine_shape)
-    grids = np.meshgrid(*[np.arange(s + 1) for s in fine_shape[::-1]], indexing="ij")
-    idx = np.stack([g.ravel() for g in grids[::-1]], axis=1).astype(np.int64)  # (nf, d): (i, j[, k]), i fastest
+    if rows is None:
+        grids = np.meshgrid(*[np.arange(s + 1) for s in fine_shape[::-1]], indexing="ij")
+        idx = np.stack([g.ravel() for g in grids[::-1]], axis=1).astype(np.int64)  # (nf, d): (i, j[, k]), i fastest
+    else:
+        idx = np.asarray(rows, dtype=np.int64)
     par = idx & 1
     lo, hi = (idx - par) // 2, (idx + par) // 2
     nf = idx.shape[0]
@@ -45,8 +49,9 @@ def lattice_prolongation(fine_shape, coarse_shape) -> sp.csr_matrix:
     return P
 
 
-def box_hierarchy(msh, min_cells: int = 2, max_levels: int = 16):
-    """[(coarse mesh, P from the previous level)] for a provider-built box/rectangle mesh."""
+def box_hierarchy(msh, min_cells: int = 2, max_levels: int = 16, first_rows: np.ndarray | None = None):
+    """[(coarse mesh, P from the previous level)] for a provider-built box/rectangle mesh.  `first_rows`: lattice
+    indices of the fine nodes the FIRST prolongation is wanted for (its rows, in that order)."""
     shape = getattr(msh, "_shape", None)
     if shape is None:
         return []
@@ -57,7 +62,7 @@ def box_hierarchy(msh, min_cells: int = 2, max_levels: int = 16):
     while len(out) < max_levels and all(n % 2 == 0 for n in fine) and min(fine) // 2 >= min_cells:
         coarse = tuple(n // 2 for n in fine)
         cm = (_mesh.create_rectangle if d == 2 else _mesh.create_box)(None, [list(p0), list(p1)], list(coarse))
-        out.append((cm, lattice_prolongation(fine, coarse)))
+        out.append((cm, lattice_prolongation(fine, coarse, first_rows if not out else None)))
         fine = coarse
     return out
 
@@ -65,17 +70,18 @@ def box_hierarchy(msh, min_cells: int = 2, max_levels: int = 16):
 def attach_pressure_multigrid(ctx, msh, xQ_local: np.ndarray, n_owned: int, **config) -> int:
     """Build the hierarchy for the pressure space whose LOCAL dof coordinates are `xQ_local` (owned
     first) and register it with the context.  Returns the number of coarse levels."""
-    levels = box_hierarchy(msh)
-    if not levels:
+    if getattr(msh, "_shape", None) is None:
         return 0
     p0, h = msh._lattice
     d = len(msh._shape)
-    idx = np.rint((xQ_local[:, :d] - p0[:d]) / h[:d]).astype(np.int64)
-    node_of_dof = _node_ids(idx, msh._shape)  # fine lattice node of each local dof
+    idx = np.rint((xQ_local[:, :d] - p0[:d]) / h[:d]).astype(np.int64)  # fine lattice node of each local dof
+    levels = box_hierarchy(msh, first_rows=idx[:n_owned])  # only the rows of the owned dofs: no table of the global size
+    if not levels:
+        return 0
     n_local = xQ_local.shape[0]
     for lvl, (cm, P) in enumerate(levels):
         if lvl == 0:
-            Pl = P[node_of_dof[:n_owned], :].tocsr()
+            Pl = P.tocsr()
             R = sp.csr_matrix(Pl.T)
             R = sp.csr_matrix((R.data, R.indices, R.indptr), shape=(P.shape[1], n_local))
         else:

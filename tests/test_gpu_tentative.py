@@ -24,15 +24,22 @@ class Inlet:
 def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, device=0):
     from oracle.ipcs_oracle import OracleIPCS
 
-    msh = bmesh.create_unit_square(comm, 10, 10)
-    dim = msh.topology.dim - 1
-    left = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 0))
-    tb = bmesh.locate_entities_boundary(msh, dim, lambda x: np.logical_or(np.isclose(x[1], 0), np.isclose(x[1], 1)))
-    right = bmesh.locate_entities_boundary(msh, dim, lambda x: np.isclose(x[0], 1))
-    facets = np.hstack([left, tb, right])
-    values = np.hstack([np.full_like(left, 1), np.full_like(tb, 2), np.full_like(right, 3)])
-    order = np.argsort(facets)
-    tags = bmesh.meshtags(msh, dim, facets[order], values[order])
+    def tagged(m):
+        dim = m.topology.dim - 1
+        left = bmesh.locate_entities_boundary(m, dim, lambda x: np.isclose(x[0], 0))
+        tb = bmesh.locate_entities_boundary(m, dim, lambda x: np.logical_or(np.isclose(x[1], 0), np.isclose(x[1], 1)))
+        right = bmesh.locate_entities_boundary(m, dim, lambda x: np.isclose(x[0], 1))
+        facets = np.hstack([left, tb, right])
+        values = np.hstack([np.full_like(left, 1), np.full_like(tb, 2), np.full_like(right, 3)])
+        order = np.argsort(facets)
+        return dim, left, tb, right, bmesh.meshtags(m, dim, facets[order], values[order])
+
+    # several ranks: the solver gets this rank's slab of the mesh (oasisx_b200.slab), the single-process oracle the
+    # whole mesh
+    smsh = bmesh.create_unit_square(comm, 10, 10)
+    msh = smsh if comm is None else bmesh.create_unit_square(None, 10, 10)
+    tags = tagged(smsh)[4]
+    dim, left, tb, right, _ = tagged(msh)
     inlet = Inlet(0)
     bc_tb = DirichletBC(0.0, LocatorMethod.TOPOLOGICAL, (tags, 2))
     bc_inlet_x = DirichletBC(inlet.eval, LocatorMethod.TOPOLOGICAL, (tags, 1))
@@ -41,7 +48,7 @@ def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, d
     bcs_p = [PressureBC(4.0, (tags, 3))]
     f = np.array([0.3, -0.1]) if body_force else None
     lu = {"ksp_type": "preonly", "pc_type": "lu"}
-    s = FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=bcs_p,
+    s = FractionalStep_AB_CN(smsh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=bcs_p,
                              solver_options=solver_options or {"tentative": lu, "pressure": lu, "scalar": lu},
                              options={"low_memory_version": low_memory}, body_force=f, device=device)
     V, Q = fem.functionspace(msh, ("Lagrange", deg_u)), fem.functionspace(msh, ("Lagrange", 1))
