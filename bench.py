@@ -208,10 +208,10 @@ def cpu_sample_cavity(n_cpu: int, n_steps: int, n_warm: int = 1):
 
 def run_cavity(args):
     """Lid-driven cavity at Re = 1000 on an N^3 unit cube (default 128^3 = 53 M dofs on ONE GPU; with several ranks
-    the same global mesh is split in z-slabs: strong scaling -- BASELINE.json's "weak scaling" would need a global mesh
-    of 128 x 128 x 128 n cubes, which the z-slab provider can build but the host set-up time of this bench does not
-    allow).  Same JSON contract as the Taylor-Green line; constant boundary values, so the end-to-end path moves no
-    boundary data after the first step."""
+    the same global mesh is split in z-slabs: strong scaling).  --weak: BASELINE.json configs[4], one N^3 block of cubes
+    per GPU, box [0,1]^2 x [0, n_gpus]; every rank builds only its own slab (oasisx_b200/slab.py), so the set-up time
+    does not grow with the job.  Same JSON contract as the Taylor-Green line; constant boundary values, so the
+    end-to-end path moves no boundary data after the first step."""
     from oasisx_b200.comm import HostComm
 
     comm = HostComm.from_env()
@@ -223,6 +223,7 @@ def run_cavity(args):
     msh, solver = make_cavity_solver(N, comm if world > 1 else None, device, world if weak else 1)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
+    t_setup_max = comm.allreduce(t_setup, "max")
     dt, nu = CAVITY_DT, CAVITY_NU
     for s in range(W):
         solver.solve(dt, nu, max_iter=1)
@@ -272,6 +273,9 @@ def run_cavity(args):
                                 f"({N}x{N}x{N * world} cubes)" if weak else f"3D lid-driven cavity P2-P1 {N}^3 unit cube")
                                + f", Re=1000 (nu={nu}, lid speed 1), dt={dt}, from rest, max_iter=1, rtol=1e-10",
                    "mesh": N, "cells": getattr(msh, "num_cells_global", msh.num_cells), "dofs": 3 * nV + nQ, "krylov": KRYLOV, "setup_s": t_setup,
+                   "setup_s_max_over_ranks": t_setup_max,
+                   "mesh_provider": "slab-local (each rank builds its own slab)" if hasattr(msh, "is_global_boundary") else
+                                    ("replicated global mesh, partitioned" if world > 1 else "single rank"),
                    "l2": "working set per step >> 126 MB L2; no flush needed"},
         "iterations": {"tentative": int(np.median([i[0] for i in its])), "pressure": int(np.median([i[1] for i in its])),
                        "update": int(np.median([i[2] for i in its]))},
@@ -835,8 +839,7 @@ def main():
     ap.add_argument("--cpu-mesh", type=int, default=0, help="box size of the bounded CPU sample (0: min(mesh, 96))")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
-    ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4]; "
-                                                         "default block 64^3: the host provider still builds the global mesh on every rank)")
+    ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4])")
     ap.add_argument("--bricks", action="store_true", help="run the brick form of the SpMM (k_spmm_brick) instead of the plain sliced-ELL kernel (A/B)")
     ap.add_argument("--dof-order", default="class", choices=["class", "generic"],
                     help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
@@ -853,7 +856,7 @@ def main():
     if args.workload == "taylor-green":
         args.workload = HEADLINE
     if args.mesh <= 0:
-        args.mesh = (64 if args.weak else 128) if args.workload == "cavity" else (64 if args.workload == "taylor-green-2d" else 96)
+        args.mesh = 128 if args.workload == "cavity" else (64 if args.workload == "taylor-green-2d" else 96)
     if args.workload == "cavity":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the Taylor-Green metric; the cavity line carries its own cpu_baseline")
