@@ -604,8 +604,8 @@ def run_ours(args):
     tg = make_field(wl)
     gd = gdim_of(wl)
     msh = make_mesh(gd, N, comm if world > 1 else None)
-    if args.dof_order == "generic":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
-        msh._dof_order = "generic"
+    if args.dof_order != "class":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
+        msh._dof_order = args.dof_order  # "sigma": plus SELL-C-sigma's window sort by row length
     solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory, bricks=args.bricks)
     ctx = solver._ctx
     t_setup = time.perf_counter() - t_setup
@@ -841,7 +841,7 @@ def main():
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
     ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4])")
     ap.add_argument("--bricks", action="store_true", help="run the brick form of the SpMM (k_spmm_brick) instead of the plain sliced-ELL kernel (A/B)")
-    ap.add_argument("--dof-order", default="class", choices=["class", "generic"],
+    ap.add_argument("--dof-order", default="class", choices=["class", "generic", "sigma"],
                     help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
                          "coordinate sort every other mesh gets (DOLFINx, unstructured): how much of the SpMM roofline fraction is the lattice")
     ap.add_argument("--low-memory", action="store_true", help="options={'low_memory_version': True}: matrix-free element vectors "

@@ -81,6 +81,18 @@ def _lex_order(x: np.ndarray) -> np.ndarray:
     return np.lexsort((q[:, 0], q[:, 1], q[:, 2]))
 
 
+def _sigma_order(x: np.ndarray, cell_dofs: np.ndarray, sigma: int = 2048) -> np.ndarray:
+    """Dof order for meshes without lattice information ("sigma"): the coordinate sort, then inside every window of
+    `sigma` consecutive dofs a stable sort by the number of adjacent cells (SELL-C-sigma's window sort, Kreutzer et al.
+    2014 [ext]).  Dofs with equally many adjacent cells have (nearly) equally long matrix rows, so the 32-row slices
+    of the sliced-ELL operator are padded far less than under the plain coordinate sort, where vertex rows (long) and
+    edge rows (short) share slices; the window keeps the rows of a slice spatially close."""
+    lex = _lex_order(x)
+    adj = np.bincount(cell_dofs.ravel(), minlength=len(x))[lex]
+    window = np.arange(len(lex)) // sigma
+    return lex[np.lexsort((np.arange(len(lex)), -adj, window))]
+
+
 class FunctionSpace:
     """Scalar Lagrange P1/P2 space (``bs == 1``) or its blocked vector version (``bs == gdim``)."""
 
@@ -110,9 +122,15 @@ class FunctionSpace:
         # renumber for locality (DOLFINx applies a graph reordering here [ext]); vertex-first
         # numbering would scatter every P2 row's columns over the whole vector
         lattice = getattr(mesh, "_lattice", None)
-        if getattr(mesh, "_dof_order", "class") != "class":
-            lattice = None  # "generic": what a mesh without lattice information (DOLFINx, unstructured) gets
-        order = _class_order(x, lattice) if (lattice is not None and degree == 2) else _lex_order(x)
+        kind = getattr(mesh, "_dof_order", "class")
+        if kind != "class":
+            lattice = None  # "generic" / "sigma": what a mesh without lattice information (unstructured) can get
+        if lattice is not None and degree == 2:
+            order = _class_order(x, lattice)
+        elif degree == 2 and kind != "generic":  # no lattice information: window-sorted coordinate order (measured
+            order = _sigma_order(x, cell_dofs)   # 0.76 of the HBM peak in the SpMM against 0.62 for the plain sort)
+        else:
+            order = _lex_order(x)
         new_of_old = np.empty(len(order), dtype=np.int64)
         new_of_old[order] = np.arange(len(order))
         self._x = np.ascontiguousarray(x[order])

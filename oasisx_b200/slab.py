@@ -195,6 +195,8 @@ class SlabFunctionSpace(fem.FunctionSpace):
             cell_dofs = np.hstack([cells, nv + ce])
             hidx = np.vstack([2 * nidx, nidx[edges[:, 0]] + nidx[edges[:, 1]]])
         order_kind = getattr(mesh, "_dof_order", "class")
+        if order_kind == "sigma":
+            raise NotImplementedError("the window-sorted dof order has no closed form: use 'class' or 'generic' on several ranks")
         gid = _global_ids(hidx, mesh._shape, degree, order_kind)
         owner = _owner_of(hidx[:, d - 1], mesh._layer_ranks, degree)
         rank = int(mesh.comm.rank)
