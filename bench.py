@@ -606,8 +606,10 @@ def run_ours(args):
     msh = make_mesh(gd, N, comm if world > 1 else None)
     if args.dof_order != "class":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
         msh._dof_order = args.dof_order  # "sigma": plus SELL-C-sigma's window sort by row length
-    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory, bricks=args.bricks)
+    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory, bricks=args.bricks > 0)
     ctx = solver._ctx
+    if args.bricks:
+        ctx.set_tuning("spmm_brick", args.bricks)
     t_setup = time.perf_counter() - t_setup
     nbc = comm.allreduce(sum(len(d) for d in solver._bc_dofs))
     from oasisx_b200 import _lib as L
@@ -711,7 +713,7 @@ def run_ours(args):
         bricks = dict(bricks, **halves)
         ctx.set_tuning("spmm_brick", 0)
         ms_p, bytes_p = ctx.bench_kernel(3, 20)
-        ctx.set_tuning("spmm_brick", 1)
+        ctx.set_tuning("spmm_brick", args.bricks)
         plain = {"kernel": "k_spmm (SELL-32, 32-bit columns, L1/L2 gathers)", "ms_per_launch": ms_p, "algorithmic_bytes": bytes_p,
                  "achieved": bytes_p / (ms_p * 1e-3) / 1e9, "frac": bytes_p / (ms_p * 1e-3) / 1e9 / peak}
     ms_a, bytes_a = ctx.bench_kernel(1, 5)
@@ -840,7 +842,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
     ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4])")
-    ap.add_argument("--bricks", action="store_true", help="run the brick form of the SpMM (k_spmm_brick) instead of the plain sliced-ELL kernel (A/B)")
+    ap.add_argument("--bricks", type=int, default=0, choices=[0, 1, 2],
+                    help="run the brick form of the SpMM instead of the plain sliced-ELL kernel (A/B): 1 = k_spmm_brick, 2 = k_spmm_brick2 (pipelined)")
     ap.add_argument("--dof-order", default="class", choices=["class", "generic", "sigma"],
                     help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
                          "coordinate sort every other mesh gets (DOLFINx, unstructured): how much of the SpMM roofline fraction is the lattice")

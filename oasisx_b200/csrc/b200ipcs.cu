@@ -39,6 +39,7 @@ struct CSR {
   // brick form of the SELL layout (bricks.hpp): brick schedule of the slices, brick offsets into it, gather lists,
   // 16-bit positions per slot
   DBuf<int> border, bptr, gptr, glist;
+  DBuf<int> worder, wptr;  // warp-major slice lists of the pipelined kernel (bricks.hpp: assign_warps)
   DBuf<unsigned short> lcols;
   int n_bricks = 0, brick_cap = 0;
   int64_t n_gather = 0;
@@ -509,11 +510,37 @@ void launch_spmm_brick(b2_ctx* c, const CSR& pat, const double* vals, const doub
   if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
 }
 
+// pipelined brick SpMM (linalg.cuh: k_spmm_brick2): one block of B2_BRICK_WARPS warps per SM, TMA-fed matrix stream
+template <int K, int DOT>
+void launch_spmm_brick2(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
+                        KryState* st, int fin, const double* rscale) {
+  constexpr int BLOCK = 32 * B2_BRICK_WARPS, CH = 8, ST = 3;
+  const size_t smem = brick2_smem_bytes(K, pat.brick_cap, B2_BRICK_WARPS, CH, ST);
+  const int cap = (int)std::min<int64_t>(c->partials.n / 16, (int64_t)c->sm * 32);
+  const int grid = std::max(1, std::min(std::min(pat.n_bricks, c->sm), cap));
+#define B2_SPMM_BRICK2(RS_)                                                                                               \
+  do {                                                                                                                    \
+    auto kern = k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST>;                                                                \
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                                       \
+                                 (int)brick2_smem_bytes(3, B2_BRICK_CAP, B2_BRICK_WARPS, CH, ST)));                       \
+    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, pat.worder.p, pat.wptr.p,      \
+                                           pat.gptr.p, pat.glist.p, pat.n_bricks, pat.brick_cap, x, ld, y, w, st, fin,    \
+                                           c->partials.p, c->d_counter, red_ptr(c), rscale, c->spmm_brick_diag);          \
+    B2_CUDA(cudaGetLastError());                                                                                          \
+    c->stats.kernel_launches++;                                                                                           \
+  } while (0)
+  if (rscale != nullptr) B2_SPMM_BRICK2(true);
+  else B2_SPMM_BRICK2(false);
+#undef B2_SPMM_BRICK2
+  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
+}
+
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin, const double* rscale) {
   if (c->spmm_brick && pat.has_bricks()) {
-    launch_spmm_brick<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+    if (c->spmm_brick >= 2) launch_spmm_brick2<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+    else launch_spmm_brick<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
     return;
   }
   const int n_list = pat.porder_len > 0 ? pat.porder_len : (pat.n_rows + 31) / 32;
@@ -2013,6 +2040,11 @@ int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order
     const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     b2bricks::build(pat.n_rows, pat.n_cols, sp.data(), sc.data(), order, hint_ptr, (int)n_hints, B2_BRICK_CAP, B2_BRICK_MAX_SLICES, threads, B);
     B2_REQUIRE(B.error == 0, "bricks: one slice touches more distinct columns than the shared-memory gather list holds");
+    b2bricks::assign_warps(pat.n_rows, sp.data(), order, B2_BRICK_WARPS, B);
+    pat.worder.alloc((int64_t)B.worder.size());
+    pat.wptr.alloc((int64_t)B.wptr.size());
+    B2_CUDA(cudaMemcpyAsync(pat.worder.p, B.worder.data(), sizeof(int) * B.worder.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.wptr.p, B.wptr.data(), sizeof(int) * B.wptr.size(), cudaMemcpyHostToDevice, c->stream));
     pat.border.alloc(n_slices);
     pat.bptr.alloc((int64_t)B.brick_ptr.size());
     pat.gptr.alloc((int64_t)B.gptr.size());
@@ -2038,11 +2070,17 @@ int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order
 // the brick builder on host arrays (no device, no context): the CPU test of the format
 int b2_host_build_bricks(int32_t n_rows, int32_t n_cols, const int32_t* slice_ptr, const int32_t* scols, const int32_t* order,
                          int64_t n_hints, const int32_t* hint_ptr, int32_t cap, int32_t max_slices, int32_t n_threads,
-                         int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols) {
+                         int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols,
+                         int32_t warps, int32_t* worder, int32_t* wptr) {
   try {
     b2bricks::Bricks B;
     b2bricks::build(n_rows, n_cols, slice_ptr, scols, order, hint_ptr, (int)n_hints, cap, max_slices, n_threads, B);
     if (B.error) return -3;
+    if (warps > 0 && worder != nullptr && wptr != nullptr) {
+      b2bricks::assign_warps(n_rows, slice_ptr, order, warps, B);
+      std::copy(B.worder.begin(), B.worder.end(), worder);
+      std::copy(B.wptr.begin(), B.wptr.end(), wptr);
+    }
     *n_bricks = B.n_bricks();
     *n_gather = (int64_t)B.glist.size();
     if (brick_ptr) std::copy(B.brick_ptr.begin(), B.brick_ptr.end(), brick_ptr);

@@ -12,6 +12,7 @@
 // 102 KB of shared memory per block, two blocks per SM) and 32-row slices per brick
 #define B2_BRICK_CAP 4352
 #define B2_BRICK_MAX_SLICES 32
+#define B2_BRICK_WARPS 16  // warps per block of the pipelined brick kernel (one block per SM)
 
 struct B2Error : std::runtime_error {
   int code;

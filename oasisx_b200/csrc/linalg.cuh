@@ -516,6 +516,214 @@ k_spmm_brick(int n_rows, const int* __restrict__ slice_ptr, const unsigned short
   if constexpr (DOT > 0) reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
 }
 
+// ---- brick SpMM, pipelined (k_spmm_brick2) ---------------------------------------------------------------------------
+// The first form above is latency-bound: 104 KB of shared memory for x leaves 2 x 16 warps per SM, whose register-staged
+// matrix loads drain at every brick barrier.  Here ONE block of 16 warps per SM owns all of the shared memory:
+//   * the matrix stream (8-byte values + 16-bit list positions of CH steps of a slice, contiguous in SELL storage) is
+//     moved by the TMA unit: lane 0 of every warp issues 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) into
+//     the warp's own ring of ST stages.  No registers, no LSU load instructions, and -- because the warp's sequence of
+//     chunks is fixed by the host (bricks.hpp: assign_warps) -- the prefetch runs ahead across slices AND across the
+//     brick barriers: the HBM pipe never drains;
+//   * the fill of a brick's x values is one batch of 8-byte cp.async gathers per thread from list entries that were
+//     loaded into registers during the previous brick: one memory latency per brick, during which the rings fill;
+//   * the warps of a block get slices of (nearly) equal total length per brick (longest first), so they reach the
+//     barrier together.
+// Same slots, same order of FMAs per row as k_spmm: y is bitwise the same.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+constexpr size_t brick2_smem_bytes(int K, int cap, int warps, int ch, int st) {
+  return sizeof(double) * (size_t)K * cap + (size_t)warps * st * ch * 32 * (sizeof(double) + sizeof(unsigned short)) +
+         sizeof(unsigned long long) * (size_t)warps * st;
+}
+
+template <int K, int DOT, bool RS, int BLOCK, int CH, int ST>
+__global__ void __launch_bounds__(BLOCK, 1)
+k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned short* __restrict__ lcols,
+              const double* __restrict__ vals, const int* __restrict__ worder, const int* __restrict__ wptr,
+              const int* __restrict__ gptr, const int* __restrict__ glist, int n_bricks, int cap,
+              const double* __restrict__ x, int ld, double* __restrict__ y, const double* __restrict__ w, KryState* st,
+              int fin, double* partials, unsigned* counter, RedCtl red_out, const double* __restrict__ rscale, int diag) {
+  // diag (timing only, results meaningless): 1 = no fill, 2 = no stream
+  if (st != nullptr && st->done) return;
+  constexpr int WPB = BLOCK / 32;
+  constexpr int ND = DOT == 0 ? 1 : DOT * K;
+  constexpr int F = (B2_BRICK_CAP + BLOCK - 1) / BLOCK;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sx = reinterpret_cast<double*>(smem_raw);  // [K][cap]
+  double* svals_all = sx + (size_t)K * cap;           // [WPB][ST][CH * 32]
+  unsigned short* scols_all = reinterpret_cast<unsigned short*>(svals_all + (size_t)WPB * ST * CH * 32);
+  unsigned long long* bars_all = reinterpret_cast<unsigned long long*>(scols_all + (size_t)WPB * ST * CH * 32);
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  double* svals = svals_all + (size_t)wib * ST * CH * 32;
+  unsigned short* scols = scols_all + (size_t)wib * ST * CH * 32;
+  unsigned long long* bars = bars_all + wib * ST;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < ST; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  // ---- producer cursor: this warp's chunks in the order it will consume them, running ST - 1 chunks ahead ----------
+  int pb = blockIdx.x, pj = 0, pj1 = 0, pt = 0, pbase = 0, plen = 0, issued = 0;
+  bool pvalid = false;
+  auto p_next_brick = [&]() {  // first brick at or after pb in which this warp has a slice
+    while (pb < n_bricks) {
+      pj = __ldg(wptr + (size_t)pb * WPB + wib);
+      pj1 = __ldg(wptr + (size_t)pb * WPB + wib + 1);
+      if (pj < pj1) return true;
+      pb += gridDim.x;
+    }
+    return false;
+  };
+  auto p_load_slice = [&]() {
+    const int s = __ldg(worder + pj);
+    pbase = __ldg(slice_ptr + s);
+    plen = (__ldg(slice_ptr + s + 1) - pbase) >> 5;
+    pt = 0;
+  };
+  pvalid = diag != 2 && p_next_brick();
+  if (pvalid) p_load_slice();
+  auto issue = [&]() {
+    if (!pvalid) return;
+    const int tn = min(CH, plen - pt);
+    const int stg = issued % ST;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was read by this warp's generic loads
+      mbar_expect_tx(bars + stg, (unsigned)(tn * 32 * 10));
+      bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
+      bulk_g2s(scols + (size_t)stg * CH * 32, lcols + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 2), bars + stg);
+    }
+    pt += tn;
+    ++issued;
+    if (pt >= plen) {
+      if (++pj >= pj1) {
+        pb += gridDim.x;
+        pvalid = p_next_brick();
+      }
+      if (pvalid) p_load_slice();
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) issue();
+  int consumed = 0;
+  double dots[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) dots[i] = 0.0;
+  // gather-list entries of the first brick (later ones are loaded during the brick before)
+  int col[F];
+  int ng = 0;
+  if (blockIdx.x < n_bricks) {
+    const int g0 = __ldg(gptr + blockIdx.x);
+    ng = __ldg(gptr + blockIdx.x + 1) - g0;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const int i = threadIdx.x + f * BLOCK;
+      col[f] = i < ng ? __ldg(glist + g0 + i) : -1;
+    }
+  }
+  for (int b = blockIdx.x; b < n_bricks; b += gridDim.x) {
+    __syncthreads();  // the previous brick's operands are no longer read
+    if (diag != 1) {
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+        if (col[f] >= 0) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) cp_async_8(sx + (size_t)k * cap + threadIdx.x + f * BLOCK, x + (size_t)k * ld + col[f]);
+        }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    {  // the next brick's list entries: in flight during this brick's stream
+      const int nb = b + gridDim.x;
+      if (nb < n_bricks) {
+        const int g0 = __ldg(gptr + nb);
+        ng = __ldg(gptr + nb + 1) - g0;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int i = threadIdx.x + f * BLOCK;
+          col[f] = i < ng ? __ldg(glist + g0 + i) : -1;
+        }
+      }
+    }
+    if (diag == 2) continue;
+    const int j1 = __ldg(wptr + (size_t)b * WPB + wib + 1);
+    for (int j = __ldg(wptr + (size_t)b * WPB + wib); j < j1; ++j) {
+      const int s = __ldg(worder + j);
+      const int len = (__ldg(slice_ptr + s + 1) - __ldg(slice_ptr + s)) >> 5;
+      const int row = (s << 5) + lane;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.0;
+      for (int t = 0; t < len; t += CH) {
+        issue();  // refill the stage consumed in the previous round
+        const int tn = min(CH, len - t);
+        const int stg = consumed % ST;
+        mbar_wait(bars + stg, (unsigned)((consumed / ST) & 1));
+        const double* sv = svals + (size_t)stg * CH * 32 + lane;
+        const unsigned short* sc = scols + (size_t)stg * CH * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+          if (u < tn) {
+            const int c = sc[u << 5];
+            const double v = sv[u << 5];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fma(v, sx[(size_t)k * cap + c], acc[k]);
+          }
+        __syncwarp();  // every lane is done with this stage before lane 0 lets the TMA overwrite it
+        ++consumed;
+      }
+      if (row < n_rows) {
+        double rs = 1.0, wv[DOT >= 1 ? K : 1];
+        if constexpr (RS) rs = __ldg(rscale + row);
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) wv[k] = __ldg(w + (size_t)k * ld + row);
+        }
+        if constexpr (RS) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] *= rs;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) dots[k] = fma(acc[k], wv[k], dots[k]);
+        }
+        if constexpr (DOT == 2) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) dots[K + k] = fma(acc[k], acc[k], dots[K + k]);
+        }
+      }
+    }
+  }
+  if constexpr (DOT > 0) reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
+}
+
 // Diagnostic variants of the SpMM (b2_set_tuning "spmm_mode"): 1 = stream values/columns only (no
 // gather), 2 = gather only (values taken as 1).  Results are meaningless; they time the two halves.
 template <int K, int MODE>

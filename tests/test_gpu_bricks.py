@@ -31,12 +31,16 @@ def test_brick_product_is_bitwise_the_plain_product(gdim, N, order):
     n = s._M.getSize()[1]
     for mat in (s._M, s._K, s._A):
         x = rng.standard_normal(n)
-        yb, yp = np.zeros(mat.getSize()[0]), np.zeros(mat.getSize()[0])
+        yb, yb2, yp = (np.zeros(mat.getSize()[0]) for _ in range(3))
+        ctx.set_tuning("spmm_brick", 1)
         mat.mult(x, yb)
+        ctx.set_tuning("spmm_brick", 2)  # the pipelined kernel (TMA-fed rings)
+        mat.mult(x, yb2)
         ctx.set_tuning("spmm_brick", 0)
         mat.mult(x, yp)
         ctx.set_tuning("spmm_brick", 1)
         assert np.array_equal(yb, yp)
+        assert np.array_equal(yb2, yp)
         ip, ix, v = mat.getValuesCSR()
         import scipy.sparse as sp
         ref = sp.csr_matrix((v, ix, ip), shape=mat.getSize()) @ x
@@ -47,7 +51,7 @@ def test_brick_product_is_bitwise_the_plain_product(gdim, N, order):
 def test_steps_with_bricks_match_plain_kernel_and_oracle(gdim, N):
     dt, nu = 0.005, 0.01
     fields = []
-    for brick in (1, 0):
+    for brick in (2, 1, 0):
         msh = make_mesh(gdim, N)
         tg = TaylorGreenRot(nu) if gdim == 3 else TaylorGreen(nu, 2)
         s = make_solver(msh, 2, tg, dt, solver_options=KRYLOV, bricks=True)
@@ -61,11 +65,12 @@ def test_steps_with_bricks_match_plain_kernel_and_oracle(gdim, N):
             st = s._ctx.stats()
             its.append((tuple(st.its_tentative), st.its_pressure, tuple(st.its_update)))
         fields.append(([s._u[i].x.array_ro().copy() for i in range(gdim)], s._p.x.array_ro().copy(), its))
-    (ub, pb, ib), (up, pp, ip_) = fields
+    (ub, pb, ib), (ub1, pb1, _), (up, pp, ip_) = fields
     sc = vscale(up)
     for i in range(gdim):
         assert relerr(ub[i], up[i], sc) <= 1e-11
-    assert relerr(pb, pp) <= 1e-10
+        assert relerr(ub1[i], up[i], sc) <= 1e-11
+    assert relerr(pb, pp) <= 1e-10 and relerr(pb1, pp) <= 1e-10
     # and against the LU oracle, at the tolerance of every other step test
     msh = make_mesh(gdim, N)
     tg = TaylorGreenRot(nu) if gdim == 3 else TaylorGreen(nu, 2)

@@ -36,7 +36,16 @@ def run(tag):
     print(f"{tag:60s} " + "  ".join(out), flush=True)
 
 
-run("brick kernel (default)")
+ctx.set_tuning("spmm_brick", 1)
+run("brick kernel, first form (2 blocks x 16 warps, register-staged stream)")
+ctx.set_tuning("spmm_brick", 2)
+run("brick kernel, pipelined (1 block x 16 warps, TMA-fed rings)")
+for mode, name in ((1, "no fill"), (2, "no stream")):
+    ctx.set_tuning("spmm_brick_diag", mode)
+    run(f"  pipelined, {name}")
+ctx.set_tuning("spmm_brick_diag", 0)
+if len(sys.argv) > 2 and sys.argv[2] == "bricks":
+    sys.exit(0)
 ctx.set_tuning("spmm_brick", 0)
 run("plain, tile-major (8,8), block 256 (round-2 default)")
 for tile in ((2, 2), (4, 4), (2, 4), (4, 2)):
