@@ -102,7 +102,7 @@ def load_library() -> C.CDLL:
         "b2_pattern_sell_slots": (i64, [vp, i32]),
         "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
         "b2_set_bricks": (i32, [vp, i32, i64, vp, i64, vp, vp]),
-        "b2_host_build_bricks": (i32, [i32, i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
+        "b2_host_build_bricks": (i32, [i32, i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "b2_pressure_mg_add_level": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
         "b2_pressure_mg_configure": (i32, [vp, i32, i32, i32, dbl]),
         "b2_get_pattern": (i32, [vp, i32, vp, vp]),

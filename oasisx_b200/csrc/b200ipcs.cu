@@ -39,7 +39,8 @@ struct CSR {
   // brick form of the SELL layout (bricks.hpp): brick schedule of the slices, brick offsets into it, gather lists,
   // 16-bit positions per slot
   DBuf<int> border, bptr, gptr, glist;
-  DBuf<int> worder, wptr;  // warp-major slice lists of the pipelined kernel (bricks.hpp: assign_warps)
+  DBuf<int> wdesc, wseq;   // work lists of the pipelined kernel (bricks.hpp: assign_warps), built for brick_grid blocks
+  int brick_grid = 0;
   DBuf<unsigned short> lcols;
   int n_bricks = 0, brick_cap = 0;
   int64_t n_gather = 0;
@@ -516,14 +517,14 @@ void launch_spmm_brick2(b2_ctx* c, const CSR& pat, const double* vals, const dou
                         KryState* st, int fin, const double* rscale) {
   constexpr int BLOCK = 32 * B2_BRICK_WARPS, CH = 8, ST = 3;
   const size_t smem = brick2_smem_bytes(K, pat.brick_cap, B2_BRICK_WARPS, CH, ST);
-  const int cap = (int)std::min<int64_t>(c->partials.n / 16, (int64_t)c->sm * 32);
-  const int grid = std::max(1, std::min(std::min(pat.n_bricks, c->sm), cap));
+  const int grid = pat.brick_grid;  // the work lists were laid out for this many blocks (one per SM)
+  B2_REQUIRE(grid >= 1 && grid <= c->partials.n / 16, "pipelined brick SpMM: work lists missing or grid exceeds the reduction scratch");
 #define B2_SPMM_BRICK2(RS_)                                                                                               \
   do {                                                                                                                    \
     auto kern = k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST>;                                                                \
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                                       \
                                  (int)brick2_smem_bytes(3, B2_BRICK_CAP, B2_BRICK_WARPS, CH, ST)));                       \
-    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, pat.worder.p, pat.wptr.p,      \
+    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, (const int4*)pat.wdesc.p, pat.wseq.p, \
                                            pat.gptr.p, pat.glist.p, pat.n_bricks, pat.brick_cap, x, ld, y, w, st, fin,    \
                                            c->partials.p, c->d_counter, red_ptr(c), rscale, c->spmm_brick_diag);          \
     B2_CUDA(cudaGetLastError());                                                                                          \
@@ -2040,11 +2041,12 @@ int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order
     const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     b2bricks::build(pat.n_rows, pat.n_cols, sp.data(), sc.data(), order, hint_ptr, (int)n_hints, B2_BRICK_CAP, B2_BRICK_MAX_SLICES, threads, B);
     B2_REQUIRE(B.error == 0, "bricks: one slice touches more distinct columns than the shared-memory gather list holds");
-    b2bricks::assign_warps(pat.n_rows, sp.data(), order, B2_BRICK_WARPS, B);
-    pat.worder.alloc((int64_t)B.worder.size());
-    pat.wptr.alloc((int64_t)B.wptr.size());
-    B2_CUDA(cudaMemcpyAsync(pat.worder.p, B.worder.data(), sizeof(int) * B.worder.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.wptr.p, B.wptr.data(), sizeof(int) * B.wptr.size(), cudaMemcpyHostToDevice, c->stream));
+    b2bricks::assign_warps(pat.n_rows, sp.data(), order, B2_BRICK_WARPS, c->sm, B);
+    pat.wdesc.alloc((int64_t)B.wdesc.size());
+    pat.wseq.alloc((int64_t)B.wseq.size());
+    pat.brick_grid = B.grid;
+    B2_CUDA(cudaMemcpyAsync(pat.wdesc.p, B.wdesc.data(), sizeof(int) * B.wdesc.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(pat.wseq.p, B.wseq.data(), sizeof(int) * B.wseq.size(), cudaMemcpyHostToDevice, c->stream));
     pat.border.alloc(n_slices);
     pat.bptr.alloc((int64_t)B.brick_ptr.size());
     pat.gptr.alloc((int64_t)B.gptr.size());
@@ -2071,15 +2073,15 @@ int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order
 int b2_host_build_bricks(int32_t n_rows, int32_t n_cols, const int32_t* slice_ptr, const int32_t* scols, const int32_t* order,
                          int64_t n_hints, const int32_t* hint_ptr, int32_t cap, int32_t max_slices, int32_t n_threads,
                          int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols,
-                         int32_t warps, int32_t* worder, int32_t* wptr) {
+                         int32_t warps, int32_t grid, int32_t* wdesc, int32_t* wseq) {
   try {
     b2bricks::Bricks B;
     b2bricks::build(n_rows, n_cols, slice_ptr, scols, order, hint_ptr, (int)n_hints, cap, max_slices, n_threads, B);
     if (B.error) return -3;
-    if (warps > 0 && worder != nullptr && wptr != nullptr) {
-      b2bricks::assign_warps(n_rows, slice_ptr, order, warps, B);
-      std::copy(B.worder.begin(), B.worder.end(), worder);
-      std::copy(B.wptr.begin(), B.wptr.end(), wptr);
+    if (warps > 0 && wdesc != nullptr && wseq != nullptr) {
+      b2bricks::assign_warps(n_rows, slice_ptr, order, warps, grid, B);
+      std::copy(B.wdesc.begin(), B.wdesc.end(), wdesc);
+      std::copy(B.wseq.begin(), B.wseq.end(), wseq);
     }
     *n_bricks = B.n_bricks();
     *n_gather = (int64_t)B.glist.size();

@@ -26,12 +26,9 @@ struct Bricks {
   std::vector<int> gptr;           // n_bricks + 1 offsets into glist
   std::vector<int> glist;          // gather lists: sorted distinct columns of each brick
   std::vector<uint16_t> lcols;     // one per SELL slot: position of the slot's column in its brick's gather list
-  // warp assignment for the pipelined kernel (k_spmm_brick2): the slices of brick b that warp w of the block works on
-  // are worder[wptr[b * warps + w] .. wptr[b * warps + w + 1]); longest-processing-time-first over the slice lengths,
-  // so that the warps of a block finish a brick together (a vertex-class slice of the P2 operator is three times as
-  // long as an edge-class one)
-  std::vector<int> worder, wptr;
-  int warps = 0;
+  // work lists of the pipelined kernel (k_spmm_brick2), see assign_warps
+  std::vector<int> wdesc, wseq;
+  int warps = 0, grid = 0;
   int max_gather = 0;              // longest gather list
   int error = 0;                   // 1: a single slice touches more than `cap` distinct columns
   int n_bricks() const { return (int)brick_ptr.size() - 1; }
@@ -126,16 +123,22 @@ inline void build(int n_rows, int n_cols, const int* slice_ptr, const int* scols
   }
 }
 
-// fills worder / wptr for blocks of `warps` warps (see Bricks)
-inline void assign_warps(int n_rows, const int* slice_ptr, const int* order, int warps, Bricks& B) {
+// Work lists of the pipelined kernel for a grid of `grid` blocks of `warps` warps: block g works on bricks g, g + grid,
+// ...; inside a brick the slices are dealt to the warps longest-processing-time-first.  wdesc holds one descriptor
+// {brick, slice, first slot, length in steps} per slice, grouped by (block, warp) in the order the warp meets them;
+// wseq[(g * warps + w)] is where the list of warp w of block g starts.
+inline void assign_warps(int n_rows, const int* slice_ptr, const int* order, int warps, int grid, Bricks& B) {
   const int nb = B.n_bricks();
+  const int n_slices = (n_rows + 31) / 32;
+  grid = std::max(1, std::min(grid, nb));
   B.warps = warps;
-  B.worder.assign((size_t)((n_rows + 31) / 32), 0);
-  B.wptr.assign((size_t)nb * warps + 1, 0);
-  std::vector<std::pair<int, int>> byLen;      // (-length, position in the schedule)
-  std::vector<std::vector<int>> mine((size_t)warps);
+  B.grid = grid;
+  B.wdesc.assign((size_t)n_slices * 4, 0);
+  B.wseq.assign((size_t)grid * warps + 1, 0);
+  // pass 1: per brick, the LPT assignment (slice ids per warp)
+  std::vector<std::vector<int>> mine((size_t)nb * warps);
+  std::vector<std::pair<int, int>> byLen;  // (-length, position in the schedule)
   std::vector<long long> load((size_t)warps);
-  size_t out = 0;
   for (int b = 0; b < nb; ++b) {
     byLen.clear();
     for (int j = B.brick_ptr[b]; j < B.brick_ptr[b + 1]; ++j) {
@@ -143,20 +146,30 @@ inline void assign_warps(int n_rows, const int* slice_ptr, const int* order, int
       byLen.emplace_back(-(slice_ptr[s + 1] - slice_ptr[s]), j);
     }
     std::sort(byLen.begin(), byLen.end());
-    for (int w = 0; w < warps; ++w) { mine[(size_t)w].clear(); load[(size_t)w] = 0; }
+    std::fill(load.begin(), load.end(), 0);
     for (const auto& e : byLen) {
       int best = 0;
       for (int w = 1; w < warps; ++w)
         if (load[(size_t)w] < load[(size_t)best]) best = w;
-      mine[(size_t)best].push_back(order != nullptr ? order[e.second] : e.second);
+      mine[(size_t)b * warps + best].push_back(order != nullptr ? order[e.second] : e.second);
       load[(size_t)best] += -e.first;
     }
-    for (int w = 0; w < warps; ++w) {
-      B.wptr[(size_t)b * warps + w] = (int)out;
-      for (int s : mine[(size_t)w]) B.worder[out++] = s;
-    }
   }
-  B.wptr[(size_t)nb * warps] = (int)out;
+  // pass 2: lay the descriptors out by (block, warp)
+  size_t out = 0;
+  for (int g = 0; g < grid; ++g)
+    for (int w = 0; w < warps; ++w) {
+      B.wseq[(size_t)g * warps + w] = (int)out;
+      for (int b = g; b < nb; b += grid)
+        for (int s : mine[(size_t)b * warps + w]) {
+          B.wdesc[4 * out + 0] = b;
+          B.wdesc[4 * out + 1] = s;
+          B.wdesc[4 * out + 2] = slice_ptr[s];
+          B.wdesc[4 * out + 3] = (slice_ptr[s + 1] - slice_ptr[s]) >> 5;
+          ++out;
+        }
+    }
+  B.wseq[(size_t)grid * warps] = (int)out;
 }
 
 }  // namespace b2bricks

@@ -563,7 +563,7 @@ constexpr size_t brick2_smem_bytes(int K, int cap, int warps, int ch, int st) {
 template <int K, int DOT, bool RS, int BLOCK, int CH, int ST>
 __global__ void __launch_bounds__(BLOCK, 1)
 k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned short* __restrict__ lcols,
-              const double* __restrict__ vals, const int* __restrict__ worder, const int* __restrict__ wptr,
+              const double* __restrict__ vals, const int4* __restrict__ wdesc, const int* __restrict__ wseq,
               const int* __restrict__ gptr, const int* __restrict__ glist, int n_bricks, int cap,
               const double* __restrict__ x, int ld, double* __restrict__ y, const double* __restrict__ w, KryState* st,
               int fin, double* partials, unsigned* counter, RedCtl red_out, const double* __restrict__ rscale, int diag) {
@@ -588,44 +588,33 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  // ---- producer cursor: this warp's chunks in the order it will consume them, running ST - 1 chunks ahead ----------
-  int pb = blockIdx.x, pj = 0, pj1 = 0, pt = 0, pbase = 0, plen = 0, issued = 0;
-  bool pvalid = false;
-  auto p_next_brick = [&]() {  // first brick at or after pb in which this warp has a slice
-    while (pb < n_bricks) {
-      pj = __ldg(wptr + (size_t)pb * WPB + wib);
-      pj1 = __ldg(wptr + (size_t)pb * WPB + wib + 1);
-      if (pj < pj1) return true;
-      pb += gridDim.x;
-    }
-    return false;
-  };
-  auto p_load_slice = [&]() {
-    const int s = __ldg(worder + pj);
-    pbase = __ldg(slice_ptr + s);
-    plen = (__ldg(slice_ptr + s + 1) - pbase) >> 5;
-    pt = 0;
-  };
-  pvalid = diag != 2 && p_next_brick();
-  if (pvalid) p_load_slice();
+  // ---- this warp's work list (bricks.hpp: assign_warps): one 16-byte descriptor {brick, slice, first slot, steps} per
+  // slice, in the order the warp meets them.  Producer and consumer each read one descriptor AHEAD of the slice they work
+  // on, so that no slice starts with a chain of dependent metadata loads (with 16 warps per SM nothing would hide it).
+  const int4* desc = wdesc + __ldg(wseq + (size_t)blockIdx.x * WPB + wib);
+  const int n_desc = __ldg(wseq + (size_t)blockIdx.x * WPB + wib + 1) - __ldg(wseq + (size_t)blockIdx.x * WPB + wib);
+  const int4 none = make_int4(-1, 0, 0, 0);
+  // ---- producer cursor: the chunks in the order they will be consumed, running ST - 1 chunks ahead ---------------------
+  int pi = 0, pt = 0, issued = 0;
+  int4 pcur = (diag != 2 && n_desc > 0) ? __ldg(desc) : none;
+  int4 pnxt = (diag != 2 && n_desc > 1) ? __ldg(desc + 1) : none;
   auto issue = [&]() {
-    if (!pvalid) return;
-    const int tn = min(CH, plen - pt);
+    if (pcur.x < 0) return;
+    const int tn = min(CH, pcur.w - pt);
     const int stg = issued % ST;
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was read by this warp's generic loads
       mbar_expect_tx(bars + stg, (unsigned)(tn * 32 * 10));
-      bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
-      bulk_g2s(scols + (size_t)stg * CH * 32, lcols + (size_t)pbase + ((size_t)pt << 5), (unsigned)(tn * 32 * 2), bars + stg);
+      bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
+      bulk_g2s(scols + (size_t)stg * CH * 32, lcols + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 2), bars + stg);
     }
     pt += tn;
     ++issued;
-    if (pt >= plen) {
-      if (++pj >= pj1) {
-        pb += gridDim.x;
-        pvalid = p_next_brick();
-      }
-      if (pvalid) p_load_slice();
+    if (pt >= pcur.w) {
+      ++pi;
+      pt = 0;
+      pcur = pnxt;
+      pnxt = (pi + 1 < n_desc) ? __ldg(desc + pi + 1) : none;
     }
   };
 #pragma unroll
@@ -646,6 +635,9 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
       col[f] = i < ng ? __ldg(glist + g0 + i) : -1;
     }
   }
+  int ci = 0;
+  int4 ccur = (diag != 2 && n_desc > 0) ? __ldg(desc) : none;
+  int4 cnxt = (diag != 2 && n_desc > 1) ? __ldg(desc + 1) : none;
   for (int b = blockIdx.x; b < n_bricks; b += gridDim.x) {
     __syncthreads();  // the previous brick's operands are no longer read
     if (diag != 1) {
@@ -671,11 +663,22 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
       }
     }
     if (diag == 2) continue;
-    const int j1 = __ldg(wptr + (size_t)b * WPB + wib + 1);
-    for (int j = __ldg(wptr + (size_t)b * WPB + wib); j < j1; ++j) {
-      const int s = __ldg(worder + j);
-      const int len = (__ldg(slice_ptr + s + 1) - __ldg(slice_ptr + s)) >> 5;
+    while (ccur.x == b) {
+      const int s = ccur.y;
+      const int len = ccur.w;
+      ++ci;
+      ccur = cnxt;
+      cnxt = (ci + 1 < n_desc) ? __ldg(desc + ci + 1) : none;
       const int row = (s << 5) + lane;
+      // the epilogue's operands are requested now: their latency passes while the slice is processed
+      double rs = 1.0, wv[DOT >= 1 ? K : 1];
+      if (row < n_rows) {
+        if constexpr (RS) rs = __ldg(rscale + row);
+        if constexpr (DOT >= 1) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) wv[k] = __ldg(w + (size_t)k * ld + row);
+        }
+      }
       double acc[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) acc[k] = 0.0;
@@ -698,12 +701,6 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
         ++consumed;
       }
       if (row < n_rows) {
-        double rs = 1.0, wv[DOT >= 1 ? K : 1];
-        if constexpr (RS) rs = __ldg(rscale + row);
-        if constexpr (DOT >= 1) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) wv[k] = __ldg(w + (size_t)k * ld + row);
-        }
         if constexpr (RS) {
 #pragma unroll
           for (int k = 0; k < K; ++k) acc[k] *= rs;

@@ -34,18 +34,19 @@ def host_build(lib, n_rows, n_cols, slice_ptr, scols, order, hint_ptr, cap, max_
     p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
     nb, ng = np.zeros(1, np.int64), np.zeros(1, np.int64)
     args = [n_rows, n_cols, p(slice_ptr), p(scols), p(order), len(hint_ptr) - 1, p(hint_ptr), cap, max_slices, threads]
-    rc = lib.b2_host_build_bricks(*args, p(nb), p(ng), None, None, None, None, 0, None, None)
+    rc = lib.b2_host_build_bricks(*args, p(nb), p(ng), None, None, None, None, 0, 0, None, None)
     if rc != 0:
         return rc, None
     bptr, gptr = np.zeros(nb[0] + 1, np.int32), np.zeros(nb[0] + 1, np.int32)
     glist, lcols = np.zeros(ng[0], np.int32), np.zeros(len(scols), np.uint16)
-    worder, wptr = np.zeros((n_rows + 31) // 32, np.int32), np.zeros(nb[0] * WARPS + 1, np.int32)
-    rc = lib.b2_host_build_bricks(*args, p(nb), p(ng), p(bptr), p(gptr), p(glist), p(lcols), WARPS, p(worder), p(wptr))
-    host_build.warp_lists = (worder, wptr)
+    grid = min(GRID, int(nb[0]))
+    wdesc, wseq = np.zeros(((n_rows + 31) // 32, 4), np.int32), np.zeros(grid * WARPS + 1, np.int32)
+    rc = lib.b2_host_build_bricks(*args, p(nb), p(ng), p(bptr), p(gptr), p(glist), p(lcols), WARPS, GRID, p(wdesc), p(wseq))
+    host_build.work_lists = (wdesc, wseq, grid)
     return rc, (bptr, gptr, glist, lcols)
 
 
-WARPS = 16
+WARPS, GRID = 16, 5
 
 
 def brick_product(n_rows, slice_ptr, vals, order, bptr, gptr, glist, lcols, x, cap):
@@ -113,15 +114,25 @@ def test_host_brick_builder_reproduces_the_csr_product(lib, case):
     ref = np.array([np.sum(np.cumsum(a[indptr[r]:indptr[r + 1]] * x[indices[indptr[r]:indptr[r + 1]]])[-1:]) for r in range(n)])
     np.testing.assert_allclose(y, sp.csr_matrix((a, indices, indptr), shape=(n, n)) @ x, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-13)
-    # warp-major slice lists of the pipelined kernel: every brick's slices dealt to the warps, longest first, balanced
-    worder, wptr = host_build.warp_lists
-    assert wptr[0] == 0 and wptr[-1] == ns and np.all(np.diff(wptr) >= 0)
+    # work lists of the pipelined kernel: block g owns bricks g, g + grid, ...; the slices of a brick are dealt to the
+    # warps longest first; a warp's descriptors {brick, slice, first slot, steps} come in the order it meets them
+    wdesc, wseq, grid = host_build.work_lists
+    assert wseq[0] == 0 and wseq[-1] == ns and np.all(np.diff(wseq) >= 0)
     slen = np.diff(slice_ptr) // 32
+    assert np.array_equal(wdesc[:, 2], slice_ptr[wdesc[:, 1]]) and np.array_equal(wdesc[:, 3], slen[wdesc[:, 1]])
+    assert sorted(wdesc[:, 1].tolist()) == list(range(ns))
+    brick_of = np.empty(ns, np.int64)
     for b in range(len(bptr) - 1):
-        seg = worder[wptr[b * WARPS]:wptr[(b + 1) * WARPS]]
-        assert sorted(seg.tolist()) == sorted(order[bptr[b]:bptr[b + 1]].tolist())
-        loads = np.array([slen[worder[wptr[b * WARPS + w]:wptr[b * WARPS + w + 1]]].sum() for w in range(WARPS)])
-        assert loads.max() - loads.min() <= slen[seg].max()  # LPT: no warp is ahead of another by more than one slice
+        brick_of[order[bptr[b]:bptr[b + 1]]] = b
+    assert np.array_equal(wdesc[:, 0], brick_of[wdesc[:, 1]])
+    loads = np.zeros((len(bptr) - 1, WARPS), np.int64)
+    for g in range(grid):
+        for w in range(WARPS):
+            mine = wdesc[wseq[g * WARPS + w]:wseq[g * WARPS + w + 1]]
+            assert np.all(mine[:, 0] % grid == g) and np.all(np.diff(mine[:, 0]) >= 0)  # its block's bricks, in order
+            np.add.at(loads[:, w], mine[:, 0], mine[:, 3])
+    for b in range(len(bptr) - 1):  # LPT: no warp is ahead of another by more than one slice
+        assert loads[b].max() - loads[b].min() <= slen[order[bptr[b]:bptr[b + 1]]].max()
     # one thread or several: the same bricks
     rc1, out1 = host_build(lib, n, n, slice_ptr, scols, order, hints, cap, max_slices, 1)
     assert rc1 == 0 and all(np.array_equal(u, v) for u, v in zip(out, out1))
