@@ -517,11 +517,12 @@ void launch_spmm_brick2(b2_ctx* c, const CSR& pat, const double* vals, const dou
                         KryState* st, int fin, const double* rscale) {
   constexpr int BLOCK = 32 * B2_BRICK_WARPS, CH = 8, ST = 3;
   const size_t smem = brick2_smem_bytes(K, pat.brick_cap, B2_BRICK_WARPS, CH, ST);
+  B2_REQUIRE(pat.brick_cap == B2_BRICK_CAP, "pipelined brick SpMM is compiled for gather lists of B2_BRICK_CAP entries");
   const int grid = pat.brick_grid;  // the work lists were laid out for this many blocks (one per SM)
   B2_REQUIRE(grid >= 1 && grid <= c->partials.n / 16, "pipelined brick SpMM: work lists missing or grid exceeds the reduction scratch");
 #define B2_SPMM_BRICK2(RS_)                                                                                               \
   do {                                                                                                                    \
-    auto kern = k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST>;                                                                \
+    auto kern = c->spmm_brick >= 3 ? k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST, false> : k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST, true>; \
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                                       \
                                  (int)brick2_smem_bytes(3, B2_BRICK_CAP, B2_BRICK_WARPS, CH, ST)));                       \
     kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, (const int4*)pat.wdesc.p, pat.wseq.p, \

@@ -25,7 +25,7 @@ struct Bricks {
   std::vector<int> brick_ptr;      // n_bricks + 1 offsets into the slice schedule `order`
   std::vector<int> gptr;           // n_bricks + 1 offsets into glist
   std::vector<int> glist;          // gather lists: sorted distinct columns of each brick
-  std::vector<uint16_t> lcols;     // one per SELL slot: position of the slot's column in its brick's gather list
+  std::vector<uint16_t> lcols;     // one per SELL slot: 8 * (position of the slot's column in its brick's gather list)
   // work lists of the pipelined kernel (k_spmm_brick2), see assign_warps
   std::vector<int> wdesc, wseq;
   int warps = 0, grid = 0;
@@ -46,7 +46,7 @@ inline void build(int n_rows, int n_cols, const int* slice_ptr, const int* scols
   const int64_t slots = slice_ptr[n_slices];
   out = Bricks();
   out.lcols.assign((size_t)slots, 0);
-  if (cap > 65536) cap = 65536;  // positions are 16-bit
+  if (cap > 8191) cap = 8191;  // 8 * position must fit 16 bits
   n_threads = std::max(1, std::min(n_threads, n_hints));
   struct Part {
     std::vector<int> ends, gsize, glist;  // per brick: end offset in order, gather length; concatenated lists
@@ -64,7 +64,9 @@ inline void build(int n_rows, int n_cols, const int* slice_ptr, const int* scols
       for (size_t i = 0; i < gather.size(); ++i) pos[(size_t)gather[i]] = (int)i;
       for (int j = j_begin; j < j_end; ++j) {
         const int s = slice_of(j);
-        for (int64_t p = slice_ptr[s]; p < slice_ptr[s + 1]; ++p) out.lcols[(size_t)p] = (uint16_t)pos[(size_t)scols[p]];
+        // stored as BYTE offsets into one component's shared-memory array (8 * position < 65536 for cap <= 8191):
+        // the kernels add them to the array base without a shift
+        for (int64_t p = slice_ptr[s]; p < slice_ptr[s + 1]; ++p) out.lcols[(size_t)p] = (uint16_t)(8 * pos[(size_t)scols[p]]);
       }
       P.ends.push_back(j_end);
       P.gsize.push_back((int)gather.size());

@@ -486,7 +486,8 @@ k_spmm_brick(int n_rows, const int* __restrict__ slice_ptr, const unsigned short
         for (int u = 0; u < UNROLL; ++u)
           if (t + u < len) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = fma(v[u], sx[k * cap + c[u]], acc[k]);
+            for (int k = 0; k < K; ++k)
+              acc[k] = fma(v[u], *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sx + k * cap) + c[u]), acc[k]);
           }
       }
       if (row < n_rows) {
@@ -554,13 +555,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 
 constexpr size_t brick2_smem_bytes(int K, int cap, int warps, int ch, int st) {
   return sizeof(double) * (size_t)K * cap + (size_t)warps * st * ch * 32 * (sizeof(double) + sizeof(unsigned short)) +
          sizeof(unsigned long long) * (size_t)warps * st;
 }
 
-template <int K, int DOT, bool RS, int BLOCK, int CH, int ST>
+template <int K, int DOT, bool RS, int BLOCK, int CH, int ST, bool TMA>
 __global__ void __launch_bounds__(BLOCK, 1)
 k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned short* __restrict__ lcols,
               const double* __restrict__ vals, const int4* __restrict__ wdesc, const int* __restrict__ wseq,
@@ -574,7 +578,7 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
   constexpr int F = (B2_BRICK_CAP + BLOCK - 1) / BLOCK;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sx = reinterpret_cast<double*>(smem_raw);  // [K][cap]
-  double* svals_all = sx + (size_t)K * cap;           // [WPB][ST][CH * 32]
+  double* svals_all = sx + (size_t)K * B2_BRICK_CAP;  // [WPB][ST][CH * 32]   (cap == B2_BRICK_CAP, checked by the host)
   unsigned short* scols_all = reinterpret_cast<unsigned short*>(svals_all + (size_t)WPB * ST * CH * 32);
   unsigned long long* bars_all = reinterpret_cast<unsigned long long*>(scols_all + (size_t)WPB * ST * CH * 32);
   const int lane = threadIdx.x & 31;
@@ -582,7 +586,7 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
   double* svals = svals_all + (size_t)wib * ST * CH * 32;
   unsigned short* scols = scols_all + (size_t)wib * ST * CH * 32;
   unsigned long long* bars = bars_all + wib * ST;
-  if (lane == 0) {
+  if (TMA && lane == 0) {
 #pragma unroll
     for (int s = 0; s < ST; ++s) mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -599,23 +603,39 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
   int4 pcur = (diag != 2 && n_desc > 0) ? __ldg(desc) : none;
   int4 pnxt = (diag != 2 && n_desc > 1) ? __ldg(desc + 1) : none;
   auto issue = [&]() {
-    if (pcur.x < 0) return;
-    const int tn = min(CH, pcur.w - pt);
-    const int stg = issued % ST;
-    if (lane == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was read by this warp's generic loads
-      mbar_expect_tx(bars + stg, (unsigned)(tn * 32 * 10));
-      bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
-      bulk_g2s(scols + (size_t)stg * CH * 32, lcols + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 2), bars + stg);
+    if (pcur.x >= 0) {
+      const int tn = min(CH, pcur.w - pt);
+      const int stg = issued % ST;
+      if constexpr (TMA) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was read by this warp's generic loads
+          mbar_expect_tx(bars + stg, (unsigned)(tn * 32 * 10));
+          bulk_g2s(svals + (size_t)stg * CH * 32, vals + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 8), bars + stg);
+          bulk_g2s(scols + (size_t)stg * CH * 32, lcols + (size_t)pcur.z + ((size_t)pt << 5), (unsigned)(tn * 32 * 2), bars + stg);
+        }
+      } else {  // 16-byte cp.async.cg per lane: CH * 256 B of values = CH / 2 copies per lane, CH * 64 B of positions = 1
+        const char* gv = reinterpret_cast<const char*>(vals + (size_t)pcur.z + ((size_t)pt << 5));
+        char* sv = reinterpret_cast<char*>(svals + (size_t)stg * CH * 32);
+#pragma unroll
+        for (int i = 0; i < CH / 2; ++i) {
+          const int off = (lane + 32 * i) * 16;
+          if (off < tn * 256) cp_async_16(sv + off, gv + off);
+        }
+        const int offc = lane * 16;
+        if (offc < tn * 64)
+          cp_async_16(reinterpret_cast<char*>(scols + (size_t)stg * CH * 32) + offc,
+                      reinterpret_cast<const char*>(lcols + (size_t)pcur.z + ((size_t)pt << 5)) + offc);
+      }
+      pt += tn;
+      ++issued;
+      if (pt >= pcur.w) {
+        ++pi;
+        pt = 0;
+        pcur = pnxt;
+        pnxt = (pi + 1 < n_desc) ? __ldg(desc + pi + 1) : none;
+      }
     }
-    pt += tn;
-    ++issued;
-    if (pt >= pcur.w) {
-      ++pi;
-      pt = 0;
-      pcur = pnxt;
-      pnxt = (pi + 1 < n_desc) ? __ldg(desc + pi + 1) : none;
-    }
+    if constexpr (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, empty or not
   };
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue();
@@ -645,9 +665,10 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
       for (int f = 0; f < F; ++f)
         if (col[f] >= 0) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) cp_async_8(sx + (size_t)k * cap + threadIdx.x + f * BLOCK, x + (size_t)k * ld + col[f]);
+          for (int k = 0; k < K; ++k) cp_async_8(sx + (size_t)k * B2_BRICK_CAP + threadIdx.x + f * BLOCK, x + (size_t)k * ld + col[f]);
         }
-      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     {  // the next brick's list entries: in flight during this brick's stream
@@ -686,18 +707,35 @@ k_spmm_brick2(int n_rows, const int* __restrict__ slice_ptr, const unsigned shor
         issue();  // refill the stage consumed in the previous round
         const int tn = min(CH, len - t);
         const int stg = consumed % ST;
-        mbar_wait(bars + stg, (unsigned)((consumed / ST) & 1));
+        if constexpr (TMA) {
+          mbar_wait(bars + stg, (unsigned)((consumed / ST) & 1));
+        } else {  // all but the ST - 1 newest groups have landed: this chunk's is among them
+          asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+          __syncwarp();
+        }
         const double* sv = svals + (size_t)stg * CH * 32 + lane;
         const unsigned short* sc = scols + (size_t)stg * CH * 32 + lane;
+        // positions are stored as byte offsets and the capacity is a compile-time constant: per entry 2 + K shared
+        // loads, one add and K FMAs (the first form of this loop spent 37 instructions per step on predicates and
+        // index arithmetic, and 16 warps per SM could not issue them fast enough)
+        const char* sxb = reinterpret_cast<const char*>(sx);
+        if (tn == CH) {
 #pragma unroll
-        for (int u = 0; u < CH; ++u)
-          if (u < tn) {
-            const int c = sc[u << 5];
+          for (int u = 0; u < CH; ++u) {
+            const unsigned c = sc[u << 5];
             const double v = sv[u << 5];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = fma(v, sx[(size_t)k * cap + c], acc[k]);
+            for (int k = 0; k < K; ++k) acc[k] = fma(v, *reinterpret_cast<const double*>(sxb + c + k * (B2_BRICK_CAP * 8)), acc[k]);
           }
-        __syncwarp();  // every lane is done with this stage before lane 0 lets the TMA overwrite it
+        } else {
+          for (int u = 0; u < tn; ++u) {
+            const unsigned c = sc[u << 5];
+            const double v = sv[u << 5];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fma(v, *reinterpret_cast<const double*>(sxb + c + k * (B2_BRICK_CAP * 8)), acc[k]);
+          }
+        }
+        __syncwarp();  // every lane is done with this stage before it is overwritten
         ++consumed;
       }
       if (row < n_rows) {

@@ -66,7 +66,7 @@ def brick_product(n_rows, slice_ptr, vals, order, bptr, gptr, glist, lcols, x, c
                 acc = 0.0
                 for t in range(length):
                     slot = base + (t << 5) + lane
-                    acc += vals[slot] * sx[lcols[slot]]
+                    acc += vals[slot] * sx[lcols[slot] // 8]  # stored as byte offsets
                 y[row] = acc
     return y
 
@@ -104,7 +104,8 @@ def test_host_brick_builder_reproduces_the_csr_product(lib, case):
     for b in range(len(bptr) - 1):
         brick_of_slice[order[bptr[b]:bptr[b + 1]]] = b
     slot_slice = np.repeat(np.arange(ns), np.diff(slice_ptr))
-    np.testing.assert_array_equal(glist[gptr[brick_of_slice[slot_slice]] + lcols.astype(np.int64)], scols)
+    assert np.all(lcols % 8 == 0)
+    np.testing.assert_array_equal(glist[gptr[brick_of_slice[slot_slice]] + lcols.astype(np.int64) // 8], scols)
     # and the product, executed the way the kernel indexes it, is the CSR product bit for bit
     a = rng.standard_normal(len(indices))
     vals = np.zeros(len(scols))

@@ -36,11 +36,15 @@ def test_brick_product_is_bitwise_the_plain_product(gdim, N, order):
         mat.mult(x, yb)
         ctx.set_tuning("spmm_brick", 2)  # the pipelined kernel (TMA-fed rings)
         mat.mult(x, yb2)
+        ctx.set_tuning("spmm_brick", 3)  # the same pipeline fed by 16-byte cp.async
+        yb3 = np.zeros(mat.getSize()[0])
+        mat.mult(x, yb3)
         ctx.set_tuning("spmm_brick", 0)
         mat.mult(x, yp)
         ctx.set_tuning("spmm_brick", 1)
         assert np.array_equal(yb, yp)
         assert np.array_equal(yb2, yp)
+        assert np.array_equal(yb3, yp)
         ip, ix, v = mat.getValuesCSR()
         import scipy.sparse as sp
         ref = sp.csr_matrix((v, ix, ip), shape=mat.getSize()) @ x

@@ -44,6 +44,12 @@ for mode, name in ((1, "no fill"), (2, "no stream")):
     ctx.set_tuning("spmm_brick_diag", mode)
     run(f"  pipelined, {name}")
 ctx.set_tuning("spmm_brick_diag", 0)
+ctx.set_tuning("spmm_brick", 3)
+run("brick kernel, pipelined, 16-byte cp.async rings instead of TMA")
+for mode, name in ((1, "no fill"), (2, "no stream")):
+    ctx.set_tuning("spmm_brick_diag", mode)
+    run(f"  cp.async rings, {name}")
+ctx.set_tuning("spmm_brick_diag", 0)
 if len(sys.argv) > 2 and sys.argv[2] == "bricks":
     sys.exit(0)
 ctx.set_tuning("spmm_brick", 0)
