@@ -49,15 +49,14 @@ KRYLOV = {
 }
 
 
-def ncu_traffic(mesh: int, brick: bool = False):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one SpMM launch from the committed `ncu --set full` capture
-    (profiles/r02_ncu_spmm_96cube.txt for k_spmm, profiles/r02_ncu_spmm_brick_96cube.txt for k_spmm_brick; first kernel
-    of the file); only valid for the mesh it was taken on, None when there is no capture of the kernel that ran."""
+def ncu_traffic(mesh: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_spmm launch from the committed `ncu --set full`
+    capture (profiles/r02_ncu_spmm_96cube.txt, first kernel of the file); only valid for the mesh it was taken on."""
     if mesh != 96:
         return None
     try:
         tot, seen = 0.0, set()
-        for line in open(os.path.join(ROOT, "profiles", "r02_ncu_spmm_brick_96cube.txt" if brick else "r02_ncu_spmm_96cube.txt")):
+        for line in open(os.path.join(ROOT, "profiles", "r02_ncu_spmm_96cube.txt")):
             f = line.split()
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[0] not in seen:
                 seen.add(f[0])
@@ -606,10 +605,8 @@ def run_ours(args):
     msh = make_mesh(gd, N, comm if world > 1 else None)
     if args.dof_order != "class":  # coordinate-sorted dofs and slices, as for a mesh without lattice information
         msh._dof_order = args.dof_order  # "sigma": plus SELL-C-sigma's window sort by row length
-    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory, bricks=args.bricks > 0)
+    solver = make_solver(msh, 2, tg, DT, solver_options=krylov, device=device, low_memory=args.low_memory)
     ctx = solver._ctx
-    if args.bricks:
-        ctx.set_tuning("spmm_brick", args.bricks)
     t_setup = time.perf_counter() - t_setup
     nbc = comm.allreduce(sum(len(d) for d in solver._bc_dofs))
     from oasisx_b200 import _lib as L
@@ -702,22 +699,9 @@ def run_ours(args):
     comm.Barrier()
     ms_k, bytes_k = ctx.bench_kernel(3, 20)   # SpMM on the P2xP2 pattern (mass operator), gdim RHS: the kernel the steps ran
     achieved = bytes_k / (ms_k * 1e-3) / 1e9
-    bricks = getattr(solver, "_brick_info", None)
-    plain = None
-    if bricks:  # the same product by the plain sliced-ELL kernel (32-bit columns, gathers through L1/L2)
-        halves = {}
-        for name, mode in (("stream_only_ms", 1), ("fill_only_ms", 2)):  # timing of the two phases of the brick kernel
-            ctx.set_tuning("spmm_brick_diag", mode)
-            halves[name] = ctx.bench_kernel(3, 10)[0]
-        ctx.set_tuning("spmm_brick_diag", 0)
-        bricks = dict(bricks, **halves)
-        ctx.set_tuning("spmm_brick", 0)
-        ms_p, bytes_p = ctx.bench_kernel(3, 20)
-        ctx.set_tuning("spmm_brick", args.bricks)
-        plain = {"kernel": "k_spmm (SELL-32, 32-bit columns, L1/L2 gathers)", "ms_per_launch": ms_p, "algorithmic_bytes": bytes_p,
-                 "achieved": bytes_p / (ms_p * 1e-3) / 1e9, "frac": bytes_p / (ms_p * 1e-3) / 1e9 / peak}
     ms_a, bytes_a = ctx.bench_kernel(1, 5)
     ms_q, bytes_q = ctx.bench_kernel(2, 50)
+    ms_d1, ms_d2 = ctx.bench_kernel(4, 20)[0], ctx.bench_kernel(5, 20)[0]  # the same SpMM with its fused epilogues
     collectives = None
     if world > 1:  # latency of the cross-GPU building blocks, 200 back-to-back launches each (every rank takes part)
         collectives = {"path": "peer memory (CUDA IPC over NVLink)" if ctx.peer_enabled() else "NCCL"}
@@ -727,17 +711,14 @@ def run_ours(args):
             except Exception:
                 collectives[name] = None
     comm.Barrier()
-    brick_on = bool(bricks)
-    roofline = {"bound": "hbm", "kernel": (f"k_spmm_brick<K={gd}> (P2xP2 operator in brick form: x staged in shared memory, 16-bit "
-                                           f"positions, {gd} right-hand sides)" if brick_on else
-                                           f"k_spmm<K={gd}> (P2xP2 SELL-32 operator, {gd} right-hand sides)"),
+    roofline = {"bound": "hbm", "kernel": f"k_spmm<K={gd}> (P2xP2 SELL-32 operator, {gd} right-hand sides)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(N, brick_on) if world == 1 else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
-                "bricks": bricks if brick_on else None, "plain_kernel": plain,
+                "traffic": ncu_traffic(N) if world == 1 else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_k,
                 "other_kernels": {
                     "assemble_first_ms": ms_a, "assemble_first_GBs": bytes_a / (ms_a * 1e-3) / 1e9,
                     "assemble_first_algorithmic_bytes": bytes_a,
-                    "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q}}
+                    "spmv_Ap_GBs": bytes_q / (ms_q * 1e-3) / 1e9, "spmv_Ap_ms": ms_q,
+                    "spmm_row_scale_1_dot_ms": ms_d1, "spmm_row_scale_2_dots_ms": ms_d2}}
     step_roofline = None
     try:
         if world == 1:
@@ -842,8 +823,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity48", action="store_true", help="skip the second (48^3) GPU-vs-CPU-port field comparison")
     ap.add_argument("--weak", action="store_true", help="cavity workload: weak scaling, one mesh^3 block of cubes per GPU (BASELINE configs[4])")
-    ap.add_argument("--bricks", type=int, default=0, choices=[0, 1, 2],
-                    help="run the brick form of the SpMM instead of the plain sliced-ELL kernel (A/B): 1 = k_spmm_brick, 2 = k_spmm_brick2 (pipelined)")
     ap.add_argument("--dof-order", default="class", choices=["class", "generic", "sigma"],
                     help="class: stencil-class dof order of the box provider (32 consecutive rows share a stencil); generic: the "
                          "coordinate sort every other mesh gets (DOLFINx, unstructured): how much of the SpMM roofline fraction is the lattice")

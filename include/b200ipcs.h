@@ -149,22 +149,6 @@ int64_t b2_pattern_sell_slots(b2_ctx* ctx, int pattern);
  * neighbourhood of the vector (host-side analogue of DOLFINx's graph reordering [ext]).  Results do
  * not depend on it. */
 int b2_set_slice_order(b2_ctx* ctx, int pattern, int64_t n_slices, const int32_t* order);
-/* Optional BRICK form of a square pattern's sliced-ELL layout (the SpMM behind every MatMult / KSP iteration of
- * fracstep.py:452,521,638,656): `order` is a schedule of the 32-row slices, `hint_ptr` (n_hints + 1 offsets into it)
- * groups the slices of one small spatial neighbourhood.  Inside a group the library packs slices into bricks whose
- * distinct columns fit a shared-memory gather list; the SpMM then loads x once per brick and streams 16-bit list
- * positions instead of 32-bit columns.  Values stay in the sliced-ELL slots; results are bitwise those of the plain
- * kernel (tuning key "spmm_brick" = 0 switches back).  info (may be NULL): {bricks, total gather entries, longest list}. */
-int b2_set_bricks(b2_ctx* ctx, int pattern, int64_t n_slices, const int32_t* order, int64_t n_hints, const int32_t* hint_ptr,
-                  int64_t* info);
-/* The brick builder on host arrays (no device needed; the CPU test of the format).  Outputs may be NULL to query the
- * sizes first: brick_ptr (n_bricks + 1), gptr (n_bricks + 1), glist (n_gather), lcols (one uint16 per slot); with
- * warps > 0 also the work lists of the pipelined kernel for `grid` blocks of `warps` warps: wdesc (4 ints per slice:
- * brick, slice, first slot, steps; grouped by block and warp), wseq (min(grid, n_bricks) * warps + 1 list offsets). */
-int b2_host_build_bricks(int32_t n_rows, int32_t n_cols, const int32_t* slice_ptr, const int32_t* scols, const int32_t* order,
-                         int64_t n_hints, const int32_t* hint_ptr, int32_t cap, int32_t max_slices, int32_t n_threads,
-                         int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols,
-                         int32_t warps, int32_t grid, int32_t* wdesc, int32_t* wseq);
 /* copies indptr (n_rows+1) and indices (nnz) back: the bit-exact CSR check of north_star */
 int b2_get_pattern(b2_ctx* ctx, int pattern, int32_t* indptr, int32_t* indices);
 

@@ -27,7 +27,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_device_count", "b2_nccl_unique_id", "b2_create", "b2_destroy", "b2_last_error",
     "b2_host_alloc", "b2_host_free", "b2_set_mesh", "b2_set_space", "b2_set_halo", "b2_set_global_sizes",
     "b2_first_plan_info", "b2_bench_assembly_strategies", "b2_peer_export", "b2_peer_import", "b2_peer_disable", "b2_peer_enabled",
-    "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_set_slice_order", "b2_set_bricks", "b2_host_build_bricks", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
+    "b2_build_patterns", "b2_pattern_nnz", "b2_pattern_sell_slots", "b2_set_slice_order", "b2_pressure_mg_add_level", "b2_pressure_mg_configure", "b2_get_pattern", "b2_set_velocity_bc_dofs",
     "b2_set_velocity_bc_values", "b2_set_velocity_bc_series", "b2_select_bc_step", "b2_reset_time_history", "b2_profiler_range", "b2_set_pressure_bc_dofs", "b2_declare_pressure_bcs", "b2_preassemble", "b2_set_vector", "b2_get_vector",
     "b2_get_matrix_values", "b2_mat_mult", "b2_set_solver_option", "b2_assemble_first", "b2_tentative_assemble",
     "b2_tentative_solve", "b2_pressure_assemble", "b2_pressure_solve", "b2_velocity_update", "b2_step_begin", "b2_step",
@@ -101,8 +101,6 @@ def load_library() -> C.CDLL:
         "b2_pattern_nnz": (i64, [vp, i32]),
         "b2_pattern_sell_slots": (i64, [vp, i32]),
         "b2_set_slice_order": (i32, [vp, i32, i64, vp]),
-        "b2_set_bricks": (i32, [vp, i32, i64, vp, i64, vp, vp]),
-        "b2_host_build_bricks": (i32, [i32, i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "b2_pressure_mg_add_level": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]),
         "b2_pressure_mg_configure": (i32, [vp, i32, i32, i32, dbl]),
         "b2_get_pattern": (i32, [vp, i32, vp, vp]),
@@ -234,13 +232,6 @@ class Context:
     def set_slice_order(self, which: int, order):
         o = _i32(order)
         self._check(self.lib.b2_set_slice_order(self._h, which, o.size, _ptr(o)), "b2_set_slice_order")
-
-    def set_bricks(self, which: int, order, hint_ptr) -> dict:
-        """Brick form of the pattern's sliced-ELL layout (b2_set_bricks); returns its statistics."""
-        o, h = _i32(order), _i32(hint_ptr)
-        info = np.zeros(3, np.int64)
-        self._check(self.lib.b2_set_bricks(self._h, which, o.size, _ptr(o), h.size - 1, _ptr(h), _ptr(info)), "b2_set_bricks")
-        return {"bricks": int(info[0]), "gather_entries": int(info[1]), "max_gather": int(info[2])}
 
     def pressure_mg_add_level(self, x, cell_nodes, P, R):
         """P, R: scipy CSR (fine-owned x coarse, coarse x fine-local)."""

@@ -19,7 +19,6 @@
 #include "elem.cuh"
 #include "linalg.cuh"
 #include "mg.cuh"
-#include "bricks.hpp"
 
 namespace {
 
@@ -32,19 +31,8 @@ struct CSR {
   int lpr = 8;  // lanes per row used by the rectangular CSR kernels on this pattern
   // SELL-32 layout of the same pattern (square operators only; see linalg.cuh)
   DBuf<int> slice_ptr, scols, diag_t, order;  // order: optional tile-major slice schedule
-  DBuf<int> porder;                           // the same schedule padded with -1 (box-aligned groups), if one was given
-  int porder_len = 0;
   int64_t slots = 0;
   bool has_sell() const { return slice_ptr.p != nullptr; }
-  // brick form of the SELL layout (bricks.hpp): brick schedule of the slices, brick offsets into it, gather lists,
-  // 16-bit positions per slot
-  DBuf<int> border, bptr, gptr, glist;
-  DBuf<int> wdesc, wseq;   // work lists of the pipelined kernel (bricks.hpp: assign_warps), built for brick_grid blocks
-  int brick_grid = 0;
-  DBuf<unsigned short> lcols;
-  int n_bricks = 0, brick_cap = 0;
-  int64_t n_gather = 0;
-  bool has_bricks() const { return n_bricks > 0; }
 };
 
 struct Space {
@@ -172,10 +160,6 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
-  int spmm_block = 256;          // threads per block of k_spmm (256 / 512 / 1024): tuning "spmm_block"
-  int spmm_brick_diag = 0;       // timing of the halves of k_spmm_brick (1: no fill, 2: no stream); results meaningless
-  int spmm_brick = 1;            // use the brick form of a pattern when it has one (b2_set_bricks); tuning "spmm_brick"
-  unsigned brick_attr_mask = 0;  // k_spmm_brick instantiations whose shared-memory limit has been raised on this device
   int spmm_min_slices = 1;   // tuning "spmm_min_slices": 0 = round 1's fixed persistent grid (sm x spmm_blocks_per_sm), else equal shares
   cudaStream_t stream = nullptr;
   std::string err;
@@ -483,71 +467,11 @@ inline RedCtl red_ptr(b2_ctx* c) {
   return c->peer_on ? RedCtl{nullptr, c->d_peer} : RedCtl{c->d_red, nullptr};
 }
 
-// brick SpMM (linalg.cuh: k_spmm_brick): persistent grid of 2 blocks per SM, K * cap * 8 bytes of shared memory each
-template <int K, int DOT>
-void launch_spmm_brick(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                       KryState* st, int fin, const double* rscale) {
-  constexpr int BLOCK = 512, UNROLL = 8;
-  const size_t smem = sizeof(double) * (size_t)K * pat.brick_cap;
-  const int cap = (int)std::min<int64_t>(c->partials.n / 16, (int64_t)c->sm * 32);
-  const int grid = std::max(1, std::min(std::min(pat.n_bricks, c->sm * 2), cap));
-#define B2_SPMM_BRICK(RS_)                                                                                                \
-  do {                                                                                                                    \
-    auto kern = k_spmm_brick<K, DOT, RS_, BLOCK, UNROLL>;                                                                 \
-    const unsigned bit = 1u << ((K - 1) * 6 + DOT * 2 + (RS_ ? 1 : 0));                                                   \
-    if (!(c->brick_attr_mask & bit)) { /* once per context (= per device) and instantiation */                            \
-      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * B2_BRICK_CAP))); \
-      c->brick_attr_mask |= bit;                                                                                          \
-    }                                                                                                                     \
-    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, pat.border.p, pat.bptr.p,      \
-                                           pat.gptr.p, pat.glist.p, pat.n_bricks, pat.brick_cap, x, ld, y, w, st, fin,    \
-                                           c->partials.p, c->d_counter, red_ptr(c), rscale, c->spmm_brick_diag);          \
-    B2_CUDA(cudaGetLastError());                                                                                          \
-    c->stats.kernel_launches++;                                                                                           \
-  } while (0)
-  if (rscale != nullptr) B2_SPMM_BRICK(true);
-  else B2_SPMM_BRICK(false);
-#undef B2_SPMM_BRICK
-  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
-}
-
-// pipelined brick SpMM (linalg.cuh: k_spmm_brick2): one block of B2_BRICK_WARPS warps per SM, TMA-fed matrix stream
-template <int K, int DOT>
-void launch_spmm_brick2(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
-                        KryState* st, int fin, const double* rscale) {
-  constexpr int BLOCK = 32 * B2_BRICK_WARPS, CH = 8, ST = 3;
-  const size_t smem = brick2_smem_bytes(K, pat.brick_cap, B2_BRICK_WARPS, CH, ST);
-  B2_REQUIRE(pat.brick_cap == B2_BRICK_CAP, "pipelined brick SpMM is compiled for gather lists of B2_BRICK_CAP entries");
-  const int grid = pat.brick_grid;  // the work lists were laid out for this many blocks (one per SM)
-  B2_REQUIRE(grid >= 1 && grid <= c->partials.n / 16, "pipelined brick SpMM: work lists missing or grid exceeds the reduction scratch");
-#define B2_SPMM_BRICK2(RS_)                                                                                               \
-  do {                                                                                                                    \
-    auto kern = c->spmm_brick >= 3 ? k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST, false> : k_spmm_brick2<K, DOT, RS_, BLOCK, CH, ST, true>; \
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                                       \
-                                 (int)brick2_smem_bytes(3, B2_BRICK_CAP, B2_BRICK_WARPS, CH, ST)));                       \
-    kern<<<grid, BLOCK, smem, c->stream>>>(pat.n_rows, pat.slice_ptr.p, pat.lcols.p, vals, (const int4*)pat.wdesc.p, pat.wseq.p, \
-                                           pat.gptr.p, pat.glist.p, pat.n_bricks, pat.brick_cap, x, ld, y, w, st, fin,    \
-                                           c->partials.p, c->d_counter, red_ptr(c), rscale, c->spmm_brick_diag);          \
-    B2_CUDA(cudaGetLastError());                                                                                          \
-    c->stats.kernel_launches++;                                                                                           \
-  } while (0)
-  if (rscale != nullptr) B2_SPMM_BRICK2(true);
-  else B2_SPMM_BRICK2(false);
-#undef B2_SPMM_BRICK2
-  if (DOT > 0) reduce_finish_host(c, fin, DOT * K);
-}
-
 template <int K, int DOT, int UNROLL, int BLOCK>
 void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* x, int ld, double* y, const double* w,
                    KryState* st, int fin, const double* rscale) {
-  if (c->spmm_brick && pat.has_bricks()) {
-    if (c->spmm_brick >= 2) launch_spmm_brick2<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
-    else launch_spmm_brick<K, DOT>(c, pat, vals, x, ld, y, w, st, fin, rscale);
-    return;
-  }
-  const int n_list = pat.porder_len > 0 ? pat.porder_len : (pat.n_rows + 31) / 32;
-  const int* order = pat.porder_len > 0 ? pat.porder.p : pat.order.p;
-  const int need = (n_list + BLOCK / 32 - 1) / (BLOCK / 32);
+  const int n_slices = (pat.n_rows + 31) / 32;
+  const int need = (n_slices + BLOCK / 32 - 1) / (BLOCK / 32);
   // Every warp takes the same whole number k of slices (k = 1 when the grid fits): a fixed persistent grid quantises
   // small operators -- the 1/4 or 1/8 slab of a multi-GPU run got 3.07 slices per warp, i.e. 3 or 4: 103 us against 86
   // on the 96 x 96 x 12 slab (tools/exp_slab.py) -- and is no faster on large ones.  The cap is what the grid-wide
@@ -558,7 +482,7 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
   B2_REQUIRE(grid <= cap, "SpMM grid exceeds the reduction scratch");
 #define B2_SPMM(STREAM_, RS_)                                                                                            \
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
-            order, n_list, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
+            pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
   if (c->spmm_stream) {
     if (rscale != nullptr) B2_SPMM(true, true);
     else B2_SPMM(true, false);
@@ -579,15 +503,7 @@ void launch_spmm_t(b2_ctx* c, const CSR& pat, const double* vals, const double* 
     else B2_LAUNCH(c, (k_spmm_diag<K, 2>), grid, 256, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals, x, ld, y);
     return;
   }
-  // (DOT == 2 at 1024 threads would need more than the 48 KB of static shared memory for its running sums)
-  if constexpr (DOT < 2) {
-    if (c->spmm_block >= 1024) {
-      launch_spmm_u<K, DOT, 8, 1024>(c, pat, vals, x, ld, y, w, st, fin, rscale);
-      return;
-    }
-  }
-  if (c->spmm_block >= 512) launch_spmm_u<K, DOT, 8, 512>(c, pat, vals, x, ld, y, w, st, fin, rscale);
-  else if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
+  if (c->spmm_unroll >= 8) launch_spmm_u<K, DOT, 8, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
   else launch_spmm_u<K, DOT, 4, 256>(c, pat, vals, x, ld, y, w, st, fin, rscale);
 }
 
@@ -2000,101 +1916,12 @@ int b2_set_slice_order(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* 
   return guarded(c, [&] {
     B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "slice order: square patterns, after b2_build_patterns");
     CSR& pat = c->pat[pattern];
-    // a permutation of the slices, optionally padded with -1 entries (box-aligned groups: see k_spmm)
-    const int64_t ns = (pat.n_rows + 31) / 32;
-    std::vector<int> compact;
-    std::vector<char> seen((size_t)ns, 0);
-    for (int64_t i = 0; i < n_slices; ++i) {
-      const int s = order[i];
-      if (s < 0) continue;
-      B2_REQUIRE(s < ns && !seen[(size_t)s], "slice order must list every 32-row slice exactly once");
-      seen[(size_t)s] = 1;
-      compact.push_back(s);
-    }
-    B2_REQUIRE((int64_t)compact.size() == ns, "slice order must list every 32-row slice exactly once");
+    B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "slice order length must equal the number of 32-row slices");
     c->cfg_version++;
-    pat.order.alloc(ns);
-    B2_CUDA(cudaMemcpyAsync(pat.order.p, compact.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
-    pat.porder_len = 0;
-    pat.porder.release();
-    if (n_slices > ns) {
-      pat.porder.alloc(n_slices);
-      pat.porder_len = (int)n_slices;
-      B2_CUDA(cudaMemcpyAsync(pat.porder.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
-    }
+    pat.order.alloc(n_slices);
+    B2_CUDA(cudaMemcpyAsync(pat.order.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
   });
-}
-
-int b2_set_bricks(b2_ctx* c, int pattern, int64_t n_slices, const int32_t* order, int64_t n_hints, const int32_t* hint_ptr,
-                  int64_t* info) {
-  return guarded(c, [&] {
-    B2_REQUIRE(c->patterns_built && (pattern == B2_PAT_VV || pattern == B2_PAT_QQ), "bricks: square patterns, after b2_build_patterns");
-    CSR& pat = c->pat[pattern];
-    B2_REQUIRE(n_slices == (pat.n_rows + 31) / 32, "brick schedule length must equal the number of 32-row slices");
-    B2_REQUIRE(n_hints >= 1 && hint_ptr[0] == 0 && hint_ptr[n_hints] == n_slices, "brick hints must cover the schedule");
-    c->cfg_version++;
-    std::vector<int> sp((size_t)n_slices + 1), sc((size_t)pat.slots);
-    B2_CUDA(cudaMemcpyAsync(sp.data(), pat.slice_ptr.p, sizeof(int) * sp.size(), cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(sc.data(), pat.scols.p, sizeof(int) * sc.size(), cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    b2bricks::Bricks B;
-    const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    b2bricks::build(pat.n_rows, pat.n_cols, sp.data(), sc.data(), order, hint_ptr, (int)n_hints, B2_BRICK_CAP, B2_BRICK_MAX_SLICES, threads, B);
-    B2_REQUIRE(B.error == 0, "bricks: one slice touches more distinct columns than the shared-memory gather list holds");
-    b2bricks::assign_warps(pat.n_rows, sp.data(), order, B2_BRICK_WARPS, c->sm, B);
-    pat.wdesc.alloc((int64_t)B.wdesc.size());
-    pat.wseq.alloc((int64_t)B.wseq.size());
-    pat.brick_grid = B.grid;
-    B2_CUDA(cudaMemcpyAsync(pat.wdesc.p, B.wdesc.data(), sizeof(int) * B.wdesc.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.wseq.p, B.wseq.data(), sizeof(int) * B.wseq.size(), cudaMemcpyHostToDevice, c->stream));
-    pat.border.alloc(n_slices);
-    pat.bptr.alloc((int64_t)B.brick_ptr.size());
-    pat.gptr.alloc((int64_t)B.gptr.size());
-    pat.glist.alloc((int64_t)B.glist.size());
-    pat.lcols.alloc(pat.slots);
-    B2_CUDA(cudaMemcpyAsync(pat.border.p, order, sizeof(int) * n_slices, cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.bptr.p, B.brick_ptr.data(), sizeof(int) * B.brick_ptr.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.gptr.p, B.gptr.data(), sizeof(int) * B.gptr.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.glist.p, B.glist.data(), sizeof(int) * B.glist.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(pat.lcols.p, B.lcols.data(), sizeof(unsigned short) * B.lcols.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    pat.n_bricks = B.n_bricks();
-    pat.brick_cap = B2_BRICK_CAP;
-    pat.n_gather = (int64_t)B.glist.size();
-    if (info != nullptr) {
-      info[0] = pat.n_bricks;
-      info[1] = pat.n_gather;
-      info[2] = B.max_gather;
-    }
-  });
-}
-
-// the brick builder on host arrays (no device, no context): the CPU test of the format
-int b2_host_build_bricks(int32_t n_rows, int32_t n_cols, const int32_t* slice_ptr, const int32_t* scols, const int32_t* order,
-                         int64_t n_hints, const int32_t* hint_ptr, int32_t cap, int32_t max_slices, int32_t n_threads,
-                         int64_t* n_bricks, int64_t* n_gather, int32_t* brick_ptr, int32_t* gptr, int32_t* glist, uint16_t* lcols,
-                         int32_t warps, int32_t grid, int32_t* wdesc, int32_t* wseq) {
-  try {
-    b2bricks::Bricks B;
-    b2bricks::build(n_rows, n_cols, slice_ptr, scols, order, hint_ptr, (int)n_hints, cap, max_slices, n_threads, B);
-    if (B.error) return -3;
-    if (warps > 0 && wdesc != nullptr && wseq != nullptr) {
-      b2bricks::assign_warps(n_rows, slice_ptr, order, warps, grid, B);
-      std::copy(B.wdesc.begin(), B.wdesc.end(), wdesc);
-      std::copy(B.wseq.begin(), B.wseq.end(), wseq);
-    }
-    *n_bricks = B.n_bricks();
-    *n_gather = (int64_t)B.glist.size();
-    if (brick_ptr) std::copy(B.brick_ptr.begin(), B.brick_ptr.end(), brick_ptr);
-    if (gptr) std::copy(B.gptr.begin(), B.gptr.end(), gptr);
-    if (glist) std::copy(B.glist.begin(), B.glist.end(), glist);
-    if (lcols) std::copy(B.lcols.begin(), B.lcols.end(), lcols);
-    return 0;
-  } catch (const std::exception& e) {
-    g_last_error = e.what();
-    return -99;
-  }
 }
 
 int b2_build_patterns(b2_ctx* c) {
@@ -2312,7 +2139,7 @@ int b2_mat_mult(b2_ctx* c, int mat, int comp, const double* x, double* y) {
     dy.alloc(pat->n_rows);
     B2_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * pat->n_cols, cudaMemcpyHostToDevice, c->stream));
     if (stride == 1) {
-      spmm(c, *pat, v->p, 1, dx.p, dy.p);  // the production SpMM (brick form when the pattern has one, else SELL-32)
+      spmm(c, *pat, v->p, 1, dx.p, dy.p);  // the production SELL kernel
     } else {
       DBuf<double> vals;
       const CSR* p2 = nullptr;
@@ -2816,9 +2643,6 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_min_slices") c->spmm_min_slices = std::max(0, value);
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
-    else if (k == "spmm_brick") c->spmm_brick = value;
-    else if (k == "spmm_brick_diag") c->spmm_brick_diag = value;
-    else if (k == "spmm_block") c->spmm_block = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
     else if (k == "peer_grid") c->peer_grid = std::max(1, std::min(value, 148));
@@ -2899,11 +2723,7 @@ int b2_bench_kernel(b2_ctx* c, int kernel, int reps, double* ms_per_launch, doub
       case 0:
       case 4:
       case 5:
-      case 3:  // algorithmic: K (not KP) components; brick form: 8 B value + 2 B list position per entry, the gather lists, x and y once
-        *bytes_per_launch = (c->spmm_brick && vv.has_bricks())
-                                ? 10.0 * vv.nnz + 4.0 * (double)vv.n_gather + 4.0 * (nV / 32 + 1) + 8.0 * K * (nV + nVc)
-                                : 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc);
-        break;
+      case 3: *bytes_per_launch = 12.0 * vv.nnz + 4.0 * (nV + 1) + 8.0 * K * (nV + nVc); break;  // algorithmic: K (not KP) components
       case 2: *bytes_per_launch = 12.0 * qq.nnz + 4.0 * (qq.n_rows + 1) + 8.0 * (qq.n_rows + qq.n_cols); break;
       case 1: {  // k_first_cells: A written once (interface rows: zero-fill + read-modify-write on top), cell data
                  // (dofs, nodes, scatter table), coordinates, uab/u1 read, b0 read, b_first + dinv written, uab = 1.5 u1 - .5 u2

@@ -8,11 +8,6 @@
 #include <string>
 
 #define B2_MAXK 3  // at most 3 velocity components solved together
-// brick SpMM (bricks.hpp, linalg.cuh: k_spmm_brick): entries of a brick's gather list (3 components x 8 B x 4352 =
-// 102 KB of shared memory per block, two blocks per SM) and 32-row slices per brick
-#define B2_BRICK_CAP 4352
-#define B2_BRICK_MAX_SLICES 32
-#define B2_BRICK_WARPS 16  // warps per block of the pipelined brick kernel (one block per SM)
 
 struct B2Error : std::runtime_error {
   int code;

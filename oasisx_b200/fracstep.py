@@ -200,15 +200,9 @@ class FractionalStep_AB_CN:
         Vs._b2_ctx = ctx  # a Projector on one of the solver's spaces shares its device context
         self._Q._scalar._b2_ctx = ctx
         ctx.build_patterns()
-        self._brick_info = None
         if deg_u == 2:  # tile-major schedule of the SELL slices (L1 reuse of the gathered vector)
             lat = getattr(mesh, "_lattice", None) if getattr(mesh, "_dof_order", "class") == "class" else None
             ctx.set_slice_order(L.PAT_VV, _fem.slice_order(Vs.tabulate_dof_coordinates()[: self._nV_owned], self._nV_owned, lat))
-            # brick form of the same operator pattern (x staged in shared memory, 16-bit column positions): opt-in,
-            # measured slower than the plain kernel in its first form
-            if options.get("spmm_bricks", False) and self._nV_owned >= 32:
-                order_b, hints = _fem.brick_schedule(Vs.tabulate_dof_coordinates()[: self._nV_owned], self._nV_owned, lat)
-                self._brick_info = ctx.set_bricks(L.PAT_VV, order_b, hints)
         self._bc_dofs: list[np.ndarray] = []
         self._bc_versions: list[tuple] = [() for _ in range(gdim)]
         self._bc_merge_maps: dict = {}

@@ -149,7 +149,7 @@ def make_oracle(msh, deg_u, tg: TaylorGreen, dt, **kw):
     return o
 
 
-def make_solver(msh, deg_u, tg: TaylorGreen, dt, solver_options=None, low_memory=False, bricks=False, **kw):
+def make_solver(msh, deg_u, tg: TaylorGreen, dt, solver_options=None, low_memory=False, **kw):
     """The set-up of ``demo/taylor_green.py:135-182`` against oasisx_b200."""
     import oasisx_b200 as oasisx
 
@@ -162,7 +162,7 @@ def make_solver(msh, deg_u, tg: TaylorGreen, dt, solver_options=None, low_memory
         lu = {"ksp_type": "preonly", "pc_type": "lu"}
         solver_options = {"tentative": lu, "pressure": lu, "scalar": lu}
     s = oasisx.FractionalStep_AB_CN(msh, ("Lagrange", deg_u), ("Lagrange", 1), bcs_u=bcs_u, bcs_p=[],
-                                    solver_options=solver_options, options={"low_memory_version": low_memory, "spmm_bricks": bricks}, **kw)
+                                    solver_options=solver_options, options={"low_memory_version": low_memory}, **kw)
     tg.t_u = -dt
     for i, f in enumerate(tg.components):
         s._u2[i].interpolate(f)
