@@ -107,6 +107,25 @@ class DirichletBC:
         arr[self._dofs] = self.current_values()
 
 
+def _same_topology(a, b) -> bool:
+    """The tags belong to the mesh (``bcs.py:223`` compares ``mesh.topology._cpp_object`` with the tags' topology)."""
+    unwrap = lambda t: getattr(t, "_cpp_object", t)
+    return a is b or unwrap(a) is unwrap(b) or bool(unwrap(a) == unwrap(b))
+
+
+def _cell_facets(mesh, fdim: int) -> np.ndarray:
+    """(n_local_cells, facets per cell) facet ids in reference-cell order (facet i opposite vertex i): the provider's
+    ``cell_entities`` or, for a DOLFINx mesh, its cell-to-facet connectivity (owned and ghost cells)."""
+    top = mesh.topology
+    if hasattr(top, "cell_entities"):
+        return top.cell_entities(fdim)
+    conn = top.connectivity(top.dim, fdim)
+    if conn is None:
+        top.create_connectivity(top.dim, fdim)
+        conn = top.connectivity(top.dim, fdim)
+    return np.asarray(conn.array).reshape(-1, top.dim + 1)
+
+
 class PressureBC:
     """Natural pressure condition on tagged facets (``bcs.py:142-268``): contributes
     ``int h n_i dv/dx_i ds`` to the tentative-velocity RHS and a homogeneous Dirichlet condition
@@ -118,7 +137,7 @@ class PressureBC:
 
     def create_bcs(self, V: _fem.FunctionSpace, Q: _fem.FunctionSpace):
         mesh = V.mesh
-        assert mesh.topology is self._subdomain_data.topology
+        assert _same_topology(mesh.topology, self._subdomain_data.topology)  # bcs.py:223
         tags = self._subdomain_data
         if isinstance(self._subdomain_id, tuple):
             facets = tags.indices[np.isin(tags.values, np.asarray(self._subdomain_id, dtype=np.int32))]
@@ -131,7 +150,7 @@ class PressureBC:
         dofs = _fem.locate_dofs_topological(Q, fdim, self._facets)
         self._bc = _DofBC(dofs, np.zeros(len(dofs)))  # bcs.py:245-253
         # (cell, local facet index) of every tagged facet: what the ds-integral kernel iterates over
-        cf = mesh.topology.cell_entities(fdim)
+        cf = _cell_facets(mesh, fdim)
         mask = np.isin(cf, self._facets)
         cells, local = np.nonzero(mask)
         local_cells = getattr(Q, "_local_cells", None)

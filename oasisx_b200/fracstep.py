@@ -113,8 +113,6 @@ class FractionalStep_AB_CN:
         if self._foreign:
             # a DOLFINx mesh: its partition, dof maps and index maps are consumed as they are (north_star: "reuses
             # DOLFINx's mesh partition"); also on one rank, where the ghost blocks are simply empty
-            if bcs_p:
-                raise NotImplementedError("PressureBC on a DOLFINx mesh needs its facet-cell connectivity: not wired yet")
             self._lp, self._V, self._Q, self._geom_x = _adapter.problem_from_dolfinx(mesh, deg_u, deg_p)
         elif hasattr(mesh, "is_global_boundary"):
             # slab-local box mesh (oasisx_b200.slab): this rank built only its own slab; same LocalProblem as the

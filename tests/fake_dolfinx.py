@@ -91,10 +91,15 @@ def make_fake(msh, deg_u, deg_p, nranks, rank, board=None, seed=0):
         ownV, ownQ = part._owners(V.dofmap.list, crank, V.num_dofs, nranks), part._owners(Q.dofmap.list, crank, Q.num_dofs, nranks)
     comm = FakeComm(rank, nranks, board if board is not None else {"phase": 0})
     tdim = msh.topology.dim
+    def connectivity(d0, d1):
+        # cell -> facet, local cells (owned then ghost) in reference-cell facet order; the facet ids are the provider's
+        assert d0 == tdim and d1 == tdim - 1
+        return types.SimpleNamespace(array=msh.topology.cell_entities(d1)[lp.cells].ravel())
+
     mesh = types.SimpleNamespace(
         comm=comm,
         geometry=types.SimpleNamespace(dim=msh.geometry.dim, x=msh.geometry.x, dofmap=lp.cell_nodes),
-        topology=types.SimpleNamespace(dim=tdim, create_connectivity=lambda a, b: None,
+        topology=types.SimpleNamespace(dim=tdim, create_connectivity=lambda a, b: None, connectivity=connectivity,
                                        index_map=lambda d: types.SimpleNamespace(size_local=lp.n_cells_owned,
                                                                                  num_ghosts=len(lp.cells) - lp.n_cells_owned)))
     spaces = {deg_u: FakeSpace(mesh, deg_u, lp.V, ownV, rng), ("q", deg_p): FakeSpace(mesh, deg_p, lp.Q, ownQ, rng)}
@@ -113,5 +118,10 @@ def make_fake(msh, deg_u, deg_p, nranks, rank, board=None, seed=0):
         loc = lsp.g2l[g]
         return Vf._fake_of_old[loc[loc >= 0]].astype(np.int32)
 
+    def fake_tags(tags):
+        """MeshTags of the provider mesh re-attached to the fake mesh (same facet ids)."""
+        return types.SimpleNamespace(topology=mesh.topology, dim=tags.dim, indices=tags.indices, values=tags.values, find=tags.find)
+
+    mesh.fake_tags = fake_tags
     mod = types.SimpleNamespace(fem=types.SimpleNamespace(functionspace=functionspace, locate_dofs_topological=locate_dofs_topological))
     return mod, mesh, lp

@@ -21,7 +21,7 @@ class Inlet:
         return (1 + self.t) * np.sin(np.pi * x[1])
 
 
-def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, device=0):
+def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, device=0, foreign=None):
     from oracle.ipcs_oracle import OracleIPCS
 
     def tagged(m):
@@ -40,6 +40,16 @@ def build(deg_u, body_force, solver_options=None, low_memory=False, comm=None, d
     msh = smsh if comm is None else bmesh.create_unit_square(None, 10, 10)
     tags = tagged(smsh)[4]
     dim, left, tb, right, _ = tagged(msh)
+    if foreign is not None:
+        # the solver sees the mesh as a DOLFINx mesh would arrive (tests/fake_dolfinx.py): oasisx_b200.adapter route,
+        # facets from the mesh's cell-to-facet connectivity, dofs located by "DOLFINx"
+        import sys
+
+        from fake_dolfinx import make_fake
+
+        mod, fmesh, _ = make_fake(msh, deg_u, 1, 1, 0)
+        foreign.setitem(sys.modules, "dolfinx", mod)
+        smsh, tags = fmesh, fmesh.fake_tags(tags)
     inlet = Inlet(0)
     bc_tb = DirichletBC(0.0, LocatorMethod.TOPOLOGICAL, (tags, 2))
     bc_inlet_x = DirichletBC(inlet.eval, LocatorMethod.TOPOLOGICAL, (tags, 1))
@@ -69,6 +79,25 @@ def _global_pressure_facets(msh, facets):
     cf = msh.topology.cell_entities(fdim)
     cells, local = np.nonzero(np.isin(cf, facets))
     return cells.astype(np.int32), local.astype(np.int32)
+
+
+def test_channel_with_pressure_bc_on_a_foreign_mesh(monkeypatch):
+    """The open channel (two Dirichlet BCs per component + PressureBC) with the mesh consumed through the DOLFINx
+    adapter: two inner-iterated steps against the oracle."""
+    kry = {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12}
+    cg = {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12}
+    s, o, inlet, _ = build(2, True, solver_options={"tentative": kry, "pressure": cg, "scalar": cg}, foreign=monkeypatch)
+    assert s._foreign and len(s._bcs_p[0]._facet_cells) == 10
+    dt, nu = 0.01, 0.5
+    inlet.t = 0.0
+    for n in range(2):
+        inlet.t += dt
+        s.solve(dt, nu, max_iter=2, max_error=1e-30)
+        o.solve(dt, nu, max_iter=2, max_error=1e-30)
+        for i in range(2):
+            assert relerr(s._u[i].x.array_ro(), o.u[i], vscale(o.u)) <= 1e-7
+        assert relerr(s._p.x.array_ro(), o.p) <= 1e-7
+    assert max(np.abs(p).max() for p in o.p_surf) > 1e-3  # the natural pressure term is there and matters
 
 
 @pytest.mark.parametrize("body_force", [True, False])

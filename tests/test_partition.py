@@ -151,6 +151,37 @@ def test_pressure_bc_facets_split_over_ranks(gdim, N):
     assert sorted(owned_seen) == sorted(glob)
 
 
+def _adapter_problems(msh, nranks, monkeypatch):
+    """``adapter.problem_from_dolfinx`` for every rank of a fake-DOLFINx partition of `msh`, all ranks driven in this one
+    process: pass 0 collects every rank's allgather contributions, later passes replay them.
+    Returns {rank: (lp, V, Q, x, provider lp, fake dolfinx module, fake mesh)}."""
+    import sys
+
+    from fake_dolfinx import _NeedOthers, make_fake
+    from oasisx_b200 import adapter
+
+    board = {"phase": 0}
+    out = {}
+
+    def sweep():
+        board["n"] = {}
+        for r in range(nranks):
+            mod, fmesh, lp = make_fake(msh, 2, 1, nranks, r, board)
+            monkeypatch.setitem(sys.modules, "dolfinx", mod)
+            try:
+                out[r] = adapter.problem_from_dolfinx(fmesh, 2, 1) + (lp, mod, fmesh)
+            except _NeedOthers:
+                pass
+        board["known"] = {k: v for k, v in board.get("calls", {}).get(0, {}).items() if len(v) == nranks}
+
+    for _ in range(6):  # every allgather call becomes known one round at a time
+        sweep()
+        if len(out) == nranks:
+            break
+    assert len(out) == nranks
+    return out
+
+
 @pytest.mark.parametrize("gdim,N,nranks", [(3, 4, 1), (3, 6, 2), (2, 12, 3)])
 def test_dolfinx_adapter_with_a_duck_typed_index_map(gdim, N, nranks, monkeypatch):
     """``adapter.problem_from_dolfinx`` on fake DOLFINx objects (contiguous owned global ranges, SHUFFLED ghost blocks):
@@ -158,40 +189,8 @@ def test_dolfinx_adapter_with_a_duck_typed_index_map(gdim, N, nranks, monkeypatc
     every owner value to its ghost copies -- and its cell dof maps address the same global dofs as the provider's."""
     import sys
 
-    from fake_dolfinx import _NeedOthers, make_fake
-    from oasisx_b200 import adapter
-
     msh = make_mesh(gdim, N)
-    board = {"phase": 0}
-    out = {}
-    for attempt in range(2):  # pass 0 collects every rank's allgather contributions, pass 1 replays them
-        board["n"] = {}
-        for r in range(nranks):
-            mod, fmesh, lp = make_fake(msh, 2, 1, nranks, r, board)
-            monkeypatch.setitem(sys.modules, "dolfinx", mod)
-            try:
-                out[r] = adapter.problem_from_dolfinx(fmesh, 2, 1) + (lp, mod)
-            except _NeedOthers:
-                pass
-        board["known"] = {k: v for k, v in board.get("calls", {}).get(0, {}).items()}
-        # allgather call k of every rank is now known; further calls need another round
-        for k in list(board["known"]):
-            if len(board["known"][k]) < nranks:
-                del board["known"][k]
-        if len(out) == nranks:
-            break
-        for _ in range(4):  # later allgather calls (second space) become known one round at a time
-            board["n"] = {}
-            for r in range(nranks):
-                mod, fmesh, lp = make_fake(msh, 2, 1, nranks, r, board)
-                monkeypatch.setitem(sys.modules, "dolfinx", mod)
-                try:
-                    out[r] = adapter.problem_from_dolfinx(fmesh, 2, 1) + (lp, mod)
-                except _NeedOthers:
-                    pass
-            board["known"] = {k: v for k, v in board["calls"][0].items() if len(v) == nranks}
-            if len(out) == nranks:
-                break
+    out = _adapter_problems(msh, nranks, monkeypatch)
     assert len(out) == nranks
     for name in ("V", "Q"):
         sps = [getattr(out[r][0], name) for r in range(nranks)]
@@ -214,7 +213,7 @@ def test_dolfinx_adapter_with_a_duck_typed_index_map(gdim, N, nranks, monkeypatc
                 np.testing.assert_array_equal(v, gvec[s.l2g])
     # the adapter space: coordinates follow the regrouped numbering; boundary dofs located through "DOLFINx" map into it
     for r in range(nranks):
-        lp_a, Va, Qa, x, lp_p, mod = out[r]
+        lp_a, Va, Qa, x, lp_p, mod, _ = out[r]
         monkeypatch.setitem(sys.modules, "dolfinx", mod)  # this rank's "DOLFINx"
         Vs = Va._scalar
         assert Vs.num_dofs == lp_a.V.n_local and Va.bs == gdim and Va.sub(0).collapse()[0] is Vs
@@ -232,3 +231,36 @@ def test_dolfinx_adapter_with_a_duck_typed_index_map(gdim, N, nranks, monkeypatc
         for k in range(gdim):
             on_bd |= np.isclose(xb[:, k], lo[k]) | np.isclose(xb[:, k], hi[k])
         assert on_bd.all() and len(d) > 0
+
+
+@pytest.mark.parametrize("gdim,N,nranks", [(2, 10, 1), (2, 10, 2), (3, 4, 2)])
+def test_pressure_bc_through_the_dolfinx_adapter(gdim, N, nranks, monkeypatch):
+    """``PressureBC.create_bcs`` on a foreign (DOLFINx) mesh: the tagged facets come from the mesh's cell-to-facet
+    connectivity (``topology.connectivity(tdim, tdim - 1)``), the pressure Dirichlet dofs from
+    ``dolfinx.fem.locate_dofs_topological`` mapped through the adapter's regrouped ghost block -- the same facets and the
+    same physical dofs as the built-in provider finds on the same partition."""
+    import sys
+
+    from oasisx_b200 import PressureBC, mesh as bmesh
+
+    msh = make_mesh(gdim, N)
+    fdim = gdim - 1
+    right = bmesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[0], 1.0))
+    tags = bmesh.meshtags(msh, fdim, np.sort(right), np.full(len(right), 3, dtype=np.int32))
+    gV, gQ = fem.functionspace(msh, ("Lagrange", 2)), fem.functionspace(msh, ("Lagrange", 1))
+    out = _adapter_problems(msh, nranks, monkeypatch)
+    for r in range(nranks):
+        lp_a, Va, Qa, x, lp_p, mod, fmesh = out[r]
+        monkeypatch.setitem(sys.modules, "dolfinx", mod)
+        bc = PressureBC(lambda x: 1.0 + x[1], (fmesh.fake_tags(tags), 3))
+        bc.create_bcs(Va._scalar, Qa)
+        # the provider on the same partition
+        V, Q = fem.LocalFunctionSpace(gV, lp_p.V, 1), fem.LocalFunctionSpace(gQ, lp_p.Q, 1)
+        V._local_cells = Q._local_cells = lp_p.cells
+        ref = PressureBC(lambda x: 1.0 + x[1], (tags, 3))
+        ref.create_bcs(V, Q)
+        assert sorted(zip(bc._facet_cells.tolist(), bc._facet_local.tolist())) == sorted(zip(ref._facet_cells.tolist(), ref._facet_local.tolist()))
+        key = lambda X: sorted(map(tuple, np.round(X, 12).tolist()))
+        assert key(Qa.tabulate_dof_coordinates()[bc.bc.dofs]) == key(Q.tabulate_dof_coordinates()[ref.bc.dofs])
+        # the nodal boundary pressure lives in the adapter's numbering
+        np.testing.assert_allclose(bc._h, 1.0 + Qa.tabulate_dof_coordinates()[:, 1])
