@@ -1,6 +1,7 @@
-"""Multi-GPU parity: 2 (and 4, if present) ranks, one per GPU, NCCL halo + all-reduce, against the CPU
-oracle.  Skipped on boxes with a single GPU (the host-side plans are covered on CPU by
-tests/test_partition.py)."""
+"""Multi-GPU parity: 2, 4 and 8 ranks, one per GPU, against the CPU oracle / CPU port; peer-memory collectives and the
+NCCL fallback.  Every rank builds only its slab of the mesh (oasisx_b200/slab.py); one case keeps the replicated mesh
++ partition route covered.  Skipped on boxes with fewer GPUs (the host-side plans are covered on CPU by
+tests/test_partition.py and tests/test_slab.py)."""
 import os
 import subprocess
 import sys
@@ -39,3 +40,15 @@ def test_multirank_matches_oracle(nranks, mode, mesh, steps, peer):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("MR_OK") == nranks
     print(res.stdout[-1500:])
+
+
+def test_multirank_replicated_mesh_route():
+    """B200_GLOBAL_MESH=1: every rank builds the whole mesh and oasisx_b200.partition cuts it (the route the slab-local
+    provider replaced as the default; still what a user-constructed Mesh object takes)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29799", os.path.join(HERE, "mr_worker.py"), "8", "3", "krylov"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, B200_PEER="1", B200_GLOBAL_MESH="1"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("MR_OK") == 2
