@@ -111,3 +111,57 @@ def test_global_mesh_switch(monkeypatch):
 def test_too_many_ranks_is_an_error():
     with pytest.raises(ValueError):
         bmesh.create_box(FakeComm(3, 4), [[0, 0, 0], [1, 1, 1]], [2, 2, 2])
+
+
+def test_slab_halo_over_gloo_two_ranks(tmp_path):
+    """world_size 2 on CPU (torch.distributed/gloo for the data, oasisx_b200.comm.HostComm as the mesh communicator):
+    each rank builds ONLY its slab, the ranks cross-check their halo plans, exchange owner values with exactly the
+    message pattern of the device halo (send_idx / recv_off) and all-reduce a dot product over the owned dofs -- the
+    result is the global vector / the global dot product, which no rank ever assembled from a global mesh."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "slab2.py"
+    script.write_text(
+        "import os, sys\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import numpy as np, torch, torch.distributed as dist\n"
+        "from oasisx_b200 import mesh as bmesh, partition as part, slab\n"
+        "from oasisx_b200.comm import HostComm\n"
+        "dist.init_process_group('gloo')\n"
+        "r, n = dist.get_rank(), dist.get_world_size()\n"
+        "os.environ['MASTER_PORT'] = str(int(os.environ['MASTER_PORT']) + 17)  # HostComm's own channel\n"
+        "comm = HostComm.from_env()\n"
+        "msh = bmesh.create_box(comm, [[-1, -1, -1], [1, 1, 1]], [5, 4, 6])\n"
+        "assert isinstance(msh, slab.SlabMesh) and msh.num_cells < msh.num_cells_global\n"
+        "lp, V, Q = slab.local_problem(msh, 2, 1)\n"
+        "for name, s in (('V', lp.V), ('Q', lp.Q)):\n"
+        "    part.check_halo_counts(comm, s.halo, name)\n"
+        "    f = lambda x: np.sin(3 * x[:, 0]) + x[:, 1] * x[:, 2]  # a field known from the coordinates alone\n"
+        "    v = torch.full((s.n_local,), float('nan'), dtype=torch.float64)\n"
+        "    v[: s.n_owned] = torch.from_numpy(f(s.x[: s.n_owned]))\n"
+        "    ops, bufs = [], []\n"
+        "    for k, q in enumerate(s.halo.neighbors):\n"
+        "        send = v[torch.from_numpy(s.halo.send_idx[s.halo.send_off[k]:s.halo.send_off[k+1]].astype(np.int64))].contiguous()\n"
+        "        recv = torch.empty(int(s.halo.recv_off[k+1] - s.halo.recv_off[k]), dtype=torch.float64)\n"
+        "        bufs.append((k, recv))\n"
+        "        ops += [dist.P2POp(dist.isend, send, int(q)), dist.P2POp(dist.irecv, recv, int(q))]\n"
+        "    for w in dist.batch_isend_irecv(ops): w.wait()\n"
+        "    for k, recv in bufs:\n"
+        "        v[s.n_owned + int(s.halo.recv_off[k]): s.n_owned + int(s.halo.recv_off[k+1])] = recv\n"
+        "    assert np.array_equal(v.numpy(), f(s.x)), (r, name)\n"
+        "    t = torch.tensor([float(s.n_owned), float(np.sum(s.l2g[: s.n_owned]))], dtype=torch.float64)\n"
+        "    dist.all_reduce(t)\n"
+        "    assert t[0].item() == s.n_global and t[1].item() == s.n_global * (s.n_global - 1) / 2, (r, name)  # every dof owned once\n"
+        "comm.Barrier()\n"
+        "dist.destroy_process_group()\n"
+        "print('ok', r)\n"
+    )
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29633", str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
