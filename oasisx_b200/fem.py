@@ -74,6 +74,46 @@ def _class_order(x: np.ndarray, lattice) -> np.ndarray:
     return np.lexsort((idx[:, 0], idx[:, 1], idx[:, 2], cls))
 
 
+def lattice_node_index(mesh) -> np.ndarray:
+    """(n_nodes, gdim) lattice indices of the geometry nodes of a provider-built box/rectangle mesh (lexicographic node
+    numbering, x fastest); a slab-local mesh carries its own table."""
+    idx = getattr(mesh, "_node_index", None)
+    if idx is None:
+        shape = mesh._shape
+        v = np.arange(mesh.geometry.x.shape[0], dtype=np.int64)
+        cols = []
+        for a in range(len(shape)):
+            cols.append(v % (shape[a] + 1))
+            v = v // (shape[a] + 1)
+        idx = mesh._node_index = np.stack(cols, axis=1)
+    return idx
+
+
+def lattice_dof_ids(hidx: np.ndarray, shape, degree: int, order: str) -> np.ndarray:
+    """Dof number of the lattice points `hidx` (half-step indices for degree 2, node indices for degree 1) on a box of
+    `shape` cubes: the closed form of `_class_order` ("class", degree 2: parity class of the half-step index, then
+    lexicographic z, y, x inside the class) or of `_lex_order` (everything else)."""
+    d = len(shape)
+    h = [hidx[:, a] for a in range(d)]
+    if degree == 1 or order != "class":
+        n = [(s + 1) if degree == 1 else (2 * s + 1) for s in shape]
+        g = h[d - 1].copy()
+        for a in range(d - 2, -1, -1):
+            g = g * n[a] + h[a]
+        return g
+    par = [h[a] & 1 for a in range(d)]
+    cls = par[0] + 2 * par[1] + (4 * par[2] if d == 3 else 0)
+    sizes = np.zeros(8 if d == 3 else 4, dtype=np.int64)
+    for c in range(len(sizes)):  # N + 1 lattice points of even parity along an axis, N of odd parity
+        sizes[c] = int(np.prod([shape[a] + 1 - ((c >> a) & 1) for a in range(d)]))
+    offset = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    j = [h[a] >> 1 for a in range(d)]
+    g = j[d - 1].copy()
+    for a in range(d - 2, -1, -1):
+        g = g * np.where(par[a] == 0, shape[a] + 1, shape[a]) + j[a]
+    return offset[cls] + g
+
+
 def _lex_order(x: np.ndarray) -> np.ndarray:
     """Permutation sorting points by (z, y, x): spatial locality for SpMV gathers."""
     span = max(float(np.ptp(x)), 1e-300)

@@ -129,33 +129,6 @@ def create_slab_mesh(comm, points, n, gdim: int) -> SlabMesh:
     return msh
 
 
-def _global_ids(hidx: np.ndarray, shape, degree: int, order: str) -> np.ndarray:
-    """Global dof number of the lattice points `hidx` (half-step indices for degree 2, node indices for degree 1):
-    the closed form of ``fem._class_order`` ("class", degree 2) or ``fem._lex_order`` (everything else)."""
-    d = len(shape)
-    h = [hidx[:, a] for a in range(d)]
-    if degree == 1 or order != "class":
-        n = [(s + 1) if degree == 1 else (2 * s + 1) for s in shape]
-        g = h[d - 1].copy()
-        for a in range(d - 2, -1, -1):
-            g = g * n[a] + h[a]
-        return g
-    par = [h[a] & 1 for a in range(d)]
-    cls = par[0] + 2 * par[1] + (4 * par[2] if d == 3 else 0)
-    # number of lattice points of parity p along axis a: N+1 even ones, N odd ones
-    cnt = lambda a, p: np.where(p == 0, shape[a] + 1, shape[a])
-    sizes = np.zeros(8 if d == 3 else 4, dtype=np.int64)
-    for c in range(len(sizes)):
-        bits = [(c >> a) & 1 for a in range(d)]
-        sizes[c] = int(np.prod([shape[a] + 1 - bits[a] for a in range(d)]))
-    offset = np.concatenate([[0], np.cumsum(sizes)[:-1]])
-    j = [h[a] >> 1 for a in range(d)]
-    g = j[d - 1].copy()
-    for a in range(d - 2, -1, -1):
-        g = g * cnt(a, par[a]) + j[a]
-    return offset[cls] + g
-
-
 def _owner_of(h_last: np.ndarray, lrank: np.ndarray, degree: int) -> np.ndarray:
     """Lowest rank whose cells touch the lattice plane/point with last-axis (half-)index `h_last`."""
     hh = h_last * 2 if degree == 1 else h_last
@@ -197,7 +170,7 @@ class SlabFunctionSpace(fem.FunctionSpace):
         order_kind = getattr(mesh, "_dof_order", "class")
         if order_kind == "sigma":
             raise NotImplementedError("the window-sorted dof order has no closed form: use 'class' or 'generic' on several ranks")
-        gid = _global_ids(hidx, mesh._shape, degree, order_kind)
+        gid = fem.lattice_dof_ids(hidx, mesh._shape, degree, order_kind)
         owner = _owner_of(hidx[:, d - 1], mesh._layer_ranks, degree)
         rank = int(mesh.comm.rank)
         mine = owner == rank
