@@ -160,7 +160,6 @@ struct DVec {
 struct b2_ctx {
   int device = 0, nranks = 1, rank = 0, sm = 148;
   int spmm_blocks_per_sm = 8, spmm_unroll = 8, spmm_mode = 0, spmm_stream = 1;  // sweep: tools/sweep_spmm.py
-  int spmm_warp_dots = 0;    // tuning "spmm_warp_dots": fused dot products of k_spmm accumulated per warp instead of per thread
   int spmm_min_slices = 1;   // tuning "spmm_min_slices": 0 = round 1's fixed persistent grid (sm x spmm_blocks_per_sm), else equal shares
   cudaStream_t stream = nullptr;
   std::string err;
@@ -484,18 +483,6 @@ void launch_spmm_u(b2_ctx* c, const CSR& pat, const double* vals, const double* 
 #define B2_SPMM(STREAM_, RS_)                                                                                            \
   B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, STREAM_, RS_>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p, vals,    \
             pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale)
-  if constexpr (DOT > 0 && UNROLL == 8) {
-    if (c->spmm_warp_dots && c->spmm_stream) {  // running dot products per warp (tuning "spmm_warp_dots")
-      if (rscale != nullptr)
-        B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true, true, 2048 / BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p,
-                  vals, pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
-      else
-        B2_LAUNCH(c, (k_spmm<K, DOT, UNROLL, BLOCK, true, false, 2048 / BLOCK, true>), grid, BLOCK, pat.n_rows, pat.slice_ptr.p, pat.scols.p,
-                  vals, pat.order.p, x, ld, y, w, st, fin, c->partials.p, c->d_counter, red_ptr(c), rscale);
-      reduce_finish_host(c, fin, DOT * K);
-      return;
-    }
-  }
   if (c->spmm_stream) {
     if (rscale != nullptr) B2_SPMM(true, true);
     else B2_SPMM(true, false);
@@ -2656,7 +2643,6 @@ int b2_set_tuning(b2_ctx* c, const char* key, int value) {
     else if (k == "spmm_min_slices") c->spmm_min_slices = std::max(0, value);
     else if (k == "spmm_mode") c->spmm_mode = value;
     else if (k == "spmm_stream") c->spmm_stream = value;
-    else if (k == "spmm_warp_dots") c->spmm_warp_dots = value;
     else if (k == "mg_dense") c->mg_dense_on = value;
     else if (k == "graphs") c->use_graphs = value;
     else if (k == "peer_grid") c->peer_grid = std::max(1, std::min(value, 148));

@@ -312,10 +312,7 @@ __global__ void k_sell_convert(int n_rows, const int* __restrict__ rowptr, const
 // a time, so the warps of a block gather from the same neighbourhood of x concurrently and share
 // those lines in L1 instead of each pulling them through the L2 fabric.
 // MINB: resident blocks per SM the register allocation is bounded for (8 x 256 threads = 32 registers, 6 = 40).
-// WD: the running dot products are kept per WARP (a warp-shuffle sum after every slice, lane 0 accumulates) instead of
-// per thread: 8 * ND doubles of shared memory per block instead of 256 * ND (12 KB per block, 96 KB per SM for two
-// fused dot products of three components -- shared memory the L1 cannot use for the gathered vector).
-template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, bool RS = false, int MINB = 2048 / BLOCK, bool WD = false>
+template <int K, int DOT, int UNROLL, int BLOCK, bool STREAM, bool RS = false, int MINB = 2048 / BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ cols,
        const double* __restrict__ vals, const int* __restrict__ order, const double* __restrict__ x, int ld,
@@ -330,17 +327,10 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   // the running dot products live in shared memory between slices: keeping them in registers across
   // the gather loop costs 8-16 registers, i.e. one to three resident blocks per SM on a kernel whose
   // speed is set by the number of loads in flight
-  __shared__ double sdots[DOT == 0 ? 1 : ND][DOT == 0 ? 1 : (WD ? BLOCK / 32 : BLOCK)];
+  __shared__ double sdots[DOT == 0 ? 1 : ND][DOT == 0 ? 1 : BLOCK];
   if constexpr (DOT > 0) {
-    if constexpr (WD) {
-      if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < ND; ++i) sdots[i][wib] = 0.0;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < ND; ++i) sdots[i][threadIdx.x] = 0.0;
-    }
+    for (int i = 0; i < ND; ++i) sdots[i][threadIdx.x] = 0.0;
   }
   for (int i = blockIdx.x * WPB + wib; i < n_slices; i += gridDim.x * WPB) {
     const int s = order != nullptr ? __ldg(order + i) : i;
@@ -377,25 +367,6 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
 #pragma unroll
       for (int k = 0; k < K; ++k) acc[k] = fma(v, __ldg(x + (size_t)k * ld + c), acc[k]);
     }
-    if constexpr (DOT >= 1 && WD) {
-      // all 32 lanes take part in the warp sums; a row beyond n_rows has zero values (acc = 0) and reads w = 0
-      const bool live = row < n_rows;
-      double rs = 1.0;
-      if constexpr (RS) rs = live ? __ldg(rscale + row) : 1.0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const double wk = live ? __ldg(w + (size_t)k * ld + row) : 0.0;
-        if constexpr (RS) acc[k] *= rs;
-        if (live) y[(size_t)k * ld + row] = acc[k];
-        const double t1 = warp_sum(acc[k] * wk);
-        if (lane == 0) sdots[k][wib] += t1;
-        if constexpr (DOT == 2) {
-          const double t2 = warp_sum(acc[k] * acc[k]);
-          if (lane == 0) sdots[K + k][wib] += t2;
-        }
-      }
-      continue;
-    }
     if (row < n_rows) {
       // epilogue: every load is issued before the first use, so that one memory latency is exposed per slice, not
       // one per dependent step (the row scale alone cost +45 us of 565 when it was loaded, used, and only then w)
@@ -411,11 +382,11 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
       }
 #pragma unroll
       for (int k = 0; k < K; ++k) y[(size_t)k * ld + row] = acc[k];
-      if constexpr (DOT >= 1 && !WD) {
+      if constexpr (DOT >= 1) {
 #pragma unroll
         for (int k = 0; k < K; ++k) sdots[k][threadIdx.x] = fma(acc[k], wv[k], sdots[k][threadIdx.x]);
       }
-      if constexpr (DOT == 2 && !WD) {
+      if constexpr (DOT == 2) {
 #pragma unroll
         for (int k = 0; k < K; ++k) sdots[K + k][threadIdx.x] = fma(acc[k], acc[k], sdots[K + k][threadIdx.x]);
       }
@@ -423,13 +394,8 @@ k_spmm(int n_rows, const int* __restrict__ slice_ptr, const int* __restrict__ co
   }
   if constexpr (DOT > 0) {
     double dots[ND];
-    if constexpr (WD) {
 #pragma unroll
-      for (int i = 0; i < ND; ++i) dots[i] = lane == 0 ? sdots[i][wib] : 0.0;
-    } else {
-#pragma unroll
-      for (int i = 0; i < ND; ++i) dots[i] = sdots[i][threadIdx.x];
-    }
+    for (int i = 0; i < ND; ++i) dots[i] = sdots[i][threadIdx.x];
     reduce_finish<ND>(dots, partials, counter, fin, st, red_out);
   }
 }
