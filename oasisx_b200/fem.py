@@ -16,7 +16,7 @@ from typing import Callable
 
 import numpy as np
 
-from .mesh import _EDGE_VERTS, Mesh
+from .mesh import _BOX_CELLS, _EDGE_VERTS, Mesh
 
 __all__ = [
     "Constant",
@@ -114,6 +114,50 @@ def lattice_dof_ids(hidx: np.ndarray, shape, degree: int, order: str) -> np.ndar
     return offset[cls] + g
 
 
+def _lattice_p2(mesh):
+    """(dof coordinates, cell dofs) of the P2 space on a provider-built box/rectangle mesh in the stencil-class order,
+    from closed forms: the 3^d lattice points of every cube get their dof numbers by `lattice_dof_ids`, a cell's ten
+    (six) dofs are a fixed selection of them, and the coordinates of a class are a tensor product of per-axis tables.
+    No edge table, no sort -- the general route spends most of the host set-up of a 96^3 box in np.unique over 37 M cell
+    edges and a four-key lexsort of 7 M points.  Same numbers and bitwise the same coordinates as the general route
+    (tests/test_host.py)."""
+    d, shape = mesh.geometry.dim, mesh._shape
+    p0, p1 = mesh._box
+    # per-axis coordinate of a half-step index: a node's own coordinate, or the midpoint of its two neighbours --
+    # exactly what 0.5 * (x_a + x_b) gives for an edge whose end points differ by at most one step along the axis
+    tabs = []
+    for a in range(d):
+        ax = np.linspace(p0[a], p1[a], shape[a] + 1)
+        t = np.empty(2 * shape[a] + 1)
+        t[0::2] = ax
+        t[1::2] = 0.5 * (ax[:-1] + ax[1:])
+        tabs.append(t)
+    n = int(np.prod([2 * s_ + 1 for s_ in shape]))
+    x = np.zeros((n, 3))
+    off = 0
+    for cls in range(2**d):  # classes in order, lexicographic (z, y, x) inside: a tensor product per class
+        sel = [tabs[a][(cls >> a) & 1::2] for a in range(d)]
+        grids = np.meshgrid(*sel[::-1], indexing="ij")  # slowest axis first
+        m = grids[0].size
+        for a in range(d):
+            x[off:off + m, a] = grids[d - 1 - a].ravel()
+        off += m
+    # dof numbers of the 3^d lattice points of every cube, cube index lexicographic with x fastest (the cell order)
+    cube = np.stack([g.ravel() for g in np.meshgrid(*[np.arange(s_) for s_ in shape[::-1]], indexing="ij")][::-1], axis=1)
+    pts = {}
+    for o in np.ndindex(*(3,) * d):
+        pts[o] = lattice_dof_ids(2 * cube + np.array(o), shape, 2, "class")
+    corner = lambda c: tuple((c >> a) & 1 for a in range(d))
+    cols = []
+    for cell in _BOX_CELLS[d]:
+        cv = [corner(c) for c in cell]
+        verts = [pts[tuple(2 * o for o in v)] for v in cv]
+        edges = [pts[tuple(cv[a][k] + cv[b][k] for k in range(d))] for a, b in _EDGE_VERTS[d]]
+        cols.append(np.stack(verts + edges, axis=1))
+    cell_dofs = np.stack(cols, axis=1).reshape(-1, cols[0].shape[1])  # (cube, cell in cube) -> rows
+    return x, cell_dofs
+
+
 def _lex_order(x: np.ndarray) -> np.ndarray:
     """Permutation sorting points by (z, y, x): spatial locality for SpMV gathers."""
     span = max(float(np.ptp(x)), 1e-300)
@@ -149,6 +193,12 @@ class FunctionSpace:
             self._scalar = _scalar
             return
         self._scalar = self
+        if (degree == 2 and getattr(mesh, "_canonical", False) and getattr(mesh, "_lattice", None) is not None
+                and getattr(mesh, "_dof_order", "class") == "class"):
+            self._x, cell_dofs = _lattice_p2(mesh)
+            self.dofmap = DofMap(cell_dofs, IndexMap(self._x.shape[0]), 1)
+            self._lattice_ids = True
+            return
         cells = mesh.geometry.dofmap.astype(np.int64)
         nv = mesh.geometry.x.shape[0]
         if degree == 1:
@@ -203,7 +253,15 @@ class FunctionSpace:
         nvloc = cells.shape[1]
         vdof[cells.ravel()] = self.dofmap.list[:, :nvloc].ravel()
         dofs = [vdof[verts]]
-        if self.degree == 2 and edim >= 1:
+        if self.degree == 2 and edim >= 1 and getattr(self, "_lattice_ids", False):
+            # closed form: the midpoint of the edge between two vertices of an entity is the lattice point at the sum of
+            # their lattice indices (no edge table)
+            nidx, shape = lattice_node_index(self.mesh), self.mesh._shape
+            k = ents.shape[1]
+            for a in range(k):
+                for b in range(a + 1, k):
+                    dofs.append(lattice_dof_ids(nidx[ents[:, a]] + nidx[ents[:, b]], shape, 2, "class"))
+        elif self.degree == 2 and edim >= 1:
             nv = self.mesh.geometry.x.shape[0]
             edges = top.entities(1)
             ekey = edges[:, 0] * nv + edges[:, 1]  # sorted by construction (np.unique)

@@ -60,6 +60,11 @@ _EDGE_VERTS = {
     2: np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int64),
     3: np.array([[2, 3], [1, 3], [1, 2], [0, 3], [0, 2], [0, 1]], dtype=np.int64),
 }
+# cells of one square / cube of the box providers as corner numbers (corner c has offsets (c & 1, c >> 1 & 1, c >> 2))
+_BOX_CELLS = {
+    2: [(0, 1, 3), (0, 2, 3)],
+    3: [(0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (0, 3, 2, 7), (0, 6, 4, 7), (0, 2, 6, 7)],
+}
 # local vertices of the facets (facet i is opposite vertex i)
 _FACET_VERTS = {
     2: np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int64),
@@ -224,6 +229,7 @@ def create_rectangle(comm, points, n, cell_type=CellType.triangle) -> Mesh:
     msh._lattice = (np.array([x0, y0, 0.0]), np.array([(x1 - x0) / nx, (y1 - y0) / ny, 1.0]))
     msh._shape = (nx, ny)
     msh._box = (np.array([x0, y0]), np.array([x1, y1]))
+    msh._canonical = True  # nodes lexicographic, cells square by square in the order above (fem._lattice_p2 relies on it)
     return msh
 
 
@@ -248,7 +254,7 @@ def create_box(comm, points, n, cell_type=CellType.tetrahedron) -> Mesh:
     sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
     v0 = (iz * sz + iy * sy + ix).ravel()
     v = [v0, v0 + sx, v0 + sy, v0 + sx + sy, v0 + sz, v0 + sx + sz, v0 + sy + sz, v0 + sx + sy + sz]
-    tets = [(0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (0, 3, 2, 7), (0, 6, 4, 7), (0, 2, 6, 7)]
+    tets = _BOX_CELLS[3]
     cells = np.empty((len(v0), 6, 4), dtype=np.int64)
     for t, tet in enumerate(tets):
         cells[:, t] = np.stack([v[a] for a in tet], axis=1)
@@ -256,6 +262,7 @@ def create_box(comm, points, n, cell_type=CellType.tetrahedron) -> Mesh:
     msh._lattice = (p0.copy(), (p1 - p0) / np.array([nx, ny, nz], dtype=np.float64))
     msh._shape = (nx, ny, nz)
     msh._box = (p0.copy(), p1.copy())
+    msh._canonical = True  # nodes lexicographic, cells cube by cube in the order above (fem._lattice_p2 relies on it)
     return msh
 
 

@@ -209,3 +209,23 @@ def test_host_comm_three_ranks_no_pickle(tmp_path):
              for r in range(3)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs) and all("COMM_OK" in o for o in outs)
+
+
+@pytest.mark.parametrize("kind,shape", [("box", (5, 4, 3)), ("rect", (7, 5)), ("box", (2, 3, 9))])
+def test_closed_form_p2_space_is_the_general_route_bit_for_bit(kind, shape):
+    """Box/rectangle meshes number their P2 dofs from the lattice in closed form (fem._lattice_p2: no edge table, no
+    sort); the general route (edge table + class-order sort) must give the same cell dofs, bitwise the same dof
+    coordinates and the same closure dofs of facets, edges and vertices."""
+    make = lambda: (bmesh.create_box(None, [[0, -1, 0.5], [1, 2, 3]], list(shape)) if kind == "box"
+                    else bmesh.create_rectangle(None, [[0, -1], [1, 2.5]], list(shape)))
+    fast_mesh, slow_mesh = make(), make()
+    slow_mesh._canonical = False
+    V, G = fem.functionspace(fast_mesh, ("Lagrange", 2)), fem.functionspace(slow_mesh, ("Lagrange", 2))
+    assert getattr(V, "_lattice_ids", False) and not getattr(G, "_lattice_ids", False)
+    assert np.array_equal(V.dofmap.list, G.dofmap.list)
+    assert np.array_equal(V.tabulate_dof_coordinates(), G.tabulate_dof_coordinates())
+    d = fast_mesh.topology.dim
+    fac = bmesh.exterior_facet_indices(fast_mesh.topology)
+    assert np.array_equal(fac, bmesh.exterior_facet_indices(slow_mesh.topology))
+    for edim, ents in ((d - 1, fac), (1, np.arange(0, fast_mesh.topology.num_entities(1), 3)), (0, np.arange(0, len(fast_mesh.geometry.x), 2))):
+        assert np.array_equal(V.entity_closure_dofs(edim, ents), G.entity_closure_dofs(edim, ents))
