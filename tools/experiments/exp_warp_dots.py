@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """k_spmm with its fused dot products accumulated per warp (tuning "spmm_warp_dots") against per thread: timings of the
 SpMM with one / two fused dot products at 96^3 (b2_bench_kernel 4 / 5), whole-step time, and the fields of three steps on
-a small box either way.  Usage: python tools/exp_warp_dots.py [mesh]"""
+a small box either way.  NEGATIVE RESULT: the tuning key exists only in commit 9937232; kept as the
+script that produced profiles/r02_spmm_warp_dots_96cube.txt.  Usage: python tools/experiments/exp_warp_dots.py [mesh]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
