@@ -19,7 +19,9 @@ from . import fem
 from .mesh import Mesh
 from .partition import HaloPlan, LocalProblem, LocalSpace
 
-_TETS = [(0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (0, 3, 2, 7), (0, 6, 4, 7), (0, 2, 6, 7)]
+from .mesh import _BOX_CELLS  # noqa: E402
+
+_TETS = _BOX_CELLS[3]
 
 
 def layer_ranks(n_layers: int, nranks: int) -> np.ndarray:
@@ -136,6 +138,49 @@ def _owner_of(h_last: np.ndarray, lrank: np.ndarray, degree: int) -> np.ndarray:
     return lrank[layer].astype(np.int32)
 
 
+def _slab_p2_block(mesh: SlabMesh):
+    """(coordinates, cell dofs, half-step lattice indices) of the P2 dofs of a slab mesh, numbered along the slab's own
+    block of the half-step lattice (x fastest) -- a preliminary local numbering the caller reorders owned-first.  Closed
+    forms as in ``fem._lattice_p2``: no edge table, no sort over cell edges (which took most of the per-rank set-up)."""
+    from .mesh import _BOX_CELLS, _EDGE_VERTS
+
+    d, shape = mesh.geometry.dim, mesh._shape
+    p0, p1 = mesh._box
+    l0, _, lg = mesh._layers
+    lo = [0] * (d - 1) + [2 * l0]                                   # first half-step index of the block per axis
+    dims = [2 * shape[a] + 1 for a in range(d - 1)] + [2 * (lg - l0) + 1]
+    tabs = []
+    for a in range(d):
+        ax = np.linspace(p0[a], p1[a], shape[a] + 1)                # the global provider's node coordinates, bitwise
+        t = np.empty(2 * shape[a] + 1)
+        t[0::2] = ax
+        t[1::2] = 0.5 * (ax[:-1] + ax[1:])
+        tabs.append(t[lo[a]:lo[a] + dims[a]])
+    grids = np.meshgrid(*[np.arange(n) for n in dims[::-1]], indexing="ij")  # slowest axis first
+    loc = [grids[d - 1 - a].ravel() for a in range(d)]             # block-local half-step indices, x fastest
+    hidx = np.stack([loc[a] + lo[a] for a in range(d)], axis=1)
+    x = np.zeros((len(hidx), 3))
+    for a in range(d):
+        x[:, a] = tabs[a][loc[a]]
+    # cells: cube by cube in the slab mesh's order (layers l0 .. lg - 1, lexicographic, x fastest)
+    ncube = [shape[a] for a in range(d - 1)] + [lg - l0]
+    cg = np.meshgrid(*[np.arange(n) for n in ncube[::-1]], indexing="ij")
+    cube = [cg[d - 1 - a].ravel() for a in range(d)]
+    stride = [1]
+    for a in range(1, d):
+        stride.append(stride[-1] * dims[a - 1])
+    flat = lambda off: sum((2 * cube[a] + off[a]) * stride[a] for a in range(d))
+    corner = lambda c: tuple((c >> a) & 1 for a in range(d))
+    cols = []
+    for cell in _BOX_CELLS[d]:
+        cv = [corner(c) for c in cell]
+        verts = [flat(tuple(2 * o for o in v)) for v in cv]
+        edges = [flat(tuple(cv[a][k] + cv[b][k] for k in range(d))) for a, b in _EDGE_VERTS[d]]
+        cols.append(np.stack(verts + edges, axis=1))
+    cell_dofs = np.stack(cols, axis=1).reshape(-1, cols[0].shape[1])
+    return x, cell_dofs, hidx
+
+
 def slab_functionspace(mesh: SlabMesh, degree: int, bs: int = 1):
     """Scalar (or blocked) Lagrange space on a slab mesh: ``fem.LocalFunctionSpace`` surface, local numbering
     owned-first then ghosts grouped by owner (each group in global order)."""
@@ -157,16 +202,11 @@ class SlabFunctionSpace(fem.FunctionSpace):
         self._scalar = self
         d = mesh.geometry.dim
         cells = mesh.geometry.dofmap.astype(np.int64)
-        nv = mesh.geometry.x.shape[0]
         nidx = mesh._node_index
         if degree == 1:
             x, cell_dofs, hidx = mesh.geometry.x, cells, nidx
         else:
-            edges = mesh.topology.entities(1)
-            ce = mesh.topology.cell_entities(1)
-            x = np.vstack([mesh.geometry.x, 0.5 * (mesh.geometry.x[edges[:, 0]] + mesh.geometry.x[edges[:, 1]])])
-            cell_dofs = np.hstack([cells, nv + ce])
-            hidx = np.vstack([2 * nidx, nidx[edges[:, 0]] + nidx[edges[:, 1]]])
+            x, cell_dofs, hidx = _slab_p2_block(mesh)  # closed form on the slab's block of the half-step lattice
         order_kind = getattr(mesh, "_dof_order", "class")
         if order_kind == "sigma":
             raise NotImplementedError("the window-sorted dof order has no closed form: use 'class' or 'generic' on several ranks")
@@ -187,6 +227,22 @@ class SlabFunctionSpace(fem.FunctionSpace):
         self.dofmap = fem.DofMap(new_of_old[cell_dofs], fem.IndexMap(n_owned, ghosts=self._gid[n_owned:], owners=self._owner[n_owned:],
                                                                      size_global=n_global), 1)
         self._local = self._build_local(n_owned, n_global)
+
+    def entity_closure_dofs(self, edim: int, entities: np.ndarray) -> np.ndarray:
+        """Sorted unique local dofs on the closure of the given (local) mesh entities; for P2 from the lattice in closed
+        form (vertex dofs at twice the node index, edge-midpoint dofs at the sum of the end points' indices)."""
+        if self.degree == 1:
+            return super().entity_closure_dofs(edim, entities)
+        mesh = self.mesh
+        ents = mesh.topology.entities(edim)[np.asarray(entities, dtype=np.int64)]
+        nidx = mesh._node_index
+        pts = [2 * nidx[np.unique(ents.ravel())]]
+        k = ents.shape[1]
+        for a in range(k):
+            for b in range(a + 1, k):
+                pts.append(nidx[ents[:, a]] + nidx[ents[:, b]])
+        gids = np.unique(fem.lattice_dof_ids(np.vstack(pts), mesh._shape, 2, getattr(mesh, "_dof_order", "class")))
+        return np.sort(self._local.g2l[gids]).astype(np.int32)
 
     def _build_local(self, n_owned: int, n_global: int) -> LocalSpace:
         mesh = self.mesh
