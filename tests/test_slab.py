@@ -165,3 +165,31 @@ def test_slab_halo_over_gloo_two_ranks(tmp_path):
          "--master-port", "29633", str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("gdim,shape,nranks", [(2, (10, 10), 2), (3, (4, 4, 6), 3)])
+def test_pressure_bc_on_a_slab_equals_the_partitioned_route(gdim, shape, nranks):
+    """PressureBC.create_bcs on slab-local spaces: the same (local cell, local facet) pairs and the same pressure Dirichlet
+    dofs as on the LocalFunctionSpaces of a partitioned replicated mesh (tests/test_partition.py covers that route)."""
+    from oasisx_b200 import PressureBC
+
+    g, locs = _meshes(gdim, shape, nranks)
+    fdim = gdim - 1
+    right = lambda x: np.isclose(x[0], 1.0)
+    gV, gQ = fem.functionspace(g, ("Lagrange", 2)), fem.functionspace(g, ("Lagrange", 1))
+    gf = bmesh.locate_entities_boundary(g, fdim, right)
+    gtags = bmesh.meshtags(g, fdim, np.sort(gf), np.full(len(gf), 3, dtype=np.int32))
+    for r, m in enumerate(locs):
+        ref_lp = part.partition(g, gV, gQ, nranks, r)
+        V, Q = fem.LocalFunctionSpace(gV, ref_lp.V, 1), fem.LocalFunctionSpace(gQ, ref_lp.Q, 1)
+        V._local_cells = Q._local_cells = ref_lp.cells
+        ref = PressureBC(lambda x: 2.0 + x[1], (gtags, 3))
+        ref.create_bcs(V, Q)
+        lp, Vs, Qs = slab.local_problem(m, 2, 1)
+        lf = bmesh.locate_entities_boundary(m, fdim, right)
+        ltags = bmesh.meshtags(m, fdim, np.sort(lf), np.full(len(lf), 3, dtype=np.int32))
+        bc = PressureBC(lambda x: 2.0 + x[1], (ltags, 3))
+        bc.create_bcs(Vs, Qs)
+        assert sorted(zip(bc._facet_cells.tolist(), bc._facet_local.tolist())) == sorted(zip(ref._facet_cells.tolist(), ref._facet_local.tolist()))
+        assert np.array_equal(np.sort(bc.bc.dofs), np.sort(ref.bc.dofs))
+        assert np.array_equal(bc._h, ref._h)
